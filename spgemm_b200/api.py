@@ -1,0 +1,326 @@
+"""Host-side mirror of the reference driver's interface for the TileSpGEMM hot path.
+
+Two layers over the C ABI (include/tilespgemm.h), both thin:
+
+* the reference-named calls -- `csr2tile_row_major`, `csr2tile_col_major`, `tilespgemm`, `tile2csr`,
+  `matrix_destroy`, `matrix_transposition` -- operating on a `HostMatrix` that wraps the same
+  `SMatrix` struct the reference driver allocates (reference src/main.cu:77-152, 168, 191, 261, 327);
+  host buffers in, host buffers out, like the reference;
+* the device-resident calls (`DeviceCSR`, `DeviceTiled`, `csr2tile`, `spgemm`, `tile2csr_device`, ...)
+  that keep everything in HBM between the stages and run C tile-row slabs.
+
+Everything computes on the GPU through libtilespgemm_b200.so; errors raise `TsgError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as L
+from .lib import Stats, TsgError  # noqa: F401  (re-exported)
+
+_libc = C.CDLL(None)
+_libc.free.argtypes = [C.c_void_p]
+_libc.free.restype = None
+
+
+def _p(a, ct):
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+def _take(ptr, n, dtype):
+    """Copy n items out of a malloc()ed C array into numpy."""
+    if n <= 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# Reference-named layer
+# ----------------------------------------------------------------------------------------------
+class HostMatrix:
+    """An `SMatrix` (reference src/common.h:150-172) plus the numpy arrays backing its CSR view."""
+
+    def __init__(self):
+        self.s = L.SMatrix()
+        self._keep = []          # numpy arrays whose memory the struct points into
+        self._tile_owned = False  # tile arrays malloc()ed by the library
+        self._csr_owned = False   # CSR arrays malloc()ed by the library (tile2csr)
+
+    @classmethod
+    def from_csr(cls, m, n, rowptr, colidx, val):
+        self = cls()
+        rp = np.ascontiguousarray(rowptr, dtype=np.int32)
+        ci = np.ascontiguousarray(colidx, dtype=np.int32)
+        v = np.ascontiguousarray(val, dtype=np.float64)
+        self._keep = [rp, ci, v]
+        s = self.s
+        s.m, s.n, s.nnz, s.isSymmetric = int(m), int(n), int(rp[m]), 0
+        s.rowpointer, s.columnindex, s.value = _p(rp, C.c_int), _p(ci, C.c_int), _p(v, C.c_double)
+        return self
+
+    def alias_csr_of(self, other: "HostMatrix"):
+        """B aliases A's CSR arrays for -aat 0 (reference src/main.cu:145-151)."""
+        s, o = self.s, other.s
+        s.m, s.n, s.nnz, s.isSymmetric = o.m, o.n, o.nnz, 0
+        s.rowpointer, s.columnindex, s.value = o.rowpointer, o.columnindex, o.value
+        self._keep = other._keep
+        return self
+
+    # numpy copies of the library-produced arrays
+    def tiles(self) -> dict:
+        s = self.s
+        nt, nnz = s.numtile, s.nnz
+        d = dict(m=s.m, n=s.n, tilem=s.tilem, tilen=s.tilen, numtile=nt, nnz=nnz,
+                 tile_ptr=_take(s.tile_ptr, s.tilem + 1, np.int32),
+                 tile_columnidx=_take(s.tile_columnidx, nt, np.int32),
+                 tile_rowidx=_take(s.tile_rowidx, nt, np.int32),
+                 tile_nnz=_take(s.tile_nnz, nt + 1, np.int32),
+                 val=_take(s.tile_csr_Value, nnz, np.float64),
+                 col=_take(s.tile_csr_Col, nnz, np.uint16),
+                 ptr=_take(s.tile_csr_Ptr, nt * 16, np.uint16),
+                 mask=_take(s.mask, nt * 16, np.uint16))
+        if s.csc_tile_ptr:
+            d["csc_tile_ptr"] = _take(s.csc_tile_ptr, s.tilen + 1, np.int32)
+            d["csc_tile_rowidx"] = _take(s.csc_tile_rowidx, nt, np.int32)
+        return d
+
+    def csr(self):
+        s = self.s
+        return (_take(s.rowpointer, s.m + 1, np.int32), _take(s.columnindex, s.nnz, np.int32),
+                _take(s.value, s.nnz, np.float64))
+
+
+def csr2tile_row_major(matrix: HostMatrix, tile_size_m: int = 16, tile_size_n: int = 16) -> None:
+    """Reference src/csr2tile.h:205."""
+    L.load().csr2tile_row_major(C.byref(matrix.s), tile_size_m, tile_size_n)
+    L.check()
+    matrix._tile_owned = True
+
+
+def csr2tile_col_major(matrix: HostMatrix, tile_size_m: int = 16, tile_size_n: int = 16) -> None:
+    """Reference src/csr2tile.h:279."""
+    L.load().csr2tile_col_major(C.byref(matrix.s), tile_size_m, tile_size_n)
+    L.check()
+    matrix._tile_owned = True
+
+
+def tilespgemm(A: HostMatrix, B: HostMatrix, nnzCub: int, tile_size_m: int = 16, tile_size_n: int = 16):
+    """Reference src/tilespgemm-cuda.h:2220. Returns (C, info) with the reference's out-parameters."""
+    Cm = HostMatrix()
+    nnzC = C.c_ulonglong(0)
+    outs = [C.c_double(0) for _ in range(7)]  # compression_rate, time_tile, gflops_tile, step1, step2, step3, malloc
+    L.load().tilespgemm(C.byref(A.s), C.byref(B.s), C.byref(Cm.s), None, None, 0, C.c_double(0), C.c_double(0),
+                        C.c_ulonglong(int(nnzCub)), C.byref(nnzC), C.byref(outs[0]), C.byref(outs[1]), C.byref(outs[2]),
+                        b"synthetic", C.byref(outs[3]), C.byref(outs[4]), C.byref(outs[5]), C.byref(outs[6]),
+                        tile_size_m, tile_size_n)
+    L.check()
+    Cm._tile_owned = True
+    info = dict(nnzC_computed=nnzC.value, compression_rate=outs[0].value, time_tile=outs[1].value,
+                gflops_tile=outs[2].value, time_step1=outs[3].value, time_step2=outs[4].value,
+                time_step3=outs[5].value, time_malloc=outs[6].value)
+    return Cm, info
+
+
+def tile2csr(matrix: HostMatrix, tile_size_m: int = 16, tile_size_n: int = 16) -> None:
+    """Reference src/tile2csr.h:72 (the driver passes (tile_size_m, tile_size_m), main.cu:327)."""
+    L.load().tile2csr(C.byref(matrix.s), tile_size_m, tile_size_n)
+    L.check()
+    matrix._csr_owned = True
+
+
+def matrix_destroy(matrix: HostMatrix) -> None:
+    """Reference src/csr2tile.h:509, plus the arrays the reference leaks."""
+    s = matrix.s
+    if matrix._tile_owned:
+        L.load().matrix_destroy(C.byref(s))
+        for name in ("tile_rowidx", "csc_tile_ptr", "csc_tile_rowidx"):
+            ptr = getattr(s, name)
+            if ptr:
+                _libc.free(C.cast(ptr, C.c_void_p))
+            setattr(s, name, None)
+        matrix._tile_owned = False
+    if matrix._csr_owned:
+        for name in ("rowpointer", "columnindex", "value"):
+            ptr = getattr(s, name)
+            if ptr:
+                _libc.free(C.cast(ptr, C.c_void_p))
+            setattr(s, name, None)
+        matrix._csr_owned = False
+
+
+def matrix_transposition(m, n, rowptr, colidx, val):
+    """Reference src/utils.h:161. Returns (cscColPtr, cscRowIdx, cscVal)."""
+    rp = np.ascontiguousarray(rowptr, dtype=np.int32)
+    ci = np.ascontiguousarray(colidx, dtype=np.int32)
+    v = np.ascontiguousarray(val, dtype=np.float64)
+    nnz = int(rp[m])
+    colptr = np.zeros(n + 1, np.int32)
+    rowidx = np.zeros(max(nnz, 1), np.int32)
+    cv = np.zeros(max(nnz, 1), np.float64)
+    L.load().matrix_transposition(int(m), int(n), nnz, _p(rp, C.c_int), _p(ci, C.c_int), _p(v, C.c_double),
+                                  _p(rowidx, C.c_int), _p(colptr, C.c_int), _p(cv, C.c_double))
+    L.check()
+    return colptr, rowidx[:nnz], cv[:nnz]
+
+
+# ----------------------------------------------------------------------------------------------
+# Device-resident layer
+# ----------------------------------------------------------------------------------------------
+def init(device: int = 0) -> None:
+    L.check(L.load().tsg_init(int(device)))
+
+
+def shutdown() -> None:
+    L.load().tsg_shutdown()
+
+
+def launch_count() -> int:
+    return int(L.load().tsg_launch_count())
+
+
+class DeviceCSR:
+    def __init__(self):
+        self.d = L.DCsr()
+
+    @classmethod
+    def upload(cls, m, n, rowptr, colidx, val):
+        self = cls()
+        rp = np.ascontiguousarray(rowptr, dtype=np.int32)
+        ci = np.ascontiguousarray(colidx, dtype=np.int32)
+        v = np.ascontiguousarray(val, dtype=np.float64)
+        L.check(L.load().tsg_csr_upload(int(m), int(n), _p(rp, C.c_int), _p(ci, C.c_int), _p(v, C.c_double), C.byref(self.d)))
+        return self
+
+    @classmethod
+    def upload_ptrs(cls, m, n, rowptr_addr, colidx_addr, val_addr):
+        """Upload from raw host addresses (e.g. pinned torch tensors' data_ptr())."""
+        self = cls()
+        L.check(L.load().tsg_csr_upload(int(m), int(n), C.c_void_p(rowptr_addr), C.c_void_p(colidx_addr),
+                                        C.c_void_p(val_addr), C.byref(self.d)))
+        return self
+
+    @classmethod
+    def wrap(cls, m, n, nnz, d_rowptr, d_colidx, d_val):
+        self = cls()
+        L.check(L.load().tsg_csr_wrap(int(m), int(n), C.c_longlong(int(nnz)), C.c_void_p(d_rowptr), C.c_void_p(d_colidx),
+                                      C.c_void_p(d_val), C.byref(self.d)))
+        return self
+
+    m = property(lambda self: self.d.m)
+    n = property(lambda self: self.d.n)
+    nnz = property(lambda self: self.d.nnz)
+
+    def download(self):
+        rp = np.zeros(self.d.m + 1, np.int32)
+        ci = np.zeros(max(self.d.nnz, 1), np.int32)
+        v = np.zeros(max(self.d.nnz, 1), np.float64)
+        L.check(L.load().tsg_csr_download(C.byref(self.d), _p(rp, C.c_int), _p(ci, C.c_int), _p(v, C.c_double)))
+        return rp, ci[:self.d.nnz], v[:self.d.nnz]
+
+    def download_into(self, rowptr_addr, colidx_addr, val_addr):
+        L.check(L.load().tsg_csr_download(C.byref(self.d), C.c_void_p(rowptr_addr), C.c_void_p(colidx_addr),
+                                          C.c_void_p(val_addr)))
+
+    def free(self):
+        L.load().tsg_csr_free(C.byref(self.d))
+
+
+class DeviceTiled:
+    def __init__(self):
+        self.d = L.DTile()
+
+    def __getattr__(self, k):
+        if k in ("m", "n", "tilem", "tilen", "numtile", "nnz", "col_major", "trow0"):
+            return getattr(self.d, k)
+        raise AttributeError(k)
+
+    def download(self) -> dict:
+        h = HostMatrix()
+        L.check(L.load().tsg_tile_download(C.byref(self.d), C.byref(h.s)))
+        h._tile_owned = True
+        out = h.tiles()
+        out["trow0"] = self.d.trow0
+        matrix_destroy(h)
+        return out
+
+    def slab_bytes(self):
+        return [int(b) for b in self.d.slab_bytes]
+
+    def free(self):
+        L.load().tsg_tile_free(C.byref(self.d))
+
+
+def csr2tile(a: DeviceCSR, col_major: bool) -> DeviceTiled:
+    t = DeviceTiled()
+    L.check(L.load().tsg_csr2tile(C.byref(a.d), int(bool(col_major)), C.byref(t.d)))
+    return t
+
+
+def tile_alloc(m, n, numtile, nnz, col_major) -> DeviceTiled:
+    t = DeviceTiled()
+    L.check(L.load().tsg_tile_alloc(int(m), int(n), int(numtile), C.c_longlong(int(nnz)), int(bool(col_major)), C.byref(t.d)))
+    return t
+
+
+def tile_upload(h: HostMatrix, col_major: bool) -> DeviceTiled:
+    t = DeviceTiled()
+    L.check(L.load().tsg_tile_upload(C.byref(h.s), int(bool(col_major)), C.byref(t.d)))
+    return t
+
+
+def transpose(a: DeviceCSR) -> DeviceCSR:
+    at = DeviceCSR()
+    L.check(L.load().tsg_transpose(C.byref(a.d), C.byref(at.d)))
+    return at
+
+
+def nnzcub(a: DeviceCSR, b: DeviceCSR) -> int:
+    out = C.c_ulonglong(0)
+    L.check(L.load().tsg_nnzcub(C.byref(a.d), C.byref(b.d), C.byref(out)))
+    return int(out.value)
+
+
+def tilerow_weights(a: DeviceTiled, b: DeviceTiled) -> np.ndarray:
+    w = np.zeros(max(a.tilem, 1), np.int64)
+    L.check(L.load().tsg_tilerow_weights(C.byref(a.d), C.byref(b.d), _p(w, C.c_longlong)))
+    return w[:a.tilem]
+
+
+def spgemm(a: DeviceTiled, b: DeviceTiled, trow0: int = 0, trow1: int = -1):
+    """Steps 1-3 for C tile-rows [trow0, trow1). Returns (C slab, stats dict)."""
+    c = DeviceTiled()
+    st = L.Stats()
+    L.check(L.load().tsg_spgemm(C.byref(a.d), C.byref(b.d), int(trow0), int(trow1), C.byref(c.d), C.byref(st)))
+    return c, st.as_dict()
+
+
+def tile2csr_device(t: DeviceTiled) -> DeviceCSR:
+    out = DeviceCSR()
+    L.check(L.load().tsg_tile2csr(C.byref(t.d), C.byref(out.d)))
+    return out
+
+
+def spgemm_csr_host(m, k, n, A, B=None, aat=False):
+    """Whole pipeline, host CSR in -> host CSR out. A, B = (rowptr, colidx, val); B=None means B=A
+    (or A^T with aat=True). Returns (rowptr, colidx, val, stats dict)."""
+    rpA, ciA, vA = (np.ascontiguousarray(A[0], np.int32), np.ascontiguousarray(A[1], np.int32),
+                    np.ascontiguousarray(A[2], np.float64))
+    if B is not None:
+        rpB, ciB, vB = (np.ascontiguousarray(B[0], np.int32), np.ascontiguousarray(B[1], np.int32),
+                        np.ascontiguousarray(B[2], np.float64))
+        bargs = (_p(rpB, C.c_int), _p(ciB, C.c_int), _p(vB, C.c_double))
+    else:
+        bargs = (None, None, None)
+    crp, cci, cv = C.POINTER(C.c_int)(), C.POINTER(C.c_int)(), C.POINTER(C.c_double)()
+    cnnz = C.c_longlong(0)
+    st = L.Stats()
+    rc = L.load().tsg_spgemm_csr_host(int(m), int(k), int(n), _p(rpA, C.c_int), _p(ciA, C.c_int), _p(vA, C.c_double),
+                                      *bargs, int(bool(aat)), C.byref(crp), C.byref(cci), C.byref(cv), C.byref(cnnz),
+                                      C.byref(st))
+    L.check(rc)
+    out = (_take(crp, m + 1, np.int32), _take(cci, cnnz.value, np.int32), _take(cv, cnnz.value, np.float64), st.as_dict())
+    for ptr in (crp, cci, cv):
+        _libc.free(C.cast(ptr, C.c_void_p))
+    return out

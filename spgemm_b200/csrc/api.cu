@@ -1,0 +1,505 @@
+// api.cu -- the C ABI of libtilespgemm_b200.so (include/tilespgemm.h): library context, the
+// reference-named drop-in entry points (host buffers) and the device-resident tsg_* API.
+#include <stdarg.h>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tsg {
+
+static Ctx g_ctx;
+static bool g_ready = false;
+static int g_err = TSG_OK;
+static char g_errmsg[512] = "";
+
+Ctx &ctx() { return g_ctx; }
+bool ctx_ready() { return g_ready; }
+int last_error() { return g_err; }
+
+void set_error(int code, const char *fmt, ...)
+{
+    if (g_err != TSG_OK) return;  // keep the first error
+    g_err = code;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_errmsg, sizeof(g_errmsg), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "[tilespgemm_b200] ERROR %d: %s\n", code, g_errmsg);
+}
+
+bool cuda_ok(cudaError_t e, const char *what, const char *file, int line)
+{
+    if (e == cudaSuccess) return true;
+    set_error(e == cudaErrorMemoryAllocation ? TSG_ERR_NOMEM : TSG_ERR_CUDA, "%s failed at %s:%d: %s", what, file, line,
+              cudaGetErrorString(e));
+    return false;
+}
+
+void *dalloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (bytes == 0) bytes = 256;
+    cudaError_t e = cudaMallocAsync(&p, bytes, g_ctx.stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error(TSG_ERR_NOMEM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+
+void dfree(void *p)
+{
+    if (p) cudaFreeAsync(p, g_ctx.stream);
+}
+
+int read_back_i32(const int *d, int *out)
+{
+    CK(cudaMemcpyAsync(&g_ctx.h_scalars[15], d, sizeof(int), cudaMemcpyDeviceToHost, g_ctx.stream));
+    CK(cudaStreamSynchronize(g_ctx.stream));
+    *out = *(const int *)&g_ctx.h_scalars[15];
+    return TSG_OK;
+}
+
+int read_back_i64(const long long *d, long long *out)
+{
+    CK(cudaMemcpyAsync(&g_ctx.h_scalars[15], d, sizeof(long long), cudaMemcpyDeviceToHost, g_ctx.stream));
+    CK(cudaStreamSynchronize(g_ctx.stream));
+    *out = g_ctx.h_scalars[15];
+    return TSG_OK;
+}
+
+static int ensure_init()
+{
+    if (g_ready) return TSG_OK;
+    int dev = 0;
+    if (!cuda_ok(cudaGetDevice(&dev), "cudaGetDevice (is a CUDA device present?)", __FILE__, __LINE__)) return g_err;
+    return tsg_init(dev);
+}
+
+static bool tiles_16(int tm, int tn)
+{
+    if (tm == TS && tn == TS) return true;
+    set_error(TSG_ERR_UNSUPPORTED, "tile size %dx%d: only 16x16 tiles are implemented", tm, tn);
+    return false;
+}
+
+}  // namespace tsg
+
+using namespace tsg;
+
+extern "C" {
+
+int tilespgemm_last_error(void) { return g_err; }
+const char *tilespgemm_last_error_string(void) { return g_errmsg; }
+void tilespgemm_clear_error(void) { g_err = TSG_OK; g_errmsg[0] = 0; }
+
+int tsg_init(int device)
+{
+    if (g_ready && g_ctx.device == device) return TSG_OK;
+    if (g_ready) tsg_shutdown();
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error(TSG_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return g_err;
+    }
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    g_ctx = Ctx();
+    g_ctx.device = device;
+    g_ctx.num_sms = prop.multiProcessorCount;
+    g_ctx.smem_optin = prop.sharedMemPerBlockOptin;
+    CK(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    CK(cudaDeviceGetDefaultMemPool(&g_ctx.pool, device));
+    unsigned long long thresh = ~0ull;  // keep freed blocks cached: no cudaMalloc/cudaFree in steady state
+    CK(cudaMemPoolSetAttribute(g_ctx.pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    CK(cudaMalloc(&g_ctx.scan_ticket, 256));
+    CK(cudaMalloc(&g_ctx.d_scalars, 16 * sizeof(long long)));
+    CK(cudaMallocHost(&g_ctx.h_scalars, 16 * sizeof(long long)));
+    g_ready = true;
+    return TSG_OK;
+}
+
+void tsg_shutdown(void)
+{
+    if (!g_ready) return;
+    cudaStreamSynchronize(g_ctx.stream);
+    if (g_ctx.scan_state) cudaFreeAsync(g_ctx.scan_state, g_ctx.stream);
+    cudaStreamSynchronize(g_ctx.stream);
+    cudaFree(g_ctx.scan_ticket);
+    cudaFree(g_ctx.d_scalars);
+    cudaFreeHost(g_ctx.h_scalars);
+    cudaStreamDestroy(g_ctx.stream);
+    g_ctx = Ctx();
+    g_ready = false;
+}
+
+void *tsg_stream(void) { return g_ready ? (void *)g_ctx.stream : nullptr; }
+
+int tsg_sync(void)
+{
+    if (ensure_init()) return g_err;
+    CK(cudaStreamSynchronize(g_ctx.stream));
+    return TSG_OK;
+}
+
+long long tsg_launch_count(void) { return g_ctx.launches; }
+
+/* ------------------------------- CSR on the device ------------------------------- */
+
+static int csr_alloc(int m, int n, long long nnz, tsg_dcsr *out)
+{
+    memset(out, 0, sizeof(*out));
+    size_t nz = (size_t)(nnz > 0 ? nnz : 1);
+    size_t o_ci = (((size_t)m + 1) * 4 + 255) & ~(size_t)255, o_v = o_ci + ((nz * 4 + 255) & ~(size_t)255);
+    char *base = (char *)dalloc(o_v + nz * 8);
+    if (!base) return g_err;
+    out->m = m; out->n = n; out->nnz = nnz; out->owner = base;
+    out->rowptr = (int *)base; out->colidx = (int *)(base + o_ci); out->val = (double *)(base + o_v);
+    return TSG_OK;
+}
+
+int tsg_csr_upload(int m, int n, const int *rowptr, const int *colidx, const double *val, tsg_dcsr *out)
+{
+    if (ensure_init()) return g_err;
+    if (m < 0 || n < 0 || !rowptr) { set_error(TSG_ERR_INPUT, "tsg_csr_upload: bad arguments"); return g_err; }
+    long long nnz = rowptr[m];
+    if (nnz < 0) { set_error(TSG_ERR_INPUT, "tsg_csr_upload: rowptr[m] = %lld", nnz); return g_err; }
+    int rc = csr_alloc(m, n, nnz, out);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out->rowptr, rowptr, ((size_t)m + 1) * 4, cudaMemcpyHostToDevice, g_ctx.stream));
+    if (nnz > 0) {
+        CK(cudaMemcpyAsync(out->colidx, colidx, (size_t)nnz * 4, cudaMemcpyHostToDevice, g_ctx.stream));
+        CK(cudaMemcpyAsync(out->val, val, (size_t)nnz * 8, cudaMemcpyHostToDevice, g_ctx.stream));
+    }
+    CK(cudaStreamSynchronize(g_ctx.stream));
+    return TSG_OK;
+}
+
+int tsg_csr_wrap(int m, int n, long long nnz, int *d_rowptr, int *d_colidx, double *d_val, tsg_dcsr *out)
+{
+    if (ensure_init()) return g_err;
+    memset(out, 0, sizeof(*out));
+    out->m = m; out->n = n; out->nnz = nnz; out->rowptr = d_rowptr; out->colidx = d_colidx; out->val = d_val; out->owner = nullptr;
+    return TSG_OK;
+}
+
+int tsg_csr_download(const tsg_dcsr *a, int *rowptr, int *colidx, double *val)
+{
+    if (ensure_init()) return g_err;
+    if (rowptr) CK(cudaMemcpyAsync(rowptr, a->rowptr, ((size_t)a->m + 1) * 4, cudaMemcpyDeviceToHost, g_ctx.stream));
+    if (a->nnz > 0) {
+        if (colidx) CK(cudaMemcpyAsync(colidx, a->colidx, (size_t)a->nnz * 4, cudaMemcpyDeviceToHost, g_ctx.stream));
+        if (val) CK(cudaMemcpyAsync(val, a->val, (size_t)a->nnz * 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+    }
+    CK(cudaStreamSynchronize(g_ctx.stream));
+    return TSG_OK;
+}
+
+void tsg_csr_free(tsg_dcsr *a)
+{
+    if (!a) return;
+    if (a->owner && g_ready) dfree(a->owner);
+    memset(a, 0, sizeof(*a));
+}
+
+int tsg_csr_validate(const tsg_dcsr *a)
+{
+    // The contract is checked by the scatter kernel of csr2tile (it sees every entry and its left
+    // neighbour anyway); a throw-away row-major conversion is the validation.
+    if (ensure_init()) return g_err;
+    tsg_dtile t;
+    int rc = csr2tile_device(a, 0, &t);
+    tsg_tile_free(&t);
+    if (rc == TSG_OK) CK(cudaStreamSynchronize(g_ctx.stream));
+    return rc;
+}
+
+int tsg_transpose(const tsg_dcsr *a, tsg_dcsr *at)
+{
+    if (ensure_init()) return g_err;
+    int rc = transpose_device(a, at);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(g_ctx.stream));
+    return TSG_OK;
+}
+
+int tsg_nnzcub(const tsg_dcsr *a, const tsg_dcsr *b, unsigned long long *out)
+{
+    if (ensure_init()) return g_err;
+    if (a->n != b->m) { set_error(TSG_ERR_UNSUPPORTED, "nnzcub: inner dimensions differ"); return g_err; }
+    return nnzcub_device(a, b, out);
+}
+
+/* ------------------------------- tiles on the device ------------------------------- */
+
+int tsg_csr2tile(const tsg_dcsr *a, int col_major, tsg_dtile *out)
+{
+    if (ensure_init()) return g_err;
+    int rc = csr2tile_device(a, col_major, out);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(g_ctx.stream));
+    return TSG_OK;
+}
+
+int tsg_tile_alloc(int m, int n, int numtile, long long nnz, int col_major, tsg_dtile *out)
+{
+    if (ensure_init()) return g_err;
+    return tile_alloc_layout(m, n, numtile, nnz, col_major, out);
+}
+
+void tsg_tile_free(tsg_dtile *t)
+{
+    if (!t) return;
+    for (int k = 0; k < 4; k++)
+        if (t->slab[k] && g_ready) dfree(t->slab[k]);
+    memset(t, 0, sizeof(*t));
+}
+
+int tsg_tile_upload(const SMatrix *h, int col_major, tsg_dtile *out)
+{
+    if (ensure_init()) return g_err;
+    if (h->numtile < 0 || h->nnz < 0) { set_error(TSG_ERR_INPUT, "tsg_tile_upload: negative sizes"); return g_err; }
+    int rc = tile_alloc_layout(h->m, h->n, h->numtile, h->nnz, col_major, out);
+    if (rc) return rc;
+    out->tilem = h->tilem; out->tilen = h->tilen;
+    cudaStream_t s = g_ctx.stream;
+    const size_t nt = (size_t)h->numtile, nz = (size_t)h->nnz;
+    CK(cudaMemcpyAsync(out->tile_ptr, h->tile_ptr, ((size_t)h->tilem + 1) * 4, cudaMemcpyHostToDevice, s));
+    if (nt) {
+        CK(cudaMemcpyAsync(out->tile_columnidx, h->tile_columnidx, nt * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(out->ptr, h->tile_csr_Ptr, nt * TS * 2, cudaMemcpyHostToDevice, s));
+        if (h->mask) CK(cudaMemcpyAsync(out->mask, h->mask, nt * TS * 2, cudaMemcpyHostToDevice, s));
+        else CK(cudaMemsetAsync(out->mask, 0, nt * TS * 2, s));
+        CK(cudaMemsetAsync(out->tile_rowidx, 0, nt * 4, s));
+    }
+    CK(cudaMemcpyAsync(out->tile_nnz, h->tile_nnz, (nt + 1) * 4, cudaMemcpyHostToDevice, s));
+    if (nz) {
+        CK(cudaMemcpyAsync(out->val, h->tile_csr_Value, nz * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(out->col, h->tile_csr_Col, nz * 2, cudaMemcpyHostToDevice, s));
+    }
+    if (col_major) {
+        CK(cudaMemcpyAsync(out->csc_tile_ptr, h->csc_tile_ptr, ((size_t)h->tilen + 1) * 4, cudaMemcpyHostToDevice, s));
+        if (nt) CK(cudaMemcpyAsync(out->csc_tile_rowidx, h->csc_tile_rowidx, nt * 4, cudaMemcpyHostToDevice, s));
+        rc = build_rm2csc_device(out);
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(s));
+    return TSG_OK;
+}
+
+int tsg_tile_download(const tsg_dtile *t, SMatrix *h)
+{
+    if (ensure_init()) return g_err;
+    if (t->nnz >= (1ll << 31)) { set_error(TSG_ERR_OVERFLOW, "tile download: nnz %lld does not fit SMatrix.nnz", t->nnz); return g_err; }
+    cudaStream_t s = g_ctx.stream;
+    const size_t nt = (size_t)t->numtile, nz = (size_t)t->nnz;
+    h->m = t->m; h->n = t->n; h->tilem = t->tilem; h->tilen = t->tilen; h->numtile = t->numtile; h->nnz = (int)t->nnz;
+    h->tile_ptr = (int *)malloc(((size_t)t->tilem + 1) * 4);
+    h->tile_columnidx = (int *)malloc((nt ? nt : 1) * 4);
+    h->tile_rowidx = (int *)calloc(nt ? nt : 1, 4);
+    h->tile_nnz = (int *)malloc((nt + 1) * 4);
+    h->tile_csr_Value = (double *)malloc((nz ? nz : 1) * 8);
+    h->tile_csr_Col = (uint16_t *)malloc((nz ? nz : 1) * 2);
+    h->tile_csr_Ptr = (uint16_t *)malloc((nt ? nt : 1) * TS * 2);
+    h->mask = (uint16_t *)malloc((nt ? nt : 1) * TS * 2);
+    h->csc_tile_ptr = nullptr; h->csc_tile_rowidx = nullptr;
+    if (!h->tile_ptr || !h->tile_columnidx || !h->tile_rowidx || !h->tile_nnz || !h->tile_csr_Value || !h->tile_csr_Col ||
+        !h->tile_csr_Ptr || !h->mask) {
+        set_error(TSG_ERR_NOMEM, "tile download: host allocation failed");
+        return g_err;
+    }
+    CK(cudaMemcpyAsync(h->tile_ptr, t->tile_ptr, ((size_t)t->tilem + 1) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->tile_nnz, t->tile_nnz, (nt + 1) * 4, cudaMemcpyDeviceToHost, s));
+    if (nt) {
+        CK(cudaMemcpyAsync(h->tile_columnidx, t->tile_columnidx, nt * 4, cudaMemcpyDeviceToHost, s));
+        // reference csr2tile_col_major allocates tile_rowidx and leaves it zero (src/csr2tile.h:336-337)
+        if (!t->col_major) CK(cudaMemcpyAsync(h->tile_rowidx, t->tile_rowidx, nt * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h->tile_csr_Ptr, t->ptr, nt * TS * 2, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h->mask, t->mask, nt * TS * 2, cudaMemcpyDeviceToHost, s));
+    }
+    if (nz) {
+        CK(cudaMemcpyAsync(h->tile_csr_Value, t->val, nz * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h->tile_csr_Col, t->col, nz * 2, cudaMemcpyDeviceToHost, s));
+    }
+    if (t->col_major) {
+        h->csc_tile_ptr = (int *)malloc(((size_t)t->tilen + 1) * 4);
+        h->csc_tile_rowidx = (int *)malloc((nt ? nt : 1) * 4);
+        if (!h->csc_tile_ptr || !h->csc_tile_rowidx) { set_error(TSG_ERR_NOMEM, "tile download: host allocation failed"); return g_err; }
+        CK(cudaMemcpyAsync(h->csc_tile_ptr, t->csc_tile_ptr, ((size_t)t->tilen + 1) * 4, cudaMemcpyDeviceToHost, s));
+        if (nt) CK(cudaMemcpyAsync(h->csc_tile_rowidx, t->csc_tile_rowidx, nt * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    return TSG_OK;
+}
+
+int tsg_tilerow_weights(const tsg_dtile *a, const tsg_dtile *b, long long *w_host)
+{
+    if (ensure_init()) return g_err;
+    if (a->n != b->m) { set_error(TSG_ERR_UNSUPPORTED, "weights: inner dimensions differ"); return g_err; }
+    int *w = nullptr, *jlo = nullptr, *jhi = nullptr;
+    int rc = tilerow_weights_device(a, b, &w, &jlo, &jhi);
+    if (rc) return rc;
+    int *hw = (int *)malloc(((size_t)a->tilem + 1) * 4);
+    CK(cudaMemcpyAsync(hw, w, (size_t)a->tilem * 4, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CK(cudaStreamSynchronize(g_ctx.stream));
+    for (int i = 0; i < a->tilem; i++) w_host[i] = hw[i];
+    free(hw);
+    dfree(w); dfree(jlo); dfree(jhi);
+    return TSG_OK;
+}
+
+int tsg_spgemm(const tsg_dtile *a, const tsg_dtile *b, int trow0, int trow1, tsg_dtile *c, tsg_stats *stats)
+{
+    if (ensure_init()) return g_err;
+    int rc = spgemm_device(a, b, trow0, trow1, c, stats);
+    if (rc) { tsg_tile_free(c); return rc; }
+    return TSG_OK;
+}
+
+int tsg_tile2csr(const tsg_dtile *t, tsg_dcsr *out)
+{
+    if (ensure_init()) return g_err;
+    int rc = tile2csr_device(t, out);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(g_ctx.stream));
+    return TSG_OK;
+}
+
+int tsg_spgemm_csr_host(int m, int k, int n, const int *a_rowptr, const int *a_colidx, const double *a_val,
+                        const int *b_rowptr, const int *b_colidx, const double *b_val, int aat,
+                        int **c_rowptr, int **c_colidx, double **c_val, long long *c_nnz, tsg_stats *stats)
+{
+    if (ensure_init()) return g_err;
+    tsg_dcsr A, B, Cc;
+    tsg_dtile tA, tB, tC;
+    memset(&A, 0, sizeof(A)); memset(&B, 0, sizeof(B)); memset(&Cc, 0, sizeof(Cc));
+    memset(&tA, 0, sizeof(tA)); memset(&tB, 0, sizeof(tB)); memset(&tC, 0, sizeof(tC));
+    int rc = tsg_csr_upload(m, k, a_rowptr, a_colidx, a_val, &A);
+    const tsg_dcsr *Bp = &A;
+    if (!rc && aat) { rc = tsg_transpose(&A, &B); Bp = &B; }
+    else if (!rc && b_rowptr) { rc = tsg_csr_upload(k, n, b_rowptr, b_colidx, b_val, &B); Bp = &B; }
+    if (!rc && Bp->n != n) { set_error(TSG_ERR_UNSUPPORTED, "spgemm_csr_host: B has %d columns, expected %d", Bp->n, n); rc = g_err; }
+    if (!rc) rc = tsg_csr2tile(&A, 0, &tA);
+    if (!rc) rc = tsg_csr2tile(Bp, 1, &tB);
+    if (!rc) rc = tsg_spgemm(&tA, &tB, 0, -1, &tC, stats);
+    if (!rc) rc = tsg_tile2csr(&tC, &Cc);
+    if (!rc) {
+        *c_nnz = Cc.nnz;
+        *c_rowptr = (int *)malloc(((size_t)Cc.m + 1) * 4);
+        *c_colidx = (int *)malloc((size_t)(Cc.nnz > 0 ? Cc.nnz : 1) * 4);
+        *c_val = (double *)malloc((size_t)(Cc.nnz > 0 ? Cc.nnz : 1) * 8);
+        if (!*c_rowptr || !*c_colidx || !*c_val) { set_error(TSG_ERR_NOMEM, "spgemm_csr_host: host allocation failed"); rc = g_err; }
+        else rc = tsg_csr_download(&Cc, *c_rowptr, *c_colidx, *c_val);
+    }
+    tsg_csr_free(&A); tsg_csr_free(&B); tsg_csr_free(&Cc);
+    tsg_tile_free(&tA); tsg_tile_free(&tB); tsg_tile_free(&tC);
+    return rc;
+}
+
+/* ------------------------------- drop-in entry points ------------------------------- */
+
+static void csr2tile_host(SMatrix *mat, int tm, int tn, int col_major)
+{
+    if (ensure_init() || !tiles_16(tm, tn)) return;
+    tsg_dcsr A;
+    tsg_dtile t;
+    memset(&t, 0, sizeof(t));
+    if (tsg_csr_upload(mat->m, mat->n, mat->rowpointer, mat->columnindex, mat->value, &A)) return;
+    if (tsg_csr2tile(&A, col_major, &t) == TSG_OK) {
+        // tsg_tile_download overwrites the size fields with identical values and fills the tile arrays;
+        // the CSR members of *mat (caller-owned, possibly aliased by B, src/main.cu:145-151) are untouched.
+        tsg_tile_download(&t, mat);
+    }
+    tsg_tile_free(&t);
+    tsg_csr_free(&A);
+}
+
+void csr2tile_row_major(SMatrix *matrix, int tile_size_m, int tile_size_n) { csr2tile_host(matrix, tile_size_m, tile_size_n, 0); }
+void csr2tile_col_major(SMatrix *matrix, int tile_size_m, int tile_size_n) { csr2tile_host(matrix, tile_size_m, tile_size_n, 1); }
+
+void tilespgemm(SMatrix *matrixA, SMatrix *matrixB, SMatrix *matrixC, unsigned int *blk_intersec_bitmask_A,
+                unsigned int *blk_intersec_bitmask_B, int blk_intersec_bitmask_len, double densityA, double densityB,
+                unsigned long long int nnzCub, unsigned long long int *nnzC_computed, double *compression_rate,
+                double *time_tile, double *gflops_tile, char *filename, double *time_step1, double *time_step2,
+                double *time_step3, double *time_malloc, int tile_size_m, int tile_size_n)
+{
+    (void)blk_intersec_bitmask_A; (void)blk_intersec_bitmask_B; (void)blk_intersec_bitmask_len;  // dense tile bitmaps: never needed
+    (void)densityA; (void)densityB; (void)filename;
+    if (ensure_init() || !tiles_16(tile_size_m, tile_size_n)) return;
+    tsg_dtile tA, tB, tC;
+    tsg_stats st;
+    memset(&tA, 0, sizeof(tA)); memset(&tB, 0, sizeof(tB)); memset(&tC, 0, sizeof(tC)); memset(&st, 0, sizeof(st));
+    if (tsg_tile_upload(matrixA, 0, &tA) == TSG_OK && tsg_tile_upload(matrixB, 1, &tB) == TSG_OK &&
+        tsg_spgemm(&tA, &tB, 0, -1, &tC, &st) == TSG_OK) {
+        int keep_sym = matrixC->isSymmetric;
+        if (tsg_tile_download(&tC, matrixC) == TSG_OK) {
+            matrixC->isSymmetric = keep_sym;
+            matrixC->m = matrixA->m; matrixC->n = matrixB->n;           // reference :2768-2771
+            matrixC->tilem = matrixA->tilem; matrixC->tilen = matrixB->tilen;
+            if (nnzC_computed) *nnzC_computed = (unsigned long long)st.nnzC;
+            if (compression_rate) *compression_rate = st.nnzC ? (double)nnzCub / (double)st.nnzC : 0.0;
+            if (time_tile) *time_tile = st.ms_total;
+            if (gflops_tile) *gflops_tile = st.ms_total > 0 ? 2.0 * (double)nnzCub / (st.ms_total * 1e6) : 0.0;
+            if (time_step1) *time_step1 = st.ms_step1;
+            if (time_step2) *time_step2 = st.ms_step2;
+            if (time_step3) *time_step3 = st.ms_step3;
+            if (time_malloc) *time_malloc = st.ms_alloc;
+            // same stdout lines as the reference (:2810-2812)
+            printf("Non-empty tiles of C = %i\n", (int)st.numblkC);
+            printf("nnzC = %i\n", (int)st.nnzC);
+            printf("CUDA  TileSpGEMM runtime is %4.2f ms, gflops = %4.2f\n", st.ms_total,
+                   st.ms_total > 0 ? 2.0 * (double)nnzCub / (st.ms_total * 1e6) : 0.0);
+        }
+    }
+    tsg_tile_free(&tA); tsg_tile_free(&tB); tsg_tile_free(&tC);
+}
+
+void tile2csr(SMatrix *matrix, int tile_size_m, int tile_size_n)
+{
+    if (ensure_init() || !tiles_16(tile_size_m, tile_size_n)) return;
+    tsg_dtile t;
+    tsg_dcsr c;
+    memset(&t, 0, sizeof(t)); memset(&c, 0, sizeof(c));
+    if (tsg_tile_upload(matrix, 0, &t) == TSG_OK && tsg_tile2csr(&t, &c) == TSG_OK) {
+        matrix->rowpointer = (int *)malloc(((size_t)c.m + 1) * 4);
+        matrix->columnindex = (int *)malloc((size_t)(c.nnz > 0 ? c.nnz : 1) * 4);
+        matrix->value = (double *)malloc((size_t)(c.nnz > 0 ? c.nnz : 1) * 8);
+        if (!matrix->rowpointer || !matrix->columnindex || !matrix->value) set_error(TSG_ERR_NOMEM, "tile2csr: host allocation failed");
+        else if (tsg_csr_download(&c, matrix->rowpointer, matrix->columnindex, matrix->value) == TSG_OK)
+            matrix->nnz = (int)c.nnz;  // reference src/tile2csr.h:103-104
+    }
+    tsg_tile_free(&t);
+    tsg_csr_free(&c);
+}
+
+void matrix_destroy(SMatrix *matrix)
+{
+    free(matrix->tile_ptr);
+    free(matrix->tile_columnidx);
+    free(matrix->tile_nnz);
+    free(matrix->tile_csr_Value);
+    free(matrix->tile_csr_Col);
+    free(matrix->tile_csr_Ptr);
+    free(matrix->mask);
+    matrix->tile_ptr = nullptr; matrix->tile_columnidx = nullptr; matrix->tile_nnz = nullptr;
+    matrix->tile_csr_Value = nullptr; matrix->tile_csr_Col = nullptr; matrix->tile_csr_Ptr = nullptr; matrix->mask = nullptr;
+}
+
+void matrix_transposition(const int m, const int n, const MAT_PTR_TYPE nnz, const MAT_PTR_TYPE *csrRowPtr, const int *csrColIdx,
+                          const MAT_VAL_TYPE *csrVal, int *cscRowIdx, MAT_PTR_TYPE *cscColPtr, MAT_VAL_TYPE *cscVal)
+{
+    (void)nnz;
+    if (ensure_init()) return;
+    tsg_dcsr A, AT;
+    memset(&AT, 0, sizeof(AT));
+    if (tsg_csr_upload(m, n, csrRowPtr, csrColIdx, csrVal, &A)) return;
+    if (tsg_transpose(&A, &AT) == TSG_OK) tsg_csr_download(&AT, cscColPtr, cscRowIdx, cscVal);
+    tsg_csr_free(&A);
+    tsg_csr_free(&AT);
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// common.cuh -- library context, error latch, stream-ordered allocation, launch accounting.
+// B200 (sm_100a) only. No CPU fallback anywhere: a failed CUDA call latches an error and the
+// C-ABI entry point returns it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../../include/tilespgemm.h"
+
+#define TS 16             // tile edge (reference src/common.h:36 BLOCK_SIZE; MaskBits = 16)
+#define FULL_MASK 0xffffffffu
+
+namespace tsg {
+
+struct Ctx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;
+    int num_sms = 148;
+    size_t smem_optin = 0;
+    long long launches = 0;
+    // scan workspace (decoupled look-back tile states + ticket)
+    unsigned long long *scan_state = nullptr;
+    size_t scan_state_cap = 0;
+    int *scan_ticket = nullptr;
+    // small pinned host scratch for scalar read-backs
+    long long *h_scalars = nullptr;   // pinned, 16 slots
+    long long *d_scalars = nullptr;   // device, 16 slots
+};
+
+Ctx &ctx();
+bool ctx_ready();
+
+void set_error(int code, const char *fmt, ...);
+int last_error();
+
+// Returns false (and latches TSG_ERR_CUDA) on failure.
+bool cuda_ok(cudaError_t e, const char *what, const char *file, int line);
+#define CK(call)                                                       \
+    do {                                                               \
+        if (!tsg::cuda_ok((call), #call, __FILE__, __LINE__)) return tsg::last_error(); \
+    } while (0)
+#define CKV(call)                                                      \
+    do {                                                               \
+        if (!tsg::cuda_ok((call), #call, __FILE__, __LINE__)) return;  \
+    } while (0)
+// after a kernel launch
+#define CK_LAUNCH()                                                    \
+    do {                                                               \
+        tsg::ctx().launches++;                                         \
+        if (!tsg::cuda_ok(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)) return tsg::last_error(); \
+    } while (0)
+
+// Stream-ordered allocation from the library pool (no cudaMalloc/cudaFree synchronisation in the
+// hot loop -- the reference calls cudaMalloc ~25x inside its timed region, tilespgemm-cuda.h:2417-2638).
+void *dalloc(size_t bytes);
+void dfree(void *p);
+template <typename T> static inline T *dalloc_n(size_t n) { return (T *)dalloc((n ? n : 1) * sizeof(T)); }
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Read one device int / long long back (stream sync). Used only where a size is needed for an
+// allocation (numblkC, nnzC): two per SpGEMM call instead of the reference's ~8.
+int read_back_i32(const int *d, int *out);
+int read_back_i64(const long long *d, long long *out);
+
+}  // namespace tsg

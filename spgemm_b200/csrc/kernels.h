@@ -1,0 +1,21 @@
+// kernels.h -- internal host-side entry points of the translation units (not part of the C ABI).
+#pragma once
+#include "common.cuh"
+
+namespace tsg {
+
+// csr2tile.cu
+int tile_alloc_layout(int m, int n, int numtile, long long nnz, int col_major, tsg_dtile *out);
+int csr2tile_device(const tsg_dcsr *A, int col_major, tsg_dtile *out);
+int transpose_device(const tsg_dcsr *A, tsg_dcsr *AT);
+int nnzcub_device(const tsg_dcsr *A, const tsg_dcsr *B, unsigned long long *out);
+
+// spgemm.cu
+int tilerow_weights_device(const tsg_dtile *A, const tsg_dtile *B, int **d_w, int **d_jlo, int **d_jhi);
+int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, tsg_dtile *C, tsg_stats *stats);
+int build_rm2csc_device(tsg_dtile *B);
+
+// tile2csr.cu
+int tile2csr_device(const tsg_dtile *T, tsg_dcsr *out);
+
+}  // namespace tsg

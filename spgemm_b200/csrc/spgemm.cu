@@ -1,0 +1,607 @@
+// spgemm.cu -- TileSpGEMM steps 1-3 on B200, for a slab [trow0, trow1) of C tile-rows.
+// Replaces reference src/tilespgemm-cuda.h:2220-2844 (host) and its kernels:
+//   step 1  tile_spgemm_step1_cuda_spa_kernel / _numeric_ (:279-392) and the nsparse hash path
+//           (src/spgemm_nsparse_kernel.h:221-311,1171-1438)
+//   step 2  tile_spgemm_step3_cuda_kernel_2level_halfwarp (:394-773)
+//   step 3  tile_spgemm_step4_cuda_kernel_smem_v3[_halfwarp] (:1273-1952)
+//
+// What is different from the reference (same results):
+//   * Step 1 is a Gustavson expansion at tile level over a WINDOWED shared-memory bitmap
+//     [Jmin, Jmax] of the tile-row (the reference's bitmap spans all tile columns and only exists
+//     for tilen <= 16384, else it falls back to a hash path). Besides C's tile list it emits, per C
+//     tile, the list of matched (A tile, B tile) pairs, so steps 2 and 3 never intersect index
+//     lists (the reference re-intersects A's tile-row with B's tile-column by binary search in both
+//     of its later steps and caches at most one pair, :538-547).
+//   * Step 2 is a 16x16x16 boolean matrix product per pair: lane r of a half-warp owns C row r,
+//     walks the set bits of A's row mask and ORs in B's row masks fetched by shuffle.
+//   * Step 3 accumulates in SHARED memory (a dense 16x16 FP64 accumulator per C tile, stored
+//     [col][lane] so it is bank-conflict free), lane r owning C row r: no atomics at all, a
+//     deterministic summation order, and the compaction through C's mask replaces the reference's
+//     per-product binary search + global atomicAdd (:1450,1558,1795,1900).
+//   * Empty C tiles are kept with Ptr = mask = 0 and nnz 0 (the reference leaves them
+//     uninitialised).
+//   * No allocation inside the step kernels' critical path comes from cudaMalloc; sizes are read
+//     back three times (pairs/window, numblkC, nnzC).
+#include "common.cuh"
+#include "scan.cuh"
+#include "kernels.h"
+
+namespace tsg {
+
+constexpr int S1_LIGHT_MAX = 2048;   // tile-rows with <= this many pairs run on one warp (deterministic pair order)
+constexpr int S1_HEAVY_THREADS = 256;
+constexpr int S1_SORT_MAX = 64;      // heavy path: pair lists up to this length are re-sorted by A tile
+
+// ---------------------------------------------------------------------------------------------
+// Step 1a: per tile-row weight w = #matched tile pairs, and the window [jlo, jhi] of tile columns
+// the row can produce. (w is also the multi-GPU / slab balancing weight: nsparse set_intprod_num,
+// src/spgemm_nsparse_kernel.h:135-151.)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_step1_weights(int trow0, int ntr, const int *__restrict__ a_tile_ptr, const int *__restrict__ a_tile_col,
+                const int *__restrict__ b_tile_ptr, const int *__restrict__ b_tile_col, int *__restrict__ w,
+                int *__restrict__ jlo, int *__restrict__ jhi, int *__restrict__ scal /*[0]=max window words,[1]=err,[2]=max w*/)
+{
+    const int i = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= ntr) return;
+    const int I = trow0 + i;
+    long long s = 0;
+    int lo = 0x7fffffff, hi = -1;
+    for (int ta = a_tile_ptr[I] + lane; ta < a_tile_ptr[I + 1]; ta += 32) {
+        int K = a_tile_col[ta];
+        int b0 = b_tile_ptr[K], b1 = b_tile_ptr[K + 1];
+        if (b1 > b0) {
+            s += b1 - b0;
+            lo = min(lo, b_tile_col[b0]);
+            hi = max(hi, b_tile_col[b1 - 1]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        s += __shfl_xor_sync(FULL_MASK, s, o);
+        lo = min(lo, __shfl_xor_sync(FULL_MASK, lo, o));
+        hi = max(hi, __shfl_xor_sync(FULL_MASK, hi, o));
+    }
+    if (lane == 0) {
+        if (s > 0x7fffffffll) { atomicOr(&scal[1], 1); s = 0x7fffffff; }
+        w[i] = (int)s;
+        jlo[i] = lo;
+        jhi[i] = hi;
+        if (s > 0) {
+            int nw = ((hi - (lo & ~31)) >> 5) + 1;
+            atomicMax(&scal[0], nw);
+            atomicMax(&scal[2], (int)s);
+        }
+    }
+}
+
+// rank of tile column J inside the window bitmap = slot of the C tile within its tile-row
+__device__ __forceinline__ int s1_rank(const unsigned *bitmap, const int *pre8, int d)
+{
+    int wd = d >> 5;
+    int r = pre8[wd >> 3];
+    for (int k = wd & ~7; k < wd; k++) r += __popc(bitmap[k]);
+    return r + __popc(bitmap[wd] & ((1u << (d & 31)) - 1));
+}
+
+// block-wide exclusive scan of one int per thread; returns exclusive value, *total = block sum
+template <int THREADS>
+__device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(FULL_MASK, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (THREADS == 32) { *total = __shfl_sync(FULL_MASK, incl, 31); return incl - v; }
+    __syncthreads();  // protect s_warp reuse
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < THREADS / 32; k++) {
+        int t = s_warp[k];
+        if (k < warp) off += t;
+        tot += t;
+    }
+    *total = tot;
+    return off + incl - v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Step 1b/1c: one CTA per C tile-row. MODE 0 counts the distinct tile columns. MODE 1 emits the
+// sorted tile-column list, and per C tile the matched (A tile, B tile) pair list.
+// THREADS = 32 handles rows with w in (0, S1_LIGHT_MAX]; THREADS = 256 the heavier ones.
+// Dynamic smem: bitmap[nw_max] | pre8[nw_max/8 + 1].
+// ---------------------------------------------------------------------------------------------
+template <int THREADS, int MODE>
+__global__ void __launch_bounds__(THREADS)
+k_step1(int trow0, int nw_max, int wmin, int wmax, const int *__restrict__ a_tile_ptr,
+        const int *__restrict__ a_tile_col, const int *__restrict__ b_tile_ptr, const int *__restrict__ b_tile_col,
+        const int *__restrict__ b_rm2csc, const int *__restrict__ w, const int *__restrict__ jlo,
+        const int *__restrict__ jhi, int *__restrict__ cnt /*MODE0 out*/, const int *__restrict__ c_tile_ptr,
+        const int *__restrict__ wptr, int *__restrict__ c_tile_col, int *__restrict__ c_tile_row,
+        int *__restrict__ pair_ptr, int *__restrict__ pair_end, int *__restrict__ pair_a, int *__restrict__ pair_b)
+{
+    extern __shared__ unsigned s1_smem[];
+    __shared__ int s_warp[THREADS / 32];
+    __shared__ int s_carry;
+    unsigned *bitmap = s1_smem;
+    int *pre8 = (int *)(s1_smem + nw_max);
+    const int i = blockIdx.x, I = trow0 + i;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARPS = THREADS / 32;
+    const int wi = w[i];
+    if (wi <= wmin || wi > wmax) return;  // other launch's row (or nothing to do: MODE 0 output is pre-zeroed)
+    const int lo = jlo[i] & ~31;
+    const int nw = ((jhi[i] - lo) >> 5) + 1;
+    const int a0 = a_tile_ptr[I], a1 = a_tile_ptr[I + 1];
+
+    for (int k = tid; k < nw; k += THREADS) bitmap[k] = 0;
+    __syncthreads();
+    for (int ta = a0 + warp; ta < a1; ta += NWARPS) {
+        int K = a_tile_col[ta];
+        for (int tb = b_tile_ptr[K] + lane; tb < b_tile_ptr[K + 1]; tb += 32) {
+            int d = b_tile_col[tb] - lo;
+            atomicOr(&bitmap[d >> 5], 1u << (d & 31));
+        }
+    }
+    __syncthreads();
+    if (MODE == 0) {
+        int s = 0, total;
+        for (int k = tid; k < nw; k += THREADS) s += __popc(bitmap[k]);
+        block_excl_scan<THREADS>(s, s_warp, &total);
+        if (tid == 0) cnt[i] = total;
+        return;
+    }
+    // ---- MODE 1 ----
+    const int ngroups = (nw + 7) >> 3;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int g0 = 0; g0 < ngroups; g0 += THREADS) {
+        int g = g0 + tid, s = 0;
+        if (g < ngroups)
+            for (int k = g * 8; k < min(g * 8 + 8, nw); k++) s += __popc(bitmap[k]);
+        int total;
+        int ex = block_excl_scan<THREADS>(s, s_warp, &total);
+        int carry = s_carry;
+        if (g < ngroups) pre8[g] = carry + ex;
+        __syncthreads();
+        if (tid == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+    const int numJ = s_carry;
+    const int cbase = c_tile_ptr[i];
+    for (int k = tid; k < nw; k += THREADS) {
+        unsigned bits = bitmap[k];
+        if (bits) {
+            int r = pre8[k >> 3];
+            for (int q = k & ~7; q < k; q++) r += __popc(bitmap[q]);
+            while (bits) {
+                int b = __ffs(bits) - 1;
+                c_tile_col[cbase + r] = lo + k * 32 + b;
+                c_tile_row[cbase + r] = I;
+                r++;
+                bits &= bits - 1;
+            }
+        }
+    }
+    // pair counts per C tile (pair_end is zero on entry)
+    for (int ta = a0 + warp; ta < a1; ta += NWARPS) {
+        int K = a_tile_col[ta];
+        for (int tb = b_tile_ptr[K] + lane; tb < b_tile_ptr[K + 1]; tb += 32) {
+            int slot = s1_rank(bitmap, pre8, b_tile_col[tb] - lo);
+            if (THREADS == 32) pair_end[cbase + slot]++;  // one A tile at a time, distinct slots per lane
+            else atomicAdd(&pair_end[cbase + slot], 1);
+        }
+        if (THREADS == 32) __syncwarp();
+    }
+    __syncthreads();
+    // exclusive scan of the counts over the tile-row's slots -> pair_ptr; pair_end becomes the cursor
+    if (tid == 0) s_carry = wptr[i];
+    __syncthreads();
+    for (int s0 = 0; s0 < numJ; s0 += THREADS) {
+        int s = s0 + tid;
+        int v = s < numJ ? pair_end[cbase + s] : 0, total;
+        int ex = block_excl_scan<THREADS>(v, s_warp, &total);
+        int carry = s_carry;
+        if (s < numJ) { pair_ptr[cbase + s] = carry + ex; pair_end[cbase + s] = carry + ex; }
+        __syncthreads();
+        if (tid == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+    // write the pairs
+    for (int ta = a0 + warp; ta < a1; ta += NWARPS) {
+        int K = a_tile_col[ta];
+        for (int tb = b_tile_ptr[K] + lane; tb < b_tile_ptr[K + 1]; tb += 32) {
+            int slot = s1_rank(bitmap, pre8, b_tile_col[tb] - lo);
+            int pos;
+            if (THREADS == 32) pos = pair_end[cbase + slot]++;
+            else pos = atomicAdd(&pair_end[cbase + slot], 1);
+            pair_a[pos] = ta;
+            pair_b[pos] = b_rm2csc[tb];
+        }
+        if (THREADS == 32) __syncwarp();
+    }
+    if (THREADS > 32) {
+        // several warps appended concurrently: restore ascending-A-tile order for short lists so the
+        // FP64 summation order is reproducible (lists longer than S1_SORT_MAX keep arrival order).
+        __syncthreads();
+        for (int s = tid; s < numJ; s += THREADS) {
+            int b = pair_ptr[cbase + s], e = pair_end[cbase + s], len = e - b;
+            if (len > 1 && len <= S1_SORT_MAX) {
+                for (int x = b + 1; x < e; x++) {
+                    int ka = pair_a[x], kb = pair_b[x], y = x - 1;
+                    while (y >= b && pair_a[y] > ka) { pair_a[y + 1] = pair_a[y]; pair_b[y + 1] = pair_b[y]; y--; }
+                    pair_a[y + 1] = ka; pair_b[y + 1] = kb;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Step 2: bitmask symbolic. Half-warp per C tile, lane r owns C row r:
+//   maskC[r] = OR over pairs, over set bits k of maskA[r], of maskB[k].
+// Writes C's row masks, per-tile exclusive row offsets (Ptr) and the tile nnz count.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_step2(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end,
+        const int *__restrict__ pair_a, const int *__restrict__ pair_b, const uint16_t *__restrict__ a_mask,
+        const uint16_t *__restrict__ b_mask, uint16_t *__restrict__ c_ptr, uint16_t *__restrict__ c_mask,
+        int *__restrict__ c_cnt)
+{
+    const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4);
+    const int l16 = threadIdx.x & 15;
+    const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
+    if (t >= numblkC) return;
+    unsigned cm = 0;
+    const int pe = pair_end[t];
+    for (int p = pair_ptr[t]; p < pe; p++) {
+        const int a = pair_a[p], b = pair_b[p];
+        unsigned am = a_mask[(size_t)a * TS + l16];
+        const unsigned bm = b_mask[(size_t)b * TS + l16];
+        while (__any_sync(hmask, am != 0)) {
+            int k = __clz(am) - 16;  // smallest column with a set bit (bit 15-k); 16 when am == 0
+            unsigned v = __shfl_sync(hmask, bm, k & 15, 16);
+            if (am) { cm |= v; am &= ~(0x8000u >> k); }
+        }
+    }
+    int n = __popc(cm), incl = n;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        int v = __shfl_up_sync(hmask, incl, o, 16);
+        if (l16 >= o) incl += v;
+    }
+    c_ptr[(size_t)t * TS + l16] = (uint16_t)(incl - n);
+    c_mask[(size_t)t * TS + l16] = (uint16_t)cm;
+    if (l16 == 15) c_cnt[t] = incl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Step 3: numeric. Half-warp per C tile, lane r owns C row r and accumulates it in shared memory:
+// acc[c][lane] (bank = lane: conflict-free for any column pattern). For each pair, lane r walks the
+// entries (r,k) of A's row r and, for each, row k of the B tile. Then the row is compacted through
+// C's mask in ascending column order.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_step3(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end,
+        const int *__restrict__ pair_a, const int *__restrict__ pair_b, const int *__restrict__ a_tile_nnz,
+        const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ a_col, const double *__restrict__ a_val,
+        const int *__restrict__ b_tile_nnz, const uint16_t *__restrict__ b_ptr, const uint16_t *__restrict__ b_col,
+        const double *__restrict__ b_val, const int *__restrict__ c_tile_nnz, const uint16_t *__restrict__ c_ptr,
+        const uint16_t *__restrict__ c_mask, uint16_t *__restrict__ c_col, double *__restrict__ c_val)
+{
+    __shared__ double acc[4][TS][32];
+    __shared__ uint16_t s_bptr[8][TS + 1];
+    const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4);
+    const int l16 = threadIdx.x & 15, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = threadIdx.x >> 4;
+    const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
+    if (t >= numblkC) return;
+    const int cbase = c_tile_nnz[t];
+    if (c_tile_nnz[t + 1] == cbase) return;  // empty tile: nothing to compute or write
+    double(*my)[32] = acc[warp];
+#pragma unroll
+    for (int c = 0; c < TS; c++) my[c][lane] = 0.0;
+    uint16_t *bp = s_bptr[half];
+    const int pe = pair_end[t];
+    for (int p = pair_ptr[t]; p < pe; p++) {
+        const int a = pair_a[p], b = pair_b[p];
+        const int abase = a_tile_nnz[a], annz = a_tile_nnz[a + 1] - abase;
+        const int bbase = b_tile_nnz[b], bnnz = b_tile_nnz[b + 1] - bbase;
+        __syncwarp(hmask);
+        bp[l16] = b_ptr[(size_t)b * TS + l16];
+        if (l16 == 0) bp[TS] = (uint16_t)bnnz;
+        __syncwarp(hmask);
+        int ia = a_ptr[(size_t)a * TS + l16];
+        const int ia1 = l16 < 15 ? (int)a_ptr[(size_t)a * TS + l16 + 1] : annz;
+        for (; ia < ia1; ia++) {
+            const int k = a_col[abase + ia] & 15;  // A stores row*16+col (src/csr2tile.h:192)
+            const double av = a_val[abase + ia];
+            const int ib1 = bp[k + 1];
+            for (int ib = bp[k]; ib < ib1; ib++) my[b_col[bbase + ib]][lane] += av * b_val[bbase + ib];
+        }
+    }
+    unsigned cm = c_mask[(size_t)t * TS + l16];
+    size_t o = (size_t)cbase + c_ptr[(size_t)t * TS + l16];
+    while (cm) {
+        int k = __clz(cm) - 16;
+        c_val[o] = my[k][lane];
+        c_col[o] = (uint16_t)k;
+        o++;
+        cm &= ~(0x8000u >> k);
+    }
+}
+
+// row-major tile index -> CSC storage id for a B uploaded from a host SMatrix (csr2tile_device
+// fills rm2csc itself). One thread per stored tile: binary search its column in its tile-row.
+__global__ void k_build_rm2csc(int tilen, const int *__restrict__ csc_tile_ptr, const int *__restrict__ csc_tile_rowidx,
+                               const int *__restrict__ tile_ptr, const int *__restrict__ tile_col, int numtile,
+                               int *__restrict__ rm2csc, int *__restrict__ err)
+{
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= numtile) return;
+    int lo = 0, hi = tilen;  // tile column J of stored tile q: csc_tile_ptr[J] <= q < csc_tile_ptr[J+1]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (csc_tile_ptr[mid] <= q) lo = mid; else hi = mid;
+    }
+    const int J = lo, I = csc_tile_rowidx[q];
+    int l = tile_ptr[I], h = tile_ptr[I + 1];
+    while (l < h) {
+        int mid = (l + h) >> 1;
+        if (tile_col[mid] < J) l = mid + 1; else h = mid;
+    }
+    if (l < tile_ptr[I + 1] && tile_col[l] == J) rm2csc[l] = q;
+    else atomicOr(err, 1);
+}
+
+int build_rm2csc_device(tsg_dtile *B)
+{
+    Ctx &c = ctx();
+    if (B->numtile == 0) return TSG_OK;
+    CK(cudaMemsetAsync(c.d_scalars, 0, sizeof(long long), c.stream));
+    k_build_rm2csc<<<ceil_div(B->numtile, 256), 256, 0, c.stream>>>(B->tilen, B->csc_tile_ptr, B->csc_tile_rowidx, B->tile_ptr,
+                                                                    B->tile_columnidx, B->numtile, B->rm2csc, (int *)c.d_scalars);
+    CK_LAUNCH();
+    int flag = 0;
+    int rc = read_back_i32((int *)c.d_scalars, &flag);
+    if (rc) return rc;
+    if (flag) { set_error(TSG_ERR_INPUT, "B: csc_tile_* and tile_ptr/tile_columnidx are inconsistent"); return last_error(); }
+    return TSG_OK;
+}
+
+int tilerow_weights_device(const tsg_dtile *A, const tsg_dtile *B, int **d_w, int **d_jlo, int **d_jhi)
+{
+    Ctx &c = ctx();
+    const int ntr = A->tilem;
+    int *w = dalloc_n<int>((size_t)ntr + 1), *jlo = dalloc_n<int>(ntr), *jhi = dalloc_n<int>(ntr);
+    if (!w || !jlo || !jhi) return last_error();
+    CK(cudaMemsetAsync(c.d_scalars, 0, 4 * sizeof(int), c.stream));
+    if (ntr > 0) {
+        k_step1_weights<<<ceil_div((long long)ntr * 32, 128), 128, 0, c.stream>>>(0, ntr, A->tile_ptr, A->tile_columnidx, B->tile_ptr,
+                                                                                 B->tile_columnidx, w, jlo, jhi, (int *)c.d_scalars);
+        CK_LAUNCH();
+    }
+    *d_w = w; *d_jlo = jlo; *d_jhi = jhi;
+    return TSG_OK;
+}
+
+template <int MODE>
+static int launch_step1(int ntr, int trow0, int nw_max, int wmax_seen, const tsg_dtile *A, const tsg_dtile *B, const int *w,
+                        const int *jlo, const int *jhi, int *cnt, const int *c_tile_ptr, const int *wptr, int *c_tile_col,
+                        int *c_tile_row, int *pair_ptr, int *pair_end, int *pair_a, int *pair_b)
+{
+    Ctx &c = ctx();
+    size_t smem = ((size_t)nw_max + (size_t)nw_max / 8 + 2) * 4;
+    if (smem > c.smem_optin) {
+        set_error(TSG_ERR_UNSUPPORTED, "step 1: tile-column window of %d words needs %zu B of shared memory (> %zu)", nw_max, smem, c.smem_optin);
+        return last_error();
+    }
+    if (smem > 48 * 1024) {
+        CK(cudaFuncSetAttribute(k_step1<32, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_step1<S1_HEAVY_THREADS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    k_step1<32, MODE><<<ntr, 32, smem, c.stream>>>(trow0, nw_max, 0, S1_LIGHT_MAX, A->tile_ptr, A->tile_columnidx, B->tile_ptr,
+                                                   B->tile_columnidx, B->rm2csc, w, jlo, jhi, cnt, c_tile_ptr, wptr, c_tile_col,
+                                                   c_tile_row, pair_ptr, pair_end, pair_a, pair_b);
+    CK_LAUNCH();
+    if (wmax_seen > S1_LIGHT_MAX) {
+        k_step1<S1_HEAVY_THREADS, MODE><<<ntr, S1_HEAVY_THREADS, smem, c.stream>>>(
+            trow0, nw_max, S1_LIGHT_MAX, 0x7fffffff, A->tile_ptr, A->tile_columnidx, B->tile_ptr, B->tile_columnidx, B->rm2csc, w,
+            jlo, jhi, cnt, c_tile_ptr, wptr, c_tile_col, c_tile_row, pair_ptr, pair_end, pair_a, pair_b);
+        CK_LAUNCH();
+    }
+    return TSG_OK;
+}
+
+int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, tsg_dtile *C, tsg_stats *stats)
+{
+    Ctx &c = ctx();
+    memset(C, 0, sizeof(*C));
+    if (A->n != B->m) { set_error(TSG_ERR_UNSUPPORTED, "spgemm: A is %dx%d but B is %dx%d", A->m, A->n, B->m, B->n); return last_error(); }
+    if (A->col_major || !B->col_major || !B->rm2csc) {
+        set_error(TSG_ERR_UNSUPPORTED, "spgemm: A must be row-major tiled and B col-major tiled (csr2tile_col_major)");
+        return last_error();
+    }
+    if (trow1 < 0 || trow1 > A->tilem) trow1 = A->tilem;
+    if (trow0 < 0) trow0 = 0;
+    if (trow0 > trow1) trow0 = trow1;
+    const int ntr = trow1 - trow0;
+    const long long launches0 = c.launches;
+    cudaEvent_t ev[5];
+    for (int k = 0; k < 5; k++) CK(cudaEventCreate(&ev[k]));
+    CK(cudaEventRecord(ev[0], c.stream));
+
+    // ---------------- step 1 ----------------
+    int *w = dalloc_n<int>((size_t)ntr + 1), *jlo = dalloc_n<int>(ntr), *jhi = dalloc_n<int>(ntr);
+    int *wptr = dalloc_n<int>((size_t)ntr + 1);
+    int *c_tile_ptr = dalloc_n<int>((size_t)ntr + 1);
+    if (!w || !jlo || !jhi || !wptr || !c_tile_ptr) return last_error();
+    int *scal = (int *)c.d_scalars;
+    CK(cudaMemsetAsync(scal, 0, 4 * sizeof(int), c.stream));
+    CK(cudaMemsetAsync(c_tile_ptr, 0, ((size_t)ntr + 1) * sizeof(int), c.stream));
+    if (ntr > 0) {
+        k_step1_weights<<<ceil_div((long long)ntr * 32, 128), 128, 0, c.stream>>>(trow0, ntr, A->tile_ptr, A->tile_columnidx, B->tile_ptr,
+                                                                                 B->tile_columnidx, w, jlo, jhi, scal);
+        CK_LAUNCH();
+    }
+    long long *wtot = c.d_scalars + 4;
+    // 64-bit scan output for the total, 32-bit offsets for the kernels (slab planning keeps it < 2^31)
+    long long *wptr64 = dalloc_n<long long>((size_t)ntr + 1);
+    if (!wptr64) return last_error();
+    int rc = exclusive_scan<long long>(w, wptr64, ntr);
+    if (rc) return rc;
+    rc = exclusive_scan<int>(w, wptr, ntr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(wtot, wptr64 + ntr, sizeof(long long), cudaMemcpyDeviceToDevice, c.stream));
+    CK(cudaMemcpyAsync(c.h_scalars, c.d_scalars, 6 * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    const int *hs = (const int *)c.h_scalars;
+    const int nw_max = hs[0] > 0 ? hs[0] : 1, werr = hs[1], wmax_seen = hs[2];
+    const long long pairs = c.h_scalars[4];
+    dfree(wptr64);
+    if (werr || pairs >= (1ll << 31)) {
+        set_error(TSG_ERR_OVERFLOW, "spgemm: %lld tile pairs in tile-rows [%d,%d) exceed 32-bit indexing; use smaller slabs", pairs, trow0, trow1);
+        return last_error();
+    }
+    if (ntr > 0 && pairs > 0) {
+        rc = launch_step1<0>(ntr, trow0, nw_max, wmax_seen, A, B, w, jlo, jhi, c_tile_ptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                             nullptr, nullptr, nullptr);
+        if (rc) return rc;
+    }
+    long long *numblk64 = dalloc_n<long long>((size_t)ntr + 1);
+    if (!numblk64) return last_error();
+    rc = exclusive_scan<long long>(c_tile_ptr, numblk64, ntr);
+    if (rc) return rc;
+    rc = exclusive_scan<int>(c_tile_ptr, c_tile_ptr, ntr);
+    if (rc) return rc;
+    long long numblkC = 0;
+    rc = read_back_i64(numblk64 + ntr, &numblkC);
+    if (rc) return rc;
+    dfree(numblk64);
+    if (numblkC >= (1ll << 27)) {  // numblkC*16 must index uint16 arrays with int offsets
+        set_error(TSG_ERR_OVERFLOW, "spgemm: %lld C tiles in tile-rows [%d,%d); use smaller slabs", numblkC, trow0, trow1);
+        return last_error();
+    }
+    CK(cudaEventRecord(ev[1], c.stream));
+
+    // C metadata allocation (slab 0)
+    const size_t nb = (size_t)(numblkC > 0 ? numblkC : 1), np = (size_t)(pairs > 0 ? pairs : 1);
+    {
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        size_t o_tp = take(((size_t)ntr + 1) * 4), o_tc = take(nb * 4), o_tr = take(nb * 4), o_tn = take((nb + 1) * 4);
+        size_t o_p = take(nb * TS * 2), o_m = take(nb * TS * 2);
+        char *base = (char *)dalloc(off);
+        if (!base) return last_error();
+        C->slab[0] = base; C->slab_bytes[0] = off;
+        C->tile_ptr = (int *)(base + o_tp); C->tile_columnidx = (int *)(base + o_tc); C->tile_rowidx = (int *)(base + o_tr);
+        C->tile_nnz = (int *)(base + o_tn); C->ptr = (uint16_t *)(base + o_p); C->mask = (uint16_t *)(base + o_m);
+    }
+    C->n = B->n; C->tilem = ntr; C->tilen = B->tilen; C->numtile = (int)numblkC; C->col_major = 0; C->trow0 = trow0;
+    {
+        long long r0 = (long long)trow0 * TS, r1 = (long long)trow1 * TS;
+        if (r1 > A->m) r1 = A->m;
+        C->m = (int)(r1 > r0 ? r1 - r0 : 0);
+    }
+    CK(cudaMemcpyAsync(C->tile_ptr, c_tile_ptr, ((size_t)ntr + 1) * 4, cudaMemcpyDeviceToDevice, c.stream));
+    int *pair_ptr = dalloc_n<int>(nb + 1), *pair_end = dalloc_n<int>(nb), *pair_a = dalloc_n<int>(np), *pair_b = dalloc_n<int>(np);
+    if (!pair_ptr || !pair_end || !pair_a || !pair_b) return last_error();
+    CK(cudaMemsetAsync(pair_end, 0, nb * 4, c.stream));
+    CK(cudaEventRecord(ev[2], c.stream));  // [1..2] = allocation
+    if (numblkC > 0) {
+        rc = launch_step1<1>(ntr, trow0, nw_max, wmax_seen, A, B, w, jlo, jhi, nullptr, C->tile_ptr, wptr, C->tile_columnidx,
+                             C->tile_rowidx, pair_ptr, pair_end, pair_a, pair_b);
+        if (rc) return rc;
+    }
+
+    // ---------------- step 2 ----------------
+    cudaEvent_t ev_s2;
+    CK(cudaEventCreate(&ev_s2));
+    CK(cudaEventRecord(ev_s2, c.stream));
+    if (numblkC > 0) {
+        k_step2<<<ceil_div(numblkC * 16, 128), 128, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->mask, B->mask,
+                                                                   C->ptr, C->mask, C->tile_nnz);
+        CK_LAUNCH();
+    }
+    long long *nnz64 = dalloc_n<long long>(nb + 1);
+    if (!nnz64) return last_error();
+    rc = exclusive_scan<long long>(C->tile_nnz, nnz64, numblkC);
+    if (rc) return rc;
+    rc = exclusive_scan<int>(C->tile_nnz, C->tile_nnz, numblkC);
+    if (rc) return rc;
+    long long nnzC = 0;
+    rc = read_back_i64(nnz64 + numblkC, &nnzC);
+    if (rc) return rc;
+    dfree(nnz64);
+    if (nnzC >= (1ll << 31)) {
+        set_error(TSG_ERR_OVERFLOW, "spgemm: nnz(C) = %lld in tile-rows [%d,%d) exceeds int32; use smaller slabs", nnzC, trow0, trow1);
+        return last_error();
+    }
+    CK(cudaEventRecord(ev[3], c.stream));
+
+    // ---------------- step 3 ----------------
+    {
+        size_t nz = (size_t)(nnzC > 0 ? nnzC : 1);
+        size_t o_c = (nz * 8 + 255) & ~(size_t)255;
+        char *base = (char *)dalloc(o_c + nz * 2);
+        if (!base) return last_error();
+        C->slab[1] = base; C->slab_bytes[1] = o_c + nz * 2;
+        C->val = (double *)base; C->col = (uint16_t *)(base + o_c);
+        C->nnz = nnzC;
+    }
+    cudaEvent_t ev_s3;
+    CK(cudaEventCreate(&ev_s3));
+    CK(cudaEventRecord(ev_s3, c.stream));
+    if (nnzC > 0) {
+        k_step3<<<ceil_div(numblkC * 16, 128), 128, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->tile_nnz, A->ptr,
+                                                                   A->col, A->val, B->tile_nnz, B->ptr, B->col, B->val, C->tile_nnz,
+                                                                   C->ptr, C->mask, C->col, C->val);
+        CK_LAUNCH();
+    }
+    CK(cudaEventRecord(ev[4], c.stream));
+    dfree(pair_ptr); dfree(pair_end); dfree(pair_a); dfree(pair_b);
+    dfree(w); dfree(jlo); dfree(jhi); dfree(wptr); dfree(c_tile_ptr);
+    CK(cudaStreamSynchronize(c.stream));
+
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        float f;
+        stats->numblkC = numblkC; stats->nnzC = nnzC; stats->pairs = pairs;
+        float s1a, al, s1b, s2, al2, s3, tot;
+        CK(cudaEventElapsedTime(&s1a, ev[0], ev[1]));
+        CK(cudaEventElapsedTime(&al, ev[1], ev[2]));
+        CK(cudaEventElapsedTime(&s1b, ev[2], ev_s2));
+        CK(cudaEventElapsedTime(&s2, ev_s2, ev[3]));
+        CK(cudaEventElapsedTime(&al2, ev[3], ev_s3));
+        CK(cudaEventElapsedTime(&s3, ev_s3, ev[4]));
+        CK(cudaEventElapsedTime(&tot, ev[0], ev[4]));
+        (void)f;
+        stats->ms_step1 = s1a + s1b; stats->ms_step2 = s2; stats->ms_step3 = s3; stats->ms_alloc = al + al2; stats->ms_total = tot;
+        stats->launches = (int)(c.launches - launches0);
+        // algorithmic bytes, SURVEY.md 8(d). A's share is the slab's tiles; B is read whole.
+        long long a_tiles = A->numtile, a_nnz = A->nnz;
+        if (ntr != A->tilem) {
+            int h[4];
+            CK(cudaMemcpy(&h[0], A->tile_ptr + trow0, 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(&h[1], A->tile_ptr + trow1, 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(&h[2], A->tile_nnz + h[0], 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(&h[3], A->tile_nnz + h[1], 4, cudaMemcpyDeviceToHost));
+            a_tiles = h[1] - h[0]; a_nnz = h[3] - h[2];
+        }
+        long long bytesA = a_nnz * 10 + a_tiles * 72 + ((long long)ntr + 1) * 4;
+        long long bytesB = B->nnz * 10 + (long long)B->numtile * 72 + ((long long)B->tilem + 1) * 4 + (long long)B->numtile * 4 +
+                           ((long long)B->tilen + 1) * 4;
+        long long bytesC = nnzC * 10 + numblkC * 76 + ((long long)ntr + 1) * 4;
+        stats->algorithmic_bytes = bytesA + bytesB + bytesC;
+    }
+    for (int k = 0; k < 5; k++) cudaEventDestroy(ev[k]);
+    cudaEventDestroy(ev_s2); cudaEventDestroy(ev_s3);
+    return TSG_OK;
+}
+
+}  // namespace tsg

@@ -1,0 +1,81 @@
+// tile2csr.cu -- tiled format -> CSR on the device. Replaces the reference's serial CPU code
+// (src/tile2csr.h:72-140; Tile_csr_to_csr_PTR :8-32, Tile_csr_to_csr :34-68).
+//
+// Same two passes as the reference, parallel over tile-rows: a half-warp owns a tile-row and lane r
+// owns matrix row 16*I + r. Pass 1 sums the per-tile row counts (Ptr[r+1]-Ptr[r], the last row
+// closing on the tile nnz, :22); an exclusive scan gives the row pointer; pass 2 walks the tiles of
+// the tile-row in ascending tile column and appends (tile_col*16 + Col, Val) at the row's cursor
+// (:55-58). Explicit zeros are kept (:27-28,59-60). Works on A/C-style tiles whose Col holds the
+// plain column (C, B); tiles in row-major storage order only.
+#include "common.cuh"
+#include "scan.cuh"
+#include "kernels.h"
+
+namespace tsg {
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_tile2csr(int m, int tilem, const int *__restrict__ tile_ptr, const int *__restrict__ tile_col,
+           const int *__restrict__ tile_nnz, const uint16_t *__restrict__ ptr, const uint16_t *__restrict__ col,
+           const double *__restrict__ val, int *__restrict__ rowptr, int *__restrict__ out_col,
+           double *__restrict__ out_val)
+{
+    const int I = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4);
+    const int r = threadIdx.x & 15;
+    if (I >= tilem) return;
+    const int row = I * TS + r;
+    const bool live = row < m;
+    int cursor = (FILL && live) ? rowptr[row] : 0;
+    int cnt = 0;
+    const int t1 = tile_ptr[I + 1];
+    for (int t = tile_ptr[I]; t < t1; t++) {
+        const int base = tile_nnz[t], tnnz = tile_nnz[t + 1] - base;
+        const int p0 = ptr[(size_t)t * TS + r];
+        const int p1 = r < TS - 1 ? (int)ptr[(size_t)t * TS + r + 1] : tnnz;
+        if (FILL) {
+            if (live) {
+                const int cb = tile_col[t] * TS;
+                for (int j = p0; j < p1; j++) {
+                    out_col[cursor] = cb + col[base + j];
+                    out_val[cursor] = val[base + j];
+                    cursor++;
+                }
+            }
+        } else {
+            cnt += p1 - p0;
+        }
+    }
+    if (!FILL && live) rowptr[row] = cnt;
+}
+
+int tile2csr_device(const tsg_dtile *T, tsg_dcsr *out)
+{
+    Ctx &c = ctx();
+    memset(out, 0, sizeof(*out));
+    if (T->col_major) { set_error(TSG_ERR_UNSUPPORTED, "tile2csr: tiles must be in row-major storage order"); return last_error(); }
+    const int m = T->m;
+    const long long nnz = T->nnz;
+    size_t nz = (size_t)(nnz > 0 ? nnz : 1);
+    size_t o_ci = (((size_t)m + 1) * 4 + 255) & ~(size_t)255, o_v = o_ci + ((nz * 4 + 255) & ~(size_t)255);
+    char *base = (char *)dalloc(o_v + nz * 8);
+    if (!base) return last_error();
+    out->m = m; out->n = T->n; out->nnz = nnz; out->owner = base;
+    out->rowptr = (int *)base; out->colidx = (int *)(base + o_ci); out->val = (double *)(base + o_v);
+    CK(cudaMemsetAsync(out->rowptr, 0, ((size_t)m + 1) * 4, c.stream));
+    const int blocks = ceil_div((long long)T->tilem * 16, 128);
+    if (T->tilem > 0 && T->numtile > 0) {
+        k_tile2csr<false><<<blocks, 128, 0, c.stream>>>(m, T->tilem, T->tile_ptr, T->tile_columnidx, T->tile_nnz, T->ptr, T->col, T->val,
+                                                        out->rowptr, nullptr, nullptr);
+        CK_LAUNCH();
+    }
+    int rc = exclusive_scan<int>(out->rowptr, out->rowptr, m);
+    if (rc) return rc;
+    if (T->tilem > 0 && nnz > 0) {
+        k_tile2csr<true><<<blocks, 128, 0, c.stream>>>(m, T->tilem, T->tile_ptr, T->tile_columnidx, T->tile_nnz, T->ptr, T->col, T->val,
+                                                       out->rowptr, out->colidx, out->val);
+        CK_LAUNCH();
+    }
+    return TSG_OK;
+}
+
+}  // namespace tsg

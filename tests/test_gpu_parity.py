@@ -1,0 +1,231 @@
+"""Parity of the CUDA path (through the C ABI, spgemm_b200.api -> libtilespgemm_b200.so) with the CPU
+oracle and the committed golden vectors. Integer/index/structure arrays are compared bit-exact; FP64
+values bit-exact under the driver's value[k] = k % 10 convention (all partial sums are exact integers)
+and within 1e-12 max relative error for general positive values (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_tiled_equal, golden_cases, load_golden
+from oracle import oracle as orc
+from spgemm_b200 import api, matrices as M
+from test_golden import golden_tiled
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+
+VAL_RTOL = 1e-12  # north_star: FP64 values within a max relative error of 1e-12
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    api.init(0)
+    yield
+
+
+def oracle_c(m, n, A, B, nB, tA=None, tB=None):
+    rpC, ciC, vC = orc.spgemm_spa(A, B, nB)
+    tA = tA or orc.csr2tile_row_major(m, n, *A)
+    tB = tB or orc.csr2tile_col_major(len(B[0]) - 1, nB, *B)
+    return (rpC, ciC, vC), orc.ctiles_from_csr(m, nB, tA, tB, (rpC, ciC, vC))
+
+
+SMALL = {
+    "lap2d_48": lambda: M.lap2d(48),
+    "lap2d_33x17": lambda: M.lap2d(33, 17),
+    "stencil27_9": lambda: M.stencil27(9),
+    "stencil27_20x7x5": lambda: M.stencil27(20, 7, 5),
+    "blockfem_120": lambda: M.blockfem(120),
+    "blockfem_band3": lambda: M.blockfem(40, dof=6, band=3),
+    "rmat_s10": lambda: M.rmat(10, 8, seed=5),
+    "rmat_s12_skewed": lambda: M.rmat(12, 16, seed=6),
+    "rand_ragged_203": lambda: M.random_sparse(203, 203, 0.03, seed=11),
+    "rand_dense_64": lambda: M.random_sparse(64, 64, 0.7, seed=14),
+    "full_48": lambda: M.random_sparse(48, 48, 5.0, seed=15),
+    "single_entry": lambda: (20, 20, np.array([0] * 6 + [1] * 15, np.int32), np.array([17], np.int32), np.array([3.0])),
+    "empty": lambda: (33, 33, np.zeros(34, np.int32), np.zeros(0, np.int32), np.zeros(0)),
+    "one_by_one": lambda: (1, 1, np.array([0, 1], np.int32), np.array([0], np.int32), np.array([2.0])),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SMALL))
+def test_csr2tile_matches_oracle(name):
+    m, n, rp, ci, v = SMALL[name]()
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    for col_major, fn in ((False, orc.csr2tile_row_major), (True, orc.csr2tile_col_major)):
+        t = api.csr2tile(d, col_major)
+        assert_tiled_equal(t.download(), fn(m, n, rp, ci, v), f"{name} col_major={col_major}")
+        t.free()
+    d.free()
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_vectors(name):
+    """csr2tile (both layouts), transposition, SpGEMM and tile2csr against the reference-generated vectors."""
+    g = load_golden(name)
+    m, n, rp, ci, v = int(g["m"]), int(g["n"]), g["rowptr"], g["colidx"], g["val"]
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
+    assert_tiled_equal(tA.download(), golden_tiled(g, "A"), name + " A")
+    assert_tiled_equal(tB.download(), golden_tiled(g, "B"), name + " B")
+    at = api.transpose(d)
+    cp, ri, cv = at.download()
+    assert np.array_equal(cp, g["T_colptr"]) and np.array_equal(ri, g["T_rowidx"]) and np.array_equal(cv, g["T_val"])
+    at.free()
+    if "C_rowptr" in g:
+        tC, st = api.spgemm(tA, tB)
+        csr = api.tile2csr_device(tC)
+        r, c, vv = csr.download()
+        assert np.array_equal(r, g["C_rowptr"]) and np.array_equal(c, g["C_colidx"])
+        err = np.max(np.abs(vv - g["C_val"]) / np.maximum(np.abs(g["C_val"]), 1e-300)) if vv.size else 0.0
+        assert err <= VAL_RTOL, err
+        assert st["nnzC"] == len(g["C_colidx"])
+        csr.free(); tC.free()
+    tA.free(); tB.free(); d.free()
+
+
+@pytest.mark.parametrize("values", ["mod10", "hash"])
+@pytest.mark.parametrize("name", sorted(SMALL))
+def test_spgemm_matches_oracle(name, values):
+    m, n, rp, ci, _ = SMALL[name]()
+    v = M.set_values(len(ci), values) if len(ci) else np.zeros(0)
+    A = (rp, ci, v)
+    csrC, tC_exp = oracle_c(m, n, A, A, n)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
+    assert api.nnzcub(d, d) == orc.nnzcub(ci, rp)
+    tC, st = api.spgemm(tA, tB)
+    got = tC.download()
+    # structure bit-exact (tile list incl. empty tiles, tile_nnz, Ptr, mask, Col); values exact for mod10
+    assert_tiled_equal(got, tC_exp, f"{name}/{values} C", val_rtol=0.0 if values == "mod10" else VAL_RTOL)
+    assert st["numblkC"] == tC_exp.numtile and st["nnzC"] == tC_exp.nnz
+    assert st["pairs"] == int(orc.tilerow_weights(orc.csr2tile_row_major(m, n, *A), orc.csr2tile_col_major(m, n, *A)).sum())
+    csr = api.tile2csr_device(tC)
+    r, c, vv = csr.download()
+    assert np.array_equal(r, csrC[0]) and np.array_equal(c, csrC[1])
+    if values == "mod10":
+        assert np.array_equal(vv, csrC[2])
+    for o in (csr, tC, tA, tB, d):
+        o.free()
+
+
+def test_aat_mode():
+    """-aat 1: B = A^T materialised by matrix_transposition (reference src/main.cu:114-142)."""
+    m, n, rp, ci, v = M.rmat(10, 8, seed=9)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    dT = api.transpose(d)
+    cp, ri, cv = dT.download()
+    ecp, eri, ecv = orc.transpose(m, n, rp, ci, v)
+    assert np.array_equal(cp, ecp) and np.array_equal(ri, eri) and np.array_equal(cv, ecv)
+    A, B = (rp, ci, v), (ecp, eri, ecv)
+    csrC, tC_exp = oracle_c(m, n, A, B, m)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(dT, True)
+    tC, _ = api.spgemm(tA, tB)
+    assert_tiled_equal(tC.download(), tC_exp, "AAT C")
+    for o in (tC, tA, tB, d, dT):
+        o.free()
+
+
+def test_rectangular_general_product():
+    """General C = A*B with distinct rectangular A and B (ragged last tiles on every edge)."""
+    m, k, rpA, ciA, vA = M.random_sparse(70, 100, 0.05, seed=21)
+    _, n, rpB, ciB, vB = M.random_sparse(100, 45, 0.06, seed=22)
+    A, B = (rpA, ciA, vA), (rpB, ciB, vB)
+    csrC, tC_exp = oracle_c(m, k, A, B, n)
+    dA, dB = api.DeviceCSR.upload(m, k, *A), api.DeviceCSR.upload(k, n, *B)
+    tA, tB = api.csr2tile(dA, False), api.csr2tile(dB, True)
+    tC, _ = api.spgemm(tA, tB)
+    assert_tiled_equal(tC.download(), tC_exp, "rect C")
+    r, c, vv, _ = api.spgemm_csr_host(m, k, n, A, B)
+    assert np.array_equal(r, csrC[0]) and np.array_equal(c, csrC[1]) and np.array_equal(vv, csrC[2])
+    for o in (tC, tA, tB, dA, dB):
+        o.free()
+
+
+def test_slabs_concatenate_to_whole():
+    """C computed slab by slab (the unit the multi-GPU path distributes) equals C computed whole."""
+    m, n, rp, ci, v = M.stencil27(12)
+    A = (rp, ci, v)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
+    oA, oB = orc.csr2tile_row_major(m, n, *A), orc.csr2tile_col_major(m, n, *A)
+    w = api.tilerow_weights(tA, tB)
+    assert np.array_equal(w, orc.tilerow_weights(oA, oB))
+    cuts = [0, 5, 6, 40, tA.tilem]
+    for t0, t1 in zip(cuts[:-1], cuts[1:]):
+        rows = slice(t0 * 16, min(t1 * 16, m))
+        sub = orc.spgemm_spa(A, A, n, rows.start, rows.stop)
+        exp = orc.ctiles_from_csr(m, n, oA, oB, sub, t0, t1)
+        tC, st = api.spgemm(tA, tB, t0, t1)
+        got = tC.download()
+        assert got["trow0"] == t0
+        assert_tiled_equal(got, exp, f"slab [{t0},{t1})")
+        assert st["pairs"] == int(w[t0:t1].sum())
+        csr = api.tile2csr_device(tC)
+        r, c, vv = csr.download()
+        assert np.array_equal(r, sub[0]) and np.array_equal(c, sub[1]) and np.array_equal(vv, sub[2])
+        csr.free(); tC.free()
+    for o in (tA, tB, d):
+        o.free()
+
+
+def test_drop_in_entry_points():
+    """The reference-named calls, used the way src/main.cu uses them (host buffers in and out)."""
+    m, n, rp, ci, v = M.lap2d(40)
+    A = api.HostMatrix.from_csr(m, n, rp, ci, v)
+    B = api.HostMatrix().alias_csr_of(A)        # -aat 0: B aliases A's CSR (main.cu:145-151)
+    api.csr2tile_row_major(A, 16, 16)
+    api.csr2tile_col_major(B, 16, 16)
+    oA, oB = orc.csr2tile_row_major(m, n, rp, ci, v), orc.csr2tile_col_major(m, n, rp, ci, v)
+    assert_tiled_equal(A.tiles(), oA, "drop-in A")
+    assert_tiled_equal(B.tiles(), oB, "drop-in B")
+    nnzCub = orc.nnzcub(ci, rp)
+    Cm, info = api.tilespgemm(A, B, nnzCub)
+    csrC, tC_exp = oracle_c(m, n, (rp, ci, v), (rp, ci, v), n, oA, oB)
+    assert_tiled_equal(Cm.tiles(), tC_exp, "drop-in C")
+    assert info["nnzC_computed"] == tC_exp.nnz
+    assert info["compression_rate"] == pytest.approx(nnzCub / tC_exp.nnz)
+    assert info["time_tile"] > 0 and info["gflops_tile"] == pytest.approx(2.0 * nnzCub / (info["time_tile"] * 1e6))
+    api.tile2csr(Cm, 16, 16)
+    r, c, vv = Cm.csr()
+    assert np.array_equal(r, csrC[0]) and np.array_equal(c, csrC[1]) and np.array_equal(vv, csrC[2])
+    cp, ri, cv = api.matrix_transposition(m, n, rp, ci, v)
+    e = orc.transpose(m, n, rp, ci, v)
+    assert np.array_equal(cp, e[0]) and np.array_equal(ri, e[1]) and np.array_equal(cv, e[2])
+    for x in (A, B, Cm):
+        api.matrix_destroy(x)
+
+
+def test_error_paths_fail_loudly():
+    m, n, rp, ci, v = M.lap2d(8)
+    A = api.HostMatrix.from_csr(m, n, rp, ci, v)
+    with pytest.raises(api.TsgError) as e:
+        api.csr2tile_row_major(A, 32, 32)           # only 16x16 tiles
+    assert e.value.code == 2
+    bad = ci.copy()
+    bad[0], bad[1] = bad[1], bad[0]                  # unsorted row
+    d = api.DeviceCSR.upload(m, n, rp, bad, v)
+    with pytest.raises(api.TsgError) as e:
+        api.csr2tile(d, False)
+    assert e.value.code == 4
+    d.free()
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA = api.csr2tile(d, False)
+    with pytest.raises(api.TsgError):
+        api.spgemm(tA, tA)                           # B must be col-major tiled
+    tA.free(); d.free()
+
+
+def test_config1_lap2d_256_full():
+    """BASELINE config 1 at full size against the oracle (the reference's CPU-runnable case)."""
+    m, n, rp, ci, v = M.lap2d(256)
+    A = (rp, ci, v)
+    csrC, tC_exp = oracle_c(m, n, A, A, n)
+    r, c, vv, st = api.spgemm_csr_host(m, n, n, A)
+    assert st["numblkC"] == 50532 and st["nnzC"] == 846852 and st["pairs"] == 97512
+    assert np.array_equal(r, csrC[0]) and np.array_equal(c, csrC[1]) and np.array_equal(vv, csrC[2])
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
+    tC, _ = api.spgemm(tA, tB)
+    assert_tiled_equal(tC.download(), tC_exp, "lap2d-256 C")
+    for o in (tC, tA, tB, d):
+        o.free()
