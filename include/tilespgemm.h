@@ -178,6 +178,11 @@ void *tsg_stream(void);
 int tsg_sync(void);
 /* Number of kernels this library has launched since tsg_init (for bench.py's gpu_launches). */
 long long tsg_launch_count(void);
+/* CUDA-event stopwatch on the library stream (torch.cuda.Event only sees torch's streams):
+ * start records an event; stop records a second one, waits for it and returns the milliseconds
+ * the stream spent between the two, host gaps included. */
+int tsg_timer_start(void);
+int tsg_timer_stop(double *ms);
 
 /* CSR on the device. upload copies from host (pinned or pageable) memory; wrap borrows device
  * pointers the caller owns (e.g. a torch tensor's data_ptr()). */

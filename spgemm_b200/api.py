@@ -180,6 +180,21 @@ def launch_count() -> int:
     return int(L.load().tsg_launch_count())
 
 
+def sync() -> None:
+    L.check(L.load().tsg_sync())
+
+
+def timer_start() -> None:
+    L.check(L.load().tsg_timer_start())
+
+
+def timer_stop() -> float:
+    """Milliseconds the library stream spent since timer_start() (CUDA events, host gaps included)."""
+    ms = C.c_double(0)
+    L.check(L.load().tsg_timer_stop(C.byref(ms)))
+    return ms.value
+
+
 class DeviceCSR:
     def __init__(self):
         self.d = L.DCsr()

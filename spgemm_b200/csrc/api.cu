@@ -148,6 +148,29 @@ int tsg_sync(void)
 
 long long tsg_launch_count(void) { return g_ctx.launches; }
 
+static cudaEvent_t g_timer[2] = {nullptr, nullptr};
+
+int tsg_timer_start(void)
+{
+    if (ensure_init()) return g_err;
+    for (int k = 0; k < 2; k++)
+        if (!g_timer[k]) CK(cudaEventCreate(&g_timer[k]));
+    CK(cudaEventRecord(g_timer[0], g_ctx.stream));
+    return TSG_OK;
+}
+
+int tsg_timer_stop(double *ms)
+{
+    if (ensure_init()) return g_err;
+    if (!g_timer[0]) { set_error(TSG_ERR_UNSUPPORTED, "tsg_timer_stop without tsg_timer_start"); return g_err; }
+    CK(cudaEventRecord(g_timer[1], g_ctx.stream));
+    CK(cudaEventSynchronize(g_timer[1]));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, g_timer[0], g_timer[1]));
+    *ms = f;
+    return TSG_OK;
+}
+
 /* ------------------------------- CSR on the device ------------------------------- */
 
 static int csr_alloc(int m, int n, long long nnz, tsg_dcsr *out)
