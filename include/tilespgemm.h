@@ -220,6 +220,10 @@ int tsg_spgemm(const tsg_dtile *a, const tsg_dtile *b, int trow0, int trow1, tsg
 /* tiles -> CSR on the device (reference src/tile2csr.h:72). */
 int tsg_tile2csr(const tsg_dtile *t, tsg_dcsr *out);
 
+/* Verification helper for slabs too large to download: per-row sum of the stored values (= C * ones)
+ * and per-row entry count, written to HOST arrays of t->m entries (either may be NULL). */
+int tsg_tile_rowsums(const tsg_dtile *t, double *sums_host, long long *counts_host);
+
 /* Whole pipeline with HOST buffers, the end-to-end call bench.py times: H2D CSR(A) [and CSR(B);
  * b_* = NULL means B = A, aat != 0 means B = A^T built on the device], csr2tile x2, steps 1-3,
  * tile2csr, D2H CSR(C). Outputs are malloc()ed; 64-bit row pointers are never needed because the

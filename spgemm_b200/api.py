@@ -317,6 +317,52 @@ def tile2csr_device(t: DeviceTiled) -> DeviceCSR:
     return out
 
 
+def tile_rowsums(t: DeviceTiled):
+    """Per-row sums (C * ones) and per-row entry counts of a row-major tiled matrix / C slab."""
+    s = np.zeros(max(t.m, 1), np.float64)
+    c = np.zeros(max(t.m, 1), np.int64)
+    L.check(L.load().tsg_tile_rowsums(C.byref(t.d), _p(s, C.c_double), _p(c, C.c_longlong)))
+    return s[:t.m], c[:t.m]
+
+
+def plan_slabs(weights: np.ndarray, max_pairs: int):
+    """Cut tile-rows into contiguous slabs of at most `max_pairs` matched tile pairs each (a single
+    tile-row heavier than that gets a slab of its own)."""
+    w = np.asarray(weights, dtype=np.int64)
+    cuts, acc = [0], 0
+    for i, x in enumerate(w):
+        if acc > 0 and acc + x > max_pairs:
+            cuts.append(i)
+            acc = 0
+        acc += int(x)
+    cuts.append(len(w))
+    return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+
+
+def spgemm_slabs(a: DeviceTiled, b: DeviceTiled, max_pairs: int = 1 << 28, sink=None, trow0: int = 0, trow1: int = -1,
+                 weights: np.ndarray | None = None):
+    """Steps 1-3 over tile-rows [trow0, trow1) executed slab by slab with a bounded device footprint
+    (R-MAT products do not fit one GPU whole, nor int32 offsets). Each slab is handed
+    to `sink(C_slab, stats)` and freed. Returns the totals (64-bit) and the per-slab stats."""
+    if trow1 < 0:
+        trow1 = a.tilem
+    w = tilerow_weights(a, b) if weights is None else weights
+    slabs = [(t0 + trow0, t1 + trow0) for t0, t1 in plan_slabs(w[trow0:trow1], max_pairs)]
+    tot = dict(numblkC=0, nnzC=0, pairs=0, ms_step1=0.0, ms_step2=0.0, ms_step3=0.0, ms_alloc=0.0, ms_total=0.0,
+               algorithmic_bytes=0, launches=0, slabs=len(slabs))
+    per = []
+    for t0, t1 in slabs:
+        c, st = spgemm(a, b, t0, t1)
+        if sink is not None:
+            sink(c, st)
+        c.free()
+        for k in tot:
+            if k != "slabs":
+                tot[k] += st[k]
+        per.append(dict(st, trow0=t0, trow1=t1))
+    return tot, per
+
+
 def spgemm_csr_host(m, k, n, A, B=None, aat=False):
     """Whole pipeline, host CSR in -> host CSR out. A, B = (rowptr, colidx, val); B=None means B=A
     (or A^T with aat=True). Returns (rowptr, colidx, val, stats dict)."""

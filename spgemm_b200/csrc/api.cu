@@ -392,6 +392,22 @@ int tsg_tile2csr(const tsg_dtile *t, tsg_dcsr *out)
     return TSG_OK;
 }
 
+int tsg_tile_rowsums(const tsg_dtile *t, double *sums_host, long long *counts_host)
+{
+    if (ensure_init()) return g_err;
+    const size_t m = (size_t)(t->m > 0 ? t->m : 1);
+    double *d_s = dalloc_n<double>(m);
+    long long *d_c = dalloc_n<long long>(m);
+    if (!d_s || !d_c) return g_err;
+    int rc = tile_rowsums_device(t, d_s, d_c);
+    if (rc) return rc;
+    if (sums_host && t->m > 0) CK(cudaMemcpyAsync(sums_host, d_s, (size_t)t->m * 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+    if (counts_host && t->m > 0) CK(cudaMemcpyAsync(counts_host, d_c, (size_t)t->m * 8, cudaMemcpyDeviceToHost, g_ctx.stream));
+    CK(cudaStreamSynchronize(g_ctx.stream));
+    dfree(d_s); dfree(d_c);
+    return TSG_OK;
+}
+
 int tsg_spgemm_csr_host(int m, int k, int n, const int *a_rowptr, const int *a_colidx, const double *a_val,
                         const int *b_rowptr, const int *b_colidx, const double *b_val, int aat,
                         int **c_rowptr, int **c_colidx, double **c_val, long long *c_nnz, tsg_stats *stats)

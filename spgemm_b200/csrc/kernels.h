@@ -17,5 +17,6 @@ int build_rm2csc_device(tsg_dtile *B);
 
 // tile2csr.cu
 int tile2csr_device(const tsg_dtile *T, tsg_dcsr *out);
+int tile_rowsums_device(const tsg_dtile *T, double *d_out, long long *d_cnt);
 
 }  // namespace tsg

@@ -336,6 +336,190 @@ k_step3(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ p
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Step 2, version 2: one warp per C tile; the entries of ALL A tiles paired with the C tile are
+// flattened over the lanes (every lane busy), each entry (r,k) ORs B's row mask k into the C row
+// mask r held in shared memory (native 32-bit ATOMS.OR; OR is order-independent, so the result is
+// deterministic). 32 pairs are loaded per chunk, one per lane, and their A-tile extents scanned.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_step2_flat(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end,
+             const int *__restrict__ pair_a, const int *__restrict__ pair_b, const int *__restrict__ a_tile_nnz,
+             const uint16_t *__restrict__ a_col, const uint16_t *__restrict__ b_mask, uint16_t *__restrict__ c_ptr,
+             uint16_t *__restrict__ c_mask, int *__restrict__ c_cnt)
+{
+    __shared__ unsigned cm_s[4][TS];
+    const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (t >= numblkC) return;
+    if (lane < TS) cm_s[w][lane] = 0;
+    __syncwarp();
+    const int p1 = pair_end[t];
+    for (int pc = pair_ptr[t]; pc < p1; pc += 32) {
+        const int p = pc + lane;
+        int b = 0, abase = 0, annz = 0;
+        if (p < p1) {
+            const int a = pair_a[p];
+            b = pair_b[p];
+            abase = a_tile_nnz[a];
+            annz = a_tile_nnz[a + 1] - abase;
+        }
+        int incl = annz;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(FULL_MASK, incl, 31);
+        const int excl = incl - annz;
+        for (int e0 = 0; e0 < total; e0 += 32) {
+            const int e = e0 + lane;
+            int q = 0;  // pair owning entry e: largest q with excl[q] <= e
+#pragma unroll
+            for (int s = 16; s; s >>= 1) {
+                int v = __shfl_sync(FULL_MASK, excl, q + s);  // q + s <= 31
+                if (v <= e) q += s;
+            }
+            const int ab = __shfl_sync(FULL_MASK, abase, q), ex = __shfl_sync(FULL_MASK, excl, q);
+            const int bb = __shfl_sync(FULL_MASK, b, q);
+            if (e < total) {
+                const unsigned col = a_col[ab + (e - ex)];  // A stores row*16+col
+                atomicOr(&cm_s[w][col >> 4], (unsigned)b_mask[bb * TS + (col & 15)]);
+            }
+        }
+    }
+    __syncwarp();
+    if (lane < TS) {
+        const unsigned cm = cm_s[w][lane];
+        const int n = __popc(cm);
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            int v = __shfl_up_sync(0xFFFFu, incl, o, 16);
+            if (lane >= o) incl += v;
+        }
+        c_ptr[(size_t)t * TS + lane] = (uint16_t)(incl - n);
+        c_mask[(size_t)t * TS + lane] = (uint16_t)cm;
+        if (lane == 15) c_cnt[t] = incl;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Step 2, version 3: one warp per C tile, one HALF-WARP per pair (two pairs in flight), 16 A entries
+// per half-warp iteration. No search for the owning pair is needed; each entry (r,k) ORs B's row
+// mask k into the C row mask r in shared memory.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_step2_hw(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end,
+           const int *__restrict__ pair_a, const int *__restrict__ pair_b, const int *__restrict__ a_tile_nnz,
+           const uint16_t *__restrict__ a_col, const uint16_t *__restrict__ b_mask, uint16_t *__restrict__ c_ptr,
+           uint16_t *__restrict__ c_mask, int *__restrict__ c_cnt)
+{
+    __shared__ unsigned cm_s[4][TS];
+    const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, l16 = lane & 15, half = lane >> 4;
+    if (t >= numblkC) return;
+    if (lane < TS) cm_s[w][lane] = 0;
+    __syncwarp();
+    const int p1 = pair_end[t];
+    unsigned *cm = cm_s[w];
+    for (int p = pair_ptr[t] + half; p < p1; p += 2) {
+        const int a = pair_a[p];
+        const uint16_t *bm = b_mask + pair_b[p] * TS;
+        const int abase = a_tile_nnz[a], aend = a_tile_nnz[a + 1];
+        for (int e = abase + l16; e < aend; e += 16) {
+            const unsigned col = a_col[e];  // A stores row*16+col
+            atomicOr(&cm[col >> 4], (unsigned)bm[col & 15]);
+        }
+    }
+    __syncwarp();
+    if (lane < TS) {
+        const unsigned m = cm[lane];
+        const int n = __popc(m);
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            int v = __shfl_up_sync(0xFFFFu, incl, o, 16);
+            if (lane >= o) incl += v;
+        }
+        c_ptr[(size_t)t * TS + lane] = (uint16_t)(incl - n);
+        c_mask[(size_t)t * TS + lane] = (uint16_t)m;
+        if (lane == 15) c_cnt[t] = incl;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Step 3, version 2: gather formulation, one LANE per C nonzero (g = position in C's Val/Col).
+// blk2tile[g/32] gives the tile holding nonzero 32*(g/32); the lane finds its tile, row r and
+// column c from tile_nnz / Ptr / mask, then for every pair (A tile a, B tile b) of the tile walks
+// A's row r: for an entry (r,k) with value av, B has (k,c) iff bit (15-c) of B's row mask k is set,
+// and its position is Ptr_b[k] + popc(mask bits of columns < c). The sum stays in a register:
+// no shared-memory accumulator, no atomics, no zeroing, fully coalesced stores, and the summation
+// order (ascending A tile, then ascending k) is exactly the serial SPA's.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_blk2tile(int numblkC, const int *__restrict__ c_tile_nnz, int *__restrict__ blk2tile)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= numblkC) return;
+    const int s = c_tile_nnz[t], e = c_tile_nnz[t + 1];
+    for (int blk = (s + 31) >> 5; (blk << 5) < e; blk++) blk2tile[blk] = t;
+}
+
+__global__ void __launch_bounds__(256)
+k_step3_gather(int numblkC, int nnzC, const int *__restrict__ blk2tile, const int *__restrict__ pair_ptr,
+               const int *__restrict__ pair_end, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
+               const int *__restrict__ a_tile_nnz, const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ a_col,
+               const double *__restrict__ a_val, const int *__restrict__ b_tile_nnz, const uint16_t *__restrict__ b_ptr,
+               const uint16_t *__restrict__ b_mask, const double *__restrict__ b_val, const int *__restrict__ c_tile_nnz,
+               const uint16_t *__restrict__ c_ptr, const uint16_t *__restrict__ c_mask, uint16_t *__restrict__ c_col,
+               double *__restrict__ c_val)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nnzC) return;
+    const int blk = g >> 5, nblk = (nnzC + 31) >> 5;
+    int lo = blk2tile[blk], hi = blk + 1 < nblk ? blk2tile[blk + 1] : numblkC - 1;
+    while (lo < hi) {  // largest tile t in [lo,hi] with tile_nnz[t] <= g (it is non-empty and holds g)
+        int mid = (lo + hi + 1) >> 1;
+        if (c_tile_nnz[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    const int t = lo;
+    const int off = g - c_tile_nnz[t];
+    // row: largest r with Ptr[r] <= off; the 16 u16 offsets are one aligned 32-byte line
+    const uint4 *pp = reinterpret_cast<const uint4 *>(c_ptr + (size_t)t * TS);
+    const uint4 q0 = pp[0], q1 = pp[1];
+    const unsigned key = (unsigned)off * 0x10001u;
+    int r = -1;
+    r += __popc(__vcmpleu2(q0.x, key)) + __popc(__vcmpleu2(q0.y, key)) + __popc(__vcmpleu2(q0.z, key)) + __popc(__vcmpleu2(q0.w, key)) +
+         __popc(__vcmpleu2(q1.x, key)) + __popc(__vcmpleu2(q1.y, key)) + __popc(__vcmpleu2(q1.z, key)) + __popc(__vcmpleu2(q1.w, key));
+    r = ((r + 1) >> 4) - 1;  // each u16 that compares <= contributes 16 set bits
+    unsigned cm = c_mask[(size_t)t * TS + r];
+    for (int n = off - (int)c_ptr[(size_t)t * TS + r]; n > 0; n--) cm &= ~(0x80000000u >> __clz(cm));
+    const int c = __clz(cm) - 16;
+    const unsigned cbit = 0x8000u >> c;
+
+    double acc = 0.0;
+    const int p1 = pair_end[t];
+    for (int p = pair_ptr[t]; p < p1; p++) {
+        const int a = pair_a[p], b = pair_b[p];
+        const int abase = a_tile_nnz[a];
+        int ia = a_ptr[a * TS + r];
+        const int ia1 = r < TS - 1 ? (int)a_ptr[a * TS + r + 1] : a_tile_nnz[a + 1] - abase;
+        if (ia < ia1) {
+            const int bbase = b_tile_nnz[b];
+            for (; ia < ia1; ia++) {
+                const int k = a_col[abase + ia] & 15;
+                const unsigned bm = b_mask[b * TS + k];
+                if (bm & cbit) {
+                    const int pos = (int)b_ptr[b * TS + k] + __popc(bm >> (16 - c));
+                    acc = fma(a_val[abase + ia], b_val[bbase + pos], acc);
+                }
+            }
+        }
+    }
+    c_val[g] = acc;
+    c_col[g] = (uint16_t)c;
+}
+
 // row-major tile index -> CSC storage id for a B uploaded from a host SMatrix (csr2tile_device
 // fills rm2csc itself). One thread per stored tile: binary search its column in its tile-row.
 __global__ void k_build_rm2csc(int tilen, const int *__restrict__ csc_tile_ptr, const int *__restrict__ csc_tile_rowidx,
@@ -483,7 +667,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     rc = read_back_i64(numblk64 + ntr, &numblkC);
     if (rc) return rc;
     dfree(numblk64);
-    if (numblkC >= (1ll << 27)) {  // numblkC*16 must index uint16 arrays with int offsets
+    if (numblkC >= (1ll << 30)) {  // numblkC*16 must index uint16 arrays with int offsets
         set_error(TSG_ERR_OVERFLOW, "spgemm: %lld C tiles in tile-rows [%d,%d); use smaller slabs", numblkC, trow0, trow1);
         return last_error();
     }
@@ -524,8 +708,16 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     CK(cudaEventCreate(&ev_s2));
     CK(cudaEventRecord(ev_s2, c.stream));
     if (numblkC > 0) {
-        k_step2<<<ceil_div(numblkC * 16, 128), 128, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->mask, B->mask,
-                                                                   C->ptr, C->mask, C->tile_nnz);
+        static const int v2 = getenv("TSG_STEP2_V1") ? 0 : (getenv("TSG_STEP2_FLAT") ? 1 : 2);
+        if (v2 == 2)
+            k_step2_hw<<<ceil_div(numblkC * 32, 128), 128, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->tile_nnz,
+                                                                          A->col, B->mask, C->ptr, C->mask, C->tile_nnz);
+        else if (v2 == 1)
+            k_step2_flat<<<ceil_div(numblkC * 32, 128), 128, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->tile_nnz,
+                                                                            A->col, B->mask, C->ptr, C->mask, C->tile_nnz);
+        else
+            k_step2<<<ceil_div(numblkC * 16, 128), 128, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->mask, B->mask,
+                                                                       C->ptr, C->mask, C->tile_nnz);
         CK_LAUNCH();
     }
     long long *nnz64 = dalloc_n<long long>(nb + 1);
@@ -557,14 +749,26 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     cudaEvent_t ev_s3;
     CK(cudaEventCreate(&ev_s3));
     CK(cudaEventRecord(ev_s3, c.stream));
+    int *blk2tile = nullptr;
     if (nnzC > 0) {
-        k_step3<<<ceil_div(numblkC * 16, 128), 128, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->tile_nnz, A->ptr,
-                                                                   A->col, A->val, B->tile_nnz, B->ptr, B->col, B->val, C->tile_nnz,
-                                                                   C->ptr, C->mask, C->col, C->val);
+        static const int v2 = getenv("TSG_STEP3_V1") ? 0 : 1;
+        if (v2) {
+            blk2tile = dalloc_n<int>((size_t)((nnzC + 31) >> 5) + 1);
+            if (!blk2tile) return last_error();
+            k_blk2tile<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>((int)numblkC, C->tile_nnz, blk2tile);
+            CK_LAUNCH();
+            k_step3_gather<<<ceil_div(nnzC, 256), 256, 0, c.stream>>>((int)numblkC, (int)nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b,
+                                                                      A->tile_nnz, A->ptr, A->col, A->val, B->tile_nnz, B->ptr, B->mask,
+                                                                      B->val, C->tile_nnz, C->ptr, C->mask, C->col, C->val);
+        } else {
+            k_step3<<<ceil_div(numblkC * 16, 128), 128, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->tile_nnz, A->ptr,
+                                                                       A->col, A->val, B->tile_nnz, B->ptr, B->col, B->val, C->tile_nnz,
+                                                                       C->ptr, C->mask, C->col, C->val);
+        }
         CK_LAUNCH();
     }
     CK(cudaEventRecord(ev[4], c.stream));
-    dfree(pair_ptr); dfree(pair_end); dfree(pair_a); dfree(pair_b);
+    dfree(pair_ptr); dfree(pair_end); dfree(pair_a); dfree(pair_b); dfree(blk2tile);
     dfree(w); dfree(jlo); dfree(jhi); dfree(wptr); dfree(c_tile_ptr);
     CK(cudaStreamSynchronize(c.stream));
 

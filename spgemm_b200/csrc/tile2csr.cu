@@ -48,6 +48,42 @@ k_tile2csr(int m, int tilem, const int *__restrict__ tile_ptr, const int *__rest
     if (!FILL && live) rowptr[row] = cnt;
 }
 
+// Per-row sums of the stored values (C * ones): a size-independent checksum for slabs too large to
+// bring back to the host. Half-warp per tile-row, lane r sums row r over the tiles of the tile-row.
+__global__ void __launch_bounds__(128)
+k_tile_rowsums(int m, int tilem, const int *__restrict__ tile_ptr, const int *__restrict__ tile_nnz,
+               const uint16_t *__restrict__ ptr, const double *__restrict__ val, double *__restrict__ out,
+               long long *__restrict__ out_cnt)
+{
+    const int I = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4);
+    const int r = threadIdx.x & 15;
+    if (I >= tilem) return;
+    const int row = I * TS + r;
+    double s = 0.0;
+    long long cnt = 0;
+    const int t1 = tile_ptr[I + 1];
+    for (int t = tile_ptr[I]; t < t1; t++) {
+        const int base = tile_nnz[t], tnnz = tile_nnz[t + 1] - base;
+        const int p0 = ptr[(size_t)t * TS + r];
+        const int p1 = r < TS - 1 ? (int)ptr[(size_t)t * TS + r + 1] : tnnz;
+        for (int j = p0; j < p1; j++) s += val[base + j];
+        cnt += p1 - p0;
+    }
+    if (row < m) { out[row] = s; out_cnt[row] = cnt; }
+}
+
+int tile_rowsums_device(const tsg_dtile *T, double *d_out, long long *d_cnt)
+{
+    Ctx &c = ctx();
+    if (T->col_major) { set_error(TSG_ERR_UNSUPPORTED, "rowsums: tiles must be in row-major storage order"); return last_error(); }
+    if (T->tilem > 0) {
+        k_tile_rowsums<<<ceil_div((long long)T->tilem * 16, 128), 128, 0, c.stream>>>(T->m, T->tilem, T->tile_ptr, T->tile_nnz, T->ptr, T->val,
+                                                                                      d_out, d_cnt);
+        CK_LAUNCH();
+    }
+    return TSG_OK;
+}
+
 int tile2csr_device(const tsg_dtile *T, tsg_dcsr *out)
 {
     Ctx &c = ctx();

@@ -229,3 +229,117 @@ def test_config1_lap2d_256_full():
     assert_tiled_equal(tC.download(), tC_exp, "lap2d-256 C")
     for o in (tC, tA, tB, d):
         o.free()
+
+
+def _expected_rowsums(A, B, nB):
+    """C * ones = A * (B * ones), exact in FP64 for the integer-valued k % 10 convention."""
+    import scipy.sparse as sp
+    mA, mB = len(A[0]) - 1, len(B[0]) - 1
+    SA = sp.csr_matrix((A[2], A[1], A[0]), shape=(mA, mB))
+    SB = sp.csr_matrix((B[2], B[1], B[0]), shape=(mB, nB))
+    return SA @ (SB @ np.ones(nB))
+
+
+def test_rmat_aat_slabwise_matches_oracle():
+    """Config 3 at reduced scale (R-MAT, Graph500 skew, C = A A^T), executed slab by slab with a small pair budget
+    so that hub tile-rows get slabs of their own and the heavy (multi-warp) step-1 path runs."""
+    m, n, rp, ci, v = M.rmat(13, 16, seed=3)
+    A = (rp, ci, v)
+    cp, ri, cv = orc.transpose(m, n, rp, ci, v)
+    B = (cp, ri, cv)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    dT = api.transpose(d)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(dT, True)
+    oA, oB = orc.csr2tile_row_major(m, n, *A), orc.csr2tile_col_major(n, m, *B)
+    w = api.tilerow_weights(tA, tB)
+    assert w.max() > 2048, "the test must exercise the heavy step-1 path"
+    exp_sums = _expected_rowsums(A, B, m)
+    whole = orc.spgemm_spa(A, B, m)
+    seen = []
+
+    def sink(tC, st):
+        t0 = tC.trow0
+        t1 = t0 + tC.tilem
+        r0, r1 = t0 * 16, min(t1 * 16, m)
+        sub = (whole[0][r0:r1 + 1] - whole[0][r0], whole[1][whole[0][r0]:whole[0][r1]], whole[2][whole[0][r0]:whole[0][r1]])
+        exp = orc.ctiles_from_csr(m, m, oA, oB, sub, t0, t1)
+        assert_tiled_equal(tC.download(), exp, f"rmat slab [{t0},{t1})")
+        s, c = api.tile_rowsums(tC)
+        assert np.array_equal(s, exp_sums[r0:r1]) and np.array_equal(c, np.diff(whole[0][r0:r1 + 1]))
+        seen.append((t0, t1))
+
+    tot, per = api.spgemm_slabs(tA, tB, max_pairs=200000, sink=sink, weights=w)
+    assert len(per) > 3 and seen[0][0] == 0 and seen[-1][1] == tA.tilem
+    assert tot["nnzC"] == whole[0][-1] and tot["pairs"] == int(w.sum())
+    for o in (tA, tB, d, dT):
+        o.free()
+
+
+def test_config2_stencil27_128_full():
+    """BASELINE config 2 at full size (2.1M rows, 55.7M nnz, 1.49e9 products): the whole CSR of C against the
+    oracle, plus the known sizes and the C*ones = A*(A*ones) property."""
+    m, n, rp, ci, v = M.stencil27(128)
+    A = (rp, ci, v)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
+    assert (tA.numtile, tB.numtile) == (3210328, 3210328)
+    assert api.nnzcub(d, d) == 1489355288
+    tC, st = api.spgemm(tA, tB)
+    assert (st["numblkC"], st["nnzC"], st["pairs"]) == (13666504, 254840104, 80858168)
+    assert st["algorithmic_bytes"] == 5179140416
+    s, c = api.tile_rowsums(tC)
+    assert np.array_equal(s, _expected_rowsums(A, A, n))
+    csr = api.tile2csr_device(tC)
+    r, cc, vv = csr.download()
+    er, ec, ev = orc.spgemm_spa(A, A, n)
+    assert np.array_equal(c, np.diff(er))
+    assert np.array_equal(r, er) and np.array_equal(cc, ec) and np.array_equal(vv, ev)
+    for o in (csr, tC, tA, tB, d):
+        o.free()
+
+
+def test_config4_blockfem_full_properties():
+    """BASELINE config 4 at full size (2M rows, dense 6x6 blocks): known sizes and size-independent properties."""
+    m, n, rp, ci, v = M.blockfem(333334)
+    A = (rp, ci, v)
+    assert (m, len(ci)) == (2000004, 36000000)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
+    assert tA.numtile == 375001 and api.nnzcub(d, d) == 647999136
+    tC, st = api.spgemm(tA, tB)
+    assert (st["numblkC"], st["nnzC"], st["pairs"]) == (624999, 59999904, 1124999)
+    s, c = api.tile_rowsums(tC)
+    assert np.array_equal(s, _expected_rowsums(A, A, n))
+    # round trip: tile2csr(C) re-tiled equals C's non-empty tiles
+    csr = api.tile2csr_device(tC)
+    back = api.csr2tile(csr, False)
+    assert back.numtile == 375001 and back.nnz == st["nnzC"]
+    for o in (back, csr, tC, tA, tB, d):
+        o.free()
+
+
+def test_config3_rmat_s16_aat_properties():
+    """Config 3 (R-MAT, Graph500 skew, AA^T) at scale 16, slab-wise: totals and row checksums against
+    A*(A^T*ones) and the oracle's per-row counts (the full scale-20 run is a bench workload)."""
+    m, n, rp, ci, v = M.rmat(16, 16, seed=1)
+    A = (rp, ci, v)
+    cp, ri, cv = orc.transpose(m, n, rp, ci, v)
+    B = (cp, ri, cv)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    dT = api.transpose(d)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(dT, True)
+    exp_sums = _expected_rowsums(A, B, m)
+    exp_cnt = np.diff(orc.spgemm_spa(A, B, m)[0])
+    sums, cnts = np.zeros(m), np.zeros(m, np.int64)
+
+    def sink(tC, st):
+        r0 = tC.trow0 * 16
+        s, c = api.tile_rowsums(tC)
+        sums[r0:r0 + len(s)] = s
+        cnts[r0:r0 + len(c)] = c
+
+    tot, per = api.spgemm_slabs(tA, tB, max_pairs=1 << 26, sink=sink)
+    assert tot["nnzC"] == int(exp_cnt.sum()) and len(per) >= 2
+    assert np.array_equal(cnts, exp_cnt) and np.array_equal(sums, exp_sums)
+    for o in (tA, tB, d, dT):
+        o.free()
