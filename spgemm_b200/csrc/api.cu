@@ -52,6 +52,33 @@ void dfree(void *p)
     if (p) cudaFreeAsync(p, g_ctx.stream);
 }
 
+bool arena_reserve(int which, size_t bytes)
+{
+    Ctx::Arena &a = g_ctx.arena[which];
+    a.off = 0;
+    if (bytes <= a.cap) return true;
+    if (a.base) dfree(a.base);
+    a.base = nullptr; a.cap = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    a.base = (char *)dalloc(want);
+    if (!a.base) return false;
+    a.cap = want;
+    return true;
+}
+
+void *arena_take_bytes(int which, size_t bytes)
+{
+    Ctx::Arena &a = g_ctx.arena[which];
+    size_t need = (bytes + 255) & ~(size_t)255;
+    if (!a.base || a.off + need > a.cap) {
+        set_error(TSG_ERR_NOMEM, "internal: scratch arena %d overflow (%zu + %zu > %zu)", which, a.off, need, a.cap);
+        return nullptr;
+    }
+    void *p = a.base + a.off;
+    a.off += need;
+    return p;
+}
+
 int read_back_i32(const int *d, int *out)
 {
     CK(cudaMemcpyAsync(&g_ctx.h_scalars[15], d, sizeof(int), cudaMemcpyDeviceToHost, g_ctx.stream));
@@ -128,6 +155,8 @@ void tsg_shutdown(void)
     if (!g_ready) return;
     cudaStreamSynchronize(g_ctx.stream);
     if (g_ctx.scan_state) cudaFreeAsync(g_ctx.scan_state, g_ctx.stream);
+    for (int k = 0; k < 3; k++)
+        if (g_ctx.arena[k].base) cudaFreeAsync(g_ctx.arena[k].base, g_ctx.stream);
     cudaStreamSynchronize(g_ctx.stream);
     cudaFree(g_ctx.scan_ticket);
     cudaFree(g_ctx.d_scalars);

@@ -25,6 +25,9 @@ struct Ctx {
     unsigned long long *scan_state = nullptr;
     size_t scan_state_cap = 0;
     int *scan_ticket = nullptr;
+    // grow-only bump arenas for the per-call scratch of spgemm_device (row-sized arrays, pair lists,
+    // block->tile map): after the largest slab has been seen no allocation happens in a step at all
+    struct Arena { char *base = nullptr; size_t cap = 0, off = 0; } arena[3];
     // small pinned host scratch for scalar read-backs
     long long *h_scalars = nullptr;   // pinned, 16 slots
     long long *d_scalars = nullptr;   // device, 16 slots
@@ -60,6 +63,13 @@ void dfree(void *p);
 template <typename T> static inline T *dalloc_n(size_t n) { return (T *)dalloc((n ? n : 1) * sizeof(T)); }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Arena `which`: make room for `bytes` (grow-only, stream-ordered re-allocation) and rewind it.
+bool arena_reserve(int which, size_t bytes);
+// Bump-allocate n elements (256-byte aligned) from arena `which`; nullptr + latched error if it does not fit.
+void *arena_take_bytes(int which, size_t bytes);
+template <typename T> static inline T *arena_take(int which, size_t n) { return (T *)arena_take_bytes(which, (n ? n : 1) * sizeof(T)); }
+static inline size_t arena_need(size_t n, size_t elem) { return (((n ? n : 1) * elem) + 255) & ~(size_t)255; }
 
 // Read one device int / long long back (stream sync). Used only where a size is needed for an
 // allocation (numblkC, nnzC): two per SpGEMM call instead of the reference's ~8.

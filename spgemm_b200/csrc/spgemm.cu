@@ -115,8 +115,21 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total)
 // Step 1b/1c: one CTA per C tile-row. MODE 0 counts the distinct tile columns. MODE 1 emits the
 // sorted tile-column list, and per C tile the matched (A tile, B tile) pair list.
 // THREADS = 32 handles rows with w in (0, S1_LIGHT_MAX]; THREADS = 256 the heavier ones.
-// Dynamic smem: bitmap[nw_max] | pre8[nw_max/8 + 1].
+// Dynamic smem: bitmap[nw_max] | pre8[nw_max/8 + 1] | (fused symbolic) bmT[8][32] u32 | cm[16][numJ_pad] u16.
+//
+// Fused bitmask symbolic (step 2) on the one-warp path: while the warp enumerates the pairs of A tile
+// (I,K) with the B tiles of tile-row K (one B tile per lane), A's 16 row masks are WARP-UNIFORM, so the
+// 16x16x16 boolean product of the pair costs one shared-memory load + OR per A entry for all <= 32
+// pairs at once, instead of a per-pair pass over a half-warp (k_step2). The C row masks of the whole
+// tile-row live in shared memory as cm[row][slot]; Ptr / mask / tile nnz are written at the end.
 // ---------------------------------------------------------------------------------------------
+struct S1Fuse {
+    const uint16_t *a_mask, *b_mask;
+    uint16_t *c_ptr, *c_mask;
+    int *c_cnt;
+    int numJ_pad;  // 0: not fused (k_step2 computes the masks from the pair lists)
+};
+
 template <int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS)
 k_step1(int trow0, int nw_max, int wmin, int wmax, const int *__restrict__ a_tile_ptr,
@@ -124,7 +137,8 @@ k_step1(int trow0, int nw_max, int wmin, int wmax, const int *__restrict__ a_til
         const int *__restrict__ b_rm2csc, const int *__restrict__ w, const int *__restrict__ jlo,
         const int *__restrict__ jhi, int *__restrict__ cnt /*MODE0 out*/, const int *__restrict__ c_tile_ptr,
         const int *__restrict__ wptr, int *__restrict__ c_tile_col, int *__restrict__ c_tile_row,
-        int *__restrict__ pair_ptr, int *__restrict__ pair_end, int *__restrict__ pair_a, int *__restrict__ pair_b)
+        int *__restrict__ pair_ptr, int *__restrict__ pair_end, int *__restrict__ pair_a, int *__restrict__ pair_b,
+        int *__restrict__ maxJ /*MODE0: max tile count over one-warp rows*/, S1Fuse fz)
 {
     extern __shared__ unsigned s1_smem[];
     __shared__ int s_warp[THREADS / 32];
@@ -154,7 +168,10 @@ k_step1(int trow0, int nw_max, int wmin, int wmax, const int *__restrict__ a_til
         int s = 0, total;
         for (int k = tid; k < nw; k += THREADS) s += __popc(bitmap[k]);
         block_excl_scan<THREADS>(s, s_warp, &total);
-        if (tid == 0) cnt[i] = total;
+        if (tid == 0) {
+            cnt[i] = total;
+            if (THREADS == 32) atomicMax(maxJ, total);
+        }
         return;
     }
     // ---- MODE 1 ----
@@ -175,6 +192,12 @@ k_step1(int trow0, int nw_max, int wmin, int wmax, const int *__restrict__ a_til
     }
     const int numJ = s_carry;
     const int cbase = c_tile_ptr[i];
+    const bool fuse = THREADS == 32 && fz.numJ_pad > 0;
+    unsigned *bmT = s1_smem + nw_max + nw_max / 8 + 2;                    // [8][32]: B row masks 2j, 2j+1 of lane's tile
+    uint16_t *cm = reinterpret_cast<uint16_t *>(bmT + 8 * 32);            // [16][numJ_pad]
+    if (fuse) {
+        for (int k = tid; k < (TS * fz.numJ_pad + 1) / 2; k += THREADS) reinterpret_cast<unsigned *>(cm)[k] = 0;
+    }
     for (int k = tid; k < nw; k += THREADS) {
         unsigned bits = bitmap[k];
         if (bits) {
@@ -213,18 +236,65 @@ k_step1(int trow0, int nw_max, int wmin, int wmax, const int *__restrict__ a_til
         if (tid == 0) s_carry = carry + total;
         __syncthreads();
     }
-    // write the pairs
+    // write the pairs (and, fused, OR the pair's boolean product into the tile-row's C masks)
     for (int ta = a0 + warp; ta < a1; ta += NWARPS) {
         int K = a_tile_col[ta];
+        unsigned amw[8];
+        if (fuse) {  // A's 16 row masks: one 32-byte line, the same for every lane
+            const uint4 *ap = reinterpret_cast<const uint4 *>(fz.a_mask + (size_t)ta * TS);
+            const uint4 x = ap[0], y = ap[1];
+            amw[0] = x.x; amw[1] = x.y; amw[2] = x.z; amw[3] = x.w; amw[4] = y.x; amw[5] = y.y; amw[6] = y.z; amw[7] = y.w;
+        }
         for (int tb = b_tile_ptr[K] + lane; tb < b_tile_ptr[K + 1]; tb += 32) {
             int slot = s1_rank(bitmap, pre8, b_tile_col[tb] - lo);
             int pos;
             if (THREADS == 32) pos = pair_end[cbase + slot]++;
             else pos = atomicAdd(&pair_end[cbase + slot], 1);
+            const int b = b_rm2csc[tb];
             pair_a[pos] = ta;
-            pair_b[pos] = b_rm2csc[tb];
+            pair_b[pos] = b;
+            if (fuse) {
+                const uint4 *bp = reinterpret_cast<const uint4 *>(fz.b_mask + (size_t)b * TS);
+                const uint4 x = bp[0], y = bp[1];
+                bmT[0 * 32 + lane] = x.x; bmT[1 * 32 + lane] = x.y; bmT[2 * 32 + lane] = x.z; bmT[3 * 32 + lane] = x.w;
+                bmT[4 * 32 + lane] = y.x; bmT[5 * 32 + lane] = y.y; bmT[6 * 32 + lane] = y.z; bmT[7 * 32 + lane] = y.w;
+#pragma unroll
+                for (int r = 0; r < TS; r++) {
+                    unsigned m = (r & 1) ? (amw[r >> 1] >> 16) : (amw[r >> 1] & 0xFFFFu);  // little-endian u16 pairs
+                    if (m) {                                                            // warp-uniform
+                        unsigned acc = 0;
+                        do {
+                            const int k = __clz(m) - 16;
+                            const unsigned wd = bmT[(k >> 1) * 32 + lane];
+                            acc |= (k & 1) ? (wd >> 16) : (wd & 0xFFFFu);
+                            m &= ~(0x8000u >> k);
+                        } while (m);
+                        cm[r * fz.numJ_pad + slot] |= (uint16_t)acc;  // distinct slots per lane
+                    }
+                }
+            }
         }
         if (THREADS == 32) __syncwarp();
+    }
+    if (fuse) {
+        __syncwarp();
+        for (int sl = lane; sl < numJ; sl += 32) {  // Ptr (exclusive row offsets), mask and nnz of each C tile
+            unsigned pw[8], mw[8];
+            int run = 0;
+#pragma unroll
+            for (int r = 0; r < TS; r += 2) {
+                const unsigned m0 = cm[r * fz.numJ_pad + sl], m1 = cm[(r + 1) * fz.numJ_pad + sl];
+                const int p0 = run, p1 = run + __popc(m0);
+                run = p1 + __popc(m1);
+                pw[r >> 1] = (unsigned)p0 | ((unsigned)p1 << 16);
+                mw[r >> 1] = m0 | (m1 << 16);
+            }
+            uint4 *dp = reinterpret_cast<uint4 *>(fz.c_ptr + (size_t)(cbase + sl) * TS);
+            uint4 *dm = reinterpret_cast<uint4 *>(fz.c_mask + (size_t)(cbase + sl) * TS);
+            dp[0] = make_uint4(pw[0], pw[1], pw[2], pw[3]); dp[1] = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+            dm[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]); dm[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+            fz.c_cnt[cbase + sl] = run;
+        }
     }
     if (THREADS > 32) {
         // several warps appended concurrently: restore ascending-A-tile order for short lists so the
@@ -252,12 +322,13 @@ __global__ void __launch_bounds__(128)
 k_step2(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end,
         const int *__restrict__ pair_a, const int *__restrict__ pair_b, const uint16_t *__restrict__ a_mask,
         const uint16_t *__restrict__ b_mask, uint16_t *__restrict__ c_ptr, uint16_t *__restrict__ c_mask,
-        int *__restrict__ c_cnt)
+        int *__restrict__ c_cnt, const int *__restrict__ c_tile_row, const int *__restrict__ w, int trow0, int light_max)
 {
     const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4);
     const int l16 = threadIdx.x & 15;
     const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
     if (t >= numblkC) return;
+    if (w && w[c_tile_row[t] - trow0] <= light_max) return;  // masks already produced by the fused step-1 path
     unsigned cm = 0;
     const int pe = pair_end[t];
     for (int p = pair_ptr[t]; p < pe; p++) {
@@ -520,6 +591,98 @@ k_step3_gather(int numblkC, int nnzC, const int *__restrict__ blk2tile, const in
     c_col[g] = (uint16_t)c;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Step 3, version 3 ("rounds"): one warp per non-empty C tile, one HALF-WARP per pair (two pairs in
+// flight), one LANE per A entry. The metadata of up to 32 pairs is fetched by the 32 lanes at once
+// (one dependent-load level for the whole tile instead of one per pair) and handed out by shuffle.
+// A lane holding entry (r,k,av) multiplies it with row k of the B tile and accumulates into a dense
+// 16x16 FP64 tile in shared memory, one copy per half-warp. Entries of one half-warp that share a
+// row r are ranked (__match_any_sync) and processed in successive rounds, so within a round every
+// lane of a half-warp writes a different row: no atomics, no conflicts, deterministic order. The two
+// copies are added while the tile is compacted through C's mask.
+// Used when C tiles are reasonably filled; hypersparse tiles (R-MAT) go to k_step3_gather.
+// ---------------------------------------------------------------------------------------------
+constexpr int S3R_WARPS = 4;
+constexpr int S3R_LD = TS + 1;  // padded row length of the accumulator
+
+__global__ void __launch_bounds__(S3R_WARPS * 32)
+k_step3_rounds(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end,
+               const int *__restrict__ pair_a, const int *__restrict__ pair_b, const int *__restrict__ a_tile_nnz,
+               const uint16_t *__restrict__ a_col, const double *__restrict__ a_val, const int *__restrict__ b_tile_nnz,
+               const uint16_t *__restrict__ b_ptr, const uint16_t *__restrict__ b_col, const double *__restrict__ b_val,
+               const int *__restrict__ c_tile_nnz, const uint16_t *__restrict__ c_ptr, const uint16_t *__restrict__ c_mask,
+               uint16_t *__restrict__ c_col, double *__restrict__ c_val)
+{
+    __shared__ double acc_s[S3R_WARPS][2][TS * S3R_LD];
+    const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, l16 = lane & 15, half = lane >> 4;
+    if (t >= numblkC) return;
+    const int cbase = c_tile_nnz[t];
+    if (c_tile_nnz[t + 1] == cbase) return;  // empty tile (warp-uniform)
+    double *acc = acc_s[w][half];
+    const unsigned cm = c_mask[t * TS + l16];
+    for (unsigned m = cm; m;) {  // zero the entries this tile can touch, in this half's copy
+        const int c = __clz(m) - 16;
+        acc[l16 * S3R_LD + c] = 0.0;
+        m &= ~(0x8000u >> c);
+    }
+    __syncwarp();
+    const unsigned lt = (1u << lane) - 1;
+    const int p1 = pair_end[t];
+    for (int pc = pair_ptr[t]; pc < p1; pc += 32) {
+        int mb = 0, mab = 0, mae = 0, mbb = 0, mbn = 0;
+        if (pc + lane < p1) {
+            const int a = pair_a[pc + lane];
+            mb = pair_b[pc + lane];
+            mab = a_tile_nnz[a];
+            mae = a_tile_nnz[a + 1];
+            mbb = b_tile_nnz[mb];
+            mbn = b_tile_nnz[mb + 1] - mbb;
+        }
+        const int npc = min(32, p1 - pc);
+        for (int q0 = 0; q0 < npc; q0 += 2) {
+            const int q = q0 + half;
+            const bool valid = q < npc;
+            const int src = valid ? q : 0;
+            const int b = __shfl_sync(FULL_MASK, mb, src), ab = __shfl_sync(FULL_MASK, mab, src);
+            const int ae_raw = __shfl_sync(FULL_MASK, mae, src);
+            const int ae = valid ? ae_raw : ab;  // an absent pair is an empty entry range
+            const int bb = __shfl_sync(FULL_MASK, mbb, src), bn = __shfl_sync(FULL_MASK, mbn, src);
+            for (int e0 = ab; __any_sync(FULL_MASK, e0 < ae); e0 += 16) {
+                const int e = e0 + l16;
+                const bool live = e < ae;
+                unsigned col = 0;
+                double av = 0.0;
+                if (live) { col = a_col[e]; av = a_val[e]; }
+                const int r = col >> 4, k = col & 15;
+                const unsigned peers = __match_any_sync(FULL_MASK, live ? (unsigned)((half << 8) | r) : (0x1000u | lane));
+                const int rank = __popc(peers & lt);
+                int ib = 0, ib1 = 0;
+                if (live) {
+                    ib = b_ptr[b * TS + k];
+                    ib1 = k < TS - 1 ? (int)b_ptr[b * TS + k + 1] : bn;
+                }
+                for (int j = 0; __any_sync(FULL_MASK, live && rank >= j); j++) {
+                    if (live && rank == j)
+                        for (; ib < ib1; ib++) acc[r * S3R_LD + b_col[bb + ib]] += av * b_val[bb + ib];
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane < TS) {
+        const double *acc0 = acc_s[w][0], *acc1 = acc_s[w][1];
+        int o = cbase + c_ptr[t * TS + lane];
+        for (unsigned m = cm; m; o++) {
+            const int c = __clz(m) - 16;
+            c_val[o] = acc0[lane * S3R_LD + c] + acc1[lane * S3R_LD + c];
+            c_col[o] = (uint16_t)c;
+            m &= ~(0x8000u >> c);
+        }
+    }
+}
+
 // row-major tile index -> CSC storage id for a B uploaded from a host SMatrix (csr2tile_device
 // fills rm2csc itself). One thread per stored tile: binary search its column in its tile-row.
 __global__ void k_build_rm2csc(int tilen, const int *__restrict__ csc_tile_ptr, const int *__restrict__ csc_tile_rowidx,
@@ -577,10 +740,11 @@ int tilerow_weights_device(const tsg_dtile *A, const tsg_dtile *B, int **d_w, in
 template <int MODE>
 static int launch_step1(int ntr, int trow0, int nw_max, int wmax_seen, const tsg_dtile *A, const tsg_dtile *B, const int *w,
                         const int *jlo, const int *jhi, int *cnt, const int *c_tile_ptr, const int *wptr, int *c_tile_col,
-                        int *c_tile_row, int *pair_ptr, int *pair_end, int *pair_a, int *pair_b)
+                        int *c_tile_row, int *pair_ptr, int *pair_end, int *pair_a, int *pair_b, int *maxJ, S1Fuse fz)
 {
     Ctx &c = ctx();
     size_t smem = ((size_t)nw_max + (size_t)nw_max / 8 + 2) * 4;
+    if (fz.numJ_pad > 0) smem += 8 * 32 * 4 + (size_t)fz.numJ_pad * TS * 2 + 4;
     if (smem > c.smem_optin) {
         set_error(TSG_ERR_UNSUPPORTED, "step 1: tile-column window of %d words needs %zu B of shared memory (> %zu)", nw_max, smem, c.smem_optin);
         return last_error();
@@ -591,12 +755,12 @@ static int launch_step1(int ntr, int trow0, int nw_max, int wmax_seen, const tsg
     }
     k_step1<32, MODE><<<ntr, 32, smem, c.stream>>>(trow0, nw_max, 0, S1_LIGHT_MAX, A->tile_ptr, A->tile_columnidx, B->tile_ptr,
                                                    B->tile_columnidx, B->rm2csc, w, jlo, jhi, cnt, c_tile_ptr, wptr, c_tile_col,
-                                                   c_tile_row, pair_ptr, pair_end, pair_a, pair_b);
+                                                   c_tile_row, pair_ptr, pair_end, pair_a, pair_b, maxJ, fz);
     CK_LAUNCH();
     if (wmax_seen > S1_LIGHT_MAX) {
         k_step1<S1_HEAVY_THREADS, MODE><<<ntr, S1_HEAVY_THREADS, smem, c.stream>>>(
             trow0, nw_max, S1_LIGHT_MAX, 0x7fffffff, A->tile_ptr, A->tile_columnidx, B->tile_ptr, B->tile_columnidx, B->rm2csc, w,
-            jlo, jhi, cnt, c_tile_ptr, wptr, c_tile_col, c_tile_row, pair_ptr, pair_end, pair_a, pair_b);
+            jlo, jhi, cnt, c_tile_ptr, wptr, c_tile_col, c_tile_row, pair_ptr, pair_end, pair_a, pair_b, maxJ, fz);
         CK_LAUNCH();
     }
     return TSG_OK;
@@ -621,10 +785,12 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     CK(cudaEventRecord(ev[0], c.stream));
 
     // ---------------- step 1 ----------------
-    int *w = dalloc_n<int>((size_t)ntr + 1), *jlo = dalloc_n<int>(ntr), *jhi = dalloc_n<int>(ntr);
-    int *wptr = dalloc_n<int>((size_t)ntr + 1);
-    int *c_tile_ptr = dalloc_n<int>((size_t)ntr + 1);
-    if (!w || !jlo || !jhi || !wptr || !c_tile_ptr) return last_error();
+    if (!arena_reserve(0, 5 * arena_need((size_t)ntr + 1, 4) + 2 * arena_need((size_t)ntr + 1, 8))) return last_error();
+    int *w = arena_take<int>(0, (size_t)ntr + 1), *jlo = arena_take<int>(0, (size_t)ntr + 1), *jhi = arena_take<int>(0, (size_t)ntr + 1);
+    int *wptr = arena_take<int>(0, (size_t)ntr + 1);
+    int *c_tile_ptr = arena_take<int>(0, (size_t)ntr + 1);
+    long long *wptr64 = arena_take<long long>(0, (size_t)ntr + 1), *numblk64 = arena_take<long long>(0, (size_t)ntr + 1);
+    if (!w || !jlo || !jhi || !wptr || !c_tile_ptr || !wptr64 || !numblk64) return last_error();
     int *scal = (int *)c.d_scalars;
     CK(cudaMemsetAsync(scal, 0, 4 * sizeof(int), c.stream));
     CK(cudaMemsetAsync(c_tile_ptr, 0, ((size_t)ntr + 1) * sizeof(int), c.stream));
@@ -635,8 +801,6 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     }
     long long *wtot = c.d_scalars + 4;
     // 64-bit scan output for the total, 32-bit offsets for the kernels (slab planning keeps it < 2^31)
-    long long *wptr64 = dalloc_n<long long>((size_t)ntr + 1);
-    if (!wptr64) return last_error();
     int rc = exclusive_scan<long long>(w, wptr64, ntr);
     if (rc) return rc;
     rc = exclusive_scan<int>(w, wptr, ntr);
@@ -647,26 +811,25 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     const int *hs = (const int *)c.h_scalars;
     const int nw_max = hs[0] > 0 ? hs[0] : 1, werr = hs[1], wmax_seen = hs[2];
     const long long pairs = c.h_scalars[4];
-    dfree(wptr64);
     if (werr || pairs >= (1ll << 31)) {
         set_error(TSG_ERR_OVERFLOW, "spgemm: %lld tile pairs in tile-rows [%d,%d) exceed 32-bit indexing; use smaller slabs", pairs, trow0, trow1);
         return last_error();
     }
     if (ntr > 0 && pairs > 0) {
         rc = launch_step1<0>(ntr, trow0, nw_max, wmax_seen, A, B, w, jlo, jhi, c_tile_ptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                             nullptr, nullptr, nullptr);
+                             nullptr, nullptr, nullptr, scal + 3, S1Fuse{nullptr, nullptr, nullptr, nullptr, nullptr, 0});
         if (rc) return rc;
     }
-    long long *numblk64 = dalloc_n<long long>((size_t)ntr + 1);
-    if (!numblk64) return last_error();
     rc = exclusive_scan<long long>(c_tile_ptr, numblk64, ntr);
     if (rc) return rc;
     rc = exclusive_scan<int>(c_tile_ptr, c_tile_ptr, ntr);
     if (rc) return rc;
     long long numblkC = 0;
-    rc = read_back_i64(numblk64 + ntr, &numblkC);
-    if (rc) return rc;
-    dfree(numblk64);
+    CK(cudaMemcpyAsync(&c.h_scalars[8], numblk64 + ntr, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaMemcpyAsync(&c.h_scalars[9], scal + 3, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    numblkC = c.h_scalars[8];
+    const int maxJ_light = *(const int *)&c.h_scalars[9];
     if (numblkC >= (1ll << 30)) {  // numblkC*16 must index uint16 arrays with int offsets
         set_error(TSG_ERR_OVERFLOW, "spgemm: %lld C tiles in tile-rows [%d,%d); use smaller slabs", numblkC, trow0, trow1);
         return last_error();
@@ -693,13 +856,24 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         C->m = (int)(r1 > r0 ? r1 - r0 : 0);
     }
     CK(cudaMemcpyAsync(C->tile_ptr, c_tile_ptr, ((size_t)ntr + 1) * 4, cudaMemcpyDeviceToDevice, c.stream));
-    int *pair_ptr = dalloc_n<int>(nb + 1), *pair_end = dalloc_n<int>(nb), *pair_a = dalloc_n<int>(np), *pair_b = dalloc_n<int>(np);
-    if (!pair_ptr || !pair_end || !pair_a || !pair_b) return last_error();
+    if (!arena_reserve(1, 2 * arena_need(nb + 1, 4) + 2 * arena_need(np, 4) + arena_need(nb + 1, 8))) return last_error();
+    int *pair_ptr = arena_take<int>(1, nb + 1), *pair_end = arena_take<int>(1, nb + 1), *pair_a = arena_take<int>(1, np), *pair_b = arena_take<int>(1, np);
+    long long *nnz64 = arena_take<long long>(1, nb + 1);
+    if (!pair_ptr || !pair_end || !pair_a || !pair_b || !nnz64) return last_error();
     CK(cudaMemsetAsync(pair_end, 0, nb * 4, c.stream));
     CK(cudaEventRecord(ev[2], c.stream));  // [1..2] = allocation
+    // the one-warp step-1 path also produces C's masks / Ptr / tile nnz (fused step 2) when the tile-row's
+    // masks fit shared memory; TSG_FUSE=0 disables the fusion (A/B measurements)
+    static const int fuse_env = getenv("TSG_FUSE") ? atoi(getenv("TSG_FUSE")) : 1;
+    S1Fuse fz{A->mask, B->mask, C->ptr, C->mask, C->tile_nnz, 0};
+    {
+        size_t need = ((size_t)nw_max + (size_t)nw_max / 8 + 2) * 4 + 8 * 32 * 4 + (size_t)(maxJ_light + 1) * TS * 2 + 4;
+        if (fuse_env && maxJ_light > 0 && need <= c.smem_optin) fz.numJ_pad = maxJ_light | 1;  // odd row stride: fewer bank conflicts
+    }
+    const bool fused = fz.numJ_pad > 0;
     if (numblkC > 0) {
         rc = launch_step1<1>(ntr, trow0, nw_max, wmax_seen, A, B, w, jlo, jhi, nullptr, C->tile_ptr, wptr, C->tile_columnidx,
-                             C->tile_rowidx, pair_ptr, pair_end, pair_a, pair_b);
+                             C->tile_rowidx, pair_ptr, pair_end, pair_a, pair_b, nullptr, fz);
         if (rc) return rc;
     }
 
@@ -707,7 +881,13 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     cudaEvent_t ev_s2;
     CK(cudaEventCreate(&ev_s2));
     CK(cudaEventRecord(ev_s2, c.stream));
-    if (numblkC > 0) {
+    if (numblkC > 0 && fused) {
+        if (wmax_seen > S1_LIGHT_MAX) {  // tile-rows of the multi-warp path still need the pair-based symbolic
+            k_step2<<<ceil_div(numblkC * 16, 128), 128, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->mask, B->mask,
+                                                                       C->ptr, C->mask, C->tile_nnz, C->tile_rowidx, w, trow0, S1_LIGHT_MAX);
+            CK_LAUNCH();
+        }
+    } else if (numblkC > 0) {
         static const int v2 = getenv("TSG_STEP2_V1") ? 0 : (getenv("TSG_STEP2_FLAT") ? 1 : 2);
         if (v2 == 2)
             k_step2_hw<<<ceil_div(numblkC * 32, 128), 128, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->tile_nnz,
@@ -717,11 +897,9 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
                                                                             A->col, B->mask, C->ptr, C->mask, C->tile_nnz);
         else
             k_step2<<<ceil_div(numblkC * 16, 128), 128, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->mask, B->mask,
-                                                                       C->ptr, C->mask, C->tile_nnz);
+                                                                       C->ptr, C->mask, C->tile_nnz, nullptr, nullptr, 0, 0);
         CK_LAUNCH();
     }
-    long long *nnz64 = dalloc_n<long long>(nb + 1);
-    if (!nnz64) return last_error();
     rc = exclusive_scan<long long>(C->tile_nnz, nnz64, numblkC);
     if (rc) return rc;
     rc = exclusive_scan<int>(C->tile_nnz, C->tile_nnz, numblkC);
@@ -729,7 +907,6 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     long long nnzC = 0;
     rc = read_back_i64(nnz64 + numblkC, &nnzC);
     if (rc) return rc;
-    dfree(nnz64);
     if (nnzC >= (1ll << 31)) {
         set_error(TSG_ERR_OVERFLOW, "spgemm: nnz(C) = %lld in tile-rows [%d,%d) exceeds int32; use smaller slabs", nnzC, trow0, trow1);
         return last_error();
@@ -751,9 +928,18 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     CK(cudaEventRecord(ev_s3, c.stream));
     int *blk2tile = nullptr;
     if (nnzC > 0) {
-        static const int v2 = getenv("TSG_STEP3_V1") ? 0 : 1;
-        if (v2) {
-            blk2tile = dalloc_n<int>((size_t)((nnzC + 31) >> 5) + 1);
+        // numeric kernel choice: "rounds" (warp per tile) when C tiles are reasonably filled, "gather" (lane per
+        // nonzero) for hypersparse tiles; TSG_STEP3 = v1 | gather | rounds overrides (A/B measurements)
+        static const char *force = getenv("TSG_STEP3");
+        int v2 = 1;  // measured (profiles/): gather beats rounds on every config
+        if (force) v2 = !strcmp(force, "v1") ? 0 : (!strcmp(force, "gather") ? 1 : 2);
+        if (v2 == 2) {
+            k_step3_rounds<<<ceil_div(numblkC * 32, S3R_WARPS * 32), S3R_WARPS * 32, 0, c.stream>>>(
+                (int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->tile_nnz, A->col, A->val, B->tile_nnz, B->ptr, B->col, B->val,
+                C->tile_nnz, C->ptr, C->mask, C->col, C->val);
+        } else if (v2 == 1) {
+            if (!arena_reserve(2, arena_need((size_t)((nnzC + 31) >> 5) + 1, 4))) return last_error();
+            blk2tile = arena_take<int>(2, (size_t)((nnzC + 31) >> 5) + 1);
             if (!blk2tile) return last_error();
             k_blk2tile<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>((int)numblkC, C->tile_nnz, blk2tile);
             CK_LAUNCH();
@@ -768,8 +954,6 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         CK_LAUNCH();
     }
     CK(cudaEventRecord(ev[4], c.stream));
-    dfree(pair_ptr); dfree(pair_end); dfree(pair_a); dfree(pair_b); dfree(blk2tile);
-    dfree(w); dfree(jlo); dfree(jhi); dfree(wptr); dfree(c_tile_ptr);
     CK(cudaStreamSynchronize(c.stream));
 
     if (stats) {
