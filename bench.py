@@ -173,6 +173,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG is VERSION/INFO
+        os.environ["NCCL_DEBUG"] = os.environ.get("TSG_NCCL_DEBUG", "WARN")
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
