@@ -79,6 +79,34 @@ void *arena_take_bytes(int which, size_t bytes)
     return p;
 }
 
+void *cslab_take(int which, size_t bytes, size_t *cap)
+{
+    Ctx::SlabCache &s = g_ctx.cslab[which];
+    if (s.p && s.cap >= bytes) {
+        void *p = s.p;
+        *cap = s.cap;
+        s.p = nullptr; s.cap = 0;
+        return p;
+    }
+    size_t want = bytes + bytes / 8 + 4096;
+    void *p = dalloc(want);
+    if (!p) { want = bytes; p = dalloc(want); }
+    *cap = p ? want : 0;
+    return p;
+}
+
+void cslab_give(int which, void *p, size_t cap)
+{
+    if (!p) return;
+    Ctx::SlabCache &s = g_ctx.cslab[which];
+    if (!s.p || cap > s.cap) {
+        if (s.p) dfree(s.p);
+        s.p = p; s.cap = cap;
+    } else {
+        dfree(p);
+    }
+}
+
 int read_back_i32(const int *d, int *out)
 {
     CK(cudaMemcpyAsync(&g_ctx.h_scalars[15], d, sizeof(int), cudaMemcpyDeviceToHost, g_ctx.stream));
@@ -157,6 +185,8 @@ void tsg_shutdown(void)
     if (g_ctx.scan_state) cudaFreeAsync(g_ctx.scan_state, g_ctx.stream);
     for (int k = 0; k < 3; k++)
         if (g_ctx.arena[k].base) cudaFreeAsync(g_ctx.arena[k].base, g_ctx.stream);
+    for (int k = 0; k < 2; k++)
+        if (g_ctx.cslab[k].p) cudaFreeAsync(g_ctx.cslab[k].p, g_ctx.stream);
     cudaStreamSynchronize(g_ctx.stream);
     cudaFree(g_ctx.scan_ticket);
     cudaFree(g_ctx.d_scalars);
@@ -306,8 +336,11 @@ int tsg_tile_alloc(int m, int n, int numtile, long long nnz, int col_major, tsg_
 void tsg_tile_free(tsg_dtile *t)
 {
     if (!t) return;
-    for (int k = 0; k < 4; k++)
-        if (t->slab[k] && g_ready) dfree(t->slab[k]);
+    for (int k = 0; k < 4; k++) {
+        if (!t->slab[k] || !g_ready) continue;
+        if (t->slab[2] == (void *)1 && k < 2) cslab_give(k, t->slab[k], t->slab_bytes[k]);  // a C slab of tsg_spgemm
+        else if (k != 2 || t->slab[2] != (void *)1) dfree(t->slab[k]);
+    }
     memset(t, 0, sizeof(*t));
 }
 

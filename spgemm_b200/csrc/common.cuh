@@ -28,6 +28,9 @@ struct Ctx {
     // grow-only bump arenas for the per-call scratch of spgemm_device (row-sized arrays, pair lists,
     // block->tile map): after the largest slab has been seen no allocation happens in a step at all
     struct Arena { char *base = nullptr; size_t cap = 0, off = 0; } arena[3];
+    // one-deep cache of the two buffers of a C slab (metadata, payload): a slab loop frees a C slab and asks for
+    // the next one of similar size; handing the same buffer back avoids 20-GB pool re-allocations
+    struct SlabCache { void *p = nullptr; size_t cap = 0; } cslab[2];
     // small pinned host scratch for scalar read-backs
     long long *h_scalars = nullptr;   // pinned, 16 slots
     long long *d_scalars = nullptr;   // device, 16 slots
@@ -70,6 +73,11 @@ bool arena_reserve(int which, size_t bytes);
 void *arena_take_bytes(int which, size_t bytes);
 template <typename T> static inline T *arena_take(int which, size_t n) { return (T *)arena_take_bytes(which, (n ? n : 1) * sizeof(T)); }
 static inline size_t arena_need(size_t n, size_t elem) { return (((n ? n : 1) * elem) + 255) & ~(size_t)255; }
+
+// C slab buffers: take a cached buffer of >= bytes (or allocate one with headroom; *cap gets its capacity) and
+// give one back on free (the larger of cached / returned is kept).
+void *cslab_take(int which, size_t bytes, size_t *cap);
+void cslab_give(int which, void *p, size_t cap);
 
 // Read one device int / long long back (stream sync). Used only where a size is needed for an
 // allocation (numblkC, nnzC): two per SpGEMM call instead of the reference's ~8.
