@@ -393,7 +393,7 @@ def run_ours(args):
         "e2e": {"value": 2.0 * nnzCub / (e2e_ms_max * 1e6), "unit": "GFLOP/s", "ms_per_step": e2e_ms_max, "steps": e2e_K,
                 "h2d_bytes_per_step": int(allv[:, 3].sum()), "d2h_bytes_per_step": int(allv[:, 4].sum())},
         "gpu_launches": int(allv[:, 2].sum()),
-        "roofline": {"bound": "hbm", "kernel": "k_step3 (numeric)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_step3_gather (numeric)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": s3_ms,
                      "algorithmic_bytes_per_launch": s3_bytes},
     }

@@ -247,7 +247,13 @@ int main(int argc, char **argv)
     t0 = now_ms();
     csr2tile_row_major(matrixA, tile_size_m, tile_size_n);
     die_on_error("csr2tile_row_major");
-    printf("CSR to Tile conversion uses %.2f ms\n", now_ms() - t0);
+    double time_conversion = now_ms() - t0;
+    printf("CSR to Tile conversion uses %.2f ms\n", time_conversion);
+    /* format footprint, same formula as the reference (src/main.cu:178-185) */
+    double tile_mb = ((matrixA->tilem + 1) * 4.0 + matrixA->numtile * 4.0 + (matrixA->numtile + 1) * 4.0 + matrixA->nnz * 8.0 +
+                      matrixA->nnz * 1.0 + matrixA->numtile * 16.0 * 1.0 + matrixA->numtile * 16.0 * 2.0) / 1024 / 1024;
+    double csr_mb = ((matrixA->m + 1) * 4.0 + matrixA->nnz * 4.0 + matrixA->nnz * 8.0) / 1024 / 1024;
+    printf("tile space overhead = %.2f MB\n", tile_mb);
     csr2tile_col_major(matrixB, tile_size_m, tile_size_n);
     die_on_error("csr2tile_col_major");
 
@@ -260,6 +266,37 @@ int main(int argc, char **argv)
         die_on_error("tilespgemm");
     }
     printf("step1 %.3f ms, step2 %.3f ms, step3 %.3f ms, alloc %.3f ms, compression rate %.3f\n", ts1, ts2, ts3, tmalloc, compression_rate);
+    /* result logs, same files and column order as the reference (src/main.cu:283-318); written only when the
+     * reference's ../data directory exists next to the working directory, or under $TSG_CSV_DIR */
+    {
+        const char *dir = getenv("TSG_CSV_DIR") ? getenv("TSG_CSV_DIR") : "../data";
+        char path[1024];
+        FILE *f;
+        snprintf(path, sizeof path, "%s/results_tile.csv", dir);
+        if ((f = fopen(path, "a"))) {
+            fprintf(f, "%s,%i,%i,%i,%llu,%llu,%f,%f,%f\n", filename, matrixA->m, matrixA->n, matrixA->nnz, nnzCub, nnzC_computed,
+                    compression_rate, time_tile, gflops_tile);
+            fclose(f);
+            snprintf(path, sizeof path, "%s/step_runtime.csv", dir);
+            if ((f = fopen(path, "a"))) {
+                fprintf(f, "%s,%i,%i,%i,%llu,%llu,%f,%f,%f,%f,%f\n", filename, matrixA->m, matrixA->n, matrixA->nnz, nnzCub, nnzC_computed,
+                        compression_rate, ts1, ts2, ts3, tmalloc);
+                fclose(f);
+            }
+            snprintf(path, sizeof path, "%s/mem-cost.csv", dir);
+            if ((f = fopen(path, "a"))) {
+                fprintf(f, "%s,%i,%i,%i,%llu,%llu,%f,%f,%f\n", filename, matrixA->m, matrixA->n, matrixA->nnz, nnzCub, nnzC_computed,
+                        compression_rate, csr_mb, tile_mb);
+                fclose(f);
+            }
+            snprintf(path, sizeof path, "%s/preprocessing.csv", dir);
+            if ((f = fopen(path, "a"))) {
+                fprintf(f, "%s,%i,%i,%i,%llu,%llu,%f,%f,%f\n", filename, matrixA->m, matrixA->n, matrixA->nnz, nnzCub, nnzC_computed,
+                        compression_rate, time_conversion, time_tile);
+                fclose(f);
+            }
+        }
+    }
 
     printf("-------------------------------check----------------------------------------\n");
     t0 = now_ms();

@@ -410,15 +410,15 @@ k_step3_gather(int numblkC, int nnzC, const int *__restrict__ blk2tile, const in
     for (int p = pair_ptr[t]; p < p1; p++) {
         const int a = pair_a[p], b = pair_b[p];
         const int abase = a_tile_nnz[a];
-        int ia = a_ptr[a * TS + r];
-        const int ia1 = r < TS - 1 ? (int)a_ptr[a * TS + r + 1] : a_tile_nnz[a + 1] - abase;
+        int ia = a_ptr[(size_t)a * TS + r];
+        const int ia1 = r < TS - 1 ? (int)a_ptr[(size_t)a * TS + r + 1] : a_tile_nnz[a + 1] - abase;
         if (ia < ia1) {
             const int bbase = b_tile_nnz[b];
             for (; ia < ia1; ia++) {
                 const int k = a_col[abase + ia] & 15;
-                const unsigned bm = b_mask[b * TS + k];
+                const unsigned bm = b_mask[(size_t)b * TS + k];
                 if (bm & cbit) {
-                    const int pos = (int)b_ptr[b * TS + k] + __popc(bm >> (16 - c));
+                    const int pos = (int)b_ptr[(size_t)b * TS + k] + __popc(bm >> (16 - c));
                     acc = fma(a_val[abase + ia], b_val[bbase + pos], acc);
                 }
             }

@@ -343,3 +343,29 @@ def test_config3_rmat_s16_aat_properties():
     assert np.array_equal(cnts, exp_cnt) and np.array_equal(sums, exp_sums)
     for o in (tA, tB, d, dT):
         o.free()
+
+
+def test_c_driver_cli(tmp_path):
+    """driver/test_b200: the reference's CLI (./test -d 0 -aat X file tile_m tile_n) on a .mtx file and on a
+    generated matrix, both -aat modes; its own serial-SPA check must pass and the reference's CSV logs are written."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "driver", "test_b200")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "driver")])
+    m, n, rp, ci, v = M.random_sparse(120, 120, 0.05, seed=5)
+    mtx = tmp_path / "rand120.mtx"
+    M.write_mtx(str(mtx), m, n, rp, ci, v)
+    env = dict(os.environ, TSG_CSV_DIR=str(tmp_path))
+    for args in (["-d", "0", "-aat", "0", str(mtx), "16", "16"], ["-d", "0", "-aat", "1", str(mtx), "16", "16"],
+                 ["-d", "0", "-aat", "0", "gen:stencil27:12", "16", "16"]):
+        out = subprocess.run([exe] + args, capture_output=True, text=True, env=env, timeout=120)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "[PASSED]" in out.stdout and "CUDA  TileSpGEMM runtime is" in out.stdout
+    rows = open(tmp_path / "results_tile.csv").read().strip().splitlines()
+    assert len(rows) == 3 and rows[0].split(",")[1:4] == ["120", "120", str(len(ci))]
+    for name in ("step_runtime.csv", "mem-cost.csv", "preprocessing.csv"):
+        assert len(open(tmp_path / name).read().strip().splitlines()) == 3
+    bad = subprocess.run([exe, "-d", "0", "-aat", "0", str(mtx), "32", "32"], capture_output=True, text=True, env=env, timeout=60)
+    assert bad.returncode != 0  # unsupported tile size: the driver exits non-zero instead of printing garbage
