@@ -33,7 +33,7 @@
 namespace tsg {
 
 constexpr int S1_LIGHT_MAX = 2048;   // tile-rows with <= this many pairs run on one warp (deterministic pair order)
-constexpr int S1_HEAVY_THREADS = 256;
+constexpr int S1_HEAVY_THREADS = 1024;  // one CTA per heavy tile-row: its window bitmap can take most of the SM's shared memory
 constexpr int S1_SORT_MAX = 64;      // heavy path: pair lists up to this length are re-sorted by A tile
 
 // ---------------------------------------------------------------------------------------------
@@ -357,6 +357,55 @@ k_step2(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ p
 }
 
 // ---------------------------------------------------------------------------------------------
+// Step 2 for HYPERSPARSE tiles (R-MAT: ~1 pair of ~1 entry per C tile): one THREAD per C tile. The
+// thread walks the tile's pairs and, for each entry (r,k) of the A tile, ORs row mask k of the B tile
+// into its private row mask r, kept in shared memory as cm[r][thread] (dynamic r without local
+// memory, conflict-free). A half-warp per tile (k_step2) would idle 15 of 16 lanes here; on
+// well-filled tiles the per-thread walks are uncoalesced and k_step2 wins (profiles/README.md).
+// ---------------------------------------------------------------------------------------------
+constexpr int S2T_THREADS = 128;
+
+__global__ void __launch_bounds__(S2T_THREADS)
+k_step2_thread(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end,
+               const int *__restrict__ pair_a, const int *__restrict__ pair_b, const int *__restrict__ a_tile_nnz,
+               const uint16_t *__restrict__ a_col, const uint16_t *__restrict__ b_mask, uint16_t *__restrict__ c_ptr,
+               uint16_t *__restrict__ c_mask, int *__restrict__ c_cnt, const int *__restrict__ c_tile_row,
+               const int *__restrict__ w, int trow0, int light_max)
+{
+    __shared__ uint16_t cm[TS][S2T_THREADS];
+    const int t = blockIdx.x * S2T_THREADS + threadIdx.x, tid = threadIdx.x;
+    if (t >= numblkC) return;
+    if (w && w[c_tile_row[t] - trow0] <= light_max) return;  // masks already produced by the fused step-1 path
+#pragma unroll
+    for (int r = 0; r < TS; r++) cm[r][tid] = 0;
+    const int p1 = pair_end[t];
+    for (int p = pair_ptr[t]; p < p1; p++) {
+        const int a = pair_a[p];
+        const uint16_t *bm = b_mask + (size_t)pair_b[p] * TS;
+        const int e1 = a_tile_nnz[a + 1];
+        for (int e = a_tile_nnz[a]; e < e1; e++) {
+            const unsigned col = a_col[e];  // A stores row*16+col
+            cm[col >> 4][tid] |= bm[col & 15];
+        }
+    }
+    unsigned pw[8], mw[8];
+    int run = 0;
+#pragma unroll
+    for (int r = 0; r < TS; r += 2) {
+        const unsigned m0 = cm[r][tid], m1 = cm[r + 1][tid];
+        const int p0 = run, pn = run + __popc(m0);
+        run = pn + __popc(m1);
+        pw[r >> 1] = (unsigned)p0 | ((unsigned)pn << 16);
+        mw[r >> 1] = m0 | (m1 << 16);
+    }
+    uint4 *dp = reinterpret_cast<uint4 *>(c_ptr + (size_t)t * TS);
+    uint4 *dm = reinterpret_cast<uint4 *>(c_mask + (size_t)t * TS);
+    dp[0] = make_uint4(pw[0], pw[1], pw[2], pw[3]); dp[1] = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+    dm[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]); dm[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+    c_cnt[t] = run;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Step 3: gather formulation, one LANE per C nonzero (g = position in C's Val/Col).
 // blk2tile[g/32] gives the tile holding nonzero 32*(g/32); the lane finds its tile, row r and
 // column c from tile_nnz / Ptr / mask, then for every pair (A tile a, B tile b) of the tile walks
@@ -631,11 +680,18 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     cudaEvent_t ev_s2;
     CK(cudaEventCreate(&ev_s2));
     CK(cudaEventRecord(ev_s2, c.stream));
-    // pair-based symbolic for the C tiles the fused step-1 path did not cover
+    // pair-based symbolic for the C tiles the fused step-1 path did not cover: half-warp per tile, or thread per
+    // tile when the tiles are hypersparse (<= 2 pairs per C tile and <= 2 entries per A tile on average)
     if (numblkC > 0 && (!fused || wmax_seen > S1_LIGHT_MAX)) {
-        k_step2<<<ceil_div(numblkC * 16, 128), 128, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->mask, B->mask,
-                                                                   C->ptr, C->mask, C->tile_nnz, C->tile_rowidx, fused ? w : nullptr, trow0,
-                                                                   S1_LIGHT_MAX);
+        const int *wf = fused ? w : nullptr;
+        const bool hypersparse = pairs <= 2 * numblkC && A->nnz <= 2ll * A->numtile;
+        if (hypersparse)
+            k_step2_thread<<<ceil_div(numblkC, S2T_THREADS), S2T_THREADS, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b,
+                                                                                         A->tile_nnz, A->col, B->mask, C->ptr, C->mask,
+                                                                                         C->tile_nnz, C->tile_rowidx, wf, trow0, S1_LIGHT_MAX);
+        else
+            k_step2<<<ceil_div(numblkC * 16, 128), 128, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->mask, B->mask,
+                                                                       C->ptr, C->mask, C->tile_nnz, C->tile_rowidx, wf, trow0, S1_LIGHT_MAX);
         CK_LAUNCH();
     }
     rc = exclusive_scan<long long>(C->tile_nnz, nnz64, numblkC);
