@@ -144,6 +144,7 @@ typedef struct {
     int m, n, tilem, tilen, numtile;
     int col_major;        /* 1: B layout (CSC-tile order, Col = col); 0: A / C layout           */
     int trow0;            /* first tile-row this object covers (slabs of C; 0 otherwise)        */
+    int cached;           /* 1: slab[0..1] are C slab buffers that tsg_tile_free hands back to the library's cache */
     long long nnz;
     int *tile_ptr;        /* [tilem+1]                                                         */
     int *tile_columnidx;  /* [numtile]                                                         */

@@ -338,8 +338,8 @@ void tsg_tile_free(tsg_dtile *t)
     if (!t) return;
     for (int k = 0; k < 4; k++) {
         if (!t->slab[k] || !g_ready) continue;
-        if (t->slab[2] == (void *)1 && k < 2) cslab_give(k, t->slab[k], t->slab_bytes[k]);  // a C slab of tsg_spgemm
-        else if (k != 2 || t->slab[2] != (void *)1) dfree(t->slab[k]);
+        if (t->cached && k < 2) cslab_give(k, t->slab[k], t->slab_bytes[k]);  // a C slab of tsg_spgemm: keep for the next slab
+        else dfree(t->slab[k]);
     }
     memset(t, 0, sizeof(*t));
 }

@@ -641,7 +641,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         char *base = (char *)cslab_take(0, off, &cap);
         if (!base) return last_error();
         C->slab[0] = base; C->slab_bytes[0] = cap;
-        C->slab[2] = (void *)1;  // marks slab[0], slab[1] as cache-managed C slab buffers (tsg_tile_free)
+        C->cached = 1;  // slab[0], slab[1] go back to the library's C slab cache in tsg_tile_free
         C->tile_ptr = (int *)(base + o_tp); C->tile_columnidx = (int *)(base + o_tc); C->tile_rowidx = (int *)(base + o_tr);
         C->tile_nnz = (int *)(base + o_tn); C->ptr = (uint16_t *)(base + o_p); C->mask = (uint16_t *)(base + o_m);
     }

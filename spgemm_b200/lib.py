@@ -45,7 +45,7 @@ class DCsr(C.Structure):
 class DTile(C.Structure):
     _fields_ = [
         ("m", C.c_int), ("n", C.c_int), ("tilem", C.c_int), ("tilen", C.c_int), ("numtile", C.c_int),
-        ("col_major", C.c_int), ("trow0", C.c_int), ("nnz", C.c_longlong),
+        ("col_major", C.c_int), ("trow0", C.c_int), ("cached", C.c_int), ("nnz", C.c_longlong),
         ("tile_ptr", C.c_void_p), ("tile_columnidx", C.c_void_p), ("tile_rowidx", C.c_void_p), ("tile_nnz", C.c_void_p),
         ("val", C.c_void_p), ("col", C.c_void_p), ("ptr", C.c_void_p), ("mask", C.c_void_p),
         ("csc_tile_ptr", C.c_void_p), ("csc_tile_rowidx", C.c_void_p), ("rm2csc", C.c_void_p),
