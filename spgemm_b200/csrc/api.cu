@@ -1,6 +1,8 @@
 // api.cu -- the C ABI of libtilespgemm_b200.so (include/tilespgemm.h): library context, the
 // reference-named drop-in entry points (host buffers) and the device-resident tsg_* API.
 #include <stdarg.h>
+#include <unordered_map>
+#include <vector>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -34,22 +36,69 @@ bool cuda_ok(cudaError_t e, const char *what, const char *file, int line)
     return false;
 }
 
+// Big blocks (>= 32 MB) are recycled by this small exact-fit cache instead of going back to the stream-ordered
+// pool: the pool splits cached blocks to serve smaller requests, so a steady-state loop that allocates the same
+// multi-GB sizes every step would now and then fall through to the driver (hundreds of ms for a 3-GB block;
+// measured in bench.py's end-to-end leg). All work is ordered on the one library stream, so a block freed here
+// may be handed out again immediately.
+struct BigBlock { void *p; size_t cap; };
+static std::vector<BigBlock> g_big_free;                // cached free blocks, oldest first
+static std::unordered_map<void *, size_t> g_big_live;   // live big blocks -> capacity
+static size_t g_big_free_bytes = 0;
+constexpr size_t BIG_MIN = (size_t)32 << 20, BIG_CACHE_MAX_BYTES = (size_t)64 << 30;
+constexpr size_t BIG_CACHE_MAX_BLOCKS = 48;
+
+static void big_cache_trim(size_t max_bytes, size_t max_blocks)
+{
+    while (!g_big_free.empty() && (g_big_free_bytes > max_bytes || g_big_free.size() > max_blocks)) {
+        cudaFreeAsync(g_big_free.front().p, g_ctx.stream);
+        g_big_free_bytes -= g_big_free.front().cap;
+        g_big_free.erase(g_big_free.begin());
+    }
+}
+
 void *dalloc(size_t bytes)
 {
     void *p = nullptr;
     if (bytes == 0) bytes = 256;
+    if (bytes >= BIG_MIN) {
+        int best = -1;
+        for (size_t k = 0; k < g_big_free.size(); k++)
+            if (g_big_free[k].cap >= bytes && g_big_free[k].cap <= bytes + bytes / 2 && (best < 0 || g_big_free[k].cap < g_big_free[best].cap))
+                best = (int)k;
+        if (best >= 0) {
+            BigBlock b = g_big_free[best];
+            g_big_free.erase(g_big_free.begin() + best);
+            g_big_free_bytes -= b.cap;
+            g_big_live[b.p] = b.cap;
+            return b.p;
+        }
+    }
     cudaError_t e = cudaMallocAsync(&p, bytes, g_ctx.stream);
+    if (e != cudaSuccess && !g_big_free.empty()) {  // give the cached blocks back and retry once
+        cudaGetLastError();
+        big_cache_trim(0, 0);
+        cudaStreamSynchronize(g_ctx.stream);
+        e = cudaMallocAsync(&p, bytes, g_ctx.stream);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         set_error(TSG_ERR_NOMEM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
         return nullptr;
     }
+    if (bytes >= BIG_MIN) g_big_live[p] = bytes;
     return p;
 }
 
 void dfree(void *p)
 {
-    if (p) cudaFreeAsync(p, g_ctx.stream);
+    if (!p) return;
+    auto it = g_big_live.find(p);
+    if (it == g_big_live.end()) { cudaFreeAsync(p, g_ctx.stream); return; }
+    g_big_free.push_back(BigBlock{p, it->second});
+    g_big_free_bytes += it->second;
+    g_big_live.erase(it);
+    big_cache_trim(BIG_CACHE_MAX_BYTES, BIG_CACHE_MAX_BLOCKS);
 }
 
 bool arena_reserve(int which, size_t bytes)
@@ -187,6 +236,8 @@ void tsg_shutdown(void)
         if (g_ctx.arena[k].base) cudaFreeAsync(g_ctx.arena[k].base, g_ctx.stream);
     for (int k = 0; k < 2; k++)
         if (g_ctx.cslab[k].p) cudaFreeAsync(g_ctx.cslab[k].p, g_ctx.stream);
+    big_cache_trim(0, 0);
+    g_big_live.clear();
     cudaStreamSynchronize(g_ctx.stream);
     cudaFree(g_ctx.scan_ticket);
     cudaFree(g_ctx.d_scalars);
