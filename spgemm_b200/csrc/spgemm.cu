@@ -477,6 +477,156 @@ k_step3_gather(int numblkC, int nnzC, const int *__restrict__ blk2tile, const in
     c_col[g] = (uint16_t)c;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Step 3 for WELL-FILLED tiles (block-FEM: ~96 nonzeros per A tile, C tiles 160 on average): the
+// dense accumulator. One warp per non-empty C tile; lane = (row r = lane/2, column half h = lane%2)
+// owns the 8 entries C[r][8h..8h+7] in REGISTERS. Per pair the B tile is expanded to a dense 16x16
+// tile in shared memory (rows padded to 18 doubles: 16-byte aligned, 2-way conflicts at worst); the two
+// lanes of row r walk A's row r and, per entry (r,k,av), do 8 FMAs with B's dense row k (4 x LDS.128).
+// No masks, popcounts or atomics in the inner loop; the row is compacted through C's mask at the end.
+// Summation order per C entry: ascending A tile, then ascending k -- the serial SPA's order.
+// ---------------------------------------------------------------------------------------------
+constexpr int S3D_WARPS = 4;
+constexpr int S3D_LD = 18;
+
+__global__ void __launch_bounds__(S3D_WARPS * 32)
+k_step3_dense(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end,
+              const int *__restrict__ pair_a, const int *__restrict__ pair_b, const int *__restrict__ a_tile_nnz,
+              const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ a_col, const double *__restrict__ a_val,
+              const int *__restrict__ b_tile_nnz, const uint16_t *__restrict__ b_ptr, const uint16_t *__restrict__ b_col,
+              const double *__restrict__ b_val, const int *__restrict__ c_tile_nnz, const uint16_t *__restrict__ c_ptr,
+              const uint16_t *__restrict__ c_mask, uint16_t *__restrict__ c_col, double *__restrict__ c_val)
+{
+    __shared__ __align__(16) double Bd_s[S3D_WARPS][TS * S3D_LD];
+    const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, r = lane >> 1, h = lane & 1;
+    if (t >= numblkC) return;
+    const int cbase = c_tile_nnz[t];
+    if (c_tile_nnz[t + 1] == cbase) return;  // empty tile (warp-uniform)
+    double *Bd = Bd_s[w];
+    double acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.0;
+    const int p1 = pair_end[t];
+    for (int p = pair_ptr[t]; p < p1; p++) {
+        const int a = pair_a[p], b = pair_b[p];
+        const int abase = a_tile_nnz[a], bbase = b_tile_nnz[b];
+        // dense B tile: zero, then lanes 0..15 scatter their row
+        double2 *z = reinterpret_cast<double2 *>(Bd + r * S3D_LD + 8 * h);
+        z[0] = z[1] = z[2] = z[3] = make_double2(0.0, 0.0);
+        __syncwarp();
+        if (lane < TS) {
+            int ib = b_ptr[(size_t)b * TS + lane];
+            const int ib1 = lane < TS - 1 ? (int)b_ptr[(size_t)b * TS + lane + 1] : b_tile_nnz[b + 1] - bbase;
+            for (; ib < ib1; ib++) Bd[lane * S3D_LD + b_col[bbase + ib]] = b_val[bbase + ib];
+        }
+        __syncwarp();
+        int ia = a_ptr[(size_t)a * TS + r];
+        const int ia1 = r < TS - 1 ? (int)a_ptr[(size_t)a * TS + r + 1] : a_tile_nnz[a + 1] - abase;
+        for (; ia < ia1; ia++) {
+            const int k = a_col[abase + ia] & 15;  // A stores row*16+col
+            const double av = a_val[abase + ia];
+            const double2 *br = reinterpret_cast<const double2 *>(Bd + k * S3D_LD + 8 * h);
+            const double2 b0 = br[0], b1 = br[1], b2 = br[2], b3 = br[3];
+            acc[0] = fma(av, b0.x, acc[0]); acc[1] = fma(av, b0.y, acc[1]);
+            acc[2] = fma(av, b1.x, acc[2]); acc[3] = fma(av, b1.y, acc[3]);
+            acc[4] = fma(av, b2.x, acc[4]); acc[5] = fma(av, b2.y, acc[5]);
+            acc[6] = fma(av, b3.x, acc[6]); acc[7] = fma(av, b3.y, acc[7]);
+        }
+        __syncwarp();  // Bd is rewritten for the next pair
+    }
+    const unsigned cm = c_mask[(size_t)t * TS + r];
+    const int rowbase = cbase + c_ptr[(size_t)t * TS + r];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int c = 8 * h + j;
+        if (cm & (0x8000u >> c)) {
+            const int pos = rowbase + __popc(cm >> (16 - c));
+            c_val[pos] = acc[j];
+            c_col[pos] = (uint16_t)c;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Step 3, FP64 tensor-core experiment (BASELINE north_star: "DMMA only for near-dense tile pairs, and
+// only if ncu shows they beat the CUDA-core path"). Same work split as k_step3_dense, but BOTH tiles of
+// a pair are expanded to dense 16x16 tiles in shared memory and the 16x16x16 product is issued as
+// 2x2 output blocks x 4 k-steps = 16 mma.sync.m8n8k4.f64 (SASS: DMMA); the 8 accumulators per lane are
+// the C fragments. (tcgen05 has no FP64 kind, so this is the only tensor-core path FP64 has.)
+// Selected with TSG_STEP3=dmma; the measured outcome is recorded in profiles/README.md.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(S3D_WARPS * 32)
+k_step3_dmma(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end,
+             const int *__restrict__ pair_a, const int *__restrict__ pair_b, const int *__restrict__ a_tile_nnz,
+             const uint16_t *__restrict__ a_col, const double *__restrict__ a_val, const int *__restrict__ b_tile_nnz,
+             const uint16_t *__restrict__ b_ptr, const uint16_t *__restrict__ b_col, const double *__restrict__ b_val,
+             const int *__restrict__ c_tile_nnz, const uint16_t *__restrict__ c_ptr, const uint16_t *__restrict__ c_mask,
+             uint16_t *__restrict__ c_col, double *__restrict__ c_val)
+{
+    __shared__ __align__(16) double AB_s[S3D_WARPS][2][TS * S3D_LD];
+    const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3;
+    if (t >= numblkC) return;
+    const int cbase = c_tile_nnz[t];
+    if (c_tile_nnz[t + 1] == cbase) return;  // empty tile (warp-uniform)
+    double *Ad = AB_s[w][0], *Bd = AB_s[w][1];
+    double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c10[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+    const int p1 = pair_end[t];
+    for (int p = pair_ptr[t]; p < p1; p++) {
+        const int a = pair_a[p], b = pair_b[p];
+        const int abase = a_tile_nnz[a], aend = a_tile_nnz[a + 1], bbase = b_tile_nnz[b];
+        double2 *z = reinterpret_cast<double2 *>(AB_s[w][0]);
+        for (int k = lane; k < 2 * TS * S3D_LD / 2; k += 32) z[k] = make_double2(0.0, 0.0);
+        __syncwarp();
+        for (int e = abase + lane; e < aend; e += 32) {
+            const unsigned col = a_col[e];  // row*16+col
+            Ad[(col >> 4) * S3D_LD + (col & 15)] = a_val[e];
+        }
+        if (lane < TS) {
+            int ib = b_ptr[(size_t)b * TS + lane];
+            const int ib1 = lane < TS - 1 ? (int)b_ptr[(size_t)b * TS + lane + 1] : b_tile_nnz[b + 1] - bbase;
+            for (; ib < ib1; ib++) Bd[lane * S3D_LD + b_col[bbase + ib]] = b_val[bbase + ib];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {
+            const double a0 = Ad[g * S3D_LD + 4 * ks + tg], a1 = Ad[(8 + g) * S3D_LD + 4 * ks + tg];
+            const double b0 = Bd[(4 * ks + tg) * S3D_LD + g], b1 = Bd[(4 * ks + tg) * S3D_LD + 8 + g];
+            dmma_m8n8k4(c00[0], c00[1], a0, b0);
+            dmma_m8n8k4(c01[0], c01[1], a0, b1);
+            dmma_m8n8k4(c10[0], c10[1], a1, b0);
+            dmma_m8n8k4(c11[0], c11[1], a1, b1);
+        }
+        __syncwarp();
+    }
+    // fragment (i,j) holds C[8i+g][8j+2tg+{0,1}]
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int R = 8 * i + g;
+        const unsigned cm = c_mask[(size_t)t * TS + R];
+        const int rowbase = cbase + c_ptr[(size_t)t * TS + R];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int c = 8 * j + 2 * tg + q;
+                if (cm & (0x8000u >> c)) {
+                    const int pos = rowbase + __popc(cm >> (16 - c));
+                    c_val[pos] = i == 0 ? (j == 0 ? c00[q] : c01[q]) : (j == 0 ? c10[q] : c11[q]);
+                    c_col[pos] = (uint16_t)c;
+                }
+            }
+        }
+    }
+}
+
 // row-major tile index -> CSC storage id for a B uploaded from a host SMatrix (csr2tile_device
 // fills rm2csc itself). One thread per stored tile: binary search its column in its tile-row.
 __global__ void k_build_rm2csc(int tilen, const int *__restrict__ csc_tile_ptr, const int *__restrict__ csc_tile_rowidx,
@@ -721,10 +871,24 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     cudaEvent_t ev_s3;
     CK(cudaEventCreate(&ev_s3));
     CK(cudaEventRecord(ev_s3, c.stream));
-    int *blk2tile = nullptr;
-    if (nnzC > 0) {
+    // numeric kernel: the dense accumulator (warp per C tile) when tiles are well filled -- A tiles hold >= 24
+    // nonzeros on average (block-FEM: 96) -- else the gather (lane per C nonzero). TSG_STEP3=dense|gather overrides.
+    static const char *s3_force = getenv("TSG_STEP3");
+    bool dense = A->nnz >= 24ll * A->numtile;
+    if (s3_force) dense = !strcmp(s3_force, "dense");
+    if (nnzC > 0 && s3_force && !strcmp(s3_force, "dmma")) {  // FP64 tensor-core experiment, never chosen automatically
+        k_step3_dmma<<<ceil_div(numblkC * 32, S3D_WARPS * 32), S3D_WARPS * 32, 0, c.stream>>>(
+            (int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->tile_nnz, A->col, A->val, B->tile_nnz, B->ptr, B->col, B->val, C->tile_nnz,
+            C->ptr, C->mask, C->col, C->val);
+        CK_LAUNCH();
+    } else if (nnzC > 0 && dense) {
+        k_step3_dense<<<ceil_div(numblkC * 32, S3D_WARPS * 32), S3D_WARPS * 32, 0, c.stream>>>(
+            (int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->tile_nnz, A->ptr, A->col, A->val, B->tile_nnz, B->ptr, B->col, B->val,
+            C->tile_nnz, C->ptr, C->mask, C->col, C->val);
+        CK_LAUNCH();
+    } else if (nnzC > 0) {
         if (!arena_reserve(2, arena_need((size_t)((nnzC + 31) >> 5) + 1, 4))) return last_error();
-        blk2tile = arena_take<int>(2, (size_t)((nnzC + 31) >> 5) + 1);
+        int *blk2tile = arena_take<int>(2, (size_t)((nnzC + 31) >> 5) + 1);
         if (!blk2tile) return last_error();
         k_blk2tile<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>((int)numblkC, C->tile_nnz, blk2tile);
         CK_LAUNCH();
