@@ -80,3 +80,21 @@ def test_two_rank_concatenation_equals_whole():
     assert np.array_equal(np.concatenate([res[0][6][:-1], res[1][6]]), tC.tile_nnz)
     assert np.array_equal(np.concatenate([res[0][7][:-1], res[1][7]]), tC.tile_ptr)
     assert res[0][8][:, 0].sum() == tC.numtile and res[0][8][:, 1].sum() == tC.nnz
+
+
+def test_slab_planner():
+    """api.plan_slabs: contiguous slabs covering all tile-rows, each within the pair budget unless a single
+    tile-row alone exceeds it (then that tile-row is a slab of its own)."""
+    from spgemm_b200 import api
+    rng = np.random.default_rng(1)
+    w = rng.integers(0, 500, 3000)
+    w[100] = 50000  # hub tile-row heavier than the budget
+    slabs = api.plan_slabs(w, 4000)
+    assert slabs[0][0] == 0 and slabs[-1][1] == len(w)
+    assert all(a[1] == b[0] for a, b in zip(slabs[:-1], slabs[1:]))
+    for t0, t1 in slabs:
+        s = int(w[t0:t1].sum())
+        assert s <= 4000 or t1 - t0 == 1 or int(w[t0:t1 - 1].sum()) <= 4000
+    assert (100, 101) in slabs or any(t0 <= 100 < t1 and int(w[t0:t1].sum()) - 50000 <= 4000 for t0, t1 in slabs)
+    assert api.plan_slabs(np.zeros(5, np.int64), 10) == [(0, 5)]
+    assert api.plan_slabs(np.zeros(0, np.int64), 10) == []
