@@ -30,6 +30,7 @@ k_tile2csr(int m, int tilem, const int *__restrict__ tile_ptr, const int *__rest
     const int t1 = tile_ptr[I + 1];
     for (int t = tile_ptr[I]; t < t1; t++) {
         const int base = tile_nnz[t], tnnz = tile_nnz[t + 1] - base;
+        if (tnnz == 0) continue;  // empty C tiles are legitimate (and 15/16 of them on hypersparse inputs): nothing to read
         const int p0 = ptr[(size_t)t * TS + r];
         const int p1 = r < TS - 1 ? (int)ptr[(size_t)t * TS + r + 1] : tnnz;
         if (FILL) {
@@ -64,6 +65,7 @@ k_tile_rowsums(int m, int tilem, const int *__restrict__ tile_ptr, const int *__
     const int t1 = tile_ptr[I + 1];
     for (int t = tile_ptr[I]; t < t1; t++) {
         const int base = tile_nnz[t], tnnz = tile_nnz[t + 1] - base;
+        if (tnnz == 0) continue;
         const int p0 = ptr[(size_t)t * TS + r];
         const int p1 = r < TS - 1 ? (int)ptr[(size_t)t * TS + r + 1] : tnnz;
         for (int j = p0; j < p1; j++) s += val[base + j];
