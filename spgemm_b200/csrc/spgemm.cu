@@ -15,17 +15,21 @@
 //   * Step 2 (C's row masks, Ptr, tile nnz) is FUSED into step 1 on the one-warp path: while the warp
 //     enumerates the B tiles paired with one A tile, A's row masks are warp-uniform, so the 16x16x16
 //     boolean product of up to 32 pairs costs one shared-memory load + OR per A entry. Tile-rows on
-//     the multi-warp path (and matrices whose B tile-rows are too short to fill a warp) use k_step2:
-//     half-warp per C tile, lane r ORs B's row masks (fetched by shuffle) selected by A's row mask r.
-//   * Step 3 is a GATHER: one lane per C nonzero, register accumulation in the serial SPA's summation
-//     order, no atomics, no accumulator memory, coalesced stores. The reference does one global
-//     atomicAdd per product plus a binary search (:1450,1558,1795,1900).
+//     the multi-warp path (and matrices whose B tile-rows are too short to fill a warp) use k_step2
+//     (half-warp per C tile, lane r ORs B's row masks, fetched by shuffle, selected by A's row mask r) or,
+//     for hypersparse tiles, k_step2_thread (one thread per C tile).
+//   * Step 3 has two kernels, chosen per call from the average fill of A's tiles: a GATHER (one lane per C
+//     nonzero, register accumulation in the serial SPA's summation order, no accumulator memory, coalesced
+//     stores) for sparse tiles, and a DENSE ACCUMULATOR (warp per C tile, 8 register accumulators per lane,
+//     the B tile expanded in shared memory) for well-filled tiles (block-FEM). Neither uses atomics; the
+//     reference does one global atomicAdd per product plus a binary search (:1450,1558,1795,1900).
+//     k_step3_dmma is the FP64 tensor-core (mma.sync m8n8k4) variant of the dense kernel, opt-in.
 //   * Empty C tiles are kept with Ptr = mask = 0 and nnz 0 (the reference leaves them
 //     uninitialised).
 //   * Scratch lives in grow-only arenas; sizes are read back three times (pairs/window, numblkC, nnzC).
 // Superseded kernels measured on the way (half-warp-per-tile numeric with a shared-memory accumulator,
-// "rounds" numeric, flattened / half-warp-per-pair symbolic, tile-row-per-warp numeric) are described in
-// profiles/README.md and kept as text under scratch/.
+// "rounds" numeric, flattened / half-warp-per-pair symbolic, tile-row-per-warp numeric, prefetching variants)
+// are described in profiles/README.md; some are kept as text under scratch/.
 #include "common.cuh"
 #include "scan.cuh"
 #include "kernels.h"
@@ -118,7 +122,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total)
 // ---------------------------------------------------------------------------------------------
 // Step 1b/1c: one CTA per C tile-row. MODE 0 counts the distinct tile columns. MODE 1 emits the
 // sorted tile-column list, and per C tile the matched (A tile, B tile) pair list.
-// THREADS = 32 handles rows with w in (0, S1_LIGHT_MAX]; THREADS = 256 the heavier ones.
+// THREADS = 32 handles rows with w in (0, S1_LIGHT_MAX]; THREADS = S1_HEAVY_THREADS the heavier ones.
 // Dynamic smem: bitmap[nw_max] | pre8[nw_max/8 + 1] | (fused symbolic) bmT[8][32] u32 | cm[16][numJ_pad] u16.
 //
 // Fused bitmask symbolic (step 2) on the one-warp path: while the warp enumerates the pairs of A tile
