@@ -426,17 +426,15 @@ __global__ void k_blk2tile(int numblkC, const int *__restrict__ c_tile_nnz, int 
     for (int blk = (s + 31) >> 5; (blk << 5) < e; blk++) blk2tile[blk] = t;
 }
 
-__global__ void __launch_bounds__(256)
-k_step3_gather(int numblkC, int nnzC, const int *__restrict__ blk2tile, const int *__restrict__ pair_ptr,
-               const int *__restrict__ pair_end, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
-               const int *__restrict__ a_tile_nnz, const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ a_col,
-               const double *__restrict__ a_val, const int *__restrict__ b_tile_nnz, const uint16_t *__restrict__ b_ptr,
-               const uint16_t *__restrict__ b_mask, const double *__restrict__ b_val, const int *__restrict__ c_tile_nnz,
-               const uint16_t *__restrict__ c_ptr, const uint16_t *__restrict__ c_mask, uint16_t *__restrict__ c_col,
-               double *__restrict__ c_val)
+__device__ __forceinline__ void
+s3_gather_one(int g, int numblkC, int nnzC, const int *__restrict__ blk2tile, const int *__restrict__ pair_ptr,
+              const int *__restrict__ pair_end, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
+              const int *__restrict__ a_tile_nnz, const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ a_col,
+              const double *__restrict__ a_val, const int *__restrict__ b_tile_nnz, const uint16_t *__restrict__ b_ptr,
+              const uint16_t *__restrict__ b_mask, const double *__restrict__ b_val, const int *__restrict__ c_tile_nnz,
+              const uint16_t *__restrict__ c_ptr, const uint16_t *__restrict__ c_mask, uint16_t *__restrict__ c_col,
+              double *__restrict__ c_val)
 {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= nnzC) return;
     const int blk = g >> 5, nblk = (nnzC + 31) >> 5;
     int lo = blk2tile[blk], hi = blk + 1 < nblk ? blk2tile[blk + 1] : numblkC - 1;
     while (lo < hi) {  // largest tile t in [lo,hi] with tile_nnz[t] <= g (it is non-empty and holds g)
@@ -479,6 +477,32 @@ k_step3_gather(int numblkC, int nnzC, const int *__restrict__ blk2tile, const in
     }
     c_val[g] = acc;
     c_col[g] = (uint16_t)c;
+}
+
+// CHUNKED = false: one nonzero per thread (straight-line code, 32 registers), blocks balanced by the hardware scheduler.
+// CHUNKED = true: a CTA walks `chunk` consecutive nonzeros (a few C tile-rows), so that the A tiles they share stay in
+// its SM's L1; used when the work per nonzero is even (no heavy tile-rows) and the grid stays large.
+template <bool CHUNKED>
+__global__ void __launch_bounds__(256)
+k_step3_gather(int chunk, int numblkC, int nnzC, const int *__restrict__ blk2tile, const int *__restrict__ pair_ptr,
+               const int *__restrict__ pair_end, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
+               const int *__restrict__ a_tile_nnz, const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ a_col,
+               const double *__restrict__ a_val, const int *__restrict__ b_tile_nnz, const uint16_t *__restrict__ b_ptr,
+               const uint16_t *__restrict__ b_mask, const double *__restrict__ b_val, const int *__restrict__ c_tile_nnz,
+               const uint16_t *__restrict__ c_ptr, const uint16_t *__restrict__ c_mask, uint16_t *__restrict__ c_col,
+               double *__restrict__ c_val)
+{
+    if (!CHUNKED) {
+        const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (g < nnzC)
+            s3_gather_one((int)g, numblkC, nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b, a_tile_nnz, a_ptr, a_col, a_val, b_tile_nnz,
+                          b_ptr, b_mask, b_val, c_tile_nnz, c_ptr, c_mask, c_col, c_val);
+        return;
+    }
+    const long long cend = min((long long)nnzC, ((long long)blockIdx.x + 1) * chunk);
+    for (long long g = (long long)blockIdx.x * chunk + threadIdx.x; g < cend; g += blockDim.x)
+        s3_gather_one((int)g, numblkC, nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b, a_tile_nnz, a_ptr, a_col, a_val, b_tile_nnz,
+                      b_ptr, b_mask, b_val, c_tile_nnz, c_ptr, c_mask, c_col, c_val);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -896,7 +920,14 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         if (!blk2tile) return last_error();
         k_blk2tile<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>((int)numblkC, C->tile_nnz, blk2tile);
         CK_LAUNCH();
-        k_step3_gather<<<ceil_div(nnzC, 256), 256, 0, c.stream>>>((int)numblkC, (int)nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b,
+        // consecutive nonzeros per CTA: 8192 when the work per nonzero is even (no heavy tile-rows) and there are
+        // enough of them to keep >= 16 CTAs per SM busy; otherwise one 256-thread pass, balanced by the block scheduler
+        int chunk = 256;
+        if (wmax_seen <= S1_LIGHT_MAX && nnzC >= (long long)c.num_sms * 16 * 8192) chunk = 8192;
+        static const int chunk_env = getenv("TSG_GATHER_CHUNK") ? atoi(getenv("TSG_GATHER_CHUNK")) : 0;
+        if (chunk_env >= 256) chunk = chunk_env;
+        auto kern = chunk > 256 ? k_step3_gather<true> : k_step3_gather<false>;
+        kern<<<ceil_div(nnzC, chunk), 256, 0, c.stream>>>(chunk, (int)numblkC, (int)nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b,
                                                                   A->tile_nnz, A->ptr, A->col, A->val, B->tile_nnz, B->ptr, B->mask,
                                                                   B->val, C->tile_nnz, C->ptr, C->mask, C->col, C->val);
         CK_LAUNCH();
