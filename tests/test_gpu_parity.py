@@ -369,3 +369,25 @@ def test_c_driver_cli(tmp_path):
         assert len(open(tmp_path / name).read().strip().splitlines()) == 3
     bad = subprocess.run([exe, "-d", "0", "-aat", "0", str(mtx), "32", "32"], capture_output=True, text=True, env=env, timeout=60)
     assert bad.returncode != 0  # unsupported tile size: the driver exits non-zero instead of printing garbage
+
+
+def test_hypersparse_rmat_a2_matches_oracle():
+    """Config 5 in miniature: R-MAT with mild skew, C = A^2. Tiles hold ~1 nonzero, so most listed C tiles are EMPTY
+    (tile-level hit, element-level miss) and must still be listed with Ptr = mask = 0; exercises the thread-per-tile
+    symbolic (k_step2_thread) and the 1024-thread step-1 path."""
+    m, n, rp, ci, v = M.rmat(16, 2, a=0.30, b=0.25, c=0.25, d=0.20, seed=2)
+    A = (rp, ci, v)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
+    assert tA.nnz <= 2 * tA.numtile                                  # hypersparse tiles
+    csrC, tC_exp = oracle_c(m, n, A, A, n)
+    empty = int((np.diff(tC_exp.tile_nnz) == 0).sum())
+    assert empty > tC_exp.numtile // 2, (empty, tC_exp.numtile)       # most C tiles are empty
+    tC, st = api.spgemm(tA, tB)
+    assert st["pairs"] <= 2 * st["numblkC"]
+    assert_tiled_equal(tC.download(), tC_exp, "hypersparse C")
+    csr = api.tile2csr_device(tC)
+    r, c, vv = csr.download()
+    assert np.array_equal(r, csrC[0]) and np.array_equal(c, csrC[1]) and np.array_equal(vv, csrC[2])
+    for o in (csr, tC, tA, tB, d):
+        o.free()
