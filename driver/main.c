@@ -93,6 +93,7 @@ static int load_mtx(const char *path, SMatrix *A)
     }
     fclose(f);
     coo_to_csr(m, n, cnt, e, A);
+    A->isSymmetric = symmetric;  /* like mmio_allinone (src/mmio_highlevel.h) */
     free(e);
     return 0;
 }
@@ -225,6 +226,10 @@ int main(int argc, char **argv)
     printf("the tile_size_m = %d\nthe tile_size_n = %d\n", tile_size_m, tile_size_n);
     for (int i = 0; i < matrixA->nnz; i++) matrixA->value[i] = i % 10;       /* main.cu:111-112 */
 
+    if (aat && matrixA->m == matrixA->n && matrixA->isSymmetric) {           /* main.cu:120-124 */
+        printf("matrix AAT does not do symmetric matrix. Exit.\n");
+        return 0;
+    }
     if (aat) {                                                               /* main.cu:114-142 */
         matrixB->m = matrixA->n; matrixB->n = matrixA->m; matrixB->nnz = matrixA->nnz;
         matrixB->rowpointer = (int *)malloc(((size_t)matrixA->n + 1) * sizeof(int));
