@@ -136,6 +136,7 @@ struct S1Fuse {
     uint16_t *c_ptr, *c_mask;
     int *c_cnt;
     int numJ_pad;  // 0: not fused (k_step2 computes the masks from the pair lists)
+    int4 *tmp;     // multi-warp path: one (slot, rank in slot, A tile, B tile) record per pair of the slab, or nullptr
 };
 
 template <int THREADS, int MODE>
@@ -219,6 +220,66 @@ k_step1(int trow0, int nw_max, int wmin, int wmax, const int *__restrict__ a_til
                 bits &= bits - 1;
             }
         }
+    }
+    if (THREADS > 32 && fz.tmp) {
+        // Multi-warp path, ONE expansion and ONE global atomic per pair: the atomicAdd that counts the pairs of a C tile
+        // also returns the pair's rank inside the tile's list; (slot, rank, A tile, B tile) is parked in a per-row
+        // scratch record, the counts are scanned, and the records are then placed -- without walking B's structure,
+        // recomputing slots or touching the counters a second time (global atomics bound this path on R-MAT).
+        if (tid == 0) s_carry = 0;
+        __syncthreads();
+        const unsigned lt = (1u << lane) - 1;
+        int4 *tmp = fz.tmp + wptr[i];
+        for (int ta = a0 + warp; ta < a1; ta += NWARPS) {
+            const int K = a_tile_col[ta];
+            const int b0 = b_tile_ptr[K], b1 = b_tile_ptr[K + 1];
+            for (int tb0 = b0; tb0 < b1; tb0 += 32) {
+                const int tb = tb0 + lane;
+                const bool valid = tb < b1;
+                int slot = 0, off = 0;
+                if (valid) {
+                    slot = s1_rank(bitmap, pre8, b_tile_col[tb] - lo);
+                    off = atomicAdd(&pair_end[cbase + slot], 1);
+                }
+                const unsigned mask = __ballot_sync(FULL_MASK, valid);  // lane 0 is always valid
+                const int leader = __ffs(mask) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&s_carry, __popc(mask));
+                base = __shfl_sync(FULL_MASK, base, leader);
+                if (valid) tmp[base + __popc(mask & lt)] = make_int4(slot, off, ta, b_rm2csc[tb]);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_carry = wptr[i];
+        __syncthreads();
+        for (int s0 = 0; s0 < numJ; s0 += THREADS) {  // counts -> [pair_ptr, pair_end)
+            int sidx = s0 + tid;
+            int v = sidx < numJ ? pair_end[cbase + sidx] : 0, total;
+            int ex = block_excl_scan<THREADS>(v, s_warp, &total);
+            int carry = s_carry;
+            if (sidx < numJ) { pair_ptr[cbase + sidx] = carry + ex; pair_end[cbase + sidx] = carry + ex + v; }
+            __syncthreads();
+            if (tid == 0) s_carry = carry + total;
+            __syncthreads();
+        }
+        for (int e = tid; e < wi; e += THREADS) {
+            const int4 rec = tmp[e];
+            const int pos = pair_ptr[cbase + rec.x] + rec.y;
+            pair_a[pos] = rec.z;
+            pair_b[pos] = rec.w;
+        }
+        __syncthreads();
+        for (int sidx = tid; sidx < numJ; sidx += THREADS) {  // arrival order -> ascending A tile for short lists
+            int b = pair_ptr[cbase + sidx], e = pair_end[cbase + sidx], len = e - b;
+            if (len > 1 && len <= S1_SORT_MAX) {
+                for (int x = b + 1; x < e; x++) {
+                    int ka = pair_a[x], kb = pair_b[x], y = x - 1;
+                    while (y >= b && pair_a[y] > ka) { pair_a[y + 1] = pair_a[y]; pair_b[y + 1] = pair_b[y]; y--; }
+                    pair_a[y + 1] = ka; pair_b[y + 1] = kb;
+                }
+            }
+        }
+        return;
     }
     // pair counts per C tile (pair_end is zero on entry)
     for (int ta = a0 + warp; ta < a1; ta += NWARPS) {
@@ -789,7 +850,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     }
     if (ntr > 0 && pairs > 0) {
         rc = launch_step1<0>(ntr, trow0, nw_max, wmax_seen, A, B, w, jlo, jhi, c_tile_ptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                             nullptr, nullptr, nullptr, scal + 3, S1Fuse{nullptr, nullptr, nullptr, nullptr, nullptr, 0});
+                             nullptr, nullptr, nullptr, scal + 3, S1Fuse{nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr});
         if (rc) return rc;
     }
     rc = exclusive_scan<long long>(c_tile_ptr, numblk64, ntr);
@@ -830,16 +891,19 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         C->m = (int)(r1 > r0 ? r1 - r0 : 0);
     }
     CK(cudaMemcpyAsync(C->tile_ptr, c_tile_ptr, ((size_t)ntr + 1) * 4, cudaMemcpyDeviceToDevice, c.stream));
-    if (!arena_reserve(1, 2 * arena_need(nb + 1, 4) + 2 * arena_need(np, 4) + arena_need(nb + 1, 8))) return last_error();
+    const bool heavy_rows = wmax_seen > S1_LIGHT_MAX;  // tile-rows on the multi-warp path park one 16-byte record per pair
+    if (!arena_reserve(1, 2 * arena_need(nb + 1, 4) + 2 * arena_need(np, 4) + arena_need(nb + 1, 8) + (heavy_rows ? arena_need(np, 16) : 0)))
+        return last_error();
     int *pair_ptr = arena_take<int>(1, nb + 1), *pair_end = arena_take<int>(1, nb + 1), *pair_a = arena_take<int>(1, np), *pair_b = arena_take<int>(1, np);
     long long *nnz64 = arena_take<long long>(1, nb + 1);
-    if (!pair_ptr || !pair_end || !pair_a || !pair_b || !nnz64) return last_error();
+    int4 *pair_tmp = heavy_rows ? arena_take<int4>(1, np) : nullptr;
+    if (!pair_ptr || !pair_end || !pair_a || !pair_b || !nnz64 || (heavy_rows && !pair_tmp)) return last_error();
     CK(cudaMemsetAsync(pair_end, 0, nb * 4, c.stream));
     CK(cudaEventRecord(ev[2], c.stream));  // [1..2] = allocation
     // the one-warp step-1 path also produces C's masks / Ptr / tile nnz (fused step 2) when the tile-row's
     // masks fit shared memory; TSG_FUSE=0 disables the fusion (A/B measurements)
     static const int fuse_env = getenv("TSG_FUSE") ? atoi(getenv("TSG_FUSE")) : -1;
-    S1Fuse fz{A->mask, B->mask, C->ptr, C->mask, C->tile_nnz, 0};
+    S1Fuse fz{A->mask, B->mask, C->ptr, C->mask, C->tile_nnz, 0, pair_tmp};
     {
         size_t need = ((size_t)nw_max + (size_t)nw_max / 8 + 2) * 4 + 8 * 32 * 4 + (size_t)(maxJ_light + 1) * TS * 2 + 4;
         // worthwhile only when B's tile-rows are long enough to fill the lanes (>= 4 tiles per tile-row on average;
