@@ -7,7 +7,8 @@
 A "step" is one pass of SpGEMM steps 1-3 (tile-level symbolic, bitmask symbolic, numeric) over the
 workload with the tiled A and B already resident in HBM (`value`). `e2e` is the same metric measured
 through the public API from HOST buffers: H2D of CSR(A) from pinned memory, csr2tile of A and B,
-steps 1-3, tile2csr, D2H of CSR(C) into pinned memory, all inside the timed region.
+steps 1-3, tile2csr, D2H of CSR(C) into pinned memory, all inside the timed region (C leaves the
+device slab by slab, the copy of one slab overlapping the computation of the next: tsg_spgemm_to_host).
 
 N > 1: C tile-rows are partitioned across the ranks (contiguous ranges balanced by the step-1
 weight); B is tiled once on rank 0 and broadcast as one buffer over NCCL; each rank computes its C
@@ -319,10 +320,9 @@ def run_ours(args):
             b, tb = a, tB
         if slab_pairs:
             api.spgemm_slabs(ta, tb, max_pairs=slab_pairs, sink=land)
-        else:
-            tc, _ = api.spgemm(ta, tb)
-            land(tc)
-            tc.free()
+        else:  # C leaves the device slab by slab, each copy overlapping the next slab's computation
+            api.spgemm_to_host(ta, tb, out_pin[0].data_ptr(), out_pin[1].data_ptr(), out_pin[2].data_ptr(), buf_nnz,
+                               nslabs=args.e2e_slabs)
         ta.free()
         if world == 1:
             tb.free()
@@ -420,6 +420,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=3, help="timed end-to-end steps (each moves GBs over PCIe)")
+    ap.add_argument("--e2e-slabs", type=int, default=0, help="slabs of the overlapped end-to-end call (0 = library default)")
     ap.add_argument("--ref-rows", type=int, default=1 << 17, help="--impl reference: rows of A in the bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

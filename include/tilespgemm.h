@@ -233,6 +233,24 @@ int tsg_spgemm_csr_host(int m, int k, int n, const int *a_rowptr, const int *a_c
                         const int *b_rowptr, const int *b_colidx, const double *b_val, int aat,
                         int **c_rowptr, int **c_colidx, double **c_val, long long *c_nnz, tsg_stats *stats);
 
+/* Steps 1-3 + tile2csr + D2H for C tile-rows [trow0, trow1) of A*B, overlapped: the range is cut into
+ * nslabs slabs of about equal step-1 weight (nslabs <= 0: up to 16, each >= 2^20 tile pairs and <= 2^28),
+ * and the CSR of slab s is copied to the host on a second stream while slab s+1 is computed (the path is
+ * PCIe-bound: 12 bytes per C nonzero leave the device). Output goes to CALLER buffers -- page-locked
+ * memory for the copies to overlap: c_rowptr holds rows+1 entries (rows = rows of the range, numbered
+ * from 0), c_colidx / c_val hold c_cap entries. *c_nnz = nnz(C) of the range. If c_cap is too small the
+ * call still counts, sets *c_nnz to the capacity needed and returns TSG_ERR_NOMEM; TSG_ERR_OVERFLOW when
+ * nnz(C) >= 2^31 (the reference's CSR, src/tile2csr.h:72, has 32-bit row pointers too). stats (may be
+ * NULL) are summed over the slabs. */
+int tsg_spgemm_to_host(const tsg_dtile *a, const tsg_dtile *b, int trow0, int trow1, int nslabs, int *c_rowptr,
+                       int *c_colidx, double *c_val, long long c_cap, long long *c_nnz, tsg_stats *stats);
+
+/* tsg_spgemm_csr_host with caller-provided output buffers and the overlap above: H2D CSR(A) [CSR(B)],
+ * csr2tile x2, then tsg_spgemm_to_host over all tile-rows. */
+int tsg_spgemm_csr_host_into(int m, int k, int n, const int *a_rowptr, const int *a_colidx, const double *a_val,
+                             const int *b_rowptr, const int *b_colidx, const double *b_val, int aat, int *c_rowptr,
+                             int *c_colidx, double *c_val, long long c_cap, long long *c_nnz, tsg_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -363,6 +363,43 @@ def spgemm_slabs(a: DeviceTiled, b: DeviceTiled, max_pairs: int = 1 << 28, sink=
     return tot, per
 
 
+def spgemm_to_host(a: DeviceTiled, b: DeviceTiled, rowptr_addr: int, colidx_addr: int, val_addr: int, cap: int,
+                   nslabs: int = 0, trow0: int = 0, trow1: int = -1):
+    """Steps 1-3 + tile2csr + D2H for C tile-rows [trow0, trow1), slab by slab with the copy of one slab
+    overlapping the computation of the next (include/tilespgemm.h: tsg_spgemm_to_host). The three addresses
+    are HOST buffers (pinned for the overlap): rows+1 int32, `cap` int32, `cap` float64. Returns
+    (nnz, stats dict); raises TsgError (code TSG_ERR_NOMEM, message naming the size needed) if cap is too small."""
+    nnz = C.c_longlong(0)
+    st = L.Stats()
+    L.check(L.load().tsg_spgemm_to_host(C.byref(a.d), C.byref(b.d), int(trow0), int(trow1), int(nslabs), C.c_void_p(rowptr_addr),
+                                        C.c_void_p(colidx_addr), C.c_void_p(val_addr), C.c_longlong(int(cap)), C.byref(nnz),
+                                        C.byref(st)))
+    return nnz.value, st.as_dict()
+
+
+def spgemm_csr_host_into(m, k, n, A, out, B=None, aat=False):
+    """Host CSR in -> host CSR out into caller arrays, overlapped (tsg_spgemm_csr_host_into). A, B = (rowptr, colidx, val);
+    out = (rowptr int32[m+1], colidx int32[cap], val float64[cap]) numpy arrays (pinned memory for full PCIe speed).
+    Returns (nnz, stats dict)."""
+    rpA, ciA, vA = (np.ascontiguousarray(A[0], np.int32), np.ascontiguousarray(A[1], np.int32),
+                    np.ascontiguousarray(A[2], np.float64))
+    if B is not None:
+        rpB, ciB, vB = (np.ascontiguousarray(B[0], np.int32), np.ascontiguousarray(B[1], np.int32),
+                        np.ascontiguousarray(B[2], np.float64))
+        bargs = (_p(rpB, C.c_int), _p(ciB, C.c_int), _p(vB, C.c_double))
+    else:
+        bargs = (None, None, None)
+    orp, oci, ov = out
+    assert orp.dtype == np.int32 and oci.dtype == np.int32 and ov.dtype == np.float64 and orp.size >= m + 1
+    cap = min(oci.size, ov.size)
+    nnz = C.c_longlong(0)
+    st = L.Stats()
+    L.check(L.load().tsg_spgemm_csr_host_into(int(m), int(k), int(n), _p(rpA, C.c_int), _p(ciA, C.c_int), _p(vA, C.c_double),
+                                              *bargs, int(bool(aat)), _p(orp, C.c_int), _p(oci, C.c_int), _p(ov, C.c_double),
+                                              C.c_longlong(int(cap)), C.byref(nnz), C.byref(st)))
+    return nnz.value, st.as_dict()
+
+
 def spgemm_csr_host(m, k, n, A, B=None, aat=False):
     """Whole pipeline, host CSR in -> host CSR out. A, B = (rowptr, colidx, val); B=None means B=A
     (or A^T with aat=True). Returns (rowptr, colidx, val, stats dict)."""

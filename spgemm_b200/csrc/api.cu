@@ -156,19 +156,48 @@ void cslab_give(int which, void *p, size_t cap)
     }
 }
 
+__global__ void k_publish(const int *__restrict__ src, int *__restrict__ dst, int nwords)
+{
+    if ((int)threadIdx.x < nwords) dst[threadIdx.x] = src[threadIdx.x];
+}
+
+int publish_words(void *h_dst, const void *d_src, int nwords)
+{
+    int *dst = (int *)((char *)g_ctx.h_scalars_dev + ((char *)h_dst - (char *)g_ctx.h_scalars));
+    k_publish<<<1, 32, 0, g_ctx.stream>>>((const int *)d_src, dst, nwords);
+    CK_LAUNCH();
+    return TSG_OK;
+}
+
+__global__ void k_copy_words(const int *__restrict__ src, int *__restrict__ dst, size_t nwords)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+int copy_words(void *d_dst, const void *d_src, size_t nwords)
+{
+    if (!nwords) return TSG_OK;
+    const size_t blocks = (nwords + 255) / 256;
+    k_copy_words<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, g_ctx.stream>>>((const int *)d_src, (int *)d_dst, nwords);
+    CK_LAUNCH();
+    return TSG_OK;
+}
+
 int read_back_i32(const int *d, int *out)
 {
-    CK(cudaMemcpyAsync(&g_ctx.h_scalars[15], d, sizeof(int), cudaMemcpyDeviceToHost, g_ctx.stream));
+    int rc = publish_words(&g_ctx.h_scalars[15], d, 1);
+    if (rc) return rc;
     CK(cudaStreamSynchronize(g_ctx.stream));
-    *out = *(const int *)&g_ctx.h_scalars[15];
+    *out = *(const volatile int *)&g_ctx.h_scalars[15];
     return TSG_OK;
 }
 
 int read_back_i64(const long long *d, long long *out)
 {
-    CK(cudaMemcpyAsync(&g_ctx.h_scalars[15], d, sizeof(long long), cudaMemcpyDeviceToHost, g_ctx.stream));
+    int rc = publish_words(&g_ctx.h_scalars[15], d, 2);
+    if (rc) return rc;
     CK(cudaStreamSynchronize(g_ctx.stream));
-    *out = g_ctx.h_scalars[15];
+    *out = *(const volatile long long *)&g_ctx.h_scalars[15];
     return TSG_OK;
 }
 
@@ -222,7 +251,8 @@ int tsg_init(int device)
     CK(cudaMemPoolSetAttribute(g_ctx.pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     CK(cudaMalloc(&g_ctx.scan_ticket, 256));
     CK(cudaMalloc(&g_ctx.d_scalars, 16 * sizeof(long long)));
-    CK(cudaMallocHost(&g_ctx.h_scalars, 16 * sizeof(long long)));
+    CK(cudaHostAlloc(&g_ctx.h_scalars, 16 * sizeof(long long), cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer(&g_ctx.h_scalars_dev, g_ctx.h_scalars, 0));
     g_ready = true;
     return TSG_OK;
 }
@@ -236,6 +266,13 @@ void tsg_shutdown(void)
         if (g_ctx.arena[k].base) cudaFreeAsync(g_ctx.arena[k].base, g_ctx.stream);
     for (int k = 0; k < 2; k++)
         if (g_ctx.cslab[k].p) cudaFreeAsync(g_ctx.cslab[k].p, g_ctx.stream);
+    if (g_ctx.copy_stream) cudaStreamSynchronize(g_ctx.copy_stream);
+    for (int k = 0; k < 2; k++) {
+        if (g_ctx.land[k].p) dfree(g_ctx.land[k].p);
+        if (g_ctx.land[k].ready) cudaEventDestroy(g_ctx.land[k].ready);
+        if (g_ctx.land[k].copied) cudaEventDestroy(g_ctx.land[k].copied);
+    }
+    if (g_ctx.copy_stream) cudaStreamDestroy(g_ctx.copy_stream);
     big_cache_trim(0, 0);
     g_big_live.clear();
     cudaStreamSynchronize(g_ctx.stream);
@@ -549,6 +586,154 @@ int tsg_spgemm_csr_host(int m, int k, int n, const int *a_rowptr, const int *a_c
     }
     tsg_csr_free(&A); tsg_csr_free(&B); tsg_csr_free(&Cc);
     tsg_tile_free(&tA); tsg_tile_free(&tB); tsg_tile_free(&tC);
+    return rc;
+}
+
+/* ---------------- end to end with overlap: C leaves the device slab by slab while the next slab is computed ---------------- */
+
+// Cut tile-rows [r0, r1) into slabs of about equal step-1 weight (tile pairs). nslabs <= 0: up to 16 slabs of >= 2^20
+// pairs each. No slab exceeds 2^28 pairs unless a single tile-row does (the bound spgemm_device's scratch is sized for).
+static void plan_slabs(const long long *w, int r0, int r1, int nslabs, std::vector<int> &cuts)
+{
+    long long total = 0;
+    for (int i = r0; i < r1; i++) total += w[i];
+    long long S = nslabs > 0 ? nslabs : total >> 20;
+    if (nslabs <= 0 && S > 16) S = 16;
+    const long long max_pairs = 1ll << 28;
+    if (S < (total + max_pairs - 1) / max_pairs) S = (total + max_pairs - 1) / max_pairs;
+    if (S < 1) S = 1;
+    const long long target = (total + S - 1) / S;
+    cuts.clear();
+    cuts.push_back(r0);
+    long long acc = 0;
+    for (int i = r0; i < r1; i++) {
+        if (acc > 0 && acc + w[i] > target) { cuts.push_back(i); acc = 0; }
+        acc += w[i];
+    }
+    if (r1 > r0) cuts.push_back(r1);
+}
+
+static int landing_init()
+{
+    Ctx &c = g_ctx;
+    if (c.copy_stream) return TSG_OK;
+    CK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CK(cudaEventCreateWithFlags(&c.land[k].ready, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.land[k].copied, cudaEventDisableTiming));
+    }
+    return TSG_OK;
+}
+
+int tsg_spgemm_to_host(const tsg_dtile *a, const tsg_dtile *b, int trow0, int trow1, int nslabs, int *c_rowptr, int *c_colidx,
+                       double *c_val, long long c_cap, long long *c_nnz, tsg_stats *stats)
+{
+    if (ensure_init()) return g_err;
+    Ctx &c = g_ctx;
+    if (trow1 < 0) trow1 = a->tilem;
+    if (trow0 < 0 || trow0 > trow1 || trow1 > a->tilem) {
+        set_error(TSG_ERR_INPUT, "spgemm_to_host: tile-row range [%d,%d) outside [0,%d]", trow0, trow1, a->tilem);
+        return g_err;
+    }
+    if (a->n != b->m) { set_error(TSG_ERR_UNSUPPORTED, "spgemm_to_host: inner dimensions differ (%d vs %d)", a->n, b->m); return g_err; }
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (c_nnz) *c_nnz = 0;
+    c_rowptr[0] = 0;
+    if (trow0 == trow1) return TSG_OK;
+    int rc = landing_init();
+    if (rc) return rc;
+    std::vector<long long> w((size_t)a->tilem + 1);
+    rc = tsg_tilerow_weights(a, b, w.data());
+    if (rc) return rc;
+    std::vector<int> cuts;
+    plan_slabs(w.data(), trow0, trow1, nslabs, cuts);
+
+    long long off = 0;
+    bool full = false;
+    for (size_t s = 0; s + 1 < cuts.size() && !rc; s++) {
+        const int r0 = cuts[s], r1 = cuts[s + 1];
+        tsg_dtile tC;
+        tsg_stats st;
+        memset(&tC, 0, sizeof(tC));
+        rc = spgemm_device(a, b, r0, r1, &tC, &st);
+        if (rc) { tsg_tile_free(&tC); break; }
+        if (stats) {
+            stats->ms_step1 += st.ms_step1; stats->ms_step2 += st.ms_step2; stats->ms_step3 += st.ms_step3;
+            stats->ms_alloc += st.ms_alloc; stats->ms_total += st.ms_total; stats->numblkC += st.numblkC;
+            stats->nnzC += st.nnzC; stats->pairs += st.pairs; stats->launches += st.launches;
+            stats->algorithmic_bytes += st.algorithmic_bytes;
+        }
+        const long long nz = tC.nnz;
+        const int rows = tC.m;
+        if (off + nz >= (1ll << 31)) {
+            set_error(TSG_ERR_OVERFLOW, "spgemm_to_host: nnz(C) passes 2^31 in tile-rows [%d,%d); 32-bit CSR row pointers cannot hold it", r0, r1);
+            rc = g_err;
+        } else if (off + nz > c_cap) {
+            full = true;  // keep counting so that the caller learns the capacity it needs
+        } else if (!full) {
+            Ctx::Landing &L = c.land[s & 1];
+            const size_t nzs = (size_t)(nz > 0 ? nz : 1);
+            const size_t o_ci = (((size_t)rows + 1) * 4 + 255) & ~(size_t)255, o_v = o_ci + ((nzs * 4 + 255) & ~(size_t)255);
+            const size_t need = o_v + nzs * 8;
+            if (L.cap < need) {  // grow: the copy that still reads the old buffer has to finish first
+                if (L.busy && !cuda_ok(cudaEventSynchronize(L.copied), "landing wait", __FILE__, __LINE__)) rc = g_err;
+                if (L.p) dfree(L.p);
+                L.cap = 0; L.busy = false;
+                L.p = rc ? nullptr : (char *)dalloc(need + need / 8);
+                if (L.p) L.cap = need + need / 8; else rc = g_err;
+            } else if (L.busy && !cuda_ok(cudaStreamWaitEvent(c.stream, L.copied, 0), "landing wait", __FILE__, __LINE__)) {
+                rc = g_err;
+            }
+            if (!rc) rc = tile2csr_into(&tC, (int *)L.p, (int *)(L.p + o_ci), (double *)(L.p + o_v), (int)off);
+            if (!rc) {
+                const size_t row_at = (size_t)(r0 - trow0) * TS;
+                bool ok = cuda_ok(cudaEventRecord(L.ready, c.stream), "landing ready", __FILE__, __LINE__) &&
+                          cuda_ok(cudaStreamWaitEvent(c.copy_stream, L.ready, 0), "landing ready", __FILE__, __LINE__) &&
+                          cuda_ok(cudaMemcpyAsync(c_rowptr + row_at, L.p, ((size_t)rows + 1) * 4, cudaMemcpyDeviceToHost, c.copy_stream),
+                                  "landing rowptr", __FILE__, __LINE__);
+                if (ok && nz > 0)
+                    ok = cuda_ok(cudaMemcpyAsync(c_colidx + off, L.p + o_ci, (size_t)nz * 4, cudaMemcpyDeviceToHost, c.copy_stream),
+                                 "landing colidx", __FILE__, __LINE__) &&
+                         cuda_ok(cudaMemcpyAsync(c_val + off, L.p + o_v, (size_t)nz * 8, cudaMemcpyDeviceToHost, c.copy_stream),
+                                 "landing val", __FILE__, __LINE__);
+                ok = ok && cuda_ok(cudaEventRecord(L.copied, c.copy_stream), "landing copied", __FILE__, __LINE__);
+                L.busy = ok;
+                if (!ok) rc = g_err;
+            }
+        }
+        tsg_tile_free(&tC);
+        off += nz;
+    }
+    cudaError_t e = cudaStreamSynchronize(c.copy_stream);  // drain on every path: the landing buffers are reused by the next call
+    c.land[0].busy = c.land[1].busy = false;
+    if (!rc && !cuda_ok(e, "landing drain", __FILE__, __LINE__)) rc = g_err;
+    if (rc) return rc;
+    if (c_nnz) *c_nnz = off;
+    if (full) {
+        set_error(TSG_ERR_NOMEM, "spgemm_to_host: C has %lld entries, the output buffers hold %lld", off, c_cap);
+        return g_err;
+    }
+    return TSG_OK;
+}
+
+int tsg_spgemm_csr_host_into(int m, int k, int n, const int *a_rowptr, const int *a_colidx, const double *a_val,
+                             const int *b_rowptr, const int *b_colidx, const double *b_val, int aat, int *c_rowptr,
+                             int *c_colidx, double *c_val, long long c_cap, long long *c_nnz, tsg_stats *stats)
+{
+    if (ensure_init()) return g_err;
+    tsg_dcsr A, B;
+    tsg_dtile tA, tB;
+    memset(&A, 0, sizeof(A)); memset(&B, 0, sizeof(B)); memset(&tA, 0, sizeof(tA)); memset(&tB, 0, sizeof(tB));
+    int rc = tsg_csr_upload(m, k, a_rowptr, a_colidx, a_val, &A);
+    const tsg_dcsr *Bp = &A;
+    if (!rc && aat) { rc = tsg_transpose(&A, &B); Bp = &B; }
+    else if (!rc && b_rowptr) { rc = tsg_csr_upload(k, n, b_rowptr, b_colidx, b_val, &B); Bp = &B; }
+    if (!rc && Bp->n != n) { set_error(TSG_ERR_UNSUPPORTED, "spgemm_csr_host_into: B has %d columns, expected %d", Bp->n, n); rc = g_err; }
+    if (!rc) rc = tsg_csr2tile(&A, 0, &tA);
+    if (!rc) rc = tsg_csr2tile(Bp, 1, &tB);
+    if (!rc) rc = tsg_spgemm_to_host(&tA, &tB, 0, -1, 0, c_rowptr, c_colidx, c_val, c_cap, c_nnz, stats);
+    tsg_csr_free(&A); tsg_csr_free(&B);
+    tsg_tile_free(&tA); tsg_tile_free(&tB);
     return rc;
 }
 

@@ -31,8 +31,13 @@ struct Ctx {
     // one-deep cache of the two buffers of a C slab (metadata, payload): a slab loop frees a C slab and asks for
     // the next one of similar size; handing the same buffer back avoids 20-GB pool re-allocations
     struct SlabCache { void *p = nullptr; size_t cap = 0; } cslab[2];
+    // end-to-end path (tsg_spgemm_to_host): a second stream for the device->host copies and two grow-only landing
+    // buffers, so that the CSR of slab s crosses PCIe while slab s+1 is computed
+    cudaStream_t copy_stream = nullptr;
+    struct Landing { char *p = nullptr; size_t cap = 0; cudaEvent_t ready = nullptr, copied = nullptr; bool busy = false; } land[2];
     // small pinned host scratch for scalar read-backs
-    long long *h_scalars = nullptr;   // pinned, 16 slots
+    long long *h_scalars = nullptr;   // pinned + mapped, 16 slots
+    long long *h_scalars_dev = nullptr;  // the same memory as the device sees it
     long long *d_scalars = nullptr;   // device, 16 slots
 };
 
@@ -79,7 +84,13 @@ static inline size_t arena_need(size_t n, size_t elem) { return (((n ? n : 1) * 
 void *cslab_take(int which, size_t bytes, size_t *cap);
 void cslab_give(int which, void *p, size_t cap);
 
-// Read one device int / long long back (stream sync). Used only where a size is needed for an
+// Enqueue a copy of `nwords` 32-bit words from device memory to a slot of ctx().h_scalars, done by a KERNEL that
+// stores into the mapped host memory. Scalar read-backs must not use the copy engine: while the end-to-end path is
+// streaming a C slab to the host, a 4-byte D2H copy would queue behind hundreds of MB and stall the next slab.
+int publish_words(void *h_dst, const void *d_src, int nwords);
+// Small device->device copy done by a kernel, for the same reason (inside spgemm_device only).
+int copy_words(void *d_dst, const void *d_src, size_t nwords);
+// Read one device int / long long back (publish + stream sync). Used only where a size is needed for an
 // allocation (numblkC, nnzC): two per SpGEMM call instead of the reference's ~8.
 int read_back_i32(const int *d, int *out);
 int read_back_i64(const long long *d, long long *out);

@@ -17,6 +17,7 @@ int build_rm2csc_device(tsg_dtile *B);
 
 // tile2csr.cu
 int tile2csr_device(const tsg_dtile *T, tsg_dcsr *out);
+int tile2csr_into(const tsg_dtile *T, int *rowptr, int *colidx, double *val, int base);
 int tile_rowsums_device(const tsg_dtile *T, double *d_out, long long *d_cnt);
 
 }  // namespace tsg

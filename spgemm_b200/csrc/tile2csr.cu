@@ -86,9 +86,42 @@ int tile_rowsums_device(const tsg_dtile *T, double *d_out, long long *d_cnt)
     return TSG_OK;
 }
 
-int tile2csr_device(const tsg_dtile *T, tsg_dcsr *out)
+__global__ void k_add_base(int *__restrict__ p, int n, int base)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] += base;
+}
+
+// CSR of T into caller-provided device arrays (rowptr: T->m + 1 ints, colidx / val: T->nnz entries).
+// `base` is added to every row pointer after the fill: a slab's CSR then continues the numbering of the slabs before it.
+int tile2csr_into(const tsg_dtile *T, int *rowptr, int *colidx, double *val, int base)
 {
     Ctx &c = ctx();
+    if (T->col_major) { set_error(TSG_ERR_UNSUPPORTED, "tile2csr: tiles must be in row-major storage order"); return last_error(); }
+    const int m = T->m;
+    CK(cudaMemsetAsync(rowptr, 0, ((size_t)m + 1) * 4, c.stream));
+    const int blocks = ceil_div((long long)T->tilem * 16, 128);
+    if (T->tilem > 0 && T->numtile > 0) {
+        k_tile2csr<false><<<blocks, 128, 0, c.stream>>>(m, T->tilem, T->tile_ptr, T->tile_columnidx, T->tile_nnz, T->ptr, T->col, T->val,
+                                                        rowptr, nullptr, nullptr);
+        CK_LAUNCH();
+    }
+    int rc = exclusive_scan<int>(rowptr, rowptr, m);
+    if (rc) return rc;
+    if (T->tilem > 0 && T->nnz > 0) {
+        k_tile2csr<true><<<blocks, 128, 0, c.stream>>>(m, T->tilem, T->tile_ptr, T->tile_columnidx, T->tile_nnz, T->ptr, T->col, T->val,
+                                                       rowptr, colidx, val);
+        CK_LAUNCH();
+    }
+    if (base) {
+        k_add_base<<<ceil_div((long long)m + 1, 256), 256, 0, c.stream>>>(rowptr, m + 1, base);
+        CK_LAUNCH();
+    }
+    return TSG_OK;
+}
+
+int tile2csr_device(const tsg_dtile *T, tsg_dcsr *out)
+{
     memset(out, 0, sizeof(*out));
     if (T->col_major) { set_error(TSG_ERR_UNSUPPORTED, "tile2csr: tiles must be in row-major storage order"); return last_error(); }
     const int m = T->m;
@@ -99,21 +132,7 @@ int tile2csr_device(const tsg_dtile *T, tsg_dcsr *out)
     if (!base) return last_error();
     out->m = m; out->n = T->n; out->nnz = nnz; out->owner = base;
     out->rowptr = (int *)base; out->colidx = (int *)(base + o_ci); out->val = (double *)(base + o_v);
-    CK(cudaMemsetAsync(out->rowptr, 0, ((size_t)m + 1) * 4, c.stream));
-    const int blocks = ceil_div((long long)T->tilem * 16, 128);
-    if (T->tilem > 0 && T->numtile > 0) {
-        k_tile2csr<false><<<blocks, 128, 0, c.stream>>>(m, T->tilem, T->tile_ptr, T->tile_columnidx, T->tile_nnz, T->ptr, T->col, T->val,
-                                                        out->rowptr, nullptr, nullptr);
-        CK_LAUNCH();
-    }
-    int rc = exclusive_scan<int>(out->rowptr, out->rowptr, m);
-    if (rc) return rc;
-    if (T->tilem > 0 && nnz > 0) {
-        k_tile2csr<true><<<blocks, 128, 0, c.stream>>>(m, T->tilem, T->tile_ptr, T->tile_columnidx, T->tile_nnz, T->ptr, T->col, T->val,
-                                                       out->rowptr, out->colidx, out->val);
-        CK_LAUNCH();
-    }
-    return TSG_OK;
+    return tile2csr_into(T, out->rowptr, out->colidx, out->val, 0);
 }
 
 }  // namespace tsg

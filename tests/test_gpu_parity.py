@@ -391,3 +391,63 @@ def test_hypersparse_rmat_a2_matches_oracle():
     assert np.array_equal(r, csrC[0]) and np.array_equal(c, csrC[1]) and np.array_equal(vv, csrC[2])
     for o in (csr, tC, tA, tB, d):
         o.free()
+
+
+def _pinned_out(rows, cap):
+    return (torch.empty(rows + 1, dtype=torch.int32).pin_memory(), torch.empty(max(cap, 1), dtype=torch.int32).pin_memory(),
+            torch.empty(max(cap, 1), dtype=torch.float64).pin_memory())
+
+
+@pytest.mark.parametrize("nslabs", [0, 1, 3, 7, 64])
+def test_overlapped_to_host_equals_oracle_csr(nslabs):
+    """tsg_spgemm_to_host: C leaves the device slab by slab on a second stream; the CSR that lands in the
+    caller's pinned buffers must be the serial SPA's, whatever the number of slabs (64 > tile-rows: one per row)."""
+    m, n, rp, ci, _ = M.stencil27(11, 9, 7)
+    v = M.set_values(len(ci), "mod10")
+    A = (rp, ci, v)
+    exp = orc.spgemm_spa(A, A, n)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
+    out = _pinned_out(m, len(exp[1]))
+    for _ in range(2):  # second pass reuses the landing buffers
+        for t in out:
+            t.fill_(-1)
+        nnz, st = api.spgemm_to_host(tA, tB, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), len(exp[1]), nslabs=nslabs)
+        assert nnz == len(exp[1]) == st["nnzC"]
+        assert np.array_equal(out[0].numpy(), exp[0])
+        assert np.array_equal(out[1].numpy()[:nnz], exp[1]) and np.array_equal(out[2].numpy()[:nnz], exp[2])
+    # a sub-range of tile-rows: row pointers are numbered from the range's first row
+    t0, t1 = 3, tA.tilem - 2
+    sub = orc.spgemm_spa(A, A, n, t0 * 16, min(t1 * 16, m))
+    nnz, _ = api.spgemm_to_host(tA, tB, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), len(exp[1]), nslabs=nslabs,
+                                trow0=t0, trow1=t1)
+    assert nnz == len(sub[1]) and np.array_equal(out[0].numpy()[:len(sub[0])], sub[0])
+    assert np.array_equal(out[1].numpy()[:nnz], sub[1]) and np.array_equal(out[2].numpy()[:nnz], sub[2])
+    for o in (tA, tB, d):
+        o.free()
+
+
+def test_overlapped_host_into_small_cases_and_capacity_error():
+    """tsg_spgemm_csr_host_into on every small case (empty, ragged, 1x1, AA^T), pageable numpy outputs included;
+    too small a capacity fails loudly and names the size needed."""
+    for name in sorted(SMALL):
+        m, n, rp, ci, _ = SMALL[name]()
+        v = M.set_values(len(ci), "mod10") if len(ci) else np.zeros(0)
+        exp = orc.spgemm_spa((rp, ci, v), (rp, ci, v), n)
+        out = (np.full(m + 1, -1, np.int32), np.full(max(len(exp[1]), 1), -1, np.int32), np.full(max(len(exp[1]), 1), -1.0))
+        nnz, _ = api.spgemm_csr_host_into(m, n, n, (rp, ci, v), out)
+        assert nnz == len(exp[1]), name
+        assert np.array_equal(out[0], exp[0]) and np.array_equal(out[1][:nnz], exp[1]) and np.array_equal(out[2][:nnz], exp[2]), name
+    m, n, rp, ci, v = M.rmat(10, 8, seed=9)
+    ecp, eri, ecv = orc.transpose(m, n, rp, ci, v)
+    exp = orc.spgemm_spa((rp, ci, v), (ecp, eri, ecv), m)
+    out = (np.zeros(m + 1, np.int32), np.zeros(len(exp[1]), np.int32), np.zeros(len(exp[1])))
+    nnz, _ = api.spgemm_csr_host_into(m, n, m, (rp, ci, v), out, aat=True)
+    assert nnz == len(exp[1]) and np.array_equal(out[0], exp[0]) and np.array_equal(out[1], exp[1])
+    assert np.allclose(out[2], exp[2], rtol=VAL_RTOL, atol=0)
+    small = (np.zeros(m + 1, np.int32), np.zeros(len(exp[1]) - 1, np.int32), np.zeros(len(exp[1]) - 1))
+    with pytest.raises(api.TsgError) as e:
+        api.spgemm_csr_host_into(m, n, m, (rp, ci, v), small, aat=True)
+    assert e.value.code == 5 and str(len(exp[1])) in str(e.value)  # TSG_ERR_NOMEM, "C has <nnz> entries"
+    nnz, _ = api.spgemm_csr_host_into(m, n, m, (rp, ci, v), out, aat=True)  # and the library is usable afterwards
+    assert nnz == len(exp[1]) and np.array_equal(out[1], exp[1])
