@@ -446,13 +446,16 @@ int tsg_tile_upload(const SMatrix *h, int col_major, tsg_dtile *out)
         CK(cudaMemcpyAsync(out->tile_columnidx, h->tile_columnidx, nt * 4, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(out->ptr, h->tile_csr_Ptr, nt * TS * 2, cudaMemcpyHostToDevice, s));
         if (h->mask) CK(cudaMemcpyAsync(out->mask, h->mask, nt * TS * 2, cudaMemcpyHostToDevice, s));
-        else CK(cudaMemsetAsync(out->mask, 0, nt * TS * 2, s));
         CK(cudaMemsetAsync(out->tile_rowidx, 0, nt * 4, s));
     }
     CK(cudaMemcpyAsync(out->tile_nnz, h->tile_nnz, (nt + 1) * 4, cudaMemcpyHostToDevice, s));
     if (nz) {
         CK(cudaMemcpyAsync(out->val, h->tile_csr_Value, nz * 8, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(out->col, h->tile_csr_Col, nz * 2, cudaMemcpyHostToDevice, s));
+    }
+    if (nt && !h->mask) {  // steps 1-3 read the row masks of A and B: rebuild them from Ptr / Col
+        rc = masks_from_tiles_device(out);
+        if (rc) return rc;
     }
     if (col_major) {
         CK(cudaMemcpyAsync(out->csc_tile_ptr, h->csc_tile_ptr, ((size_t)h->tilen + 1) * 4, cudaMemcpyHostToDevice, s));

@@ -352,6 +352,33 @@ int transpose_device(const tsg_dcsr *A, tsg_dcsr *AT)
     return TSG_OK;
 }
 
+// Row masks of a tiled matrix from its Ptr / Col arrays, for tiles uploaded without a mask array (SMatrix.mask == NULL).
+// Half-warp per tile, lane = row; Col & 15 is the column in both layouts (A stores row*16 + col, B / C the column).
+__global__ void __launch_bounds__(128)
+k_masks_from_tiles(int numtile, const int *__restrict__ tile_nnz, const uint16_t *__restrict__ ptr, const uint16_t *__restrict__ col,
+                   uint16_t *__restrict__ mask)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = (int)(gid >> 4), r = threadIdx.x & 15;
+    if (t >= numtile) return;
+    const int base = tile_nnz[t];
+    const int p0 = ptr[(size_t)t * TS + r];
+    const int p1 = r < TS - 1 ? (int)ptr[(size_t)t * TS + r + 1] : tile_nnz[t + 1] - base;
+    unsigned m = 0;
+    for (int j = p0; j < p1; j++) m |= 0x8000u >> (col[base + j] & 15);
+    mask[(size_t)t * TS + r] = (uint16_t)m;
+}
+
+int masks_from_tiles_device(tsg_dtile *T)
+{
+    Ctx &c = ctx();
+    if (T->numtile > 0) {
+        k_masks_from_tiles<<<ceil_div((long long)T->numtile * 16, 128), 128, 0, c.stream>>>(T->numtile, T->tile_nnz, T->ptr, T->col, T->mask);
+        CK_LAUNCH();
+    }
+    return TSG_OK;
+}
+
 int nnzcub_device(const tsg_dcsr *A, const tsg_dcsr *B, unsigned long long *out)
 {
     Ctx &c = ctx();

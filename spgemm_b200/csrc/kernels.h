@@ -9,6 +9,7 @@ int tile_alloc_layout(int m, int n, int numtile, long long nnz, int col_major, t
 int csr2tile_device(const tsg_dcsr *A, int col_major, tsg_dtile *out);
 int transpose_device(const tsg_dcsr *A, tsg_dcsr *AT);
 int nnzcub_device(const tsg_dcsr *A, const tsg_dcsr *B, unsigned long long *out);
+int masks_from_tiles_device(tsg_dtile *T);
 
 // spgemm.cu
 int tilerow_weights_device(const tsg_dtile *A, const tsg_dtile *B, int **d_w, int **d_jlo, int **d_jhi);

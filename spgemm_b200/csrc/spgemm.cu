@@ -470,15 +470,6 @@ k_step2_thread(int numblkC, const int *__restrict__ pair_ptr, const int *__restr
     c_cnt[t] = run;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Step 3: gather formulation, one LANE per C nonzero (g = position in C's Val/Col).
-// blk2tile[g/32] gives the tile holding nonzero 32*(g/32); the lane finds its tile, row r and
-// column c from tile_nnz / Ptr / mask, then for every pair (A tile a, B tile b) of the tile walks
-// A's row r: for an entry (r,k) with value av, B has (k,c) iff bit (15-c) of B's row mask k is set,
-// and its position is Ptr_b[k] + popc(mask bits of columns < c). The sum stays in a register:
-// no shared-memory accumulator, no atomics, no zeroing, fully coalesced stores, and the summation
-// order (ascending A tile, then ascending k) is exactly the serial SPA's.
-// ---------------------------------------------------------------------------------------------
 // first/last tile and nonzero of A's tile-rows [trow0, trow1), stored straight into mapped host memory
 __global__ void k_slab_extent(const int *__restrict__ tile_ptr, const int *__restrict__ tile_nnz, int trow0, int trow1, int *out)
 {
@@ -488,6 +479,17 @@ __global__ void k_slab_extent(const int *__restrict__ tile_ptr, const int *__res
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Step 3: gather formulation, one LANE per C nonzero (g = position in C's Val/Col).
+// blk2tile[g/32] gives the tile holding nonzero 32*(g/32); the lane finds its tile, row r and
+// column c from tile_nnz / Ptr / mask, then for every pair (A tile a, B tile b) of the tile reads
+// A's row mask r (zero: the pair does not touch this row -- two thirds of the pairs on a stencil --
+// and nothing else of the pair is loaded); its bits are the k's of A's row r in ascending order.
+// For an entry (r,k) with value av, B has (k,c) iff bit (15-c) of B's row mask k is set,
+// and its position is Ptr_b[k] + popc(mask bits of columns < c). The sum stays in a register:
+// no shared-memory accumulator, no atomics, no zeroing, fully coalesced stores, and the summation
+// order (ascending A tile, then ascending k) is exactly the serial SPA's.
+// ---------------------------------------------------------------------------------------------
 __global__ void k_blk2tile(int numblkC, const int *__restrict__ c_tile_nnz, int *__restrict__ blk2tile)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -499,7 +501,7 @@ __global__ void k_blk2tile(int numblkC, const int *__restrict__ c_tile_nnz, int 
 __device__ __forceinline__ void
 s3_gather_one(int g, int numblkC, int nnzC, const int *__restrict__ blk2tile, const int *__restrict__ pair_ptr,
               const int *__restrict__ pair_end, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
-              const int *__restrict__ a_tile_nnz, const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ a_col,
+              const int *__restrict__ a_tile_nnz, const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ a_mask,
               const double *__restrict__ a_val, const int *__restrict__ b_tile_nnz, const uint16_t *__restrict__ b_ptr,
               const uint16_t *__restrict__ b_mask, const double *__restrict__ b_val, const int *__restrict__ c_tile_nnz,
               const uint16_t *__restrict__ c_ptr, const uint16_t *__restrict__ c_mask, uint16_t *__restrict__ c_col,
@@ -529,20 +531,22 @@ s3_gather_one(int g, int numblkC, int nnzC, const int *__restrict__ blk2tile, co
     double acc = 0.0;
     const int p1 = pair_end[t];
     for (int p = pair_ptr[t]; p < p1; p++) {
-        const int a = pair_a[p], b = pair_b[p];
-        const int abase = a_tile_nnz[a];
-        int ia = a_ptr[(size_t)a * TS + r];
-        const int ia1 = r < TS - 1 ? (int)a_ptr[(size_t)a * TS + r + 1] : a_tile_nnz[a + 1] - abase;
-        if (ia < ia1) {
+        const int a = pair_a[p];
+        unsigned am = a_mask[(size_t)a * TS + r];  // A's row r: one load decides whether the pair contributes at all,
+        if (am) {                                  // and its bits are the k's (ascending), so A's Col array is never read
+            const int b = pair_b[p];
+            int ia = a_tile_nnz[a] + a_ptr[(size_t)a * TS + r];
             const int bbase = b_tile_nnz[b];
-            for (; ia < ia1; ia++) {
-                const int k = a_col[abase + ia] & 15;
+            do {
+                const int k = __clz(am) - 16;
+                am ^= 0x8000u >> k;
                 const unsigned bm = b_mask[(size_t)b * TS + k];
                 if (bm & cbit) {
                     const int pos = (int)b_ptr[(size_t)b * TS + k] + __popc(bm >> (16 - c));
-                    acc = fma(a_val[abase + ia], b_val[bbase + pos], acc);
+                    acc = fma(a_val[ia], b_val[bbase + pos], acc);
                 }
-            }
+                ia++;
+            } while (am);
         }
     }
     c_val[g] = acc;
@@ -556,7 +560,7 @@ template <bool CHUNKED>
 __global__ void __launch_bounds__(256)
 k_step3_gather(int chunk, int numblkC, int nnzC, const int *__restrict__ blk2tile, const int *__restrict__ pair_ptr,
                const int *__restrict__ pair_end, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
-               const int *__restrict__ a_tile_nnz, const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ a_col,
+               const int *__restrict__ a_tile_nnz, const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ a_mask,
                const double *__restrict__ a_val, const int *__restrict__ b_tile_nnz, const uint16_t *__restrict__ b_ptr,
                const uint16_t *__restrict__ b_mask, const double *__restrict__ b_val, const int *__restrict__ c_tile_nnz,
                const uint16_t *__restrict__ c_ptr, const uint16_t *__restrict__ c_mask, uint16_t *__restrict__ c_col,
@@ -565,13 +569,13 @@ k_step3_gather(int chunk, int numblkC, int nnzC, const int *__restrict__ blk2til
     if (!CHUNKED) {
         const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
         if (g < nnzC)
-            s3_gather_one((int)g, numblkC, nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b, a_tile_nnz, a_ptr, a_col, a_val, b_tile_nnz,
+            s3_gather_one((int)g, numblkC, nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b, a_tile_nnz, a_ptr, a_mask, a_val, b_tile_nnz,
                           b_ptr, b_mask, b_val, c_tile_nnz, c_ptr, c_mask, c_col, c_val);
         return;
     }
     const long long cend = min((long long)nnzC, ((long long)blockIdx.x + 1) * chunk);
     for (long long g = (long long)blockIdx.x * chunk + threadIdx.x; g < cend; g += blockDim.x)
-        s3_gather_one((int)g, numblkC, nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b, a_tile_nnz, a_ptr, a_col, a_val, b_tile_nnz,
+        s3_gather_one((int)g, numblkC, nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b, a_tile_nnz, a_ptr, a_mask, a_val, b_tile_nnz,
                       b_ptr, b_mask, b_val, c_tile_nnz, c_ptr, c_mask, c_col, c_val);
 }
 
@@ -1005,7 +1009,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         if (chunk_env >= 256) chunk = chunk_env;
         auto kern = chunk > 256 ? k_step3_gather<true> : k_step3_gather<false>;
         kern<<<ceil_div(nnzC, chunk), 256, 0, c.stream>>>(chunk, (int)numblkC, (int)nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b,
-                                                                  A->tile_nnz, A->ptr, A->col, A->val, B->tile_nnz, B->ptr, B->mask,
+                                                                  A->tile_nnz, A->ptr, A->mask, A->val, B->tile_nnz, B->ptr, B->mask,
                                                                   B->val, C->tile_nnz, C->ptr, C->mask, C->col, C->val);
         CK_LAUNCH();
     }

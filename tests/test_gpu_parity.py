@@ -451,3 +451,26 @@ def test_overlapped_host_into_small_cases_and_capacity_error():
     assert e.value.code == 5 and str(len(exp[1])) in str(e.value)  # TSG_ERR_NOMEM, "C has <nnz> entries"
     nnz, _ = api.spgemm_csr_host_into(m, n, m, (rp, ci, v), out, aat=True)  # and the library is usable afterwards
     assert nnz == len(exp[1]) and np.array_equal(out[1], exp[1])
+
+
+def test_drop_in_tiles_without_mask_arrays():
+    """An SMatrix whose `mask` member is NULL (a caller that tiled A and B itself and kept only Ptr/Col/Val):
+    the library rebuilds the row masks on the device, steps 1-3 read them."""
+    import ctypes as C
+    m, n, rp, ci, _ = M.stencil27(7, 6, 5)
+    v = M.set_values(len(ci), "mod10")
+    A = api.HostMatrix.from_csr(m, n, rp, ci, v)
+    B = api.HostMatrix().alias_csr_of(A)
+    api.csr2tile_row_major(A, 16, 16)
+    api.csr2tile_col_major(B, 16, 16)
+    keep = (A.s.mask, B.s.mask)
+    null = type(A.s.mask)()
+    A.s.mask, B.s.mask = null, null
+    try:
+        Cm, _ = api.tilespgemm(A, B, orc.nnzcub(ci, rp))
+    finally:
+        A.s.mask, B.s.mask = keep       # matrix_destroy frees them
+    _, tC_exp = oracle_c(m, n, (rp, ci, v), (rp, ci, v), n)
+    assert_tiled_equal(Cm.tiles(), tC_exp, "C from mask-less A, B")
+    for x in (A, B, Cm):
+        api.matrix_destroy(x)
