@@ -498,6 +498,7 @@ __global__ void k_blk2tile(int numblkC, const int *__restrict__ c_tile_nnz, int 
     for (int blk = (s + 31) >> 5; (blk << 5) < e; blk++) blk2tile[blk] = t;
 }
 
+template <int UNROLL>
 __device__ __forceinline__ void
 s3_gather_one(int g, int numblkC, int nnzC, const int *__restrict__ blk2tile, const int *__restrict__ pair_ptr,
               const int *__restrict__ pair_end, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
@@ -523,31 +524,46 @@ s3_gather_one(int g, int numblkC, int nnzC, const int *__restrict__ blk2tile, co
     r += __popc(__vcmpleu2(q0.x, key)) + __popc(__vcmpleu2(q0.y, key)) + __popc(__vcmpleu2(q0.z, key)) + __popc(__vcmpleu2(q0.w, key)) +
          __popc(__vcmpleu2(q1.x, key)) + __popc(__vcmpleu2(q1.y, key)) + __popc(__vcmpleu2(q1.z, key)) + __popc(__vcmpleu2(q1.w, key));
     r = ((r + 1) >> 4) - 1;  // each u16 that compares <= contributes 16 set bits
-    unsigned cm = c_mask[(size_t)t * TS + r];
-    for (int n = off - (int)c_ptr[(size_t)t * TS + r]; n > 0; n--) cm &= ~(0x80000000u >> __clz(cm));
-    const int c = __clz(cm) - 16;
+    unsigned cm = __brev(c_mask[(size_t)t * TS + r]) >> 16;  // bit c = column c present
+    for (int n = off - (int)c_ptr[(size_t)t * TS + r]; n > 0; n--) cm &= cm - 1;  // drop the n smaller columns
+    const int c = __ffs(cm) - 1;
     const unsigned cbit = 0x8000u >> c;
 
     double acc = 0.0;
+    // one pair: `am` = A's row mask r (non-zero); its bits are the k's in ascending order, so A's Col array is never read
+    auto pair_contrib = [&](int a, int b, unsigned am) {
+        int ia = a_tile_nnz[a] + a_ptr[(size_t)a * TS + r];
+        const int bbase = b_tile_nnz[b];
+        do {
+            const int k = __clz(am) - 16;
+            am ^= 0x8000u >> k;
+            const unsigned bm = b_mask[(size_t)b * TS + k];
+            if (bm & cbit) {
+                const int pos = (int)b_ptr[(size_t)b * TS + k] + __popc(bm >> (16 - c));
+                acc = fma(a_val[ia], b_val[bbase + pos], acc);
+            }
+            ia++;
+        } while (am);
+    };
     const int p1 = pair_end[t];
-    for (int p = pair_ptr[t]; p < p1; p++) {
-        const int a = pair_a[p];
-        unsigned am = a_mask[(size_t)a * TS + r];  // A's row r: one load decides whether the pair contributes at all,
-        if (am) {                                  // and its bits are the k's (ascending), so A's Col array is never read
-            const int b = pair_b[p];
-            int ia = a_tile_nnz[a] + a_ptr[(size_t)a * TS + r];
-            const int bbase = b_tile_nnz[b];
-            do {
-                const int k = __clz(am) - 16;
-                am ^= 0x8000u >> k;
-                const unsigned bm = b_mask[(size_t)b * TS + k];
-                if (bm & cbit) {
-                    const int pos = (int)b_ptr[(size_t)b * TS + k] + __popc(bm >> (16 - c));
-                    acc = fma(a_val[ia], b_val[bbase + pos], acc);
-                }
-                ia++;
-            } while (am);
+    int p = pair_ptr[t];
+    if (UNROLL > 1) {  // the row masks of UNROLL pairs in flight; contributions are still added in pair order
+        for (; p + UNROLL <= p1; p += UNROLL) {
+            int a[UNROLL];
+            unsigned am[UNROLL];
+#pragma unroll
+            for (int j = 0; j < UNROLL; j++) a[j] = pair_a[p + j];
+#pragma unroll
+            for (int j = 0; j < UNROLL; j++) am[j] = a_mask[(size_t)a[j] * TS + r];
+#pragma unroll
+            for (int j = 0; j < UNROLL; j++)
+                if (am[j]) pair_contrib(a[j], pair_b[p + j], am[j]);
         }
+    }
+    for (; p < p1; p++) {
+        const int a = pair_a[p];
+        const unsigned am = a_mask[(size_t)a * TS + r];  // zero: the pair does not touch row r, nothing else of it is loaded
+        if (am) pair_contrib(a, pair_b[p], am);
     }
     c_val[g] = acc;
     c_col[g] = (uint16_t)c;
@@ -556,7 +572,7 @@ s3_gather_one(int g, int numblkC, int nnzC, const int *__restrict__ blk2tile, co
 // CHUNKED = false: one nonzero per thread (straight-line code, 32 registers), blocks balanced by the hardware scheduler.
 // CHUNKED = true: a CTA walks `chunk` consecutive nonzeros (a few C tile-rows), so that the A tiles they share stay in
 // its SM's L1; used when the work per nonzero is even (no heavy tile-rows) and the grid stays large.
-template <bool CHUNKED>
+template <bool CHUNKED, int UNROLL>
 __global__ void __launch_bounds__(256)
 k_step3_gather(int chunk, int numblkC, int nnzC, const int *__restrict__ blk2tile, const int *__restrict__ pair_ptr,
                const int *__restrict__ pair_end, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
@@ -569,13 +585,13 @@ k_step3_gather(int chunk, int numblkC, int nnzC, const int *__restrict__ blk2til
     if (!CHUNKED) {
         const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
         if (g < nnzC)
-            s3_gather_one((int)g, numblkC, nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b, a_tile_nnz, a_ptr, a_mask, a_val, b_tile_nnz,
+            s3_gather_one<UNROLL>((int)g, numblkC, nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b, a_tile_nnz, a_ptr, a_mask, a_val, b_tile_nnz,
                           b_ptr, b_mask, b_val, c_tile_nnz, c_ptr, c_mask, c_col, c_val);
         return;
     }
     const long long cend = min((long long)nnzC, ((long long)blockIdx.x + 1) * chunk);
     for (long long g = (long long)blockIdx.x * chunk + threadIdx.x; g < cend; g += blockDim.x)
-        s3_gather_one((int)g, numblkC, nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b, a_tile_nnz, a_ptr, a_mask, a_val, b_tile_nnz,
+        s3_gather_one<UNROLL>((int)g, numblkC, nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b, a_tile_nnz, a_ptr, a_mask, a_val, b_tile_nnz,
                       b_ptr, b_mask, b_val, c_tile_nnz, c_ptr, c_mask, c_col, c_val);
 }
 
@@ -1007,7 +1023,9 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         if (wmax_seen <= S1_LIGHT_MAX && nnzC >= (long long)c.num_sms * 16 * 8192) chunk = 8192;
         static const int chunk_env = getenv("TSG_GATHER_CHUNK") ? atoi(getenv("TSG_GATHER_CHUNK")) : 0;
         if (chunk_env >= 256) chunk = chunk_env;
-        auto kern = chunk > 256 ? k_step3_gather<true> : k_step3_gather<false>;
+        static const int unroll_env = getenv("TSG_GATHER_UNROLL") ? atoi(getenv("TSG_GATHER_UNROLL")) : 2;
+        auto kern = chunk > 256 ? (unroll_env == 4 ? k_step3_gather<true, 4> : unroll_env == 2 ? k_step3_gather<true, 2> : k_step3_gather<true, 1>)
+                                : (unroll_env == 4 ? k_step3_gather<false, 4> : unroll_env == 2 ? k_step3_gather<false, 2> : k_step3_gather<false, 1>);
         kern<<<ceil_div(nnzC, chunk), 256, 0, c.stream>>>(chunk, (int)numblkC, (int)nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b,
                                                                   A->tile_nnz, A->ptr, A->mask, A->val, B->tile_nnz, B->ptr, B->mask,
                                                                   B->val, C->tile_nnz, C->ptr, C->mask, C->col, C->val);
