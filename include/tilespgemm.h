@@ -245,6 +245,12 @@ int tsg_spgemm_csr_host(int m, int k, int n, const int *a_rowptr, const int *a_c
 int tsg_spgemm_to_host(const tsg_dtile *a, const tsg_dtile *b, int trow0, int trow1, int nslabs, int *c_rowptr,
                        int *c_colidx, double *c_val, long long c_cap, long long *c_nnz, tsg_stats *stats);
 
+/* The slab plan tsg_spgemm_to_host uses (pure host code, no device needed): boundaries of the slabs of
+ * tile-rows [trow0, trow1) given the step-1 weights (tsg_tilerow_weights; indexed by absolute tile-row).
+ * Writes nslabs+1 ascending boundaries cuts[0] = trow0 .. cuts[nslabs] = trow1 and returns the number of
+ * slabs (0 for an empty range), or -1 (error latched) if cuts_cap is too small (trow1-trow0+1 always fits). */
+int tsg_plan_slabs(const long long *weights, int trow0, int trow1, int nslabs, int *cuts, int cuts_cap);
+
 /* tsg_spgemm_csr_host with caller-provided output buffers and the overlap above: H2D CSR(A) [CSR(B)],
  * csr2tile x2, then tsg_spgemm_to_host over all tile-rows. */
 int tsg_spgemm_csr_host_into(int m, int k, int n, const int *a_rowptr, const int *a_colidx, const double *a_val,

@@ -339,6 +339,18 @@ def plan_slabs(weights: np.ndarray, max_pairs: int):
     return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
 
 
+def plan_to_host_slabs(weights: np.ndarray, nslabs: int = 0, trow0: int = 0, trow1: int = -1):
+    """The slab boundaries tsg_spgemm_to_host would use for these step-1 weights (host-only: tsg_plan_slabs)."""
+    w = np.ascontiguousarray(weights, dtype=np.int64)
+    if trow1 < 0:
+        trow1 = len(w)
+    cuts = np.zeros(max(trow1 - trow0, 0) + 2, np.int32)
+    n = L.load().tsg_plan_slabs(_p(w, C.c_longlong), int(trow0), int(trow1), int(nslabs), _p(cuts, C.c_int), int(cuts.size))
+    if n < 0:
+        L.check()
+    return [int(x) for x in cuts[:n + 1]] if n > 0 else []
+
+
 def spgemm_slabs(a: DeviceTiled, b: DeviceTiled, max_pairs: int = 1 << 28, sink=None, trow0: int = 0, trow1: int = -1,
                  weights: np.ndarray | None = None):
     """Steps 1-3 over tile-rows [trow0, trow1) executed slab by slab with a bounded device footprint

@@ -604,16 +604,32 @@ static void plan_slabs(const long long *w, int r0, int r1, int nslabs, std::vect
     if (nslabs <= 0 && S > 16) S = 16;
     const long long max_pairs = 1ll << 28;
     if (S < (total + max_pairs - 1) / max_pairs) S = (total + max_pairs - 1) / max_pairs;
+    if (S > r1 - r0) S = r1 - r0;  // more slabs than tile-rows means one per row
     if (S < 1) S = 1;
-    const long long target = (total + S - 1) / S;
     cuts.clear();
     cuts.push_back(r0);
-    long long acc = 0;
+    long long acc = 0, done = 0, k = 1;  // slab k ends with the tile-row that takes the running total past k/S of the total
     for (int i = r0; i < r1; i++) {
-        if (acc > 0 && acc + w[i] > target) { cuts.push_back(i); acc = 0; }
+        if (acc > 0 && acc + w[i] > max_pairs) { cuts.push_back(i); acc = 0; }  // hard bound (a heavier single row stands alone)
         acc += w[i];
+        done += w[i];
+        if (i + 1 < r1 && total > 0 && (__int128)done * S >= (__int128)k * total) {
+            cuts.push_back(i + 1);
+            acc = 0;
+            k = (long long)((__int128)done * S / total) + 1;
+        }
     }
     if (r1 > r0) cuts.push_back(r1);
+}
+
+int tsg_plan_slabs(const long long *weights, int trow0, int trow1, int nslabs, int *cuts, int cuts_cap)
+{
+    if (!weights || !cuts || trow0 < 0 || trow1 < trow0) { set_error(TSG_ERR_INPUT, "plan_slabs: bad arguments"); return -1; }
+    std::vector<int> c;
+    plan_slabs(weights, trow0, trow1, nslabs, c);
+    if ((int)c.size() > cuts_cap) { set_error(TSG_ERR_NOMEM, "plan_slabs: %zu boundaries, room for %d", c.size(), cuts_cap); return -1; }
+    for (size_t i = 0; i < c.size(); i++) cuts[i] = c[i];
+    return (int)c.size() - 1;
 }
 
 static int landing_init()

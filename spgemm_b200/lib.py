@@ -19,7 +19,7 @@ EXPORTS = [
     "tsg_csr_upload", "tsg_csr_wrap", "tsg_csr_download", "tsg_csr_free", "tsg_csr_validate",
     "tsg_transpose", "tsg_nnzcub", "tsg_csr2tile", "tsg_tile_upload", "tsg_tile_download", "tsg_tile_alloc",
     "tsg_tile_free", "tsg_tilerow_weights", "tsg_spgemm", "tsg_tile2csr", "tsg_tile_rowsums", "tsg_spgemm_csr_host",
-    "tsg_spgemm_to_host", "tsg_spgemm_csr_host_into",
+    "tsg_spgemm_to_host", "tsg_spgemm_csr_host_into", "tsg_plan_slabs",
 ]
 
 

@@ -98,3 +98,30 @@ def test_slab_planner():
     assert (100, 101) in slabs or any(t0 <= 100 < t1 and int(w[t0:t1].sum()) - 50000 <= 4000 for t0, t1 in slabs)
     assert api.plan_slabs(np.zeros(5, np.int64), 10) == [(0, 5)]
     assert api.plan_slabs(np.zeros(0, np.int64), 10) == []
+
+
+def test_c_slab_planner_of_the_overlapped_copy_out():
+    """tsg_plan_slabs (host-only part of tsg_spgemm_to_host): ascending boundaries covering the range, slabs of about
+    equal weight, never more than 2^28 pairs unless a single tile-row is heavier, default <= 16 slabs of >= 2^20 pairs."""
+    from spgemm_b200 import api
+    rng = np.random.default_rng(3)
+    w = rng.integers(0, 5000, 3000).astype(np.int64)
+    for nslabs in (1, 2, 7, 16, 100):
+        cuts = api.plan_to_host_slabs(w, nslabs)
+        assert cuts[0] == 0 and cuts[-1] == len(w) and all(b > a for a, b in zip(cuts[:-1], cuts[1:]))
+        sums = [int(w[a:b].sum()) for a, b in zip(cuts[:-1], cuts[1:])]
+        target = -(-int(w.sum()) // nslabs)
+        assert max(sums) <= target + int(w.max()) and len(sums) <= nslabs
+    assert api.plan_to_host_slabs(w, 0) == [0, len(w)] or len(api.plan_to_host_slabs(w, 0)) - 1 <= 16   # 7.5e6 pairs: >= 2^20 each
+    assert len(api.plan_to_host_slabs(w, 0)) - 1 == min(16, int(w.sum()) >> 20) or int(w.sum()) < (1 << 20)
+    # sub-range, absolute indices
+    cuts = api.plan_to_host_slabs(w, 4, 100, 900)
+    assert cuts[0] == 100 and cuts[-1] == 900
+    # a tile-row heavier than 2^28 pairs gets a slab of its own; everything else stays within the bound
+    big = np.array([10, 1 << 29, 10, 1 << 27, 1 << 27, 1 << 27, 5], np.int64)
+    cuts = api.plan_to_host_slabs(big, 1)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        assert int(big[a:b].sum()) <= (1 << 28) or b - a == 1 or int(big[a:b].sum()) - int(big[a:b].max()) < (1 << 28)
+    assert len(cuts) - 1 >= 3
+    assert api.plan_to_host_slabs(np.zeros(5, np.int64), 0) == [0, 5]
+    assert api.plan_to_host_slabs(np.zeros(0, np.int64), 0) == []
