@@ -842,8 +842,14 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     if (trow0 > trow1) trow0 = trow1;
     const int ntr = trow1 - trow0;
     const long long launches0 = c.launches;
-    cudaEvent_t ev[5];
-    for (int k = 0; k < 5; k++) CK(cudaEventCreate(&ev[k]));
+    // timing events of this call; destroyed on every return path (errors included)
+    struct Events {
+        cudaEvent_t e[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+    } evs;
+    for (int k = 0; k < 7; k++) CK(cudaEventCreate(&evs.e[k]));
+    cudaEvent_t *ev = evs.e;
+    const cudaEvent_t ev_s2 = evs.e[5], ev_s3 = evs.e[6];
     CK(cudaEventRecord(ev[0], c.stream));
 
     // ---------------- step 1 ----------------
@@ -952,8 +958,6 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     }
 
     // ---------------- step 2 ----------------
-    cudaEvent_t ev_s2;
-    CK(cudaEventCreate(&ev_s2));
     CK(cudaEventRecord(ev_s2, c.stream));
     // pair-based symbolic for the C tiles the fused step-1 path did not cover: half-warp per tile, or thread per
     // tile when the tiles are hypersparse (<= 2 pairs per C tile and <= 2 entries per A tile on average)
@@ -993,8 +997,6 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         C->val = (double *)base; C->col = (uint16_t *)(base + o_c);
         C->nnz = nnzC;
     }
-    cudaEvent_t ev_s3;
-    CK(cudaEventCreate(&ev_s3));
     CK(cudaEventRecord(ev_s3, c.stream));
     // numeric kernel: the dense accumulator (warp per C tile) when tiles are well filled -- A tiles hold >= 24
     // nonzeros on average (block-FEM: 96) -- else the gather (lane per C nonzero). TSG_STEP3=dense|gather overrides.
@@ -1066,8 +1068,6 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         long long bytesC = nnzC * 10 + numblkC * 76 + ((long long)ntr + 1) * 4;
         stats->algorithmic_bytes = bytesA + bytesB + bytesC;
     }
-    for (int k = 0; k < 5; k++) cudaEventDestroy(ev[k]);
-    cudaEventDestroy(ev_s2); cudaEventDestroy(ev_s3);
     return TSG_OK;
 }
 
