@@ -87,7 +87,8 @@ void csr2tile_col_major(SMatrix *matrix, int tile_size_m, int tile_size_n);
  * device. The dense tile bitmaps (src/main.cu:195-232) are accepted and ignored; pass NULL/0.
  * Fills C->{m,n,tilem,tilen,numtile,nnz,tile_ptr,tile_columnidx,tile_nnz,tile_csr_Value,
  * tile_csr_Col,tile_csr_Ptr} as the reference does (:2750-2775) plus C->mask and C->tile_rowidx.
- * Empty C tiles are kept with Ptr = mask = 0. *gflops_tile =
+ * Empty C tiles are kept with Ptr = mask = 0. A->mask / B->mask may be NULL
+ * (tiles built elsewhere): the row masks are then rebuilt on the device from Ptr / Col. *gflops_tile =
  * 2*nnzCub/(ms*1e6), *compression_rate = nnzCub/nnzC, times in ms (:2804-2808). */
 void tilespgemm(SMatrix *matrixA, SMatrix *matrixB, SMatrix *matrixC,
                 unsigned int *blk_intersec_bitmask_A, unsigned int *blk_intersec_bitmask_B,
