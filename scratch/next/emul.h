@@ -34,6 +34,7 @@ template <typename T> static inline T atomicCAS(T *p, T cmp, T val) { T old = *p
 template <typename T> static inline T atomicAdd(T *p, T v) { T old = *p; *p = old + v; return old; }
 template <typename T> static inline T atomicExch(T *p, T v) { T old = *p; *p = v; return old; }
 template <typename T> static inline T atomicMax(T *p, T v) { T old = *p; if (v > old) *p = v; return old; }
+template <typename T> static inline T atomicMin(T *p, T v) { T old = *p; if (v < old) *p = v; return old; }
 
 // LAUNCH(kernel, blocks, threads, args...): every thread of every block, serially
 #define LAUNCH(kern, nblocks, nthreads, ...)                                                   \

@@ -1,12 +1,13 @@
 // plans.cuh -- DRAFT for round 2: recipe-cached symbolic + numeric steps.
 // Not compiled into libtilespgemm_b200.so and not yet run on a GPU. The index logic is checked on the host by
 // scratch/next/test_plans_emul.py (serial emulation through emul.h, bit-exact against the oracle); `nvcc -c` of
-// plans_compile_check.cu checks that it is valid CUDA for sm_100a. What the emulation cannot check is the concurrent
-// behaviour of the two hash-table insert protocols (k_pattern_ids, k_recipe_ids).
+// plans_compile_check.cu checks that it is valid CUDA for sm_100a. The deduplication never makes a thread wait for another
+// (insert = one atomicCAS on the key word, owner = atomicMin, full-key verification in a second kernel), so what the
+// emulation leaves unchecked is performance, not protocol.
 //
 // Pipeline (after step 1 has produced the pair lists, with its fused symbolic switched off):
-//   k_pattern_ids   tile -> pattern id: the 32-byte block of 16 row masks, deduplicated in a device hash table (full compare)
-//   k_recipe_ids    C tile -> recipe id: the sequence of (A pattern, B pattern) over its pairs, deduplicated likewise
+//   k_pattern_insert / _verify   tile -> pattern id: the 32-byte block of 16 row masks, deduplicated through a device hash table
+//   k_recipe_insert / _flags / _reps / _verify   C tile -> recipe id: the sequence of (A pattern, B pattern) over its pairs
 //   k_plan_build    one thread per distinct recipe, from a representative C tile: the tile's masks / Ptr / nnz and, per C
 //                   nonzero in storage order, the (pair, position in A's tile, position in B's tile) sources in the serial
 //                   SPA's order (ascending pair, then ascending k)   [count pass, scan, fill pass]
@@ -41,80 +42,110 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long h, unsign
     return h;
 }
 
-// state[slot]: 0 empty, 1 being written, 2 ready. blk: two uint4 per slot (the 16 row masks).
+// ---- deduplication without waiting: (1) insert the 64-bit hash with one atomicCAS on the key word, (2) the smallest item
+// index that landed in a slot becomes its owner (atomicMin: deterministic), (3) every item compares its full key with
+// the owner's; a true 64-bit collision raises *fail (the generic kernels then run instead). No thread ever waits for another.
+constexpr int NO_OWNER = 0x7fffffff;
+
+__device__ __forceinline__ int table_insert(unsigned long long *keys, int cap, unsigned long long h, int *count, int limit, int *fail)
+{
+    if (h == 0ull) h = 1ull;  // 0 marks an empty slot
+    unsigned slot = (unsigned)(h >> 20) & (unsigned)(cap - 1);
+    for (int probe = 0; probe < cap; probe++, slot = (slot + 1) & (unsigned)(cap - 1)) {
+        if (*(volatile int *)fail) return -1;
+        const unsigned long long old = atomicCAS(&keys[slot], 0ull, h);
+        if (old == 0ull) {
+            if (atomicAdd(count, 1) >= limit) *fail = 1;
+            return (int)slot;
+        }
+        if (old == h) return (int)slot;
+    }
+    *fail = 1;
+    return -1;
+}
+
+// Tiles of A (index t) and of B (index numtileA + t) share one table: `first` is 0 for A's launch, numtileA for B's.
 __global__ void __launch_bounds__(256)
-k_pattern_ids(int numtile, const uint16_t *__restrict__ mask, unsigned *state, uint4 *blk, int *count, int *__restrict__ pat_id,
-              int *fail)
+k_pattern_insert(int numtile, int first, const uint16_t *__restrict__ mask, unsigned long long *keys, int *owner, int *count,
+                 int *__restrict__ pat_id, int *fail)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= numtile) return;
-    pat_id[t] = -1;
     const uint4 *mp = reinterpret_cast<const uint4 *>(mask + (size_t)t * TS);
     const uint4 x = mp[0], y = mp[1];
     unsigned long long h = 0x243F6A8885A308D3ull;
     h = mix64(h, ((unsigned long long)x.x << 32) | x.y); h = mix64(h, ((unsigned long long)x.z << 32) | x.w);
     h = mix64(h, ((unsigned long long)y.x << 32) | y.y); h = mix64(h, ((unsigned long long)y.z << 32) | y.w);
-    unsigned slot = (unsigned)h & (PCAP - 1);
-    for (int probe = 0; probe < PCAP; probe++, slot = (slot + 1) & (PCAP - 1)) {
-        if (*(volatile int *)fail) return;
-        unsigned st = atomicCAS(&state[slot], 0u, 1u);
-        if (st == 0u) {
-            blk[2 * slot] = x; blk[2 * slot + 1] = y;
-            __threadfence();
-            atomicExch(&state[slot], 2u);
-            if (atomicAdd(count, 1) >= PCAP / 2) *fail = 1;
-            pat_id[t] = (int)slot;
-            return;
-        }
-        while (st == 1u) st = *(volatile unsigned *)&state[slot];
-        __threadfence();
-        const uint4 a = LD_CG(&blk[2 * slot]), b = LD_CG(&blk[2 * slot + 1]);
-        if (a.x == x.x && a.y == x.y && a.z == x.z && a.w == x.w && b.x == y.x && b.y == y.y && b.z == y.z && b.w == y.w) {
-            pat_id[t] = (int)slot;
-            return;
-        }
-    }
-    *fail = 1;
+    const int slot = table_insert(keys, PCAP, h, count, PCAP / 2, fail);
+    pat_id[t] = slot;
+    if (slot >= 0) atomicMin(&owner[slot], first + t);
 }
 
-// rhash / rrep / rdense per slot: hash of the sequence, representative C tile, dense recipe number.
 __global__ void __launch_bounds__(256)
-k_recipe_ids(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end, const int *__restrict__ pair_a,
-             const int *__restrict__ pair_b, const int *__restrict__ patA, const int *__restrict__ patB, unsigned *state,
-             unsigned long long *rhash, int *rrep, int *rdense, int *count, int *__restrict__ recipe_id, int *rep_tile, int *fail)
+k_pattern_verify(int numtile, const uint16_t *__restrict__ mask, const int *__restrict__ pat_id, const int *__restrict__ owner,
+                 int numtileA, const uint16_t *__restrict__ a_mask, const uint16_t *__restrict__ b_mask, int *fail)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= numtile) return;
+    const int slot = pat_id[t];
+    if (slot < 0) { *fail = 1; return; }
+    const int o = owner[slot];
+    const uint4 *op = reinterpret_cast<const uint4 *>(o < numtileA ? a_mask + (size_t)o * TS : b_mask + (size_t)(o - numtileA) * TS);
+    const uint4 *mp = reinterpret_cast<const uint4 *>(mask + (size_t)t * TS);
+    const uint4 x = mp[0], y = mp[1], a = op[0], b = op[1];
+    if (!(a.x == x.x && a.y == x.y && a.z == x.z && a.w == x.w && b.x == y.x && b.y == y.y && b.z == y.z && b.w == y.w)) *fail = 2;
+}
+
+// Recipe of a C tile = the (A pattern, B pattern) sequence of its pairs.
+__global__ void __launch_bounds__(256)
+k_recipe_insert(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end, const int *__restrict__ pair_a,
+                const int *__restrict__ pair_b, const int *__restrict__ patA, const int *__restrict__ patB,
+                unsigned long long *keys, int *owner, int *count, int *__restrict__ rslot, int *fail)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= numblkC) return;
-    recipe_id[t] = -1;
+    rslot[t] = -1;
     const int p0 = pair_ptr[t], p1 = pair_end[t];
     if (p1 - p0 > 0xFFFF) { *fail = 1; return; }  // the plan entry keeps the pair index in 16 bits
     unsigned long long h = mix64(0x13198A2E03707344ull, (unsigned long long)(p1 - p0));
     for (int p = p0; p < p1; p++) h = mix64(h, ((unsigned long long)(unsigned)patA[pair_a[p]] << 32) | (unsigned)patB[pair_b[p]]);
-    unsigned slot = (unsigned)h & (RCAP - 1);
-    for (int probe = 0; probe < RCAP; probe++, slot = (slot + 1) & (RCAP - 1)) {
-        if (*(volatile int *)fail) return;
-        unsigned st = atomicCAS(&state[slot], 0u, 1u);
-        if (st == 0u) {
-            const int d = atomicAdd(count, 1);
-            rhash[slot] = h; rrep[slot] = t; rdense[slot] = d;
-            if (d >= RCAP / 2) *fail = 1; else rep_tile[d] = t;
-            __threadfence();
-            atomicExch(&state[slot], 2u);
-            recipe_id[t] = d;
-            return;
-        }
-        while (st == 1u) st = *(volatile unsigned *)&state[slot];
-        __threadfence();
-        if (LD_CG(&rhash[slot]) != h) continue;
-        const int u = LD_CG(&rrep[slot]);
-        const int q0 = pair_ptr[u];
-        if (pair_end[u] - q0 != p1 - p0) continue;
-        bool same = true;
-        for (int i = 0; i < p1 - p0 && same; i++)
-            same = patA[pair_a[p0 + i]] == patA[pair_a[q0 + i]] && patB[pair_b[p0 + i]] == patB[pair_b[q0 + i]];
-        if (same) { recipe_id[t] = LD_CG(&rdense[slot]); return; }
-    }
-    *fail = 1;
+    const int slot = table_insert(keys, RCAP, h, count, RCAP / 2, fail);
+    rslot[t] = slot;
+    if (slot >= 0) atomicMin(&owner[slot], t);
+}
+
+// flags[slot] = 1 where the slot has an owner; the caller scans them into dense recipe numbers (rdense).
+__global__ void __launch_bounds__(256)
+k_recipe_flags(const int *__restrict__ owner, int *__restrict__ flags)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < RCAP) flags[s] = owner[s] != NO_OWNER;
+}
+
+__global__ void __launch_bounds__(256)
+k_recipe_reps(const int *__restrict__ owner, const int *__restrict__ rdense, int *__restrict__ rep_tile)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < RCAP && owner[s] != NO_OWNER) rep_tile[rdense[s]] = owner[s];
+}
+
+__global__ void __launch_bounds__(256)
+k_recipe_verify(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end, const int *__restrict__ pair_a,
+                const int *__restrict__ pair_b, const int *__restrict__ patA, const int *__restrict__ patB,
+                const int *__restrict__ rslot, const int *__restrict__ owner, const int *__restrict__ rdense,
+                int *__restrict__ recipe_id, int *fail)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= numblkC) return;
+    const int slot = rslot[t];
+    if (slot < 0) { *fail = 1; return; }
+    const int u = owner[slot];
+    const int p0 = pair_ptr[t], n = pair_end[t] - p0, q0 = pair_ptr[u];
+    bool same = pair_end[u] - q0 == n;
+    for (int i = 0; i < n && same; i++)
+        same = patA[pair_a[p0 + i]] == patA[pair_a[q0 + i]] && patB[pair_b[p0 + i]] == patB[pair_b[q0 + i]];
+    if (!same) *fail = 2;
+    recipe_id[t] = rdense[slot];
 }
 
 // One thread per distinct recipe. FILL = false: masks / Ptr / nnz of the recipe's C tile and the number of plan entries

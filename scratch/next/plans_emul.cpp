@@ -19,19 +19,28 @@ extern "C" int emul_plans(int numtileA, const uint16_t *a_mask, const uint16_t *
                           uint16_t *c_mask, uint16_t *c_ptr, int *c_tile_nnz, uint16_t *c_col, double *c_val, long long nnz_cap,
                           long long *info)
 {
-    std::vector<unsigned> pstate(PCAP, 0u), rstate(RCAP, 0u);
-    std::vector<uint4> pblk(2 * PCAP);
-    std::vector<unsigned long long> rhash(RCAP);
-    std::vector<int> rrep(RCAP), rdense(RCAP), rep_tile(RCAP / 2), patA(numtileA > 0 ? numtileA : 1), patB(numtileB > 0 ? numtileB : 1),
-        recipe_id(numblkC > 0 ? numblkC : 1);
-    int npat = 0, nrec = 0, fail = 0;
+    std::vector<unsigned long long> pkeys(PCAP, 0ull), rkeys(RCAP, 0ull);
+    std::vector<int> powner(PCAP, NO_OWNER), rowner(RCAP, NO_OWNER), rflags(RCAP + 1, 0), rdense(RCAP + 1, 0), rep_tile(RCAP / 2 + 1),
+        patA(numtileA > 0 ? numtileA : 1), patB(numtileB > 0 ? numtileB : 1), rslot(numblkC > 0 ? numblkC : 1), recipe_id(numblkC > 0 ? numblkC : 1);
+    int npat = 0, nrec_seen = 0, fail = 0;
 
-    if (numtileA) LAUNCH(k_pattern_ids, ceil_div(numtileA, 256), 256, numtileA, a_mask, pstate.data(), pblk.data(), &npat, patA.data(), &fail);
-    if (numtileB) LAUNCH(k_pattern_ids, ceil_div(numtileB, 256), 256, numtileB, b_mask, pstate.data(), pblk.data(), &npat, patB.data(), &fail);
+    if (numtileA) LAUNCH(k_pattern_insert, ceil_div(numtileA, 256), 256, numtileA, 0, a_mask, pkeys.data(), powner.data(), &npat, patA.data(), &fail);
+    if (numtileB) LAUNCH(k_pattern_insert, ceil_div(numtileB, 256), 256, numtileB, numtileA, b_mask, pkeys.data(), powner.data(), &npat, patB.data(), &fail);
+    if (fail) return 1;
+    if (numtileA) LAUNCH(k_pattern_verify, ceil_div(numtileA, 256), 256, numtileA, a_mask, patA.data(), powner.data(), numtileA, a_mask, b_mask, &fail);
+    if (numtileB) LAUNCH(k_pattern_verify, ceil_div(numtileB, 256), 256, numtileB, b_mask, patB.data(), powner.data(), numtileA, a_mask, b_mask, &fail);
     if (fail) return 1;
     if (numblkC)
-        LAUNCH(k_recipe_ids, ceil_div(numblkC, 256), 256, numblkC, pair_ptr, pair_end, pair_a, pair_b, patA.data(), patB.data(),
-               rstate.data(), rhash.data(), rrep.data(), rdense.data(), &nrec, recipe_id.data(), rep_tile.data(), &fail);
+        LAUNCH(k_recipe_insert, ceil_div(numblkC, 256), 256, numblkC, pair_ptr, pair_end, pair_a, pair_b, patA.data(), patB.data(),
+               rkeys.data(), rowner.data(), &nrec_seen, rslot.data(), &fail);
+    if (fail) return 1;
+    LAUNCH(k_recipe_flags, ceil_div(RCAP, 256), 256, rowner.data(), rflags.data());
+    int nrec = 0;
+    for (int s = 0; s < RCAP; s++) { rdense[s] = nrec; nrec += rflags[s]; }                   // device: exclusive_scan
+    LAUNCH(k_recipe_reps, ceil_div(RCAP, 256), 256, rowner.data(), rdense.data(), rep_tile.data());
+    if (numblkC)
+        LAUNCH(k_recipe_verify, ceil_div(numblkC, 256), 256, numblkC, pair_ptr, pair_end, pair_a, pair_b, patA.data(), patB.data(),
+               rslot.data(), rowner.data(), rdense.data(), recipe_id.data(), &fail);
     if (fail) return 1;
 
     std::vector<uint16_t> plan_mask((size_t)nrec * TS + 1), plan_ptr((size_t)nrec * TS + 1);
