@@ -266,4 +266,50 @@ k_numeric_from_plans(int numblkC, int nnzC, const int *__restrict__ blk2tile, co
     c_col[g] = plan_col[(size_t)R * 256 + off];
 }
 
+// Variant B of the numeric step: the value bases of a pair's two tiles are looked up once per pair by a streaming kernel
+// (k_pair_bases) instead of twice per product through pair_a -> a_tile_nnz / pair_b -> b_tile_nnz.
+struct int2_ { int x, y; };
+
+__global__ void __launch_bounds__(256)
+k_pair_bases(long long npairs, const int *__restrict__ pair_a, const int *__restrict__ pair_b, const int *__restrict__ a_tile_nnz,
+             const int *__restrict__ b_tile_nnz, int2_ *__restrict__ pair_base)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    int2_ v;
+    v.x = a_tile_nnz[pair_a[p]];
+    v.y = b_tile_nnz[pair_b[p]];
+    pair_base[p] = v;
+}
+
+__global__ void __launch_bounds__(256)
+k_numeric_from_plans_b(int numblkC, int nnzC, const int *__restrict__ blk2tile, const int *__restrict__ c_tile_nnz,
+                       const int *__restrict__ recipe_id, const unsigned *__restrict__ plan_start,
+                       const uint8_t *__restrict__ plan_col, const unsigned *__restrict__ plan_ent,
+                       const int *__restrict__ pair_ptr, const int2_ *__restrict__ pair_base, const double *__restrict__ a_val,
+                       const double *__restrict__ b_val, uint16_t *__restrict__ c_col, double *__restrict__ c_val)
+{
+    const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gl >= nnzC) return;
+    const int g = (int)gl;
+    const int blk = g >> 5, nblk = (nnzC + 31) >> 5;
+    int lo = blk2tile[blk], hi = blk + 1 < nblk ? blk2tile[blk + 1] : numblkC - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (c_tile_nnz[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    const int t = lo, off = g - c_tile_nnz[t];
+    const int R = recipe_id[t];
+    const unsigned s1 = plan_start[(size_t)R * PLAN_ROWS + off + 1];
+    const int2_ *pb = pair_base + pair_ptr[t];
+    double acc = 0.0;
+    for (unsigned s = plan_start[(size_t)R * PLAN_ROWS + off]; s < s1; s++) {
+        const unsigned e = plan_ent[s];
+        const int2_ base = pb[e >> 16];
+        acc = fma(a_val[base.x + (int)(e & 255u)], b_val[base.y + (int)((e >> 8) & 255u)], acc);
+    }
+    c_val[g] = acc;
+    c_col[g] = plan_col[(size_t)R * 256 + off];
+}
+
 }  // namespace plans

@@ -2,6 +2,7 @@
 // spgemm_device would do between step 1 (pair lists) and the end of step 3. Built by scratch/next/Makefile into
 // libplans_emul.so and driven by test_plans_emul.py. NOT part of the product.
 #include <stdlib.h>
+#include <string.h>
 #include <vector>
 #include "plans.cuh"
 
@@ -76,5 +77,16 @@ extern "C" int emul_plans(int numtileA, const uint16_t *a_mask, const uint16_t *
         LAUNCH(k_numeric_from_plans, ceil_div(nnzC, 256), 256, numblkC, (int)nnzC, blk2tile.data(), c_tile_nnz, recipe_id.data(),
                plan_start.data(), plan_col.data(), plan_ent.data(), pair_ptr, pair_a, pair_b, a_tile_nnz, a_val, b_tile_nnz, b_val, c_col,
                c_val);
+    // variant B (per-pair value bases) must give the same bits
+    const long long npairs = numblkC ? pair_end[numblkC - 1] : 0;
+    std::vector<int2_> pair_base((size_t)npairs + 1);
+    std::vector<uint16_t> col_b((size_t)nnzC + 1);
+    std::vector<double> val_b((size_t)nnzC + 1);
+    if (npairs) LAUNCH(k_pair_bases, ceil_div(npairs, 256), 256, npairs, pair_a, pair_b, a_tile_nnz, b_tile_nnz, pair_base.data());
+    if (nnzC)
+        LAUNCH(k_numeric_from_plans_b, ceil_div(nnzC, 256), 256, numblkC, (int)nnzC, blk2tile.data(), c_tile_nnz, recipe_id.data(),
+               plan_start.data(), plan_col.data(), plan_ent.data(), pair_ptr, pair_base.data(), a_val, b_val, col_b.data(), val_b.data());
+    for (long long g = 0; g < nnzC; g++)
+        if (col_b[g] != c_col[g] || memcmp(&val_b[g], &c_val[g], sizeof(double))) return 3;
     return 0;
 }
