@@ -53,7 +53,8 @@ __device__ __forceinline__ int table_insert(unsigned long long *keys, int cap, u
     unsigned slot = (unsigned)(h >> 20) & (unsigned)(cap - 1);
     for (int probe = 0; probe < cap; probe++, slot = (slot + 1) & (unsigned)(cap - 1)) {
         if (*(volatile int *)fail) return -1;
-        const unsigned long long old = atomicCAS(&keys[slot], 0ull, h);
+        unsigned long long old = *(volatile unsigned long long *)&keys[slot];  // millions of items, a few dozen hot slots: read first
+        if (old == 0ull) old = atomicCAS(&keys[slot], 0ull, h);
         if (old == 0ull) {
             if (atomicAdd(count, 1) >= limit) *fail = 1;
             return (int)slot;
@@ -78,7 +79,7 @@ k_pattern_insert(int numtile, int first, const uint16_t *__restrict__ mask, unsi
     h = mix64(h, ((unsigned long long)y.x << 32) | y.y); h = mix64(h, ((unsigned long long)y.z << 32) | y.w);
     const int slot = table_insert(keys, PCAP, h, count, PCAP / 2, fail);
     pat_id[t] = slot;
-    if (slot >= 0) atomicMin(&owner[slot], first + t);
+    if (slot >= 0 && first + t < *(volatile int *)&owner[slot]) atomicMin(&owner[slot], first + t);  // owner only ever decreases
 }
 
 __global__ void __launch_bounds__(256)
@@ -111,7 +112,7 @@ k_recipe_insert(int numblkC, const int *__restrict__ pair_ptr, const int *__rest
     for (int p = p0; p < p1; p++) h = mix64(h, ((unsigned long long)(unsigned)patA[pair_a[p]] << 32) | (unsigned)patB[pair_b[p]]);
     const int slot = table_insert(keys, RCAP, h, count, RCAP / 2, fail);
     rslot[t] = slot;
-    if (slot >= 0) atomicMin(&owner[slot], t);
+    if (slot >= 0 && t < *(volatile int *)&owner[slot]) atomicMin(&owner[slot], t);
 }
 
 // flags[slot] = 1 where the slot has an owner; the caller scans them into dense recipe numbers (rdense).
