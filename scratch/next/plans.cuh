@@ -45,7 +45,7 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long h, unsign
 // ---- deduplication without waiting: (1) insert the 64-bit hash with one atomicCAS on the key word, (2) the smallest item
 // index that landed in a slot becomes its owner (atomicMin: deterministic), (3) every item compares its full key with
 // the owner's; a true 64-bit collision raises *fail (the generic kernels then run instead). No thread ever waits for another.
-constexpr int NO_OWNER = 0x7fffffff;
+constexpr int NO_OWNER = 0x7f7f7f7f;  // what cudaMemset(0x7f) leaves; item indices stay below it
 
 __device__ __forceinline__ int table_insert(unsigned long long *keys, int cap, unsigned long long h, int *count, int limit, int *fail)
 {
