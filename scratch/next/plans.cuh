@@ -18,10 +18,7 @@
 #pragma once
 #include <stdint.h>
 #ifndef __CUDACC__
-#include "emul.h"
-#define LD_CG(p) (*(p))
-#else
-#define LD_CG(p) __ldcg(p)
+#include "emul.h"  // scratch/next: serial host emulation of these kernels
 #endif
 
 #ifndef TS
@@ -123,11 +120,12 @@ k_recipe_flags(const int *__restrict__ owner, int *__restrict__ flags)
     if (s < RCAP) flags[s] = owner[s] != NO_OWNER;
 }
 
+// rep_tile holds RCAP/2 entries: inserts that raced past the limit before they saw *fail must not write beyond it
 __global__ void __launch_bounds__(256)
 k_recipe_reps(const int *__restrict__ owner, const int *__restrict__ rdense, int *__restrict__ rep_tile)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < RCAP && owner[s] != NO_OWNER) rep_tile[rdense[s]] = owner[s];
+    if (s < RCAP && owner[s] != NO_OWNER && rdense[s] < RCAP / 2) rep_tile[rdense[s]] = owner[s];
 }
 
 __global__ void __launch_bounds__(256)

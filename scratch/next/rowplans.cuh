@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256)
 k_reps(int cap, const int *__restrict__ owner, const int *__restrict__ dense, int *__restrict__ rep)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < cap && owner[s] != NO_OWNER) rep[dense[s]] = owner[s];
+    if (s < cap && owner[s] != NO_OWNER && dense[s] < cap / 2) rep[dense[s]] = owner[s];  // rep holds cap/2 entries
 }
 
 // One thread per distinct row recipe (representative tile-row x = rep[R], relative to trow0). Per recipe, MAXW-strided:
