@@ -109,12 +109,25 @@ def step3_bytes(tA, tB, st):
             + st["nnzC"] * 10)
 
 
+def numeric_kernels(st):
+    """Names of the numeric (step 3) kernels this workload actually launched (tsg_stats)."""
+    names = []
+    if st.get("rows_staged", 0) > 0:
+        names.append(f"k_step3_rows ({st['rows_staged']} tile-rows, {st['rows_smem']} B smem)")
+    if st.get("tiles_dense", 0) > 0:
+        names.append(f"k_step3_dense ({st['tiles_dense']} tiles)")
+    if st.get("rows_gather", 0) > 0:
+        names.append(f"k_step3_gather ({st['rows_gather']} tile-rows)")
+    return " + ".join(names) if names else "none"
+
+
 def run_reference(args):
     """Reference CPU arm: unmodified spgemm_spa (two-pass protocol) from oracle/_ref on a row sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle as orc, ref
+    orc.set_num_threads()  # torchrun exports OMP_NUM_THREADS=1 to its workers: take every host core back
     gen, aat, desc = WORKLOADS[args.workload]
     m, n, rp, ci, v = gen()
     A = (rp, ci, v)
@@ -126,6 +139,7 @@ def run_reference(args):
     R = min(m, args.ref_rows)
     sample = (rp[:R + 1], ci[:rp[R]], v[:rp[R]])
     products = orc.nnzcub(sample[1], B[0])
+    total_products = orc.nnzcub(ci, B[0])
     kind = "reference" if ref.available() else "port"
     fn = (lambda: ref.spgemm_spa(sample, B, nB)) if kind == "reference" else (lambda: orc.spgemm_spa(sample, B, nB))
     for _ in range(args.warmup):
@@ -136,13 +150,14 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     gf = 2.0 * products / dt / 1e9
     cores = orc.num_threads()
-    sample_desc = (f"rows [0,{R}) of A ({products} products of the workload's {orc.nnzcub(ci, B[0])}) x whole B; "
+    sample_desc = (f"rows [0,{R}) of A ({products} products of the workload's {total_products}) x whole B; "
                    + ("reference spgemm_spa (src/spgemm_serialref_spa_new.h, structure-only, count+fill passes)"
                       if kind == "reference" else "oracle SPA with values"))
     line = {"impl": "reference", "metric": "spgemm_gflops", "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "tile": "16x16", "aat": int(aat)},
+            "config": {"workload": args.workload, "description": desc, "tile": "16x16", "aat": int(aat), "m": m, "n": n,
+                       "nnzA": int(len(ci)), "nnzCub": int(total_products), "sample_fraction": products / max(total_products, 1)},
             "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": sample_desc},
             "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -388,7 +403,7 @@ def run_ours(args):
         "e2e": {"value": 2.0 * nnzCub / (e2e_ms_max * 1e6), "unit": "GFLOP/s", "ms_per_step": e2e_ms_max, "steps": e2e_K,
                 "h2d_bytes_per_step": int(allv[:, 3].sum()), "d2h_bytes_per_step": int(allv[:, 4].sum())},
         "gpu_launches": int(allv[:, 2].sum()),
-        "roofline": {"bound": "hbm", "kernel": "k_step3_gather (numeric)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": numeric_kernels(stats[-1]), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": s3_ms,
                      "algorithmic_bytes_per_launch": s3_bytes},
     }

@@ -169,6 +169,11 @@ typedef struct {
     double ms_step1, ms_step2, ms_step3, ms_alloc, ms_total; /* device time, CUDA events  */
     long long algorithmic_bytes; /* bytes(A)+bytes(B)+bytes(C written)  */
     int launches;             /* kernels launched by this call                       */
+    /* step 3 picks the accumulator per C tile / tile-row (csrc/numeric.cu): */
+    int rows_staged;          /* C tile-rows computed by k_step3_rows (sparse accumulator in shared memory) */
+    int rows_gather;          /* C tile-rows computed by k_step3_gather (lane per nonzero)                  */
+    int tiles_dense;          /* C tiles computed by k_step3_dense (dense accumulator in registers)         */
+    int rows_smem;            /* dynamic shared memory of k_step3_rows, bytes                               */
 } tsg_stats;
 
 /* Select the device (like the driver's cudaSetDevice, reference src/main.cu:49) and create the

@@ -217,3 +217,24 @@ def tilerow_weights(tA: Tiled, tB: Tiled) -> np.ndarray:
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int | None = None) -> int:
+    """OpenMP team size of the oracle (None: every host core). torchrun exports OMP_NUM_THREADS=1 to its workers,
+    which would time the CPU baseline on one core."""
+    lib().orc_set_num_threads(int(n or os.cpu_count() or 1))
+    return num_threads()
+
+
+def spgemm_rowcounts(A, B, nB, row0=0, row1=None) -> np.ndarray:
+    """nnz of every row of C = A*B, rows [row0,row1): the count pass of the SPA only (no C is built)."""
+    rpA, ciA = np.ascontiguousarray(A[0], np.int64), np.ascontiguousarray(A[1], np.int32)
+    rpB, ciB = np.ascontiguousarray(B[0], np.int64), np.ascontiguousarray(B[1], np.int32)
+    mA = rpA.size - 1
+    if row1 is None:
+        row1 = mA
+    out = np.zeros(max(row1 - row0, 0), np.int64)
+    rc = lib().orc_spgemm_rowcounts(int(mA), int(nB), _p(rpA, C.c_int64), _p(ciA, C.c_int), _p(rpB, C.c_int64), _p(ciB, C.c_int),
+                                    int(row0), int(row1), _p(out, C.c_int64))
+    assert rc == 0
+    return out

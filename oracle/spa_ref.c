@@ -30,6 +30,7 @@
 #else
 static int omp_get_max_threads(void) { return 1; }
 static int omp_get_thread_num(void) { return 0; }
+static void omp_set_num_threads(int n) { (void)n; }
 #endif
 
 #define T 16 /* tile edge; src/common.h:36 BLOCK_SIZE, MaskBits = 16 (src/common.h:146) */
@@ -72,6 +73,8 @@ void orc_csr_free(orc_csr *c)
 }
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline legs of bench.py ask for all host cores back */
+void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 static int cmp_int(const void *a, const void *b)
 {
@@ -409,6 +412,51 @@ int orc_spgemm_spa(int mA, int nB, const int64_t *rpA, const int *ciA, const dou
     }
     for (int t = 0; t < nth; t++) free(touch_g[t]);
     free(touch_g); free(tcap); free(flag_g); free(acc_g);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------
+ * Count-only SPA: nnz of every row of C = A*B for rows [row0,row1), the
+ * get_nnzC_only pass of the reference protocol
+ * (src/spgemm_serialref_spa_new.h:29-62; call protocol
+ * src/external/cusparse/main.cu:196-212). Used where C itself is too large to
+ * build on the host (R-MAT scale 20+: nnz(C) ~ 1e10): bench.py compares these
+ * counts and A*(B*1) with the device's per-row counts and sums.
+ * ---------------------------------------------------------------------- */
+int orc_spgemm_rowcounts(int mA, int nB, const int64_t *rpA, const int *ciA, const int64_t *rpB, const int *ciB,
+                         int row0, int row1, int64_t *counts)
+{
+    if (row0 < 0) row0 = 0;
+    if (row1 > mA) row1 = mA;
+    int nth = omp_get_max_threads();
+    char *flag_g = (char *)calloc((size_t)nth * (nB > 0 ? nB : 1), 1);
+    int **touch_g = (int **)calloc(nth, sizeof(int *));
+    size_t *tcap = (size_t *)calloc(nth, sizeof(size_t));
+    if (!flag_g || !touch_g || !tcap) return 1;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = row0; i < row1; i++) {
+        int tid = omp_get_thread_num();
+        char *flag = flag_g + (size_t)tid * nB;
+        size_t cnt = 0;
+        for (int64_t ja = rpA[i]; ja < rpA[i + 1]; ja++) {
+            int k = ciA[ja];
+            for (int64_t jb = rpB[k]; jb < rpB[k + 1]; jb++) {
+                int c = ciB[jb];
+                if (!flag[c]) {
+                    flag[c] = 1;
+                    if (cnt == tcap[tid]) {
+                        tcap[tid] = tcap[tid] ? tcap[tid] * 2 : 1024;
+                        touch_g[tid] = (int *)realloc(touch_g[tid], tcap[tid] * sizeof(int));
+                    }
+                    touch_g[tid][cnt++] = c;
+                }
+            }
+        }
+        for (size_t k = 0; k < cnt; k++) flag[touch_g[tid][k]] = 0;
+        counts[i - row0] = (int64_t)cnt;
+    }
+    for (int t = 0; t < nth; t++) free(touch_g[t]);
+    free(touch_g); free(tcap); free(flag_g);
     return 0;
 }
 

@@ -250,8 +250,8 @@ int tsg_init(int device)
     unsigned long long thresh = ~0ull;  // keep freed blocks cached: no cudaMalloc/cudaFree in steady state
     CK(cudaMemPoolSetAttribute(g_ctx.pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     CK(cudaMalloc(&g_ctx.scan_ticket, 256));
-    CK(cudaMalloc(&g_ctx.d_scalars, 16 * sizeof(long long)));
-    CK(cudaHostAlloc(&g_ctx.h_scalars, 16 * sizeof(long long), cudaHostAllocMapped));
+    CK(cudaMalloc(&g_ctx.d_scalars, 32 * sizeof(long long)));
+    CK(cudaHostAlloc(&g_ctx.h_scalars, 32 * sizeof(long long), cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer(&g_ctx.h_scalars_dev, g_ctx.h_scalars, 0));
     g_ready = true;
     return TSG_OK;
@@ -681,6 +681,8 @@ int tsg_spgemm_to_host(const tsg_dtile *a, const tsg_dtile *b, int trow0, int tr
             stats->ms_alloc += st.ms_alloc; stats->ms_total += st.ms_total; stats->numblkC += st.numblkC;
             stats->nnzC += st.nnzC; stats->pairs += st.pairs; stats->launches += st.launches;
             stats->algorithmic_bytes += st.algorithmic_bytes;
+            stats->rows_staged += st.rows_staged; stats->rows_gather += st.rows_gather; stats->tiles_dense += st.tiles_dense;
+            if (st.rows_smem > stats->rows_smem) stats->rows_smem = st.rows_smem;
         }
         const long long nz = tC.nnz;
         const int rows = tC.m;

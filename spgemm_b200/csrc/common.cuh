@@ -36,9 +36,9 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr;
     struct Landing { char *p = nullptr; size_t cap = 0; cudaEvent_t ready = nullptr, copied = nullptr; bool busy = false; } land[2];
     // small pinned host scratch for scalar read-backs
-    long long *h_scalars = nullptr;   // pinned + mapped, 16 slots
+    long long *h_scalars = nullptr;   // pinned + mapped, 32 slots
     long long *h_scalars_dev = nullptr;  // the same memory as the device sees it
-    long long *d_scalars = nullptr;   // device, 16 slots
+    long long *d_scalars = nullptr;   // device, 32 slots
 };
 
 Ctx &ctx();

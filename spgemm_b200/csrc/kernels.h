@@ -16,6 +16,18 @@ int tilerow_weights_device(const tsg_dtile *A, const tsg_dtile *B, int **d_w, in
 int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, tsg_dtile *C, tsg_stats *stats);
 int build_rm2csc_device(tsg_dtile *B);
 
+// numeric.cu (step 3)
+struct PairLists { const int *ptr, *end, *a, *b; };  // pairs of C tile t: (a[p], b[p]) for p in [ptr[t], end[t]); b = storage id of the B tile
+struct NumericBufs {
+    uint8_t *row_kind;  // [ntr]     which kernel computes the (non-dense) tiles of each C tile-row
+    int *dense_list;    // [numblkC] C tiles that take the dense accumulator
+    int dense_th, smem_cap;
+};
+size_t numeric_scratch_bytes(int ntr, long long numblkC);
+int numeric_classify_device(const tsg_dtile *A, const tsg_dtile *C, int trow0, int ntr, const int *wptr, NumericBufs *nb, int *d_ns);
+int numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, int trow0, int ntr, const int *wptr, const PairLists &pl,
+                   const NumericBufs &nb, const int *h_ns, bool heavy_rows, tsg_stats *stats);
+
 // tile2csr.cu
 int tile2csr_device(const tsg_dtile *T, tsg_dcsr *out);
 int tile2csr_into(const tsg_dtile *T, int *rowptr, int *colidx, double *val, int base);

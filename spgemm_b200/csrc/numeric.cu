@@ -1,0 +1,657 @@
+// numeric.cu -- TileSpGEMM step 3 (numeric) on B200. Replaces the reference's
+// tile_spgemm_step4_cuda_kernel_smem_v3[_halfwarp] / _dns_noatomic_halfwarp (src/tilespgemm-cuda.h:1273-2218)
+// and the binning that selects between them (:711-735, launches :2650-2728).
+//
+// The accumulator is chosen PER C TILE from its nonzero count (BASELINE north_star), and per C tile-row from what
+// fits shared memory:
+//   * k_step3_rows   -- sparse accumulator in SHARED MEMORY. One CTA per C tile-row. The tile-row's share of A
+//                       (row masks, row pointers, values -- contiguous in A's row-major tile order), C's symbolic
+//                       result (masks, row pointers) and the tile-row's pair lists are staged into shared memory
+//                       with cp.async.bulk (TMA bulk copies, one mbarrier) and plain coalesced loads; one thread
+//                       owns one non-empty ROW of one C tile and walks the tile's pairs once: A's row mask gives
+//                       the k's, B's row k (mask + Ptr + values, read through L1) gives the products, each added
+//                       to the row's compact accumulator in shared memory in the serial SPA's order (ascending A
+//                       tile, then k). The finished tile-row leaves with coalesced stores. Every product is
+//                       computed once and nothing is searched: ~20 thread-instructions per product where the
+//                       lane-per-nonzero gather needs ~115.
+//   * k_step3_dense  -- dense accumulator in REGISTERS for well-filled C tiles (nnz >= dense_th), warp per tile,
+//                       over a compacted list of those tiles.  k_step3_dmma: its FP64 tensor-core variant, opt-in.
+//   * k_step3_gather -- lane per C nonzero, register accumulation: C tile-rows that do not fit shared memory
+//                       (R-MAT hub rows) or whose tiles are hypersparse (R-MAT: ~1 nonzero per tile, 15/16 of
+//                       the listed tiles empty), where walking (tile, row) slots would be mostly wasted.
+// All three add the contributions of a C entry in the same order, so values do not depend on the selection.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tsg {
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + bulk-copy helpers (PTX; SASS: SYNCS.*, UBLKCP)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(void *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// global -> shared bulk copy; dst, src 16-byte aligned, bytes a positive multiple of 16
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, void *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Classification. Row kinds: what computes the (non-dense) tiles of a C tile-row.
+// ---------------------------------------------------------------------------------------------
+enum : uint8_t { ROW_NONE = 0, ROW_STAGED = 1, ROW_GATHER = 2 };
+enum { NS_MAXNEED = 0, NS_ROWS_STAGED = 1, NS_ROWS_GATHER = 2, NS_DENSE = 3, NS_GLO = 4, NS_GHI = 5 };
+
+__host__ __device__ __forceinline__ size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// shared-memory bytes k_step3_rows needs for one tile-row (must match the carve-up in the kernel)
+__host__ __device__ __forceinline__ size_t s3r_need(int nA, int nnzA, int numJ, int nnzC, int W)
+{
+    return 2 * al16((size_t)nA * 32) + al16(((size_t)nnzA + 2) * 8) + 2 * al16((size_t)numJ * 32) + al16((size_t)nnzC * 8) +
+           al16(((size_t)nA + 1) * 4) + al16(((size_t)numJ + 1) * 4) + 2 * al16((size_t)numJ * 4) + 2 * al16((size_t)W * 4) +
+           al16((size_t)nnzC * 2);
+}
+
+__global__ void k_ns_init(int *scal)
+{
+    if (threadIdx.x < 8) scal[threadIdx.x] = threadIdx.x == NS_GLO ? 0x7fffffff : 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_s3_classify_rows(int ntr, int trow0, const int *__restrict__ a_tile_ptr, const int *__restrict__ a_tile_nnz,
+                   const int *__restrict__ c_tile_ptr, const int *__restrict__ c_tile_nnz, const int *__restrict__ wptr,
+                   int smem_cap, int min_fill, int force_kind, uint8_t *__restrict__ row_kind, int *__restrict__ scal)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint8_t kind = ROW_NONE;
+    int need = 0, n0 = 0x7fffffff, n1 = 0;
+    if (i < ntr) {
+        const int c0 = c_tile_ptr[i], c1 = c_tile_ptr[i + 1], numJ = c1 - c0;
+        if (numJ > 0) {
+            n0 = c_tile_nnz[c0]; n1 = c_tile_nnz[c1];
+            const int nnzC = n1 - n0;
+            if (nnzC > 0) {
+                const int a0 = a_tile_ptr[trow0 + i], a1 = a_tile_ptr[trow0 + i + 1];
+                const size_t nb = s3r_need(a1 - a0, a_tile_nnz[a1] - a_tile_nnz[a0], numJ, nnzC, wptr[i + 1] - wptr[i]);
+                const bool fits = nb <= (size_t)smem_cap && (long long)nnzC >= (long long)min_fill * numJ;
+                kind = force_kind ? (uint8_t)force_kind : (fits ? ROW_STAGED : ROW_GATHER);
+                if (kind == ROW_STAGED && nb > (size_t)smem_cap) kind = ROW_GATHER;  // a forced choice still has to fit
+                need = kind == ROW_STAGED ? (int)nb : 0;
+            }
+        }
+        row_kind[i] = kind;
+    }
+    const unsigned ms = __ballot_sync(FULL_MASK, kind == ROW_STAGED), mg = __ballot_sync(FULL_MASK, kind == ROW_GATHER);
+    if (kind != ROW_GATHER) { n0 = 0x7fffffff; n1 = 0; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        need = max(need, __shfl_xor_sync(FULL_MASK, need, o));
+        n0 = min(n0, __shfl_xor_sync(FULL_MASK, n0, o));
+        n1 = max(n1, __shfl_xor_sync(FULL_MASK, n1, o));
+    }
+    if (lane == 0) {
+        if (ms) { atomicAdd(&scal[NS_ROWS_STAGED], __popc(ms)); atomicMax(&scal[NS_MAXNEED], need); }
+        if (mg) { atomicAdd(&scal[NS_ROWS_GATHER], __popc(mg)); atomicMin(&scal[NS_GLO], n0); atomicMax(&scal[NS_GHI], n1); }
+    }
+}
+
+// compacted list of the C tiles that take the dense accumulator (order irrelevant: tiles are independent)
+__global__ void __launch_bounds__(256)
+k_s3_classify_tiles(int numblkC, const int *__restrict__ c_tile_nnz, int dense_th, int *__restrict__ dense_list,
+                    int *__restrict__ scal)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool dense = t < numblkC && c_tile_nnz[t + 1] - c_tile_nnz[t] >= dense_th;
+    const unsigned m = __ballot_sync(FULL_MASK, dense);
+    if (!m) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&scal[NS_DENSE], __popc(m));
+    base = __shfl_sync(FULL_MASK, base, 0);
+    if (dense) dense_list[base + __popc(m & ((1u << lane) - 1))] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_step3_rows: sparse accumulator in shared memory, CTA per C tile-row (see the file header).
+// ---------------------------------------------------------------------------------------------
+struct S3Rows {
+    int trow0, dense_th;
+    const int *a_tile_ptr, *a_tile_nnz;
+    const uint16_t *a_ptr, *a_mask;
+    const double *a_val;
+    const int *b_tile_nnz;
+    const uint16_t *b_ptr, *b_mask;
+    const double *b_val;
+    const int *c_tile_ptr, *c_tile_nnz;
+    const uint16_t *c_ptr, *c_mask;
+    uint16_t *c_col;
+    double *c_val;
+    const int *wptr, *pair_ptr, *pair_end, *pair_a, *pair_b;
+    const uint8_t *row_kind;
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_step3_rows(const __grid_constant__ S3Rows P)
+{
+    extern __shared__ __align__(128) unsigned char s3r_smem[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const int i = blockIdx.x, tid = threadIdx.x;
+    if (P.row_kind[i] != ROW_STAGED) return;
+    const int I = P.trow0 + i;
+    const int a0 = P.a_tile_ptr[I], nA = P.a_tile_ptr[I + 1] - a0;
+    const int av0 = P.a_tile_nnz[a0], av1 = P.a_tile_nnz[a0 + nA];
+    const int c0 = P.c_tile_ptr[i], numJ = P.c_tile_ptr[i + 1] - c0;
+    const int n0 = P.c_tile_nnz[c0], nnzC = P.c_tile_nnz[c0 + numJ] - n0;
+    const int w0 = P.wptr[i], W = P.wptr[i + 1] - w0;
+    const int av0a = av0 & ~1;                       // bulk copies need 16-byte aligned sources: start at an even element
+    const int nav = (av1 - av0a + 1) & ~1;           // and copy an even number of doubles (the slab is padded)
+
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { unsigned char *p = s3r_smem + off; off += al16(bytes); return p; };
+    uint16_t *s_am = (uint16_t *)carve((size_t)nA * 32);
+    uint16_t *s_ap = (uint16_t *)carve((size_t)nA * 32);
+    double *s_aval = (double *)carve(((size_t)(av1 - av0) + 2) * 8);
+    uint16_t *s_cm = (uint16_t *)carve((size_t)numJ * 32);
+    uint16_t *s_cp = (uint16_t *)carve((size_t)numJ * 32);
+    double *s_out = (double *)carve((size_t)nnzC * 8);
+    int *s_annz = (int *)carve(((size_t)nA + 1) * 4);
+    int *s_cnnz = (int *)carve(((size_t)numJ + 1) * 4);
+    int *s_pp = (int *)carve((size_t)numJ * 4);
+    int *s_pe = (int *)carve((size_t)numJ * 4);
+    int *s_pa = (int *)carve((size_t)W * 4);
+    int *s_pb = (int *)carve((size_t)W * 4);
+    uint16_t *s_ocol = (uint16_t *)carve((size_t)nnzC * 2);
+
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {  // one elected thread arms the barrier and issues the five bulk copies
+        mbar_expect_tx(&s_bar, (uint32_t)(nA * 64 + nav * 8 + numJ * 64));
+        bulk_g2s(s_am, P.a_mask + (size_t)a0 * TS, (uint32_t)nA * 32, &s_bar);
+        bulk_g2s(s_ap, P.a_ptr + (size_t)a0 * TS, (uint32_t)nA * 32, &s_bar);
+        if (nav > 0) bulk_g2s(s_aval, P.a_val + av0a, (uint32_t)nav * 8, &s_bar);
+        bulk_g2s(s_cm, P.c_mask + (size_t)c0 * TS, (uint32_t)numJ * 32, &s_bar);
+        bulk_g2s(s_cp, P.c_ptr + (size_t)c0 * TS, (uint32_t)numJ * 32, &s_bar);
+    }
+    // everything whose source is only 4-byte aligned: plain coalesced loads, overlapping the bulk copies
+    for (int k = tid; k <= nA; k += THREADS) s_annz[k] = P.a_tile_nnz[a0 + k] - av0a;
+    int dense_here = 0;
+    for (int k = tid; k <= numJ; k += THREADS) {
+        const int v = P.c_tile_nnz[c0 + k] - n0;
+        s_cnnz[k] = v;
+        if (k < numJ) {
+            s_pp[k] = P.pair_ptr[c0 + k] - w0;
+            s_pe[k] = P.pair_end[c0 + k] - w0;
+            dense_here |= (P.c_tile_nnz[c0 + k + 1] - n0 - v) >= P.dense_th;
+        }
+    }
+    for (int k = tid; k < W; k += THREADS) { s_pa[k] = P.pair_a[w0 + k] - a0; s_pb[k] = P.pair_b[w0 + k]; }
+    for (int k = tid; k < nnzC; k += THREADS) s_out[k] = 0.0;
+    const int has_dense = __syncthreads_or(dense_here);
+    mbar_wait(&s_bar, 0);
+
+    for (int idx = tid; idx < numJ * TS; idx += THREADS) {
+        const int s = idx >> 4, r = idx & 15;
+        const unsigned cm = s_cm[idx];
+        if (!cm) continue;
+        const int tb = s_cnnz[s];
+        if (s_cnnz[s + 1] - tb >= P.dense_th) continue;  // this tile takes the dense accumulator (k_step3_dense)
+        const int rowbase = tb + s_cp[idx];
+        {
+            unsigned m = cm;
+            int o = rowbase;
+            do { const int c = __clz(m) - 16; m ^= 0x8000u >> c; s_ocol[o++] = (uint16_t)c; } while (m);
+        }
+        const unsigned cmr = __brev(cm) >> 16;  // bit c = column c
+        const double *__restrict__ bvals = P.b_val;
+        const int pe = s_pe[s];
+        for (int p = s_pp[s]; p < pe; p++) {
+            const int a = s_pa[p];
+            unsigned am = s_am[a * TS + r];
+            if (!am) continue;  // the pair does not touch this row
+            const int b = s_pb[p];
+            int ia = s_annz[a] + s_ap[a * TS + r];
+            const int bbase = P.b_tile_nnz[b];
+            const uint16_t *bmk = P.b_mask + (size_t)b * TS, *bpt = P.b_ptr + (size_t)b * TS;
+            do {  // the bits of A's row mask are the k's of the row, ascending
+                const int k = __clz(am) - 16;
+                am ^= 0x8000u >> k;
+                const double av = s_aval[ia++];
+                unsigned bm = __brev((unsigned)bmk[k]) >> 16;  // bit c = column c
+                int ib = bbase + bpt[k];
+                while (bm) {  // B's row k: every entry is a product into C's row r
+                    const unsigned low = bm & (0u - bm);
+                    const int o = rowbase + __popc(cmr & (low - 1));  // rank of the column in C's row
+                    bm ^= low;
+                    s_out[o] = fma(av, bvals[ib++], s_out[o]);
+                }
+            } while (am);
+        }
+    }
+    __syncthreads();
+    if (!has_dense) {
+        for (int k = tid; k < nnzC; k += THREADS) { P.c_val[n0 + k] = s_out[k]; P.c_col[n0 + k] = s_ocol[k]; }
+    } else {  // leave the ranges of the dense tiles alone
+        for (int k = tid; k < nnzC; k += THREADS) {
+            int lo = 0, hi = numJ - 1;  // largest s with s_cnnz[s] <= k
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_cnnz[mid] <= k) lo = mid; else hi = mid - 1;
+            }
+            if (s_cnnz[lo + 1] - s_cnnz[lo] >= P.dense_th) continue;
+            P.c_val[n0 + k] = s_out[k];
+            P.c_col[n0 + k] = s_ocol[k];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gather formulation, one LANE per C nonzero (g = position in C's Val/Col).
+// blk2tile[g/32] gives the tile holding nonzero 32*(g/32); the lane finds its tile, row r and
+// column c from tile_nnz / Ptr / mask, then for every pair (A tile a, B tile b) of the tile reads
+// A's row mask r (zero: the pair does not touch this row and nothing else of the pair is loaded);
+// its bits are the k's of A's row r in ascending order. For an entry (r,k) with value av, B has
+// (k,c) iff bit (15-c) of B's row mask k is set, at Ptr_b[k] + popc(mask bits of columns < c).
+// The sum stays in a register: no accumulator memory, no atomics, coalesced stores, and the
+// summation order (ascending A tile, then ascending k) is the serial SPA's.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_blk2tile(int numblkC, const int *__restrict__ c_tile_nnz, int *__restrict__ blk2tile)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= numblkC) return;
+    const int s = c_tile_nnz[t], e = c_tile_nnz[t + 1];
+    for (int blk = (s + 31) >> 5; (blk << 5) < e; blk++) blk2tile[blk] = t;
+}
+
+struct S3Gather {
+    int numblkC, nnzC, trow0, dense_th;
+    const int *blk2tile, *pair_ptr, *pair_end, *pair_a, *pair_b;
+    const int *a_tile_nnz;
+    const uint16_t *a_ptr, *a_mask;
+    const double *a_val;
+    const int *b_tile_nnz;
+    const uint16_t *b_ptr, *b_mask;
+    const double *b_val;
+    const int *c_tile_nnz, *c_tile_row;
+    const uint16_t *c_ptr, *c_mask;
+    uint16_t *c_col;
+    double *c_val;
+    const uint8_t *row_kind;  // nullptr: every tile is gathered
+};
+
+template <int UNROLL>
+__device__ __forceinline__ void s3_gather_one(int g, const S3Gather &P)
+{
+    const int blk = g >> 5, nblk = (P.nnzC + 31) >> 5;
+    int lo = P.blk2tile[blk], hi = blk + 1 < nblk ? P.blk2tile[blk + 1] : P.numblkC - 1;
+    while (lo < hi) {  // largest tile t in [lo,hi] with tile_nnz[t] <= g (it is non-empty and holds g)
+        int mid = (lo + hi + 1) >> 1;
+        if (P.c_tile_nnz[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    const int t = lo;
+    const int tbase = P.c_tile_nnz[t];
+    if (P.row_kind) {  // tiles computed by the other numeric kernels
+        if (P.row_kind[P.c_tile_row[t] - P.trow0] != ROW_GATHER) return;
+        if (P.c_tile_nnz[t + 1] - tbase >= P.dense_th) return;
+    }
+    const int off = g - tbase;
+    // row: largest r with Ptr[r] <= off; the 16 u16 offsets are one aligned 32-byte line
+    const uint4 *pp = reinterpret_cast<const uint4 *>(P.c_ptr + (size_t)t * TS);
+    const uint4 q0 = pp[0], q1 = pp[1];
+    const unsigned key = (unsigned)off * 0x10001u;
+    int r = -1;
+    r += __popc(__vcmpleu2(q0.x, key)) + __popc(__vcmpleu2(q0.y, key)) + __popc(__vcmpleu2(q0.z, key)) + __popc(__vcmpleu2(q0.w, key)) +
+         __popc(__vcmpleu2(q1.x, key)) + __popc(__vcmpleu2(q1.y, key)) + __popc(__vcmpleu2(q1.z, key)) + __popc(__vcmpleu2(q1.w, key));
+    r = ((r + 1) >> 4) - 1;  // each u16 that compares <= contributes 16 set bits
+    unsigned cm = __brev(P.c_mask[(size_t)t * TS + r]) >> 16;  // bit c = column c present
+    for (int n = off - (int)P.c_ptr[(size_t)t * TS + r]; n > 0; n--) cm &= cm - 1;  // drop the n smaller columns
+    const int c = __ffs(cm) - 1;
+    const unsigned cbit = 0x8000u >> c;
+
+    double acc = 0.0;
+    // one pair: `am` = A's row mask r (non-zero); its bits are the k's in ascending order, so A's Col array is never read
+    auto pair_contrib = [&](int a, int b, unsigned am) {
+        int ia = P.a_tile_nnz[a] + P.a_ptr[(size_t)a * TS + r];
+        const int bbase = P.b_tile_nnz[b];
+        do {
+            const int k = __clz(am) - 16;
+            am ^= 0x8000u >> k;
+            const unsigned bm = P.b_mask[(size_t)b * TS + k];
+            if (bm & cbit) {
+                const int pos = (int)P.b_ptr[(size_t)b * TS + k] + __popc(bm >> (16 - c));
+                acc = fma(P.a_val[ia], P.b_val[bbase + pos], acc);
+            }
+            ia++;
+        } while (am);
+    };
+    const int p1 = P.pair_end[t];
+    int p = P.pair_ptr[t];
+    if (UNROLL > 1) {  // the row masks of UNROLL pairs in flight; contributions are still added in pair order
+        for (; p + UNROLL <= p1; p += UNROLL) {
+            int a[UNROLL];
+            unsigned am[UNROLL];
+#pragma unroll
+            for (int j = 0; j < UNROLL; j++) a[j] = P.pair_a[p + j];
+#pragma unroll
+            for (int j = 0; j < UNROLL; j++) am[j] = P.a_mask[(size_t)a[j] * TS + r];
+#pragma unroll
+            for (int j = 0; j < UNROLL; j++)
+                if (am[j]) pair_contrib(a[j], P.pair_b[p + j], am[j]);
+        }
+    }
+    for (; p < p1; p++) {
+        const int a = P.pair_a[p];
+        const unsigned am = P.a_mask[(size_t)a * TS + r];  // zero: the pair does not touch row r, nothing else of it is loaded
+        if (am) pair_contrib(a, P.pair_b[p], am);
+    }
+    P.c_val[g] = acc;
+    P.c_col[g] = (uint16_t)c;
+}
+
+// CHUNKED = false: one nonzero per thread, blocks balanced by the hardware scheduler.
+// CHUNKED = true: a CTA walks `chunk` consecutive nonzeros (a few C tile-rows), so that the A tiles they share stay in
+// its SM's L1; used when the work per nonzero is even (no heavy tile-rows) and the grid stays large.
+template <bool CHUNKED, int UNROLL>
+__global__ void __launch_bounds__(256)
+k_step3_gather(int chunk, int g0, int g1, const __grid_constant__ S3Gather P)
+{
+    if (!CHUNKED) {
+        const long long g = (long long)g0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (g < g1) s3_gather_one<UNROLL>((int)g, P);
+        return;
+    }
+    const long long cend = min((long long)g1, (long long)g0 + ((long long)blockIdx.x + 1) * chunk);
+    for (long long g = (long long)g0 + (long long)blockIdx.x * chunk + threadIdx.x; g < cend; g += blockDim.x)
+        s3_gather_one<UNROLL>((int)g, P);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense accumulator for WELL-FILLED C tiles (block-FEM: C tiles hold 160 nonzeros on average). One warp per listed
+// C tile; lane = (row r = lane/2, column half h = lane%2) owns the 8 entries C[r][8h..8h+7] in REGISTERS. Per pair
+// the B tile is expanded to a dense 16x16 tile in shared memory (rows padded to 18 doubles: 16-byte aligned, 2-way
+// conflicts at worst); the two lanes of row r walk A's row r and, per entry (r,k,av), do 8 FMAs with B's dense row k
+// (4 x LDS.128). No masks, popcounts or atomics in the inner loop; the row is compacted through C's mask at the end.
+// Summation order per C entry: ascending A tile, then ascending k -- the serial SPA's order.
+// ---------------------------------------------------------------------------------------------
+constexpr int S3D_WARPS = 4;
+constexpr int S3D_LD = 18;
+
+struct S3Dense {
+    int ntiles;
+    const int *list;  // C tiles to compute (nullptr: tiles 0..ntiles-1, empty ones skipped)
+    const int *pair_ptr, *pair_end, *pair_a, *pair_b;
+    const int *a_tile_nnz;
+    const uint16_t *a_ptr, *a_col;
+    const double *a_val;
+    const int *b_tile_nnz;
+    const uint16_t *b_ptr, *b_col;
+    const double *b_val;
+    const int *c_tile_nnz;
+    const uint16_t *c_ptr, *c_mask;
+    uint16_t *c_col;
+    double *c_val;
+};
+
+__global__ void __launch_bounds__(S3D_WARPS * 32)
+k_step3_dense(const __grid_constant__ S3Dense P)
+{
+    __shared__ __align__(16) double Bd_s[S3D_WARPS][TS * S3D_LD];
+    const int wi = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, r = lane >> 1, h = lane & 1;
+    if (wi >= P.ntiles) return;
+    const int t = P.list ? P.list[wi] : wi;
+    const int cbase = P.c_tile_nnz[t];
+    if (P.c_tile_nnz[t + 1] == cbase) return;  // empty tile (warp-uniform)
+    double *Bd = Bd_s[w];
+    double acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.0;
+    const int p1 = P.pair_end[t];
+    for (int p = P.pair_ptr[t]; p < p1; p++) {
+        const int a = P.pair_a[p], b = P.pair_b[p];
+        const int abase = P.a_tile_nnz[a], bbase = P.b_tile_nnz[b];
+        // dense B tile: zero, then lanes 0..15 scatter their row
+        double2 *z = reinterpret_cast<double2 *>(Bd + r * S3D_LD + 8 * h);
+        z[0] = z[1] = z[2] = z[3] = make_double2(0.0, 0.0);
+        __syncwarp();
+        if (lane < TS) {
+            int ib = P.b_ptr[(size_t)b * TS + lane];
+            const int ib1 = lane < TS - 1 ? (int)P.b_ptr[(size_t)b * TS + lane + 1] : P.b_tile_nnz[b + 1] - bbase;
+            for (; ib < ib1; ib++) Bd[lane * S3D_LD + P.b_col[bbase + ib]] = P.b_val[bbase + ib];
+        }
+        __syncwarp();
+        int ia = P.a_ptr[(size_t)a * TS + r];
+        const int ia1 = r < TS - 1 ? (int)P.a_ptr[(size_t)a * TS + r + 1] : P.a_tile_nnz[a + 1] - abase;
+        for (; ia < ia1; ia++) {
+            const int k = P.a_col[abase + ia] & 15;  // A stores row*16+col
+            const double av = P.a_val[abase + ia];
+            const double2 *br = reinterpret_cast<const double2 *>(Bd + k * S3D_LD + 8 * h);
+            const double2 b0 = br[0], b1 = br[1], b2 = br[2], b3 = br[3];
+            acc[0] = fma(av, b0.x, acc[0]); acc[1] = fma(av, b0.y, acc[1]);
+            acc[2] = fma(av, b1.x, acc[2]); acc[3] = fma(av, b1.y, acc[3]);
+            acc[4] = fma(av, b2.x, acc[4]); acc[5] = fma(av, b2.y, acc[5]);
+            acc[6] = fma(av, b3.x, acc[6]); acc[7] = fma(av, b3.y, acc[7]);
+        }
+        __syncwarp();  // Bd is rewritten for the next pair
+    }
+    const unsigned cm = P.c_mask[(size_t)t * TS + r];
+    const int rowbase = cbase + P.c_ptr[(size_t)t * TS + r];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int c = 8 * h + j;
+        if (cm & (0x8000u >> c)) {
+            const int pos = rowbase + __popc(cm >> (16 - c));
+            P.c_val[pos] = acc[j];
+            P.c_col[pos] = (uint16_t)c;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 tensor-core experiment (BASELINE north_star: "DMMA only for near-dense tile pairs, and only if ncu shows
+// they beat the CUDA-core path"). Same work split as k_step3_dense, but BOTH tiles of a pair are expanded to dense
+// 16x16 tiles in shared memory and the 16x16x16 product is issued as 2x2 output blocks x 4 k-steps = 16
+// mma.sync.m8n8k4.f64 (SASS: DMMA); the 8 accumulators per lane are the C fragments. (tcgen05 has no FP64 kind, so
+// this is the only tensor-core path FP64 has.) Selected with TSG_STEP3=dmma; outcome in profiles/README.md.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(S3D_WARPS * 32)
+k_step3_dmma(const __grid_constant__ S3Dense P)
+{
+    __shared__ __align__(16) double AB_s[S3D_WARPS][2][TS * S3D_LD];
+    const int wi = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3;
+    if (wi >= P.ntiles) return;
+    const int t = P.list ? P.list[wi] : wi;
+    const int cbase = P.c_tile_nnz[t];
+    if (P.c_tile_nnz[t + 1] == cbase) return;  // empty tile (warp-uniform)
+    double *Ad = AB_s[w][0], *Bd = AB_s[w][1];
+    double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c10[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+    const int p1 = P.pair_end[t];
+    for (int p = P.pair_ptr[t]; p < p1; p++) {
+        const int a = P.pair_a[p], b = P.pair_b[p];
+        const int abase = P.a_tile_nnz[a], aend = P.a_tile_nnz[a + 1], bbase = P.b_tile_nnz[b];
+        double2 *z = reinterpret_cast<double2 *>(AB_s[w][0]);
+        for (int k = lane; k < 2 * TS * S3D_LD / 2; k += 32) z[k] = make_double2(0.0, 0.0);
+        __syncwarp();
+        for (int e = abase + lane; e < aend; e += 32) {
+            const unsigned col = P.a_col[e];  // row*16+col
+            Ad[(col >> 4) * S3D_LD + (col & 15)] = P.a_val[e];
+        }
+        if (lane < TS) {
+            int ib = P.b_ptr[(size_t)b * TS + lane];
+            const int ib1 = lane < TS - 1 ? (int)P.b_ptr[(size_t)b * TS + lane + 1] : P.b_tile_nnz[b + 1] - bbase;
+            for (; ib < ib1; ib++) Bd[lane * S3D_LD + P.b_col[bbase + ib]] = P.b_val[bbase + ib];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {
+            const double a0 = Ad[g * S3D_LD + 4 * ks + tg], a1 = Ad[(8 + g) * S3D_LD + 4 * ks + tg];
+            const double b0 = Bd[(4 * ks + tg) * S3D_LD + g], b1 = Bd[(4 * ks + tg) * S3D_LD + 8 + g];
+            dmma_m8n8k4(c00[0], c00[1], a0, b0);
+            dmma_m8n8k4(c01[0], c01[1], a0, b1);
+            dmma_m8n8k4(c10[0], c10[1], a1, b0);
+            dmma_m8n8k4(c11[0], c11[1], a1, b1);
+        }
+        __syncwarp();
+    }
+    // fragment (i,j) holds C[8i+g][8j+2tg+{0,1}]
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int R = 8 * i + g;
+        const unsigned cm = P.c_mask[(size_t)t * TS + R];
+        const int rowbase = cbase + P.c_ptr[(size_t)t * TS + R];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int c = 8 * j + 2 * tg + q;
+                if (cm & (0x8000u >> c)) {
+                    const int pos = rowbase + __popc(cm >> (16 - c));
+                    P.c_val[pos] = i == 0 ? (j == 0 ? c00[q] : c01[q]) : (j == 0 ? c10[q] : c11[q]);
+                    P.c_col[pos] = (uint16_t)c;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+static int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return s && *s ? atoi(s) : dflt;
+}
+
+// TSG_STEP3 = auto (default) | rows | gather | dense | dmma : force one accumulator for every tile (A/B measurements)
+static const char *s3_mode()
+{
+    const char *m = getenv("TSG_STEP3");  // read on every call: the tests switch it between calls
+    return m && *m ? m : "auto";
+}
+
+size_t numeric_scratch_bytes(int ntr, long long numblkC)
+{
+    return arena_need((size_t)ntr + 1, 1) + arena_need((size_t)(numblkC > 0 ? numblkC : 1), 4);
+}
+
+// Enqueue the classification of the slab's tile-rows and tiles (after C's tile_nnz has been scanned). Results: row_kind,
+// dense_list and the NS_* counters in d_ns (device ints), which the caller reads back together with nnz(C).
+int numeric_classify_device(const tsg_dtile *A, const tsg_dtile *C, int trow0, int ntr, const int *wptr, NumericBufs *nb, int *d_ns)
+{
+    Ctx &c = ctx();
+    const char *mode = s3_mode();
+    const long long numblkC = C->numtile;
+    k_ns_init<<<1, 32, 0, c.stream>>>(d_ns);
+    CK_LAUNCH();
+    int force_kind = 0, dense_th = env_int("TSG_DENSE_TH", 96);
+    if (!strcmp(mode, "gather")) { force_kind = ROW_GATHER; dense_th = 1 << 20; }
+    else if (!strcmp(mode, "rows")) { force_kind = ROW_STAGED; dense_th = 1 << 20; }
+    else if (!strcmp(mode, "dense") || !strcmp(mode, "dmma")) dense_th = 1;
+    nb->dense_th = dense_th;
+    size_t cap = (size_t)env_int("TSG_ROWS_SMEM_KB", 72) * 1024;
+    if (cap > c.smem_optin) cap = c.smem_optin;
+    nb->smem_cap = (int)cap;
+    if (ntr > 0 && numblkC > 0) {
+        k_s3_classify_rows<<<ceil_div(ntr, 256), 256, 0, c.stream>>>(ntr, trow0, A->tile_ptr, A->tile_nnz, C->tile_ptr, C->tile_nnz, wptr,
+                                                                      (int)cap, env_int("TSG_ROWS_MIN_FILL", 8), force_kind,
+                                                                      nb->row_kind, d_ns);
+        CK_LAUNCH();
+        if (dense_th <= 256) {
+            k_s3_classify_tiles<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>((int)numblkC, C->tile_nnz, dense_th, nb->dense_list, d_ns);
+            CK_LAUNCH();
+        }
+    }
+    return TSG_OK;
+}
+
+int numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, int trow0, int ntr, const int *wptr, const PairLists &pl,
+                   const NumericBufs &nb, const int *h_ns, bool heavy_rows, tsg_stats *stats)
+{
+    Ctx &c = ctx();
+    const long long numblkC = C->numtile, nnzC = C->nnz;
+    if (nnzC <= 0 || numblkC <= 0) return TSG_OK;
+    const char *mode = s3_mode();
+    const int n_staged = h_ns[NS_ROWS_STAGED], n_gather = h_ns[NS_ROWS_GATHER], n_dense = h_ns[NS_DENSE];
+    if (stats) { stats->rows_staged = n_staged; stats->rows_gather = n_gather; stats->tiles_dense = n_dense; stats->rows_smem = h_ns[NS_MAXNEED]; }
+
+    if (n_dense > 0) {
+        S3Dense P{n_dense, nb.dense_list, pl.ptr, pl.end, pl.a, pl.b, A->tile_nnz, A->ptr, A->col, A->val, B->tile_nnz, B->ptr, B->col, B->val,
+                  C->tile_nnz, C->ptr, C->mask, C->col, C->val};
+        const int blocks = ceil_div((long long)n_dense * 32, S3D_WARPS * 32);
+        if (!strcmp(mode, "dmma")) k_step3_dmma<<<blocks, S3D_WARPS * 32, 0, c.stream>>>(P);
+        else k_step3_dense<<<blocks, S3D_WARPS * 32, 0, c.stream>>>(P);
+        CK_LAUNCH();
+    }
+    if (n_staged > 0) {
+        S3Rows P{trow0, nb.dense_th, A->tile_ptr, A->tile_nnz, A->ptr, A->mask, A->val, B->tile_nnz, B->ptr, B->mask, B->val,
+                 C->tile_ptr, C->tile_nnz, C->ptr, C->mask, C->col, C->val, wptr, pl.ptr, pl.end, pl.a, pl.b, nb.row_kind};
+        const size_t smem = ((size_t)h_ns[NS_MAXNEED] + 1023) & ~(size_t)1023;
+        // 128-thread CTAs when a tile-row has few (tile, row) slots (2D meshes): fewer idle threads, more CTAs per SM
+        const bool narrow = numblkC * TS < (long long)ntr * 192;
+        if (smem > 48 * 1024) {
+            if (narrow) CK(cudaFuncSetAttribute(k_step3_rows<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else CK(cudaFuncSetAttribute(k_step3_rows<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        if (narrow) k_step3_rows<128><<<ntr, 128, smem, c.stream>>>(P);
+        else k_step3_rows<256><<<ntr, 256, smem, c.stream>>>(P);
+        CK_LAUNCH();
+    }
+    if (n_gather > 0) {
+        const int g0 = h_ns[NS_GLO], g1 = h_ns[NS_GHI];  // nonzero range spanned by the gathered tile-rows
+        if (!arena_reserve(2, arena_need((size_t)((nnzC + 31) >> 5) + 1, 4))) return last_error();
+        int *blk2tile = arena_take<int>(2, (size_t)((nnzC + 31) >> 5) + 1);
+        if (!blk2tile) return last_error();
+        k_blk2tile<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>((int)numblkC, C->tile_nnz, blk2tile);
+        CK_LAUNCH();
+        const bool all = n_staged == 0 && n_dense == 0;
+        S3Gather P{(int)numblkC, (int)nnzC, trow0, nb.dense_th, blk2tile, pl.ptr, pl.end, pl.a, pl.b, A->tile_nnz, A->ptr, A->mask, A->val,
+                   B->tile_nnz, B->ptr, B->mask, B->val, C->tile_nnz, C->tile_rowidx, C->ptr, C->mask, C->col, C->val,
+                   all ? nullptr : nb.row_kind};
+        // consecutive nonzeros per CTA: 8192 when the work per nonzero is even (no heavy tile-rows) and there are
+        // enough of them to keep >= 16 CTAs per SM busy; otherwise one 256-thread pass, balanced by the block scheduler
+        const long long span = (long long)g1 - g0;
+        int chunk = 256;
+        if (!heavy_rows && span >= (long long)c.num_sms * 16 * 8192) chunk = 8192;
+        const int chunk_env = env_int("TSG_GATHER_CHUNK", 0);
+        if (chunk_env >= 256) chunk = chunk_env;
+        if (chunk > 256) k_step3_gather<true, 2><<<ceil_div(span, chunk), 256, 0, c.stream>>>(chunk, g0, g1, P);
+        else k_step3_gather<false, 2><<<ceil_div(span, 256), 256, 0, c.stream>>>(256, g0, g1, P);
+        CK_LAUNCH();
+    }
+    return TSG_OK;
+}
+
+}  // namespace tsg

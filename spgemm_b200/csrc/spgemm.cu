@@ -479,272 +479,6 @@ __global__ void k_slab_extent(const int *__restrict__ tile_ptr, const int *__res
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Step 3: gather formulation, one LANE per C nonzero (g = position in C's Val/Col).
-// blk2tile[g/32] gives the tile holding nonzero 32*(g/32); the lane finds its tile, row r and
-// column c from tile_nnz / Ptr / mask, then for every pair (A tile a, B tile b) of the tile reads
-// A's row mask r (zero: the pair does not touch this row -- two thirds of the pairs on a stencil --
-// and nothing else of the pair is loaded); its bits are the k's of A's row r in ascending order.
-// For an entry (r,k) with value av, B has (k,c) iff bit (15-c) of B's row mask k is set,
-// and its position is Ptr_b[k] + popc(mask bits of columns < c). The sum stays in a register:
-// no shared-memory accumulator, no atomics, no zeroing, fully coalesced stores, and the summation
-// order (ascending A tile, then ascending k) is exactly the serial SPA's.
-// ---------------------------------------------------------------------------------------------
-__global__ void k_blk2tile(int numblkC, const int *__restrict__ c_tile_nnz, int *__restrict__ blk2tile)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= numblkC) return;
-    const int s = c_tile_nnz[t], e = c_tile_nnz[t + 1];
-    for (int blk = (s + 31) >> 5; (blk << 5) < e; blk++) blk2tile[blk] = t;
-}
-
-template <int UNROLL>
-__device__ __forceinline__ void
-s3_gather_one(int g, int numblkC, int nnzC, const int *__restrict__ blk2tile, const int *__restrict__ pair_ptr,
-              const int *__restrict__ pair_end, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
-              const int *__restrict__ a_tile_nnz, const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ a_mask,
-              const double *__restrict__ a_val, const int *__restrict__ b_tile_nnz, const uint16_t *__restrict__ b_ptr,
-              const uint16_t *__restrict__ b_mask, const double *__restrict__ b_val, const int *__restrict__ c_tile_nnz,
-              const uint16_t *__restrict__ c_ptr, const uint16_t *__restrict__ c_mask, uint16_t *__restrict__ c_col,
-              double *__restrict__ c_val)
-{
-    const int blk = g >> 5, nblk = (nnzC + 31) >> 5;
-    int lo = blk2tile[blk], hi = blk + 1 < nblk ? blk2tile[blk + 1] : numblkC - 1;
-    while (lo < hi) {  // largest tile t in [lo,hi] with tile_nnz[t] <= g (it is non-empty and holds g)
-        int mid = (lo + hi + 1) >> 1;
-        if (c_tile_nnz[mid] <= g) lo = mid; else hi = mid - 1;
-    }
-    const int t = lo;
-    const int off = g - c_tile_nnz[t];
-    // row: largest r with Ptr[r] <= off; the 16 u16 offsets are one aligned 32-byte line
-    const uint4 *pp = reinterpret_cast<const uint4 *>(c_ptr + (size_t)t * TS);
-    const uint4 q0 = pp[0], q1 = pp[1];
-    const unsigned key = (unsigned)off * 0x10001u;
-    int r = -1;
-    r += __popc(__vcmpleu2(q0.x, key)) + __popc(__vcmpleu2(q0.y, key)) + __popc(__vcmpleu2(q0.z, key)) + __popc(__vcmpleu2(q0.w, key)) +
-         __popc(__vcmpleu2(q1.x, key)) + __popc(__vcmpleu2(q1.y, key)) + __popc(__vcmpleu2(q1.z, key)) + __popc(__vcmpleu2(q1.w, key));
-    r = ((r + 1) >> 4) - 1;  // each u16 that compares <= contributes 16 set bits
-    unsigned cm = __brev(c_mask[(size_t)t * TS + r]) >> 16;  // bit c = column c present
-    for (int n = off - (int)c_ptr[(size_t)t * TS + r]; n > 0; n--) cm &= cm - 1;  // drop the n smaller columns
-    const int c = __ffs(cm) - 1;
-    const unsigned cbit = 0x8000u >> c;
-
-    double acc = 0.0;
-    // one pair: `am` = A's row mask r (non-zero); its bits are the k's in ascending order, so A's Col array is never read
-    auto pair_contrib = [&](int a, int b, unsigned am) {
-        int ia = a_tile_nnz[a] + a_ptr[(size_t)a * TS + r];
-        const int bbase = b_tile_nnz[b];
-        do {
-            const int k = __clz(am) - 16;
-            am ^= 0x8000u >> k;
-            const unsigned bm = b_mask[(size_t)b * TS + k];
-            if (bm & cbit) {
-                const int pos = (int)b_ptr[(size_t)b * TS + k] + __popc(bm >> (16 - c));
-                acc = fma(a_val[ia], b_val[bbase + pos], acc);
-            }
-            ia++;
-        } while (am);
-    };
-    const int p1 = pair_end[t];
-    int p = pair_ptr[t];
-    if (UNROLL > 1) {  // the row masks of UNROLL pairs in flight; contributions are still added in pair order
-        for (; p + UNROLL <= p1; p += UNROLL) {
-            int a[UNROLL];
-            unsigned am[UNROLL];
-#pragma unroll
-            for (int j = 0; j < UNROLL; j++) a[j] = pair_a[p + j];
-#pragma unroll
-            for (int j = 0; j < UNROLL; j++) am[j] = a_mask[(size_t)a[j] * TS + r];
-#pragma unroll
-            for (int j = 0; j < UNROLL; j++)
-                if (am[j]) pair_contrib(a[j], pair_b[p + j], am[j]);
-        }
-    }
-    for (; p < p1; p++) {
-        const int a = pair_a[p];
-        const unsigned am = a_mask[(size_t)a * TS + r];  // zero: the pair does not touch row r, nothing else of it is loaded
-        if (am) pair_contrib(a, pair_b[p], am);
-    }
-    c_val[g] = acc;
-    c_col[g] = (uint16_t)c;
-}
-
-// CHUNKED = false: one nonzero per thread (straight-line code, 32 registers), blocks balanced by the hardware scheduler.
-// CHUNKED = true: a CTA walks `chunk` consecutive nonzeros (a few C tile-rows), so that the A tiles they share stay in
-// its SM's L1; used when the work per nonzero is even (no heavy tile-rows) and the grid stays large.
-template <bool CHUNKED, int UNROLL>
-__global__ void __launch_bounds__(256)
-k_step3_gather(int chunk, int numblkC, int nnzC, const int *__restrict__ blk2tile, const int *__restrict__ pair_ptr,
-               const int *__restrict__ pair_end, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
-               const int *__restrict__ a_tile_nnz, const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ a_mask,
-               const double *__restrict__ a_val, const int *__restrict__ b_tile_nnz, const uint16_t *__restrict__ b_ptr,
-               const uint16_t *__restrict__ b_mask, const double *__restrict__ b_val, const int *__restrict__ c_tile_nnz,
-               const uint16_t *__restrict__ c_ptr, const uint16_t *__restrict__ c_mask, uint16_t *__restrict__ c_col,
-               double *__restrict__ c_val)
-{
-    if (!CHUNKED) {
-        const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-        if (g < nnzC)
-            s3_gather_one<UNROLL>((int)g, numblkC, nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b, a_tile_nnz, a_ptr, a_mask, a_val, b_tile_nnz,
-                          b_ptr, b_mask, b_val, c_tile_nnz, c_ptr, c_mask, c_col, c_val);
-        return;
-    }
-    const long long cend = min((long long)nnzC, ((long long)blockIdx.x + 1) * chunk);
-    for (long long g = (long long)blockIdx.x * chunk + threadIdx.x; g < cend; g += blockDim.x)
-        s3_gather_one<UNROLL>((int)g, numblkC, nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b, a_tile_nnz, a_ptr, a_mask, a_val, b_tile_nnz,
-                      b_ptr, b_mask, b_val, c_tile_nnz, c_ptr, c_mask, c_col, c_val);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Step 3 for WELL-FILLED tiles (block-FEM: ~96 nonzeros per A tile, C tiles 160 on average): the
-// dense accumulator. One warp per non-empty C tile; lane = (row r = lane/2, column half h = lane%2)
-// owns the 8 entries C[r][8h..8h+7] in REGISTERS. Per pair the B tile is expanded to a dense 16x16
-// tile in shared memory (rows padded to 18 doubles: 16-byte aligned, 2-way conflicts at worst); the two
-// lanes of row r walk A's row r and, per entry (r,k,av), do 8 FMAs with B's dense row k (4 x LDS.128).
-// No masks, popcounts or atomics in the inner loop; the row is compacted through C's mask at the end.
-// Summation order per C entry: ascending A tile, then ascending k -- the serial SPA's order.
-// ---------------------------------------------------------------------------------------------
-constexpr int S3D_WARPS = 4;
-constexpr int S3D_LD = 18;
-
-__global__ void __launch_bounds__(S3D_WARPS * 32)
-k_step3_dense(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end,
-              const int *__restrict__ pair_a, const int *__restrict__ pair_b, const int *__restrict__ a_tile_nnz,
-              const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ a_col, const double *__restrict__ a_val,
-              const int *__restrict__ b_tile_nnz, const uint16_t *__restrict__ b_ptr, const uint16_t *__restrict__ b_col,
-              const double *__restrict__ b_val, const int *__restrict__ c_tile_nnz, const uint16_t *__restrict__ c_ptr,
-              const uint16_t *__restrict__ c_mask, uint16_t *__restrict__ c_col, double *__restrict__ c_val)
-{
-    __shared__ __align__(16) double Bd_s[S3D_WARPS][TS * S3D_LD];
-    const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, r = lane >> 1, h = lane & 1;
-    if (t >= numblkC) return;
-    const int cbase = c_tile_nnz[t];
-    if (c_tile_nnz[t + 1] == cbase) return;  // empty tile (warp-uniform)
-    double *Bd = Bd_s[w];
-    double acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = 0.0;
-    const int p1 = pair_end[t];
-    for (int p = pair_ptr[t]; p < p1; p++) {
-        const int a = pair_a[p], b = pair_b[p];
-        const int abase = a_tile_nnz[a], bbase = b_tile_nnz[b];
-        // dense B tile: zero, then lanes 0..15 scatter their row
-        double2 *z = reinterpret_cast<double2 *>(Bd + r * S3D_LD + 8 * h);
-        z[0] = z[1] = z[2] = z[3] = make_double2(0.0, 0.0);
-        __syncwarp();
-        if (lane < TS) {
-            int ib = b_ptr[(size_t)b * TS + lane];
-            const int ib1 = lane < TS - 1 ? (int)b_ptr[(size_t)b * TS + lane + 1] : b_tile_nnz[b + 1] - bbase;
-            for (; ib < ib1; ib++) Bd[lane * S3D_LD + b_col[bbase + ib]] = b_val[bbase + ib];
-        }
-        __syncwarp();
-        int ia = a_ptr[(size_t)a * TS + r];
-        const int ia1 = r < TS - 1 ? (int)a_ptr[(size_t)a * TS + r + 1] : a_tile_nnz[a + 1] - abase;
-        for (; ia < ia1; ia++) {
-            const int k = a_col[abase + ia] & 15;  // A stores row*16+col
-            const double av = a_val[abase + ia];
-            const double2 *br = reinterpret_cast<const double2 *>(Bd + k * S3D_LD + 8 * h);
-            const double2 b0 = br[0], b1 = br[1], b2 = br[2], b3 = br[3];
-            acc[0] = fma(av, b0.x, acc[0]); acc[1] = fma(av, b0.y, acc[1]);
-            acc[2] = fma(av, b1.x, acc[2]); acc[3] = fma(av, b1.y, acc[3]);
-            acc[4] = fma(av, b2.x, acc[4]); acc[5] = fma(av, b2.y, acc[5]);
-            acc[6] = fma(av, b3.x, acc[6]); acc[7] = fma(av, b3.y, acc[7]);
-        }
-        __syncwarp();  // Bd is rewritten for the next pair
-    }
-    const unsigned cm = c_mask[(size_t)t * TS + r];
-    const int rowbase = cbase + c_ptr[(size_t)t * TS + r];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const int c = 8 * h + j;
-        if (cm & (0x8000u >> c)) {
-            const int pos = rowbase + __popc(cm >> (16 - c));
-            c_val[pos] = acc[j];
-            c_col[pos] = (uint16_t)c;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Step 3, FP64 tensor-core experiment (BASELINE north_star: "DMMA only for near-dense tile pairs, and
-// only if ncu shows they beat the CUDA-core path"). Same work split as k_step3_dense, but BOTH tiles of
-// a pair are expanded to dense 16x16 tiles in shared memory and the 16x16x16 product is issued as
-// 2x2 output blocks x 4 k-steps = 16 mma.sync.m8n8k4.f64 (SASS: DMMA); the 8 accumulators per lane are
-// the C fragments. (tcgen05 has no FP64 kind, so this is the only tensor-core path FP64 has.)
-// Selected with TSG_STEP3=dmma; the measured outcome is recorded in profiles/README.md.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
-
-__global__ void __launch_bounds__(S3D_WARPS * 32)
-k_step3_dmma(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end,
-             const int *__restrict__ pair_a, const int *__restrict__ pair_b, const int *__restrict__ a_tile_nnz,
-             const uint16_t *__restrict__ a_col, const double *__restrict__ a_val, const int *__restrict__ b_tile_nnz,
-             const uint16_t *__restrict__ b_ptr, const uint16_t *__restrict__ b_col, const double *__restrict__ b_val,
-             const int *__restrict__ c_tile_nnz, const uint16_t *__restrict__ c_ptr, const uint16_t *__restrict__ c_mask,
-             uint16_t *__restrict__ c_col, double *__restrict__ c_val)
-{
-    __shared__ __align__(16) double AB_s[S3D_WARPS][2][TS * S3D_LD];
-    const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3;
-    if (t >= numblkC) return;
-    const int cbase = c_tile_nnz[t];
-    if (c_tile_nnz[t + 1] == cbase) return;  // empty tile (warp-uniform)
-    double *Ad = AB_s[w][0], *Bd = AB_s[w][1];
-    double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c10[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
-    const int p1 = pair_end[t];
-    for (int p = pair_ptr[t]; p < p1; p++) {
-        const int a = pair_a[p], b = pair_b[p];
-        const int abase = a_tile_nnz[a], aend = a_tile_nnz[a + 1], bbase = b_tile_nnz[b];
-        double2 *z = reinterpret_cast<double2 *>(AB_s[w][0]);
-        for (int k = lane; k < 2 * TS * S3D_LD / 2; k += 32) z[k] = make_double2(0.0, 0.0);
-        __syncwarp();
-        for (int e = abase + lane; e < aend; e += 32) {
-            const unsigned col = a_col[e];  // row*16+col
-            Ad[(col >> 4) * S3D_LD + (col & 15)] = a_val[e];
-        }
-        if (lane < TS) {
-            int ib = b_ptr[(size_t)b * TS + lane];
-            const int ib1 = lane < TS - 1 ? (int)b_ptr[(size_t)b * TS + lane + 1] : b_tile_nnz[b + 1] - bbase;
-            for (; ib < ib1; ib++) Bd[lane * S3D_LD + b_col[bbase + ib]] = b_val[bbase + ib];
-        }
-        __syncwarp();
-#pragma unroll
-        for (int ks = 0; ks < 4; ks++) {
-            const double a0 = Ad[g * S3D_LD + 4 * ks + tg], a1 = Ad[(8 + g) * S3D_LD + 4 * ks + tg];
-            const double b0 = Bd[(4 * ks + tg) * S3D_LD + g], b1 = Bd[(4 * ks + tg) * S3D_LD + 8 + g];
-            dmma_m8n8k4(c00[0], c00[1], a0, b0);
-            dmma_m8n8k4(c01[0], c01[1], a0, b1);
-            dmma_m8n8k4(c10[0], c10[1], a1, b0);
-            dmma_m8n8k4(c11[0], c11[1], a1, b1);
-        }
-        __syncwarp();
-    }
-    // fragment (i,j) holds C[8i+g][8j+2tg+{0,1}]
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        const int R = 8 * i + g;
-        const unsigned cm = c_mask[(size_t)t * TS + R];
-        const int rowbase = cbase + c_ptr[(size_t)t * TS + R];
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int c = 8 * j + 2 * tg + q;
-                if (cm & (0x8000u >> c)) {
-                    const int pos = rowbase + __popc(cm >> (16 - c));
-                    c_val[pos] = i == 0 ? (j == 0 ? c00[q] : c01[q]) : (j == 0 ? c10[q] : c11[q]);
-                    c_col[pos] = (uint16_t)c;
-                }
-            }
-        }
-    }
-}
-
 // row-major tile index -> CSC storage id for a B uploaded from a host SMatrix (csr2tile_device
 // fills rm2csc itself). One thread per stored tile: binary search its column in its tile-row.
 __global__ void k_build_rm2csc(int tilen, const int *__restrict__ csc_tile_ptr, const int *__restrict__ csc_tile_rowidx,
@@ -931,12 +665,15 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     rc = copy_words(C->tile_ptr, c_tile_ptr, (size_t)ntr + 1);
     if (rc) return rc;
     const bool heavy_rows = wmax_seen > S1_LIGHT_MAX;  // tile-rows on the multi-warp path park one 16-byte record per pair
-    if (!arena_reserve(1, 2 * arena_need(nb + 1, 4) + 2 * arena_need(np, 4) + arena_need(nb + 1, 8) + (heavy_rows ? arena_need(np, 16) : 0)))
+    if (!arena_reserve(1, 2 * arena_need(nb + 1, 4) + 2 * arena_need(np, 4) + arena_need(nb + 1, 8) + (heavy_rows ? arena_need(np, 16) : 0) +
+                              numeric_scratch_bytes(ntr, numblkC)))
         return last_error();
     int *pair_ptr = arena_take<int>(1, nb + 1), *pair_end = arena_take<int>(1, nb + 1), *pair_a = arena_take<int>(1, np), *pair_b = arena_take<int>(1, np);
     long long *nnz64 = arena_take<long long>(1, nb + 1);
     int4 *pair_tmp = heavy_rows ? arena_take<int4>(1, np) : nullptr;
-    if (!pair_ptr || !pair_end || !pair_a || !pair_b || !nnz64 || (heavy_rows && !pair_tmp)) return last_error();
+    NumericBufs nbufs{arena_take<uint8_t>(1, (size_t)ntr + 1), arena_take<int>(1, nb), 0, 0};
+    if (!pair_ptr || !pair_end || !pair_a || !pair_b || !nnz64 || (heavy_rows && !pair_tmp) || !nbufs.row_kind || !nbufs.dense_list)
+        return last_error();
     CK(cudaMemsetAsync(pair_end, 0, nb * 4, c.stream));
     CK(cudaEventRecord(ev[2], c.stream));  // [1..2] = allocation
     // the one-warp step-1 path also produces C's masks / Ptr / tile nnz (fused step 2) when the tile-row's
@@ -977,13 +714,20 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     if (rc) return rc;
     rc = exclusive_scan<int>(C->tile_nnz, C->tile_nnz, numblkC);
     if (rc) return rc;
+    // pick the accumulator per C tile-row / tile (numeric.cu); its counters come back with nnz(C) in one read-back
+    int *d_ns = (int *)(c.d_scalars + 16);
+    rc = numeric_classify_device(A, C, trow0, ntr, wptr, &nbufs, d_ns);
+    if (rc) return rc;
     long long nnzC = 0;
-    rc = read_back_i64(nnz64 + numblkC, &nnzC);
+    rc = publish_words(&c.h_scalars[16], d_ns, 8);
+    if (!rc) rc = read_back_i64(nnz64 + numblkC, &nnzC);
     if (rc) return rc;
     if (nnzC >= (1ll << 31)) {
         set_error(TSG_ERR_OVERFLOW, "spgemm: nnz(C) = %lld in tile-rows [%d,%d) exceeds int32; use smaller slabs", nnzC, trow0, trow1);
         return last_error();
     }
+    int h_ns[8];
+    memcpy(h_ns, (const void *)&c.h_scalars[16], sizeof(h_ns));
     CK(cudaEventRecord(ev[3], c.stream));
 
     // ---------------- step 3 ----------------
@@ -998,41 +742,10 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         C->nnz = nnzC;
     }
     CK(cudaEventRecord(ev_s3, c.stream));
-    // numeric kernel: the dense accumulator (warp per C tile) when tiles are well filled -- A tiles hold >= 24
-    // nonzeros on average (block-FEM: 96) -- else the gather (lane per C nonzero). TSG_STEP3=dense|gather overrides.
-    static const char *s3_force = getenv("TSG_STEP3");
-    bool dense = A->nnz >= 24ll * A->numtile;
-    if (s3_force) dense = !strcmp(s3_force, "dense");
-    if (nnzC > 0 && s3_force && !strcmp(s3_force, "dmma")) {  // FP64 tensor-core experiment, never chosen automatically
-        k_step3_dmma<<<ceil_div(numblkC * 32, S3D_WARPS * 32), S3D_WARPS * 32, 0, c.stream>>>(
-            (int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->tile_nnz, A->col, A->val, B->tile_nnz, B->ptr, B->col, B->val, C->tile_nnz,
-            C->ptr, C->mask, C->col, C->val);
-        CK_LAUNCH();
-    } else if (nnzC > 0 && dense) {
-        k_step3_dense<<<ceil_div(numblkC * 32, S3D_WARPS * 32), S3D_WARPS * 32, 0, c.stream>>>(
-            (int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->tile_nnz, A->ptr, A->col, A->val, B->tile_nnz, B->ptr, B->col, B->val,
-            C->tile_nnz, C->ptr, C->mask, C->col, C->val);
-        CK_LAUNCH();
-    } else if (nnzC > 0) {
-        if (!arena_reserve(2, arena_need((size_t)((nnzC + 31) >> 5) + 1, 4))) return last_error();
-        int *blk2tile = arena_take<int>(2, (size_t)((nnzC + 31) >> 5) + 1);
-        if (!blk2tile) return last_error();
-        k_blk2tile<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>((int)numblkC, C->tile_nnz, blk2tile);
-        CK_LAUNCH();
-        // consecutive nonzeros per CTA: 8192 when the work per nonzero is even (no heavy tile-rows) and there are
-        // enough of them to keep >= 16 CTAs per SM busy; otherwise one 256-thread pass, balanced by the block scheduler
-        int chunk = 256;
-        if (wmax_seen <= S1_LIGHT_MAX && nnzC >= (long long)c.num_sms * 16 * 8192) chunk = 8192;
-        static const int chunk_env = getenv("TSG_GATHER_CHUNK") ? atoi(getenv("TSG_GATHER_CHUNK")) : 0;
-        if (chunk_env >= 256) chunk = chunk_env;
-        static const int unroll_env = getenv("TSG_GATHER_UNROLL") ? atoi(getenv("TSG_GATHER_UNROLL")) : 2;
-        auto kern = chunk > 256 ? (unroll_env == 4 ? k_step3_gather<true, 4> : unroll_env == 2 ? k_step3_gather<true, 2> : k_step3_gather<true, 1>)
-                                : (unroll_env == 4 ? k_step3_gather<false, 4> : unroll_env == 2 ? k_step3_gather<false, 2> : k_step3_gather<false, 1>);
-        kern<<<ceil_div(nnzC, chunk), 256, 0, c.stream>>>(chunk, (int)numblkC, (int)nnzC, blk2tile, pair_ptr, pair_end, pair_a, pair_b,
-                                                                  A->tile_nnz, A->ptr, A->mask, A->val, B->tile_nnz, B->ptr, B->mask,
-                                                                  B->val, C->tile_nnz, C->ptr, C->mask, C->col, C->val);
-        CK_LAUNCH();
-    }
+    tsg_stats nst;
+    memset(&nst, 0, sizeof(nst));
+    rc = numeric_device(A, B, C, trow0, ntr, wptr, PairLists{pair_ptr, pair_end, pair_a, pair_b}, nbufs, h_ns, heavy_rows, &nst);
+    if (rc) return rc;
     CK(cudaEventRecord(ev[4], c.stream));
     if (stats && ntr != A->tilem) {  // the slab's share of A (tiles, nonzeros) for the byte count below
         k_slab_extent<<<1, 32, 0, c.stream>>>(A->tile_ptr, A->tile_nnz, trow0, trow1,
@@ -1056,6 +769,8 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         (void)f;
         stats->ms_step1 = s1a + s1b; stats->ms_step2 = s2; stats->ms_step3 = s3; stats->ms_alloc = al + al2; stats->ms_total = tot;
         stats->launches = (int)(c.launches - launches0);
+        stats->rows_staged = nst.rows_staged; stats->rows_gather = nst.rows_gather; stats->tiles_dense = nst.tiles_dense;
+        stats->rows_smem = nst.rows_smem;
         // algorithmic bytes, SURVEY.md 8(d). A's share is the slab's tiles; B is read whole.
         long long a_tiles = A->numtile, a_nnz = A->nnz;
         if (ntr != A->tilem) {

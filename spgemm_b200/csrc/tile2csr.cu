@@ -1,52 +1,76 @@
 // tile2csr.cu -- tiled format -> CSR on the device. Replaces the reference's serial CPU code
 // (src/tile2csr.h:72-140; Tile_csr_to_csr_PTR :8-32, Tile_csr_to_csr :34-68).
 //
-// Same two passes as the reference, parallel over tile-rows: a half-warp owns a tile-row and lane r
-// owns matrix row 16*I + r. Pass 1 sums the per-tile row counts (Ptr[r+1]-Ptr[r], the last row
-// closing on the tile nnz, :22); an exclusive scan gives the row pointer; pass 2 walks the tiles of
-// the tile-row in ascending tile column and appends (tile_col*16 + Col, Val) at the row's cursor
-// (:55-58). Explicit zeros are kept (:27-28,59-60). Works on A/C-style tiles whose Col holds the
-// plain column (C, B); tiles in row-major storage order only.
+// Same two passes as the reference, but in ONE kernel and parallel over rows: pass 1 sums the per-tile row counts
+// (Ptr[r+1]-Ptr[r], the last row closing on the tile nnz, :22), pass 2 walks the tiles of the tile-row in ascending
+// tile column and appends (tile_col*16 + Col, Val) at the row's cursor (:55-58). Explicit zeros are kept
+// (:27-28,59-60). Works on A/C-style tiles whose Col holds the plain column (C, B) -- for A's packed row*16+col the
+// column is Col & 15 and callers do not need it; tiles in row-major storage order only.
 #include "common.cuh"
-#include "scan.cuh"
 #include "kernels.h"
 
 namespace tsg {
 
-template <bool FILL>
-__global__ void __launch_bounds__(128)
-k_tile2csr(int m, int tilem, const int *__restrict__ tile_ptr, const int *__restrict__ tile_col,
-           const int *__restrict__ tile_nnz, const uint16_t *__restrict__ ptr, const uint16_t *__restrict__ col,
-           const double *__restrict__ val, int *__restrict__ rowptr, int *__restrict__ out_col,
-           double *__restrict__ out_val)
+// One CTA per tile-row, warp r = matrix row 16*I + r, lanes = the tile-row's tiles. The number of entries in front of
+// a tile-row is already known -- tile_nnz[tile_ptr[I]], the scanned tile offsets -- so no separate counting pass or
+// global scan is needed: the 16 warps count their rows, a 16-entry prefix in shared memory gives every row pointer,
+// and the warps then append (tile_col*16 + Col, Val) tile by tile, 32 tiles at a time, each lane at the offset a warp
+// scan of the per-tile counts gives it. A tile-row with 10^5 tiles (R-MAT hubs) is walked by 512 threads, not 16.
+constexpr int T2C_THREADS = TS * 32;
+
+__global__ void __launch_bounds__(T2C_THREADS)
+k_tile2csr_rows(int m, int tilem, const int *__restrict__ tile_ptr, const int *__restrict__ tile_col,
+                const int *__restrict__ tile_nnz, const uint16_t *__restrict__ ptr, const uint16_t *__restrict__ col,
+                const double *__restrict__ val, int base, int *__restrict__ rowptr, int *__restrict__ out_col,
+                double *__restrict__ out_val)
 {
-    const int I = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4);
-    const int r = threadIdx.x & 15;
-    if (I >= tilem) return;
+    __shared__ int s_cnt[TS];
+    const int I = blockIdx.x, r = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = tile_ptr[I], t1 = tile_ptr[I + 1];
     const int row = I * TS + r;
-    const bool live = row < m;
-    int cursor = (FILL && live) ? rowptr[row] : 0;
     int cnt = 0;
-    const int t1 = tile_ptr[I + 1];
-    for (int t = tile_ptr[I]; t < t1; t++) {
-        const int base = tile_nnz[t], tnnz = tile_nnz[t + 1] - base;
-        if (tnnz == 0) continue;  // empty C tiles are legitimate (and 15/16 of them on hypersparse inputs): nothing to read
+    for (int t = t0 + lane; t < t1; t += 32) {
+        const int b = tile_nnz[t], tn = tile_nnz[t + 1] - b;
+        if (tn == 0) continue;  // empty C tiles are legitimate (15/16 of them on hypersparse inputs): nothing to read
         const int p0 = ptr[(size_t)t * TS + r];
-        const int p1 = r < TS - 1 ? (int)ptr[(size_t)t * TS + r + 1] : tnnz;
-        if (FILL) {
-            if (live) {
-                const int cb = tile_col[t] * TS;
-                for (int j = p0; j < p1; j++) {
-                    out_col[cursor] = cb + col[base + j];
-                    out_val[cursor] = val[base + j];
-                    cursor++;
-                }
-            }
-        } else {
-            cnt += p1 - p0;
-        }
+        cnt += (r < TS - 1 ? (int)ptr[(size_t)t * TS + r + 1] : tn) - p0;
     }
-    if (!FILL && live) rowptr[row] = cnt;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(FULL_MASK, cnt, o);
+    if (lane == 0) s_cnt[r] = cnt;
+    __syncthreads();
+    int cursor = tile_nnz[t0];  // entries of the slab in front of this tile-row
+    for (int q = 0; q < r; q++) cursor += s_cnt[q];
+    if (lane == 0 && row < m) rowptr[row] = cursor + base;
+    if (I == tilem - 1 && threadIdx.x == 0) rowptr[m] = tile_nnz[t1] + base;
+    if (row >= m || cnt == 0) return;
+    for (int tb = t0; tb < t1; tb += 32) {
+        const int t = tb + lane;
+        int b = 0, p0 = 0, n = 0;
+        if (t < t1) {
+            b = tile_nnz[t];
+            const int tn = tile_nnz[t + 1] - b;
+            if (tn) {
+                p0 = ptr[(size_t)t * TS + r];
+                n = (r < TS - 1 ? (int)ptr[(size_t)t * TS + r + 1] : tn) - p0;
+            }
+        }
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (n) {
+            const int cb = tile_col[t] * TS;
+            int dst = cursor + incl - n;
+            for (int j = b + p0; j < b + p0 + n; j++, dst++) {
+                out_col[dst] = cb + col[j];
+                out_val[dst] = val[j];
+            }
+        }
+        cursor += __shfl_sync(FULL_MASK, incl, 31);
+    }
 }
 
 // Per-row sums of the stored values (C * ones): a size-independent checksum for slabs too large to
@@ -99,23 +123,16 @@ int tile2csr_into(const tsg_dtile *T, int *rowptr, int *colidx, double *val, int
     Ctx &c = ctx();
     if (T->col_major) { set_error(TSG_ERR_UNSUPPORTED, "tile2csr: tiles must be in row-major storage order"); return last_error(); }
     const int m = T->m;
-    CK(cudaMemsetAsync(rowptr, 0, ((size_t)m + 1) * 4, c.stream));
-    const int blocks = ceil_div((long long)T->tilem * 16, 128);
-    if (T->tilem > 0 && T->numtile > 0) {
-        k_tile2csr<false><<<blocks, 128, 0, c.stream>>>(m, T->tilem, T->tile_ptr, T->tile_columnidx, T->tile_nnz, T->ptr, T->col, T->val,
-                                                        rowptr, nullptr, nullptr);
+    if (T->tilem > 0) {
+        k_tile2csr_rows<<<T->tilem, T2C_THREADS, 0, c.stream>>>(m, T->tilem, T->tile_ptr, T->tile_columnidx, T->tile_nnz, T->ptr, T->col,
+                                                                T->val, base, rowptr, colidx, val);
         CK_LAUNCH();
-    }
-    int rc = exclusive_scan<int>(rowptr, rowptr, m);
-    if (rc) return rc;
-    if (T->tilem > 0 && T->nnz > 0) {
-        k_tile2csr<true><<<blocks, 128, 0, c.stream>>>(m, T->tilem, T->tile_ptr, T->tile_columnidx, T->tile_nnz, T->ptr, T->col, T->val,
-                                                       rowptr, colidx, val);
-        CK_LAUNCH();
-    }
-    if (base) {
-        k_add_base<<<ceil_div((long long)m + 1, 256), 256, 0, c.stream>>>(rowptr, m + 1, base);
-        CK_LAUNCH();
+    } else {  // no rows: the row pointer is the single entry `base`
+        CK(cudaMemsetAsync(rowptr, 0, 4, c.stream));
+        if (base) {
+            k_add_base<<<1, 32, 0, c.stream>>>(rowptr, 1, base);
+            CK_LAUNCH();
+        }
     }
     return TSG_OK;
 }

@@ -474,3 +474,76 @@ def test_drop_in_tiles_without_mask_arrays():
     assert_tiled_equal(Cm.tiles(), tC_exp, "C from mask-less A, B")
     for x in (A, B, Cm):
         api.matrix_destroy(x)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Step 3 picks the accumulator per C tile (dense registers / sparse shared memory / lane-per-nonzero gather):
+# whatever it picks, C is the serial SPA's.
+# ---------------------------------------------------------------------------------------------------------------
+def _mixed_matrix():
+    """Block-diagonal [block-FEM | 27-point stencil | R-MAT]: well-filled tiles, sparse tiles and hypersparse tiles
+    with a hub tile-row in ONE matrix, so that one call exercises all three numeric kernels."""
+    import scipy.sparse as sp
+    parts = []
+    for gen in (lambda: M.blockfem(60), lambda: M.stencil27(9, 8, 7), lambda: M.rmat(10, 6, seed=4)):
+        m, n, rp, ci, v = gen()
+        parts.append(sp.csr_matrix((np.ones(len(ci)), ci, rp), shape=(m, n)))
+    S = sp.block_diag(parts, format="csr")
+    S.sort_indices()
+    return S.shape[0], S.shape[1], S.indptr.astype(np.int32), S.indices.astype(np.int32)
+
+
+@pytest.mark.parametrize("mode", ["auto", "rows", "gather", "dense", "dmma"])
+@pytest.mark.parametrize("values", ["mod10", "hash"])
+def test_numeric_kernel_selection(monkeypatch, mode, values):
+    m, n, rp, ci = _mixed_matrix()
+    v = M.set_values(len(ci), values)
+    A = (rp, ci, v)
+    _, tC_exp = oracle_c(m, n, A, A, n)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
+    monkeypatch.setenv("TSG_STEP3", mode)
+    if mode == "auto":
+        monkeypatch.setenv("TSG_ROWS_MIN_FILL", "4")  # let the small R-MAT block split between rows and gather
+    tC, st = api.spgemm(tA, tB)
+    exact = values == "mod10"
+    assert_tiled_equal(tC.download(), tC_exp, f"mixed/{mode}/{values}", val_rtol=0.0 if exact else VAL_RTOL)
+    if mode == "auto":
+        assert st["tiles_dense"] > 0 and st["rows_staged"] > 0, st
+    elif mode == "rows":
+        assert st["rows_staged"] > 0 and st["tiles_dense"] == 0 and st["rows_gather"] == 0, st
+    elif mode == "gather":
+        assert st["rows_gather"] > 0 and st["tiles_dense"] == 0 and st["rows_staged"] == 0, st
+    else:
+        assert st["tiles_dense"] == int((np.diff(tC_exp.tile_nnz) > 0).sum()), st
+    for o in (tC, tA, tB, d):
+        o.free()
+
+
+def test_numeric_rows_too_wide_for_shared_memory_fall_back(monkeypatch):
+    """A shared-memory budget smaller than most tile-rows: those rows take the gather, the rest stay staged."""
+    m, n, rp, ci, _ = M.stencil27(12, 9, 8)
+    v = M.set_values(len(ci), "mod10")
+    A = (rp, ci, v)
+    _, tC_exp = oracle_c(m, n, A, A, n)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
+    monkeypatch.setenv("TSG_ROWS_SMEM_KB", "12")
+    tC, st = api.spgemm(tA, tB)
+    assert st["rows_gather"] > 0 and st["rows_staged"] > 0, st
+    assert_tiled_equal(tC.download(), tC_exp, "smem-capped C")
+    for o in (tC, tA, tB, d):
+        o.free()
+
+
+def test_values_reproducible_run_to_run():
+    """Same inputs, two runs: bit-identical values (no atomics, fixed summation order) on the light path."""
+    m, n, rp, ci, _ = M.stencil27(10)
+    v = M.set_values(len(ci), "hash")
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
+    a, _ = api.spgemm(tA, tB)
+    b, _ = api.spgemm(tA, tB)
+    assert np.array_equal(a.download()["val"], b.download()["val"])
+    for o in (a, b, tA, tB, d):
+        o.free()
