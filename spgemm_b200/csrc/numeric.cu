@@ -72,13 +72,33 @@ __host__ __device__ __forceinline__ size_t al16(size_t x) { return (x + 15) & ~(
 __host__ __device__ __forceinline__ size_t s3r_need(int nA, int nnzA, int numJ, int nnzC, int W)
 {
     return 2 * al16((size_t)nA * 32) + al16(((size_t)nnzA + 2) * 8) + 2 * al16((size_t)numJ * 32) + al16((size_t)nnzC * 8) +
-           al16(((size_t)nA + 1) * 4) + al16(((size_t)numJ + 1) * 4) + 2 * al16((size_t)numJ * 4) + 2 * al16((size_t)W * 4) +
-           al16((size_t)nnzC * 2);
+           al16(((size_t)nA + 1) * 4) + al16(((size_t)numJ + 1) * 4) + 2 * al16((size_t)numJ * 4) + 3 * al16((size_t)W * 4) +
+           al16((size_t)nnzC * 2) + al16(((size_t)nnzA + 2) * 2) + al16((size_t)numJ * 2);
 }
 
 __global__ void k_ns_init(int *scal)
 {
     if (threadIdx.x < 8) scal[threadIdx.x] = threadIdx.x == NS_GLO ? 0x7fffffff : 0;
+}
+
+// Pass 1, one thread per C tile: the compacted list of the tiles that take the dense accumulator (order irrelevant:
+// tiles are independent), and row_kind[row] = ROW_STAGED for every tile-row that holds at least one non-empty tile
+// left to the sparse accumulators (pass 2 decides between staged and gather for exactly those rows).
+__global__ void __launch_bounds__(256)
+k_s3_classify_tiles(int numblkC, int trow0, const int *__restrict__ c_tile_nnz, const int *__restrict__ c_tile_row, int dense_th,
+                    int *__restrict__ dense_list, uint8_t *__restrict__ row_kind, int *__restrict__ scal)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int cnt = t < numblkC ? c_tile_nnz[t + 1] - c_tile_nnz[t] : 0;
+    const bool dense = cnt >= dense_th;
+    if (cnt > 0 && !dense) row_kind[c_tile_row[t] - trow0] = ROW_STAGED;  // benign race: every writer stores the same value
+    const unsigned m = __ballot_sync(FULL_MASK, dense);
+    if (!m) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&scal[NS_DENSE], __popc(m));
+    base = __shfl_sync(FULL_MASK, base, 0);
+    if (dense) dense_list[base + __popc(m & ((1u << lane) - 1))] = t;
 }
 
 __global__ void __launch_bounds__(256)
@@ -92,7 +112,7 @@ k_s3_classify_rows(int ntr, int trow0, const int *__restrict__ a_tile_ptr, const
     int need = 0, n0 = 0x7fffffff, n1 = 0;
     if (i < ntr) {
         const int c0 = c_tile_ptr[i], c1 = c_tile_ptr[i + 1], numJ = c1 - c0;
-        if (numJ > 0) {
+        if (numJ > 0 && row_kind[i] != ROW_NONE) {  // pass 1 found a tile for the sparse accumulators
             n0 = c_tile_nnz[c0]; n1 = c_tile_nnz[c1];
             const int nnzC = n1 - n0;
             if (nnzC > 0) {
@@ -120,32 +140,33 @@ k_s3_classify_rows(int ntr, int trow0, const int *__restrict__ a_tile_ptr, const
     }
 }
 
-// compacted list of the C tiles that take the dense accumulator (order irrelevant: tiles are independent)
-__global__ void __launch_bounds__(256)
-k_s3_classify_tiles(int numblkC, const int *__restrict__ c_tile_nnz, int dense_th, int *__restrict__ dense_list,
-                    int *__restrict__ scal)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const bool dense = t < numblkC && c_tile_nnz[t + 1] - c_tile_nnz[t] >= dense_th;
-    const unsigned m = __ballot_sync(FULL_MASK, dense);
-    if (!m) return;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&scal[NS_DENSE], __popc(m));
-    base = __shfl_sync(FULL_MASK, base, 0);
-    if (dense) dense_list[base + __popc(m & ((1u << lane) - 1))] = t;
-}
-
 // ---------------------------------------------------------------------------------------------
 // k_step3_rows: sparse accumulator in shared memory, CTA per C tile-row (see the file header).
+//
+// A HALF-WARP owns one C tile at a time (tiles are taken in descending order of their pair count, so the two
+// half-warps of a warp run tiles of similar shape in lockstep). Its pairs are processed in two phases:
+//   phase A, lanes = the 16 ROWS of the C tile, pairs whose A and B tiles both hold > S3R_SPARSE_MAX entries: lane r
+//            walks A's row r (the bits of its row mask are the k's) and B's rows k, every product lands in the row's
+//            compact accumulator. All 16 lanes are busy on well-filled pairs.
+//   phase B, lanes = PAIRS whose A or B tile holds <= S3R_SPARSE_MAX entries (the one-entry corner tiles of a stencil,
+//            R-MAT-like tiles): with lanes = rows such a pair would keep 1 of 16 lanes busy. Each lane enumerates the
+//            few products of its pair; per round every lane contributes one product (o, v), equal targets are summed
+//            in lane order (__match_any_sync + shuffles) and the lowest lane of each group updates the accumulator.
+// The order in which a C entry's contributions are added is fixed (phase A in pair order, then phase B in pair
+// order), so results are reproducible run to run; it is not the serial SPA's order for entries that receive from
+// both phases (values agree to rounding, and exactly for integer-valued inputs).
 // ---------------------------------------------------------------------------------------------
+constexpr int S3R_SPARSE_MAX = 2;
+constexpr unsigned PF_ASPARSE = 0x80000000u, PF_BSPARSE = 0x40000000u, PF_INDEX = 0x3fffffffu;
+constexpr int S3R_BUCKETS = 64;
+
 struct S3Rows {
     int trow0, dense_th;
     const int *a_tile_ptr, *a_tile_nnz;
-    const uint16_t *a_ptr, *a_mask;
+    const uint16_t *a_ptr, *a_mask, *a_col;
     const double *a_val;
     const int *b_tile_nnz;
-    const uint16_t *b_ptr, *b_mask;
+    const uint16_t *b_ptr, *b_mask, *b_col;
     const double *b_val;
     const int *c_tile_ptr, *c_tile_nnz;
     const uint16_t *c_ptr, *c_mask;
@@ -156,11 +177,13 @@ struct S3Rows {
 };
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 4 * 256 / THREADS)
 k_step3_rows(const __grid_constant__ S3Rows P)
 {
     extern __shared__ __align__(128) unsigned char s3r_smem[];
     __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ int s_hist[S3R_BUCKETS];
+    __shared__ int s_nord;
     const int i = blockIdx.x, tid = threadIdx.x;
     if (P.row_kind[i] != ROW_STAGED) return;
     const int I = P.trow0 + i;
@@ -186,9 +209,13 @@ k_step3_rows(const __grid_constant__ S3Rows P)
     int *s_pe = (int *)carve((size_t)numJ * 4);
     int *s_pa = (int *)carve((size_t)W * 4);
     int *s_pb = (int *)carve((size_t)W * 4);
+    int *s_pbn = (int *)carve((size_t)W * 4);
     uint16_t *s_ocol = (uint16_t *)carve((size_t)nnzC * 2);
+    uint16_t *s_acol = (uint16_t *)carve(((size_t)(av1 - av0) + 2) * 2);
+    uint16_t *s_order = (uint16_t *)carve((size_t)numJ * 2);
 
-    if (tid == 0) mbar_init(&s_bar, 1);
+    if (tid == 0) { mbar_init(&s_bar, 1); s_nord = 0; }
+    if (tid < S3R_BUCKETS) s_hist[tid] = 0;
     __syncthreads();
     if (tid == 0) {  // one elected thread arms the barrier and issues the five bulk copies
         mbar_expect_tx(&s_bar, (uint32_t)(nA * 64 + nav * 8 + numJ * 64));
@@ -198,60 +225,176 @@ k_step3_rows(const __grid_constant__ S3Rows P)
         bulk_g2s(s_cm, P.c_mask + (size_t)c0 * TS, (uint32_t)numJ * 32, &s_bar);
         bulk_g2s(s_cp, P.c_ptr + (size_t)c0 * TS, (uint32_t)numJ * 32, &s_bar);
     }
-    // everything whose source is only 4-byte aligned: plain coalesced loads, overlapping the bulk copies
+    // everything whose source is only 2/4-byte aligned: plain coalesced loads, overlapping the bulk copies
     for (int k = tid; k <= nA; k += THREADS) s_annz[k] = P.a_tile_nnz[a0 + k] - av0a;
+    for (int k = tid; k < av1 - av0a; k += THREADS) s_acol[k] = P.a_col[av0a + k];
     int dense_here = 0;
     for (int k = tid; k <= numJ; k += THREADS) {
         const int v = P.c_tile_nnz[c0 + k] - n0;
         s_cnnz[k] = v;
         if (k < numJ) {
-            s_pp[k] = P.pair_ptr[c0 + k] - w0;
-            s_pe[k] = P.pair_end[c0 + k] - w0;
-            dense_here |= (P.c_tile_nnz[c0 + k + 1] - n0 - v) >= P.dense_th;
+            const int pp = P.pair_ptr[c0 + k] - w0, pe = P.pair_end[c0 + k] - w0;
+            s_pp[k] = pp;
+            s_pe[k] = pe;
+            const int cnt = P.c_tile_nnz[c0 + k + 1] - n0 - v;
+            if (cnt >= P.dense_th) dense_here = 1;
+            else if (cnt > 0) atomicAdd(&s_hist[S3R_BUCKETS - 1 - min(pe - pp, S3R_BUCKETS - 1)], 1);  // most pairs first
         }
     }
-    for (int k = tid; k < W; k += THREADS) { s_pa[k] = P.pair_a[w0 + k] - a0; s_pb[k] = P.pair_b[w0 + k]; }
+    for (int k = tid; k < W; k += THREADS) {
+        const int ta = P.pair_a[w0 + k], b = P.pair_b[w0 + k];
+        const int bn0 = P.b_tile_nnz[b];
+        unsigned f = (unsigned)(ta - a0);
+        if (P.a_tile_nnz[ta + 1] - P.a_tile_nnz[ta] <= S3R_SPARSE_MAX) f |= PF_ASPARSE;
+        if (P.b_tile_nnz[b + 1] - bn0 <= S3R_SPARSE_MAX) f |= PF_BSPARSE;
+        s_pa[k] = (int)f;
+        s_pb[k] = b;
+        s_pbn[k] = bn0;
+    }
     for (int k = tid; k < nnzC; k += THREADS) s_out[k] = 0.0;
     const int has_dense = __syncthreads_or(dense_here);
+    if (tid < 32) {  // exclusive scan of the 64 bucket counts by one warp
+        const int v0 = s_hist[2 * tid], v1 = s_hist[2 * tid + 1];
+        int incl = v0 + v1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL_MASK, incl, o);
+            if (tid >= o) incl += t;
+        }
+        s_hist[2 * tid] = incl - v0 - v1;
+        s_hist[2 * tid + 1] = incl - v1;
+        if (tid == 31) s_nord = incl;
+    }
+    __syncthreads();
+    for (int k = tid; k < numJ; k += THREADS) {  // counting sort of the sparse-accumulator tiles by pair count, descending
+        const int cnt = s_cnnz[k + 1] - s_cnnz[k];
+        if (cnt > 0 && cnt < P.dense_th) s_order[atomicAdd(&s_hist[S3R_BUCKETS - 1 - min(s_pe[k] - s_pp[k], S3R_BUCKETS - 1)], 1)] = (uint16_t)k;
+    }
+    __syncthreads();
     mbar_wait(&s_bar, 0);
 
-    for (int idx = tid; idx < numJ * TS; idx += THREADS) {
-        const int s = idx >> 4, r = idx & 15;
-        const unsigned cm = s_cm[idx];
-        if (!cm) continue;
+    const int lane = tid & 31, l16 = tid & 15;
+    const unsigned hm = 0xFFFFu << (lane & 16);
+    const int nord = s_nord;
+    const double *__restrict__ bvals = P.b_val;
+    for (int q = tid >> 4; q < nord; q += THREADS / 16) {
+        const int s = s_order[q];
         const int tb = s_cnnz[s];
-        if (s_cnnz[s + 1] - tb >= P.dense_th) continue;  // this tile takes the dense accumulator (k_step3_dense)
-        const int rowbase = tb + s_cp[idx];
+        const int pp = s_pp[s], pe = s_pe[s];
+        // ---------------- phase A: lane = row l16 of the tile ----------------
         {
-            unsigned m = cm;
-            int o = rowbase;
-            do { const int c = __clz(m) - 16; m ^= 0x8000u >> c; s_ocol[o++] = (uint16_t)c; } while (m);
-        }
-        const unsigned cmr = __brev(cm) >> 16;  // bit c = column c
-        const double *__restrict__ bvals = P.b_val;
-        const int pe = s_pe[s];
-        for (int p = s_pp[s]; p < pe; p++) {
-            const int a = s_pa[p];
-            unsigned am = s_am[a * TS + r];
-            if (!am) continue;  // the pair does not touch this row
-            const int b = s_pb[p];
-            int ia = s_annz[a] + s_ap[a * TS + r];
-            const int bbase = P.b_tile_nnz[b];
-            const uint16_t *bmk = P.b_mask + (size_t)b * TS, *bpt = P.b_ptr + (size_t)b * TS;
-            do {  // the bits of A's row mask are the k's of the row, ascending
-                const int k = __clz(am) - 16;
-                am ^= 0x8000u >> k;
-                const double av = s_aval[ia++];
-                unsigned bm = __brev((unsigned)bmk[k]) >> 16;  // bit c = column c
-                int ib = bbase + bpt[k];
-                while (bm) {  // B's row k: every entry is a product into C's row r
-                    const unsigned low = bm & (0u - bm);
-                    const int o = rowbase + __popc(cmr & (low - 1));  // rank of the column in C's row
-                    bm ^= low;
-                    s_out[o] = fma(av, bvals[ib++], s_out[o]);
+            const int r = l16;
+            const unsigned cm = s_cm[s * TS + r];
+            if (cm) {
+                const int rowbase = tb + s_cp[s * TS + r];
+                {
+                    unsigned m = cm;
+                    int o = rowbase;
+                    do { const int c = __clz(m) - 16; m ^= 0x8000u >> c; s_ocol[o++] = (uint16_t)c; } while (m);
                 }
-            } while (am);
+                const unsigned cmr = __brev(cm) >> 16;  // bit c = column c
+                for (int p = pp; p < pe; p++) {
+                    const unsigned fa = (unsigned)s_pa[p];
+                    if (fa & (PF_ASPARSE | PF_BSPARSE)) continue;  // phase B (uniform over the half-warp)
+                    unsigned am = s_am[fa * TS + r];
+                    if (!am) continue;  // the pair does not touch this row
+                    const int b = s_pb[p];
+                    int ia = s_annz[fa] + s_ap[fa * TS + r];
+                    const int bbase = s_pbn[p];
+                    const uint16_t *bmk = P.b_mask + (size_t)b * TS, *bpt = P.b_ptr + (size_t)b * TS;
+                    do {  // the bits of A's row mask are the k's of the row, ascending
+                        const int k = __clz(am) - 16;
+                        am ^= 0x8000u >> k;
+                        const double av = s_aval[ia++];
+                        unsigned bm = __brev((unsigned)bmk[k]) >> 16;
+                        int ib = bbase + bpt[k];
+                        while (bm) {  // B's row k: every entry is a product into C's row r
+                            const unsigned low = bm & (0u - bm);
+                            const int o = rowbase + __popc(cmr & (low - 1));  // rank of the column in C's row
+                            bm ^= low;
+                            s_out[o] = fma(av, bvals[ib++], s_out[o]);
+                        }
+                    } while (am);
+                }
+            }
         }
+        __syncwarp(hm);
+        // ---------------- phase B: lane = one sparse pair ----------------
+        for (int base = pp; base < pe; base += 16) {
+            const int p = base + l16;
+            const unsigned fa = p < pe ? (unsigned)s_pa[p] : 0u;
+            const bool spA = (fa & PF_ASPARSE) != 0, spB = !spA && (fa & PF_BSPARSE) != 0;
+            if (!__any_sync(hm, spA || spB)) continue;
+            const int a = (int)(fa & PF_INDEX);
+            int b = 0, bbase = 0;
+            if (spA || spB) { b = s_pb[p]; bbase = s_pbn[p]; }
+            // product stream state
+            int e = 0, e1 = 0;            // spA: A entries [e, e1) (indices into s_aval / s_acol); spB: B entries [e, e1) (global)
+            unsigned rem = 0;             // spA: remaining columns of B's row k (bit c); spB: remaining rows r with A(r,k) (bit r)
+            int ib = 0, rb = 0, kc = 0;   // spA: next B value index, row base of C's row; spB: kc = k | c << 4
+            unsigned cmr = 0;
+            double x = 0.0;               // spA: A's value; spB: B's value
+            if (spA) { e = s_annz[a]; e1 = s_annz[a + 1]; }
+            else if (spB) { e = bbase; e1 = P.b_tile_nnz[b + 1]; }
+            while (true) {
+                int o = -1 - lane;
+                double v = 0.0;
+                if (spA) {
+                    while (!rem && e < e1) {  // next A entry (r, k): B's row k
+                        const unsigned col = s_acol[e];
+                        const int r = col >> 4, k = col & 15;
+                        x = s_aval[e++];
+                        rem = __brev((unsigned)P.b_mask[(size_t)b * TS + k]) >> 16;
+                        ib = bbase + P.b_ptr[(size_t)b * TS + k];
+                        cmr = __brev((unsigned)s_cm[s * TS + r]) >> 16;
+                        rb = tb + s_cp[s * TS + r];
+                    }
+                    if (rem) {
+                        const unsigned low = rem & (0u - rem);
+                        rem ^= low;
+                        o = rb + __popc(cmr & (low - 1));
+                        v = x * bvals[ib++];
+                    }
+                } else if (spB) {
+                    while (!rem && e < e1) {  // next B entry (k, c): the rows of A that hold column k
+                        const int c = P.b_col[e];
+                        x = bvals[e];
+                        const int j = e - bbase;
+                        e++;
+                        int k = 0;  // row of B's entry j: the last row whose Ptr is <= j
+#pragma unroll
+                        for (int q2 = 1; q2 < TS; q2++) k += (int)P.b_ptr[(size_t)b * TS + q2] <= j;
+                        kc = k | (c << 4);
+                        const unsigned bit = 0x8000u >> k;
+#pragma unroll
+                        for (int r = 0; r < TS; r++) rem |= (s_am[a * TS + r] & bit) ? (1u << r) : 0u;
+                    }
+                    if (rem) {
+                        const int r = __ffs(rem) - 1;
+                        rem &= rem - 1;
+                        const int k = kc & 15, c = kc >> 4;
+                        const unsigned am = s_am[a * TS + r];
+                        const double av = s_aval[s_annz[a] + s_ap[a * TS + r] + __popc(am >> (16 - k))];
+                        const unsigned cr = __brev((unsigned)s_cm[s * TS + r]) >> 16;
+                        o = tb + s_cp[s * TS + r] + __popc(cr & ((1u << c) - 1));
+                        v = av * x;
+                    }
+                }
+                if (!__any_sync(hm, o >= 0)) break;
+                // equal targets: summed in lane order by every lane of the group, committed by its lowest lane
+                const unsigned peers = __match_any_sync(hm, o);
+                double sum = 0.0;
+                unsigned left = o >= 0 ? peers : 0u;
+                while (__any_sync(hm, left != 0)) {
+                    const int src = left ? __ffs(left) - 1 : lane;
+                    const double y = __shfl_sync(hm, v, src);
+                    if (left) { sum += y; left &= left - 1; }
+                }
+                if (o >= 0 && lane == __ffs(peers) - 1) s_out[o] += sum;
+                __syncwarp(hm);
+            }
+        }
+        __syncwarp(hm);
     }
     __syncthreads();
     if (!has_dense) {
@@ -585,14 +728,14 @@ int numeric_classify_device(const tsg_dtile *A, const tsg_dtile *C, int trow0, i
     if (cap > c.smem_optin) cap = c.smem_optin;
     nb->smem_cap = (int)cap;
     if (ntr > 0 && numblkC > 0) {
+        CK(cudaMemsetAsync(nb->row_kind, 0, (size_t)ntr, c.stream));
+        k_s3_classify_tiles<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>((int)numblkC, trow0, C->tile_nnz, C->tile_rowidx, dense_th,
+                                                                         nb->dense_list, nb->row_kind, d_ns);
+        CK_LAUNCH();
         k_s3_classify_rows<<<ceil_div(ntr, 256), 256, 0, c.stream>>>(ntr, trow0, A->tile_ptr, A->tile_nnz, C->tile_ptr, C->tile_nnz, wptr,
                                                                       (int)cap, env_int("TSG_ROWS_MIN_FILL", 8), force_kind,
                                                                       nb->row_kind, d_ns);
         CK_LAUNCH();
-        if (dense_th <= 256) {
-            k_s3_classify_tiles<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>((int)numblkC, C->tile_nnz, dense_th, nb->dense_list, d_ns);
-            CK_LAUNCH();
-        }
     }
     return TSG_OK;
 }
@@ -616,8 +759,8 @@ int numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, int tro
         CK_LAUNCH();
     }
     if (n_staged > 0) {
-        S3Rows P{trow0, nb.dense_th, A->tile_ptr, A->tile_nnz, A->ptr, A->mask, A->val, B->tile_nnz, B->ptr, B->mask, B->val,
-                 C->tile_ptr, C->tile_nnz, C->ptr, C->mask, C->col, C->val, wptr, pl.ptr, pl.end, pl.a, pl.b, nb.row_kind};
+        S3Rows P{trow0, nb.dense_th, A->tile_ptr, A->tile_nnz, A->ptr, A->mask, A->col, A->val, B->tile_nnz, B->ptr, B->mask, B->col,
+                 B->val, C->tile_ptr, C->tile_nnz, C->ptr, C->mask, C->col, C->val, wptr, pl.ptr, pl.end, pl.a, pl.b, nb.row_kind};
         const size_t smem = ((size_t)h_ns[NS_MAXNEED] + 1023) & ~(size_t)1023;
         // 128-thread CTAs when a tile-row has few (tile, row) slots (2D meshes): fewer idle threads, more CTAs per SM
         const bool narrow = numblkC * TS < (long long)ntr * 192;
