@@ -71,7 +71,8 @@ typedef struct
  * Part 1 -- drop-in entry points (host buffers in, host buffers out; malloc()-owned results so
  * the driver's free()/matrix_destroy() keep working). Only 16x16 tiles are implemented;
  * any other tile_size_m/tile_size_n sets TSG_ERR_UNSUPPORTED.
- * Input contract: CSR rows sorted by column and duplicate-free (checked on the device).
+ * Input contract: CSR rows sorted by column and duplicate-free. csr2tile_row_major / csr2tile_col_major accept rows
+ * that are not (they sort and merge on the device first, see tsg_csr_canonicalize); the tsg_* API reports TSG_ERR_INPUT.
  * ---------------------------------------------------------------------------------------- */
 
 /* Replaces reference src/csr2tile.h:205. Fills tilem, tilen, numtile, tile_ptr, tile_columnidx,
@@ -197,8 +198,18 @@ int tsg_csr_upload(int m, int n, const int *rowptr, const int *colidx, const dou
 int tsg_csr_wrap(int m, int n, long long nnz, int *d_rowptr, int *d_colidx, double *d_val, tsg_dcsr *out);
 int tsg_csr_download(const tsg_dcsr *a, int *rowptr, int *colidx, double *val);
 void tsg_csr_free(tsg_dcsr *a);
-/* Checks the input contract (sorted, duplicate-free, in-range columns). */
+/* Checks the input contract (sorted, duplicate-free, in-range columns). upload and wrap already check the index
+ * ranges (column in [0,n), row pointer monotone and ending at nnz: TSG_ERR_INPUT) before anything indexes by them. */
 int tsg_csr_validate(const tsg_dcsr *a);
+/* Rows [row0, row1) of a device CSR as a CSR of its own: the row pointer is a rebased copy, colidx / val are BORROWED
+ * from `a`, which must outlive the slice (free the slice with tsg_csr_free). No host round trip: this is how a rank of
+ * the multi-GPU path takes its tile-rows out of the broadcast matrix. */
+int tsg_csr_row_slice(const tsg_dcsr *a, int row0, int row1, tsg_dcsr *out);
+/* Canonical form of a CSR whose rows are unsorted and / or hold duplicate columns -- what the reference's MatrixMarket
+ * loader produces (src/mmio_highlevel.h:593-759: neither sorted nor merged): entries ordered by (row, column), duplicates
+ * merged (dup_policy 0: summed in their original order; 1: first one kept). The drop-in csr2tile_* entry points do this
+ * by themselves when they meet such input; the device API is strict (TSG_ERR_INPUT) and leaves the choice to the caller. */
+int tsg_csr_canonicalize(const tsg_dcsr *a, int dup_policy, tsg_dcsr *out);
 
 /* Device matrix_transposition (reference src/utils.h:161): AT = A^T as CSR, stable. */
 int tsg_transpose(const tsg_dcsr *a, tsg_dcsr *at);

@@ -238,6 +238,20 @@ class DeviceCSR:
         L.check(L.load().tsg_csr_download(C.byref(self.d), C.c_void_p(rowptr_addr), C.c_void_p(colidx_addr),
                                           C.c_void_p(val_addr)))
 
+    def row_slice(self, row0: int, row1: int) -> "DeviceCSR":
+        """Rows [row0, row1) as a CSR of its own (rebased row pointer; colidx / val borrowed from self, which must
+        outlive the slice)."""
+        out = DeviceCSR()
+        L.check(L.load().tsg_csr_row_slice(C.byref(self.d), int(row0), int(row1), C.byref(out.d)))
+        out._parent = self
+        return out
+
+    def canonicalize(self, dup_policy: str = "sum") -> "DeviceCSR":
+        """Sorted, duplicate-free copy (tsg_csr_canonicalize); dup_policy 'sum' or 'first'."""
+        out = DeviceCSR()
+        L.check(L.load().tsg_csr_canonicalize(C.byref(self.d), {"sum": 0, "first": 1}[dup_policy], C.byref(out.d)))
+        return out
+
     def free(self):
         L.load().tsg_csr_free(C.byref(self.d))
 

@@ -57,7 +57,11 @@ static void big_cache_trim(size_t max_bytes, size_t max_blocks)
     }
 }
 
-void *dalloc(size_t bytes)
+static void *dalloc_impl(size_t bytes, bool quiet);
+void *dalloc(size_t bytes) { return dalloc_impl(bytes, false); }
+
+// quiet: a failure returns nullptr without latching an error (the caller has a smaller request to fall back to)
+static void *dalloc_impl(size_t bytes, bool quiet)
 {
     void *p = nullptr;
     if (bytes == 0) bytes = 256;
@@ -83,7 +87,7 @@ void *dalloc(size_t bytes)
     }
     if (e != cudaSuccess) {
         cudaGetLastError();
-        set_error(TSG_ERR_NOMEM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        if (!quiet) set_error(TSG_ERR_NOMEM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
         return nullptr;
     }
     if (bytes >= BIG_MIN) g_big_live[p] = bytes;
@@ -138,7 +142,7 @@ void *cslab_take(int which, size_t bytes, size_t *cap)
         return p;
     }
     size_t want = bytes + bytes / 8 + 4096;
-    void *p = dalloc(want);
+    void *p = dalloc_impl(want, true);  // headroom is optional: only the exact-size retry may latch an error
     if (!p) { want = bytes; p = dalloc(want); }
     *cap = p ? want : 0;
     return p;
@@ -340,12 +344,17 @@ int tsg_csr_upload(int m, int n, const int *rowptr, const int *colidx, const dou
     if (nnz < 0) { set_error(TSG_ERR_INPUT, "tsg_csr_upload: rowptr[m] = %lld", nnz); return g_err; }
     int rc = csr_alloc(m, n, nnz, out);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(out->rowptr, rowptr, ((size_t)m + 1) * 4, cudaMemcpyHostToDevice, g_ctx.stream));
-    if (nnz > 0) {
-        CK(cudaMemcpyAsync(out->colidx, colidx, (size_t)nnz * 4, cudaMemcpyHostToDevice, g_ctx.stream));
-        CK(cudaMemcpyAsync(out->val, val, (size_t)nnz * 8, cudaMemcpyHostToDevice, g_ctx.stream));
+    if (!cuda_ok(cudaMemcpyAsync(out->rowptr, rowptr, ((size_t)m + 1) * 4, cudaMemcpyHostToDevice, g_ctx.stream), "upload rowptr", __FILE__, __LINE__)) {
+        tsg_csr_free(out);
+        return g_err;
     }
-    CK(cudaStreamSynchronize(g_ctx.stream));
+    if (nnz > 0 && (!cuda_ok(cudaMemcpyAsync(out->colidx, colidx, (size_t)nnz * 4, cudaMemcpyHostToDevice, g_ctx.stream), "upload colidx", __FILE__, __LINE__) ||
+                    !cuda_ok(cudaMemcpyAsync(out->val, val, (size_t)nnz * 8, cudaMemcpyHostToDevice, g_ctx.stream), "upload val", __FILE__, __LINE__))) {
+        tsg_csr_free(out);
+        return g_err;
+    }
+    rc = csr_check_device(out);  // column range / row pointer monotonicity, before any kernel indexes by them (synchronises)
+    if (rc) { tsg_csr_free(out); return rc; }
     return TSG_OK;
 }
 
@@ -354,6 +363,24 @@ int tsg_csr_wrap(int m, int n, long long nnz, int *d_rowptr, int *d_colidx, doub
     if (ensure_init()) return g_err;
     memset(out, 0, sizeof(*out));
     out->m = m; out->n = n; out->nnz = nnz; out->rowptr = d_rowptr; out->colidx = d_colidx; out->val = d_val; out->owner = nullptr;
+    int rc = csr_check_device(out);
+    if (rc) memset(out, 0, sizeof(*out));
+    return rc;
+}
+
+int tsg_csr_row_slice(const tsg_dcsr *a, int row0, int row1, tsg_dcsr *out)
+{
+    if (ensure_init()) return g_err;
+    return csr_row_slice_device(a, row0, row1, out);
+}
+
+int tsg_csr_canonicalize(const tsg_dcsr *a, int dup_policy, tsg_dcsr *out)
+{
+    if (ensure_init()) return g_err;
+    if (dup_policy != 0 && dup_policy != 1) { set_error(TSG_ERR_INPUT, "canonicalize: dup_policy must be 0 (sum) or 1 (keep first)"); return g_err; }
+    int rc = csr_canonicalize_device(a, dup_policy, out);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(g_ctx.stream));
     return TSG_OK;
 }
 
@@ -518,14 +545,20 @@ int tsg_tilerow_weights(const tsg_dtile *a, const tsg_dtile *b, long long *w_hos
     if (a->n != b->m) { set_error(TSG_ERR_UNSUPPORTED, "weights: inner dimensions differ"); return g_err; }
     int *w = nullptr, *jlo = nullptr, *jhi = nullptr;
     int rc = tilerow_weights_device(a, b, &w, &jlo, &jhi);
-    if (rc) return rc;
-    int *hw = (int *)malloc(((size_t)a->tilem + 1) * 4);
-    CK(cudaMemcpyAsync(hw, w, (size_t)a->tilem * 4, cudaMemcpyDeviceToHost, g_ctx.stream));
-    CK(cudaStreamSynchronize(g_ctx.stream));
-    for (int i = 0; i < a->tilem; i++) w_host[i] = hw[i];
-    free(hw);
+    std::vector<int> hw((size_t)a->tilem + 1);
+    int overflow = 0;
+    if (!rc && a->tilem > 0 &&
+        !cuda_ok(cudaMemcpyAsync(hw.data(), w, (size_t)a->tilem * 4, cudaMemcpyDeviceToHost, g_ctx.stream), "weights D2H", __FILE__, __LINE__))
+        rc = g_err;
+    if (!rc) rc = read_back_i32((int *)g_ctx.d_scalars + 1, &overflow);  // k_step1_weights raises scal[1] when a row's weight passes int32
+    if (!rc && overflow) {
+        set_error(TSG_ERR_OVERFLOW, "weights: a tile-row has more than 2^31-1 matched tile pairs");
+        rc = g_err;
+    }
+    if (!rc)
+        for (int i = 0; i < a->tilem; i++) w_host[i] = hw[i];
     dfree(w); dfree(jlo); dfree(jhi);
-    return TSG_OK;
+    return rc;
 }
 
 int tsg_spgemm(const tsg_dtile *a, const tsg_dtile *b, int trow0, int trow1, tsg_dtile *c, tsg_stats *stats)
@@ -551,14 +584,16 @@ int tsg_tile_rowsums(const tsg_dtile *t, double *sums_host, long long *counts_ho
     const size_t m = (size_t)(t->m > 0 ? t->m : 1);
     double *d_s = dalloc_n<double>(m);
     long long *d_c = dalloc_n<long long>(m);
-    if (!d_s || !d_c) return g_err;
-    int rc = tile_rowsums_device(t, d_s, d_c);
-    if (rc) return rc;
-    if (sums_host && t->m > 0) CK(cudaMemcpyAsync(sums_host, d_s, (size_t)t->m * 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    if (counts_host && t->m > 0) CK(cudaMemcpyAsync(counts_host, d_c, (size_t)t->m * 8, cudaMemcpyDeviceToHost, g_ctx.stream));
-    CK(cudaStreamSynchronize(g_ctx.stream));
+    int rc = (!d_s || !d_c) ? g_err : tile_rowsums_device(t, d_s, d_c);
+    if (!rc && sums_host && t->m > 0 &&
+        !cuda_ok(cudaMemcpyAsync(sums_host, d_s, (size_t)t->m * 8, cudaMemcpyDeviceToHost, g_ctx.stream), "rowsums D2H", __FILE__, __LINE__))
+        rc = g_err;
+    if (!rc && counts_host && t->m > 0 &&
+        !cuda_ok(cudaMemcpyAsync(counts_host, d_c, (size_t)t->m * 8, cudaMemcpyDeviceToHost, g_ctx.stream), "rowcounts D2H", __FILE__, __LINE__))
+        rc = g_err;
+    if (!cuda_ok(cudaStreamSynchronize(g_ctx.stream), "rowsums sync", __FILE__, __LINE__)) rc = g_err;
     dfree(d_s); dfree(d_c);
-    return TSG_OK;
+    return rc;
 }
 
 int tsg_spgemm_csr_host(int m, int k, int n, const int *a_rowptr, const int *a_colidx, const double *a_val,
@@ -763,17 +798,32 @@ int tsg_spgemm_csr_host_into(int m, int k, int n, const int *a_rowptr, const int
 static void csr2tile_host(SMatrix *mat, int tm, int tn, int col_major)
 {
     if (ensure_init() || !tiles_16(tm, tn)) return;
-    tsg_dcsr A;
+    tsg_dcsr A, An;
     tsg_dtile t;
-    memset(&t, 0, sizeof(t));
+    memset(&t, 0, sizeof(t)); memset(&An, 0, sizeof(An));
     if (tsg_csr_upload(mat->m, mat->n, mat->rowpointer, mat->columnindex, mat->value, &A)) return;
-    if (tsg_csr2tile(&A, col_major, &t) == TSG_OK) {
+    int rc = tsg_csr2tile(&A, col_major, &t);
+    if (rc == TSG_ERR_INPUT && last_input_flags() == 2) {
+        // The reference's loader neither sorts rows nor merges duplicates (src/mmio_highlevel.h:593-759) and its csr2tile
+        // takes whatever order it is given (src/csr2tile.h:152-168). The kernels here need sorted, duplicate-free rows:
+        // bring the matrix into that form on the device (duplicates summed; TSG_DUP_POLICY=first keeps the first) and retry.
+        // With duplicates the tiled matrix then holds fewer entries than mat->nnz says; mat->nnz is updated.
+        static bool told = false;
+        if (!told) { fprintf(stderr, "[tilespgemm_b200] note: CSR rows unsorted or with duplicates; canonicalised on the device\n"); told = true; }
+        tilespgemm_clear_error();
+        tsg_tile_free(&t);
+        const char *pol = getenv("TSG_DUP_POLICY");
+        rc = tsg_csr_canonicalize(&A, pol && !strcmp(pol, "first") ? 1 : 0, &An);
+        if (!rc) rc = tsg_csr2tile(&An, col_major, &t);
+    }
+    if (rc == TSG_OK) {
         // tsg_tile_download overwrites the size fields with identical values and fills the tile arrays;
         // the CSR members of *mat (caller-owned, possibly aliased by B, src/main.cu:145-151) are untouched.
         tsg_tile_download(&t, mat);
     }
     tsg_tile_free(&t);
     tsg_csr_free(&A);
+    tsg_csr_free(&An);
 }
 
 void csr2tile_row_major(SMatrix *matrix, int tile_size_m, int tile_size_n) { csr2tile_host(matrix, tile_size_m, tile_size_n, 0); }

@@ -22,6 +22,8 @@
 
 namespace tsg {
 
+static int g_input_flags = 0;  // flags of the last csr2tile contract violation (the drop-in entry points retry on 2)
+
 // ---------------------------------------------------------------------------------------------
 // Tile discovery. FILL = false: count tiles per tile-row. FILL = true: emit, at row-major tile id,
 // tile column / tile row / tile nnz count / per-row exclusive offsets (Ptr) / row masks.
@@ -317,10 +319,182 @@ int csr2tile_device(const tsg_dcsr *A, int col_major, tsg_dtile *out)
     rc = read_back_i32(err, &flag);
     if (rc) return rc;
     if (flag) {
+        g_input_flags = flag;
         set_error(TSG_ERR_INPUT, "csr2tile: CSR input violates the contract (flags=%d: 1=column out of range, 2=row not sorted/duplicate, 4=internal)", flag);
         return last_error();
     }
     return TSG_OK;
+}
+
+int last_input_flags() { return g_input_flags; }
+
+// ---------------------------------------------------------------------------------------------
+// Range validation of a CSR on the device: rowptr[0] = 0, rowptr non-decreasing, rowptr[m] = nnz, 0 <= col < n.
+// Everything downstream indexes arrays by these values (k_boundaries writes ptr[key], k_nnzcub reads rowptrB[col]),
+// so it runs once per CSR that enters the library (tsg_csr_upload / tsg_csr_wrap), before any other kernel sees it.
+// Sortedness inside a row is checked later, by the scatter kernel of csr2tile (it only compares, never indexes).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_csr_check(int m, int n, long long nnz, const int *__restrict__ rowptr, const int *__restrict__ colidx, int *__restrict__ err)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int bad = 0;
+    if (t0 == 0 && (rowptr[0] != 0 || (long long)rowptr[m] != nnz)) bad |= 8;
+    for (long long i = t0; i < m; i += stride)
+        if (rowptr[i] > rowptr[i + 1] || rowptr[i] < 0) bad |= 8;
+    for (long long p = t0; p < nnz; p += stride) {
+        const int c = colidx[p];
+        if (c < 0 || c >= n) bad |= 1;
+    }
+    if (bad) atomicOr(err, bad);
+}
+
+int csr_check_device(const tsg_dcsr *A)
+{
+    Ctx &c = ctx();
+    if (A->m < 0 || A->n < 0 || A->nnz < 0) { set_error(TSG_ERR_INPUT, "CSR with negative sizes"); return last_error(); }
+    CK(cudaMemsetAsync(c.d_scalars, 0, sizeof(long long), c.stream));
+    const long long work = A->nnz > A->m ? A->nnz : (long long)A->m + 1;
+    int blocks = (int)min((long long)c.num_sms * 16, (work + 255) / 256);
+    if (blocks < 1) blocks = 1;
+    k_csr_check<<<blocks, 256, 0, c.stream>>>(A->m, A->n, A->nnz, A->rowptr, A->colidx, (int *)c.d_scalars);
+    CK_LAUNCH();
+    int flag = 0;
+    int rc = read_back_i32((int *)c.d_scalars, &flag);
+    if (rc) return rc;
+    if (flag) {
+        set_error(TSG_ERR_INPUT, "CSR input out of range (flags=%d: 1=column index outside [0,n), 8=row pointer not monotone / rowptr[m] != nnz)", flag);
+        return last_error();
+    }
+    return TSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rows [r0, r1) of a device CSR as a CSR of its own: a rebased copy of the row pointer; colidx / val are BORROWED
+// from the parent (which must outlive the slice). This is how each rank of the multi-GPU path takes its tile-rows
+// out of the broadcast matrix without a host round trip.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_rebase(const int *__restrict__ in, int *__restrict__ out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int base = in[0];
+    if (i < n) out[i] = in[i] - base;
+}
+
+int csr_row_slice_device(const tsg_dcsr *A, int r0, int r1, tsg_dcsr *out)
+{
+    Ctx &c = ctx();
+    memset(out, 0, sizeof(*out));
+    if (r0 < 0 || r1 < r0 || r1 > A->m) { set_error(TSG_ERR_INPUT, "csr_row_slice: rows [%d,%d) outside [0,%d]", r0, r1, A->m); return last_error(); }
+    int *rp = dalloc_n<int>((size_t)(r1 - r0) + 1);
+    if (!rp) return last_error();
+    k_rebase<<<ceil_div((long long)(r1 - r0) + 1, 256), 256, 0, c.stream>>>(A->rowptr + r0, rp, r1 - r0 + 1);
+    CK_LAUNCH();
+    int ends[2] = {0, 0};
+    int rc = publish_words(&c.h_scalars[14], A->rowptr + r0, 1);
+    if (!rc) rc = read_back_i32(A->rowptr + r1, &ends[1]);
+    if (rc) { dfree(rp); return rc; }
+    ends[0] = *(const volatile int *)&c.h_scalars[14];
+    out->m = r1 - r0; out->n = A->n; out->nnz = (long long)ends[1] - ends[0];
+    out->rowptr = rp; out->colidx = A->colidx + ends[0]; out->val = A->val + ends[0]; out->owner = rp;
+    return TSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Canonical form of a CSR whose rows are not sorted and / or hold duplicate columns (the reference's MatrixMarket
+// loader, src/mmio_highlevel.h:593-759, neither sorts nor merges): entries ordered by (row, column), duplicates
+// merged -- dup_policy 0: values summed in their original order; 1: the first one kept. Two stable LSD radix sorts
+// (by column, then by row) give the order; a flag scan compacts.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_rows_of_perm(int m, const int *__restrict__ rowptr, long long nnz, const uint32_t *__restrict__ perm,
+                               uint32_t *__restrict__ rows)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nnz) return;
+    const int p = (int)perm[q];
+    int lo = 0, hi = m;  // largest row with rowptr[row] <= p
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (rowptr[mid] <= p) lo = mid; else hi = mid;
+    }
+    rows[q] = (uint32_t)lo;
+}
+
+__global__ void k_canon_flags(long long nnz, const uint32_t *__restrict__ rows, const uint32_t *__restrict__ perm,
+                              const int *__restrict__ colidx, int *__restrict__ keep)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nnz) return;
+    keep[q] = q == 0 || rows[q] != rows[q - 1] || colidx[perm[q]] != colidx[perm[q - 1]];
+}
+
+__global__ void k_canon_emit(long long nnz, int dup_policy, const uint32_t *__restrict__ rows, const uint32_t *__restrict__ perm,
+                             const int *__restrict__ colidx, const double *__restrict__ val, const int *__restrict__ newpos,
+                             int *__restrict__ out_col, double *__restrict__ out_val)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nnz) return;
+    if (newpos[q + 1] == newpos[q]) return;  // a duplicate: merged into the first of its run
+    const int col = colidx[perm[q]];
+    double v = val[perm[q]];
+    if (dup_policy == 0)
+        for (long long x = q + 1; x < nnz && newpos[x + 1] == newpos[x]; x++) v += val[perm[x]];
+    out_col[newpos[q]] = col;
+    out_val[newpos[q]] = v;
+}
+
+__global__ void k_canon_rowptr(int m, const int *__restrict__ rowptr, const int *__restrict__ newpos, int *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= m) out[i] = newpos[rowptr[i]];
+}
+
+int csr_canonicalize_device(const tsg_dcsr *A, int dup_policy, tsg_dcsr *out)
+{
+    Ctx &c = ctx();
+    memset(out, 0, sizeof(*out));
+    const long long nnz = A->nnz;
+    if (nnz >= (1ll << 31)) { set_error(TSG_ERR_OVERFLOW, "canonicalize: nnz too large"); return last_error(); }
+    const size_t nz = (size_t)(nnz > 0 ? nnz : 1);
+    uint32_t *ka = dalloc_n<uint32_t>(nz), *kb = dalloc_n<uint32_t>(nz), *va = dalloc_n<uint32_t>(nz), *vb = dalloc_n<uint32_t>(nz);
+    int *keep = dalloc_n<int>(nz + 1);
+    int rc = (!ka || !kb || !va || !vb || !keep) ? last_error() : TSG_OK;
+    uint32_t *ks = ka, *perm = va;
+    long long kept = 0;
+    if (!rc && nnz > 0) {
+        k_copy_u32<<<ceil_div(nnz, 256), 256, 0, c.stream>>>(A->colidx, ka, nnz);
+        rc = radix_sort_pairs(ka, nullptr, kb, vb, nnz, bits_for(A->n), &ks, &perm, va);
+        if (!rc) {  // second key: the row of every entry, in the order the first sort left them
+            uint32_t *rows = ks == ka ? kb : ka, *spare_v = perm == va ? vb : va;
+            k_rows_of_perm<<<ceil_div(nnz, 256), 256, 0, c.stream>>>(A->m, A->rowptr, nnz, perm, rows);
+            uint32_t *ks2 = nullptr, *perm2 = nullptr;
+            rc = radix_sort_pairs(rows, perm, ks, spare_v, nnz, bits_for(A->m), &ks2, &perm2, nullptr);
+            ks = ks2; perm = perm2;
+        }
+        if (!rc) {
+            k_canon_flags<<<ceil_div(nnz, 256), 256, 0, c.stream>>>(nnz, ks, perm, A->colidx, keep);
+            rc = exclusive_scan<int>(keep, keep, nnz);
+        }
+        if (!rc) { int k32 = 0; rc = read_back_i32(keep + nnz, &k32); kept = k32; }
+    }
+    if (!rc) {
+        const size_t kz = (size_t)(kept > 0 ? kept : 1);
+        const size_t o_ci = (((size_t)A->m + 1) * 4 + 255) & ~(size_t)255, o_v = o_ci + ((kz * 4 + 255) & ~(size_t)255);
+        char *base = (char *)dalloc(o_v + kz * 8);
+        if (!base) rc = last_error();
+        else {
+            out->m = A->m; out->n = A->n; out->nnz = kept; out->owner = base;
+            out->rowptr = (int *)base; out->colidx = (int *)(base + o_ci); out->val = (double *)(base + o_v);
+            if (nnz > 0) {
+                k_canon_emit<<<ceil_div(nnz, 256), 256, 0, c.stream>>>(nnz, dup_policy, ks, perm, A->colidx, A->val, keep, out->colidx, out->val);
+                k_canon_rowptr<<<ceil_div((long long)A->m + 1, 256), 256, 0, c.stream>>>(A->m, A->rowptr, keep, out->rowptr);
+                if (!cuda_ok(cudaGetLastError(), "canonicalize kernels", __FILE__, __LINE__)) rc = last_error();
+            } else if (!cuda_ok(cudaMemsetAsync(out->rowptr, 0, ((size_t)A->m + 1) * 4, c.stream), "memset", __FILE__, __LINE__)) rc = last_error();
+        }
+    }
+    dfree(ka); dfree(kb); dfree(va); dfree(vb); dfree(keep);
+    if (rc && out->owner) { dfree(out->owner); memset(out, 0, sizeof(*out)); }
+    return rc;
 }
 
 int transpose_device(const tsg_dcsr *A, tsg_dcsr *AT)

@@ -10,6 +10,10 @@ int csr2tile_device(const tsg_dcsr *A, int col_major, tsg_dtile *out);
 int transpose_device(const tsg_dcsr *A, tsg_dcsr *AT);
 int nnzcub_device(const tsg_dcsr *A, const tsg_dcsr *B, unsigned long long *out);
 int masks_from_tiles_device(tsg_dtile *T);
+int csr_check_device(const tsg_dcsr *A);
+int csr_row_slice_device(const tsg_dcsr *A, int r0, int r1, tsg_dcsr *out);
+int csr_canonicalize_device(const tsg_dcsr *A, int dup_policy, tsg_dcsr *out);
+int last_input_flags();
 
 // spgemm.cu
 int tilerow_weights_device(const tsg_dtile *A, const tsg_dtile *B, int **d_w, int **d_jlo, int **d_jhi);

@@ -72,8 +72,9 @@ __host__ __device__ __forceinline__ size_t al16(size_t x) { return (x + 15) & ~(
 __host__ __device__ __forceinline__ size_t s3r_need(int nA, int nnzA, int numJ, int nnzC, int W)
 {
     return 2 * al16((size_t)nA * 32) + al16(((size_t)nnzA + 2) * 8) + 2 * al16((size_t)numJ * 32) + al16((size_t)nnzC * 8) +
-           al16(((size_t)nA + 1) * 4) + al16(((size_t)numJ + 1) * 4) + 2 * al16((size_t)numJ * 4) + 3 * al16((size_t)W * 4) +
-           al16((size_t)nnzC * 2) + al16(((size_t)nnzA + 2) * 2) + al16((size_t)numJ * 2);
+           al16(((size_t)nA + 1) * 4) + al16(((size_t)numJ + 1) * 4) + 3 * al16((size_t)numJ * 4) + 4 * al16((size_t)W * 4) +
+           al16((size_t)nnzC * 2) + al16(((size_t)nnzA + 2) * 2) + al16((size_t)numJ * 2) +
+           al16((size_t)(nnzC < numJ * 15 ? nnzC : numJ * 15) * 2);
 }
 
 __global__ void k_ns_init(int *scal)
@@ -143,32 +144,37 @@ k_s3_classify_rows(int ntr, int trow0, const int *__restrict__ a_tile_ptr, const
 // ---------------------------------------------------------------------------------------------
 // k_step3_rows: sparse accumulator in shared memory, CTA per C tile-row (see the file header).
 //
-// A HALF-WARP owns one C tile at a time (tiles are taken in descending order of their pair count, so the two
-// half-warps of a warp run tiles of similar shape in lockstep). Its pairs are processed in two phases:
-//   phase A, lanes = the 16 ROWS of the C tile, pairs whose A and B tiles both hold > S3R_SPARSE_MAX entries: lane r
-//            walks A's row r (the bits of its row mask are the k's) and B's rows k, every product lands in the row's
-//            compact accumulator. All 16 lanes are busy on well-filled pairs.
-//   phase B, lanes = PAIRS whose A or B tile holds <= S3R_SPARSE_MAX entries (the one-entry corner tiles of a stencil,
-//            R-MAT-like tiles): with lanes = rows such a pair would keep 1 of 16 lanes busy. Each lane enumerates the
-//            few products of its pair; per round every lane contributes one product (o, v), equal targets are summed
-//            in lane order (__match_any_sync + shuffles) and the lowest lane of each group updates the accumulator.
-// The order in which a C entry's contributions are added is fixed (phase A in pair order, then phase B in pair
-// order), so results are reproducible run to run; it is not the serial SPA's order for entries that receive from
-// both phases (values agree to rounding, and exactly for integer-valued inputs).
+// What ncu showed on the way here (profiles/README.md, r2a/r2b): with one thread per (tile, row) and every pair walked
+// by every row, a warp averaged 10 active lanes of 32 -- most tiles of a stencil's C hold a handful of entries, and two
+// thirds of a tile's pairs involve a one-entry "corner" tile that touches a single row. So the work of a tile-row is
+// split three ways, each part laid out so that the lanes of a warp do the same thing:
+//   R  well-filled C tiles (>= S3R_ROWS_MIN entries): a HALF-WARP owns the tile, lane = row. It walks the pairs whose
+//      A tile holds more than S3R_SPARSE_MAX entries: A's row mask gives the k's, B's rows k the products, each added
+//      to the row's compact accumulator. Pairs whose B tile is sparse take a short path (B's one or two entries are
+//      warp-uniform). Tiles are handed out in descending order of their pair count from a shared counter.
+//   G  the other non-empty C tiles: lane = C NONZERO, over a compacted list, register accumulation (the gather
+//      formulation, but with A, C's structure and the pair lists in shared memory).
+//   S  A tiles with <= S3R_SPARSE_MAX entries, for all C tiles at once, in Gustavson order: for an entry (r, k, v) of
+//      such a tile (I,K), lane = one B tile of tile-row K; the lanes update different C tiles, so nothing conflicts,
+//      and the pair lists are not even read. Entries are spread over the warps by r (equal r never runs concurrently).
+// The order in which a C entry's contributions are added is fixed (R/G in pair order, then S in ascending A tile), so
+// results are reproducible run to run; for entries fed by both it is not the serial SPA's order (values agree to
+// rounding, and exactly for integer-valued inputs).
 // ---------------------------------------------------------------------------------------------
-constexpr int S3R_SPARSE_MAX = 2;
+constexpr int S3R_SPARSE_MAX = 2;   // tiles with at most this many entries are "sparse" (phase S / short path)
+constexpr int S3R_ROWS_MIN = 16;    // C tiles with at least this many entries run lane-per-row (phase R)
 constexpr unsigned PF_ASPARSE = 0x80000000u, PF_BSPARSE = 0x40000000u, PF_INDEX = 0x3fffffffu;
 constexpr int S3R_BUCKETS = 64;
 
 struct S3Rows {
     int trow0, dense_th;
-    const int *a_tile_ptr, *a_tile_nnz;
+    const int *a_tile_ptr, *a_tile_col, *a_tile_nnz;
     const uint16_t *a_ptr, *a_mask, *a_col;
     const double *a_val;
-    const int *b_tile_nnz;
+    const int *b_tile_ptr, *b_tile_col, *b_rm2csc, *b_tile_nnz;
     const uint16_t *b_ptr, *b_mask, *b_col;
     const double *b_val;
-    const int *c_tile_ptr, *c_tile_nnz;
+    const int *c_tile_ptr, *c_tile_col, *c_tile_nnz;
     const uint16_t *c_ptr, *c_mask;
     uint16_t *c_col;
     double *c_val;
@@ -176,14 +182,23 @@ struct S3Rows {
     const uint8_t *row_kind;
 };
 
+// row of entry j of a tile whose 16 exclusive row offsets are q0,q1: the last row whose offset is <= j
+__device__ __forceinline__ int s3_row_of(const uint4 q0, const uint4 q1, int j)
+{
+    const unsigned key = (unsigned)j * 0x10001u;
+    const int n = __popc(__vcmpleu2(q0.x, key)) + __popc(__vcmpleu2(q0.y, key)) + __popc(__vcmpleu2(q0.z, key)) + __popc(__vcmpleu2(q0.w, key)) +
+                  __popc(__vcmpleu2(q1.x, key)) + __popc(__vcmpleu2(q1.y, key)) + __popc(__vcmpleu2(q1.z, key)) + __popc(__vcmpleu2(q1.w, key));
+    return (n >> 4) - 1;  // each u16 that compares <= contributes 16 set bits
+}
+
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 4 * 256 / THREADS)
+__global__ void __launch_bounds__(THREADS, 3 * 256 / THREADS)
 k_step3_rows(const __grid_constant__ S3Rows P)
 {
     extern __shared__ __align__(128) unsigned char s3r_smem[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ int s_hist[S3R_BUCKETS];
-    __shared__ int s_nord;
+    __shared__ int s_nord, s_ngather, s_next;
     const int i = blockIdx.x, tid = threadIdx.x;
     if (P.row_kind[i] != ROW_STAGED) return;
     const int I = P.trow0 + i;
@@ -207,14 +222,17 @@ k_step3_rows(const __grid_constant__ S3Rows P)
     int *s_cnnz = (int *)carve(((size_t)numJ + 1) * 4);
     int *s_pp = (int *)carve((size_t)numJ * 4);
     int *s_pe = (int *)carve((size_t)numJ * 4);
+    int *s_ccol = (int *)carve((size_t)numJ * 4);
     int *s_pa = (int *)carve((size_t)W * 4);
     int *s_pb = (int *)carve((size_t)W * 4);
     int *s_pbn = (int *)carve((size_t)W * 4);
+    int *s_pd = (int *)carve((size_t)W * 4);
     uint16_t *s_ocol = (uint16_t *)carve((size_t)nnzC * 2);
     uint16_t *s_acol = (uint16_t *)carve(((size_t)(av1 - av0) + 2) * 2);
     uint16_t *s_order = (uint16_t *)carve((size_t)numJ * 2);
+    uint16_t *s_gitem = (uint16_t *)carve((size_t)min(nnzC, numJ * (S3R_ROWS_MIN - 1)) * 2);
 
-    if (tid == 0) { mbar_init(&s_bar, 1); s_nord = 0; }
+    if (tid == 0) { mbar_init(&s_bar, 1); s_nord = 0; s_ngather = 0; s_next = 0; }
     if (tid < S3R_BUCKETS) s_hist[tid] = 0;
     __syncthreads();
     if (tid == 0) {  // one elected thread arms the barrier and issues the five bulk copies
@@ -236,20 +254,33 @@ k_step3_rows(const __grid_constant__ S3Rows P)
             const int pp = P.pair_ptr[c0 + k] - w0, pe = P.pair_end[c0 + k] - w0;
             s_pp[k] = pp;
             s_pe[k] = pe;
+            s_ccol[k] = P.c_tile_col[c0 + k];
             const int cnt = P.c_tile_nnz[c0 + k + 1] - n0 - v;
             if (cnt >= P.dense_th) dense_here = 1;
-            else if (cnt > 0) atomicAdd(&s_hist[S3R_BUCKETS - 1 - min(pe - pp, S3R_BUCKETS - 1)], 1);  // most pairs first
+            else if (cnt >= S3R_ROWS_MIN) atomicAdd(&s_hist[S3R_BUCKETS - 1 - min(pe - pp, S3R_BUCKETS - 1)], 1);  // most pairs first
+            else if (cnt > 0) {  // phase G: its nonzeros join the compacted list
+                const int base = atomicAdd(&s_ngather, cnt);
+                for (int j = 0; j < cnt; j++) s_gitem[base + j] = (uint16_t)(v + j);
+            }
         }
     }
     for (int k = tid; k < W; k += THREADS) {
         const int ta = P.pair_a[w0 + k], b = P.pair_b[w0 + k];
-        const int bn0 = P.b_tile_nnz[b];
+        const int bn0 = P.b_tile_nnz[b], bn = P.b_tile_nnz[b + 1] - bn0;
         unsigned f = (unsigned)(ta - a0);
+        int desc = 0;
         if (P.a_tile_nnz[ta + 1] - P.a_tile_nnz[ta] <= S3R_SPARSE_MAX) f |= PF_ASPARSE;
-        if (P.b_tile_nnz[b + 1] - bn0 <= S3R_SPARSE_MAX) f |= PF_BSPARSE;
+        else if (bn <= S3R_SPARSE_MAX) {  // B's one or two entries as (k, c) pairs: n | k0 << 2 | c0 << 6 | k1 << 10 | c1 << 14
+            f |= PF_BSPARSE;
+            const uint4 *pq = reinterpret_cast<const uint4 *>(P.b_ptr + (size_t)b * TS);
+            const uint4 q0 = pq[0], q1 = pq[1];
+            desc = bn;
+            for (int j = 0; j < bn; j++) desc |= (s3_row_of(q0, q1, j) | ((int)P.b_col[bn0 + j] << 4)) << (2 + 8 * j);
+        }
         s_pa[k] = (int)f;
         s_pb[k] = b;
         s_pbn[k] = bn0;
+        s_pd[k] = desc;
     }
     for (int k = tid; k < nnzC; k += THREADS) s_out[k] = 0.0;
     const int has_dense = __syncthreads_or(dense_here);
@@ -266,135 +297,156 @@ k_step3_rows(const __grid_constant__ S3Rows P)
         if (tid == 31) s_nord = incl;
     }
     __syncthreads();
-    for (int k = tid; k < numJ; k += THREADS) {  // counting sort of the sparse-accumulator tiles by pair count, descending
+    for (int k = tid; k < numJ; k += THREADS) {  // counting sort of the phase-R tiles by pair count, descending
         const int cnt = s_cnnz[k + 1] - s_cnnz[k];
-        if (cnt > 0 && cnt < P.dense_th) s_order[atomicAdd(&s_hist[S3R_BUCKETS - 1 - min(s_pe[k] - s_pp[k], S3R_BUCKETS - 1)], 1)] = (uint16_t)k;
+        if (cnt >= S3R_ROWS_MIN && cnt < P.dense_th)
+            s_order[atomicAdd(&s_hist[S3R_BUCKETS - 1 - min(s_pe[k] - s_pp[k], S3R_BUCKETS - 1)], 1)] = (uint16_t)k;
     }
     __syncthreads();
     mbar_wait(&s_bar, 0);
 
     const int lane = tid & 31, l16 = tid & 15;
     const unsigned hm = 0xFFFFu << (lane & 16);
-    const int nord = s_nord;
     const double *__restrict__ bvals = P.b_val;
-    for (int q = tid >> 4; q < nord; q += THREADS / 16) {
+
+    // ---------------- phase R: half-warp per well-filled tile, lane = row ----------------
+    const int nord = s_nord;
+    while (true) {
+        int q = 0;
+        if (l16 == 0) q = atomicAdd(&s_next, 1);
+        q = __shfl_sync(hm, q, lane & 16);
+        if (q >= nord) break;
         const int s = s_order[q];
-        const int tb = s_cnnz[s];
-        const int pp = s_pp[s], pe = s_pe[s];
-        // ---------------- phase A: lane = row l16 of the tile ----------------
+        const int r = l16;
+        const unsigned cm = s_cm[s * TS + r];
+        if (!cm) continue;
+        const int rowbase = s_cnnz[s] + s_cp[s * TS + r];
         {
-            const int r = l16;
-            const unsigned cm = s_cm[s * TS + r];
-            if (cm) {
-                const int rowbase = tb + s_cp[s * TS + r];
-                {
-                    unsigned m = cm;
-                    int o = rowbase;
-                    do { const int c = __clz(m) - 16; m ^= 0x8000u >> c; s_ocol[o++] = (uint16_t)c; } while (m);
-                }
-                const unsigned cmr = __brev(cm) >> 16;  // bit c = column c
-                for (int p = pp; p < pe; p++) {
-                    const unsigned fa = (unsigned)s_pa[p];
-                    if (fa & (PF_ASPARSE | PF_BSPARSE)) continue;  // phase B (uniform over the half-warp)
-                    unsigned am = s_am[fa * TS + r];
-                    if (!am) continue;  // the pair does not touch this row
-                    const int b = s_pb[p];
-                    int ia = s_annz[fa] + s_ap[fa * TS + r];
-                    const int bbase = s_pbn[p];
-                    const uint16_t *bmk = P.b_mask + (size_t)b * TS, *bpt = P.b_ptr + (size_t)b * TS;
-                    do {  // the bits of A's row mask are the k's of the row, ascending
-                        const int k = __clz(am) - 16;
-                        am ^= 0x8000u >> k;
-                        const double av = s_aval[ia++];
-                        unsigned bm = __brev((unsigned)bmk[k]) >> 16;
-                        int ib = bbase + bpt[k];
-                        while (bm) {  // B's row k: every entry is a product into C's row r
-                            const unsigned low = bm & (0u - bm);
-                            const int o = rowbase + __popc(cmr & (low - 1));  // rank of the column in C's row
-                            bm ^= low;
-                            s_out[o] = fma(av, bvals[ib++], s_out[o]);
-                        }
-                    } while (am);
-                }
-            }
+            unsigned m = cm;
+            int o = rowbase;
+            do { const int c = __clz(m) - 16; m ^= 0x8000u >> c; s_ocol[o++] = (uint16_t)c; } while (m);
         }
-        __syncwarp(hm);
-        // ---------------- phase B: lane = one sparse pair ----------------
-        for (int base = pp; base < pe; base += 16) {
-            const int p = base + l16;
-            const unsigned fa = p < pe ? (unsigned)s_pa[p] : 0u;
-            const bool spA = (fa & PF_ASPARSE) != 0, spB = !spA && (fa & PF_BSPARSE) != 0;
-            if (!__any_sync(hm, spA || spB)) continue;
+        const unsigned cmr = __brev(cm) >> 16;  // bit c = column c
+        const int pe = s_pe[s];
+        for (int p = s_pp[s]; p < pe; p++) {
+            const unsigned fa = (unsigned)s_pa[p];
+            if (fa & PF_ASPARSE) continue;  // phase S
             const int a = (int)(fa & PF_INDEX);
-            int b = 0, bbase = 0;
-            if (spA || spB) { b = s_pb[p]; bbase = s_pbn[p]; }
-            // product stream state
-            int e = 0, e1 = 0;            // spA: A entries [e, e1) (indices into s_aval / s_acol); spB: B entries [e, e1) (global)
-            unsigned rem = 0;             // spA: remaining columns of B's row k (bit c); spB: remaining rows r with A(r,k) (bit r)
-            int ib = 0, rb = 0, kc = 0;   // spA: next B value index, row base of C's row; spB: kc = k | c << 4
-            unsigned cmr = 0;
-            double x = 0.0;               // spA: A's value; spB: B's value
-            if (spA) { e = s_annz[a]; e1 = s_annz[a + 1]; }
-            else if (spB) { e = bbase; e1 = P.b_tile_nnz[b + 1]; }
-            while (true) {
-                int o = -1 - lane;
-                double v = 0.0;
-                if (spA) {
-                    while (!rem && e < e1) {  // next A entry (r, k): B's row k
-                        const unsigned col = s_acol[e];
-                        const int r = col >> 4, k = col & 15;
-                        x = s_aval[e++];
-                        rem = __brev((unsigned)P.b_mask[(size_t)b * TS + k]) >> 16;
-                        ib = bbase + P.b_ptr[(size_t)b * TS + k];
-                        cmr = __brev((unsigned)s_cm[s * TS + r]) >> 16;
-                        rb = tb + s_cp[s * TS + r];
-                    }
-                    if (rem) {
-                        const unsigned low = rem & (0u - rem);
-                        rem ^= low;
-                        o = rb + __popc(cmr & (low - 1));
-                        v = x * bvals[ib++];
-                    }
-                } else if (spB) {
-                    while (!rem && e < e1) {  // next B entry (k, c): the rows of A that hold column k
-                        const int c = P.b_col[e];
-                        x = bvals[e];
-                        const int j = e - bbase;
-                        e++;
-                        int k = 0;  // row of B's entry j: the last row whose Ptr is <= j
-#pragma unroll
-                        for (int q2 = 1; q2 < TS; q2++) k += (int)P.b_ptr[(size_t)b * TS + q2] <= j;
-                        kc = k | (c << 4);
-                        const unsigned bit = 0x8000u >> k;
-#pragma unroll
-                        for (int r = 0; r < TS; r++) rem |= (s_am[a * TS + r] & bit) ? (1u << r) : 0u;
-                    }
-                    if (rem) {
-                        const int r = __ffs(rem) - 1;
-                        rem &= rem - 1;
-                        const int k = kc & 15, c = kc >> 4;
-                        const unsigned am = s_am[a * TS + r];
-                        const double av = s_aval[s_annz[a] + s_ap[a * TS + r] + __popc(am >> (16 - k))];
-                        const unsigned cr = __brev((unsigned)s_cm[s * TS + r]) >> 16;
-                        o = tb + s_cp[s * TS + r] + __popc(cr & ((1u << c) - 1));
-                        v = av * x;
+            unsigned am = s_am[a * TS + r];
+            if (!am) continue;  // the pair does not touch this row
+            const int bbase = s_pbn[p];
+            int ia = s_annz[a] + s_ap[a * TS + r];
+            if (fa & PF_BSPARSE) {  // B holds one or two entries (k, c): at most that many products for this row
+                int d = s_pd[p];
+                for (int j = 0, nj = d & 3; j < nj; j++) {
+                    const int k = (d >> 2) & 15, c = (d >> 6) & 15;
+                    d >>= 8;
+                    if (am & (0x8000u >> k)) {
+                        const int o = rowbase + __popc(cmr & ((1u << c) - 1));
+                        s_out[o] = fma(s_aval[ia + __popc(am >> (16 - k))], bvals[bbase + j], s_out[o]);
                     }
                 }
-                if (!__any_sync(hm, o >= 0)) break;
-                // equal targets: summed in lane order by every lane of the group, committed by its lowest lane
-                const unsigned peers = __match_any_sync(hm, o);
-                double sum = 0.0;
-                unsigned left = o >= 0 ? peers : 0u;
-                while (__any_sync(hm, left != 0)) {
-                    const int src = left ? __ffs(left) - 1 : lane;
-                    const double y = __shfl_sync(hm, v, src);
-                    if (left) { sum += y; left &= left - 1; }
+                continue;
+            }
+            const int b = s_pb[p];
+            const uint16_t *bmk = P.b_mask + (size_t)b * TS, *bpt = P.b_ptr + (size_t)b * TS;
+            do {  // the bits of A's row mask are the k's of the row, ascending
+                const int k = __clz(am) - 16;
+                am ^= 0x8000u >> k;
+                const double av = s_aval[ia++];
+                unsigned bm = __brev((unsigned)bmk[k]) >> 16;
+                int ib = bbase + bpt[k];
+                while (bm) {  // B's row k: every entry is a product into C's row r
+                    const unsigned low = bm & (0u - bm);
+                    const int o = rowbase + __popc(cmr & (low - 1));  // rank of the column in C's row
+                    bm ^= low;
+                    s_out[o] = fma(av, bvals[ib++], s_out[o]);
                 }
-                if (o >= 0 && lane == __ffs(peers) - 1) s_out[o] += sum;
-                __syncwarp(hm);
+            } while (am);
+        }
+    }
+
+    // ---------------- phase G: lane = one nonzero of the sparsely filled tiles ----------------
+    const int ngather = s_ngather;
+    for (int g = tid; g < ngather; g += THREADS) {
+        const int o = s_gitem[g];
+        int lo = 0, hi = numJ - 1;  // the tile holding nonzero o: largest s with s_cnnz[s] <= o
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_cnnz[mid] <= o) lo = mid; else hi = mid - 1;
+        }
+        const int s = lo;
+        const uint4 *pq = reinterpret_cast<const uint4 *>(s_cp + s * TS);
+        const int r = s3_row_of(pq[0], pq[1], o - s_cnnz[s]);
+        unsigned cmr = __brev((unsigned)s_cm[s * TS + r]) >> 16;
+        for (int n = o - s_cnnz[s] - (int)s_cp[s * TS + r]; n > 0; n--) cmr &= cmr - 1;  // drop the n smaller columns
+        const int c = __ffs(cmr) - 1;
+        const unsigned cbit = 0x8000u >> c;
+        s_ocol[o] = (uint16_t)c;
+        double acc = 0.0;
+        const int pe = s_pe[s];
+        for (int p = s_pp[s]; p < pe; p++) {
+            const unsigned fa = (unsigned)s_pa[p];
+            if (fa & PF_ASPARSE) continue;  // phase S
+            const int a = (int)(fa & PF_INDEX);
+            unsigned am = s_am[a * TS + r];
+            if (!am) continue;
+            const int b = s_pb[p], bbase = s_pbn[p];
+            int ia = s_annz[a] + s_ap[a * TS + r];
+            do {
+                const int k = __clz(am) - 16;
+                am ^= 0x8000u >> k;
+                const unsigned bm = P.b_mask[(size_t)b * TS + k];
+                if (bm & cbit) acc = fma(s_aval[ia], bvals[bbase + (int)P.b_ptr[(size_t)b * TS + k] + __popc(bm >> (16 - c))], acc);
+                ia++;
+            } while (am);
+        }
+        s_out[o] = acc;
+    }
+    __syncthreads();
+
+    // ---------------- phase S: sparse A tiles in Gustavson order, lane = one B tile of tile-row K ----------------
+    {
+        constexpr int NW = THREADS / 32;
+        const int warp = tid >> 5;
+        for (int a = 0; a < nA; a++) {
+            const int e1 = s_annz[a + 1];
+            if (e1 - s_annz[a] > S3R_SPARSE_MAX) continue;
+            for (int e = s_annz[a]; e < e1; e++) {
+                const unsigned col = s_acol[e];
+                const int r = col >> 4, k = col & 15;
+                if ((r & (NW - 1)) != warp) continue;  // equal rows never run concurrently: no two warps update the same C entry
+                const double av = s_aval[e];
+                const int K = P.a_tile_col[a0 + a];
+                const int t1 = P.b_tile_ptr[K + 1];
+                for (int tb = P.b_tile_ptr[K] + lane; tb < t1; tb += 32) {
+                    const int J = P.b_tile_col[tb];
+                    int lo = 0, hi = numJ - 1;  // C tile (I, J) is listed: find its slot
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_ccol[mid] < J) lo = mid + 1; else hi = mid;
+                    }
+                    const int s = lo;
+                    const int cnt = s_cnnz[s + 1] - s_cnnz[s];
+                    if (cnt == 0 || cnt >= P.dense_th) continue;  // empty, or the dense accumulator's
+                    const unsigned cm = s_cm[s * TS + r];
+                    if (!cm) continue;
+                    const int b = P.b_rm2csc[tb];
+                    unsigned bm = __brev((unsigned)P.b_mask[(size_t)b * TS + k]) >> 16;
+                    if (!bm) continue;
+                    int ib = P.b_tile_nnz[b] + P.b_ptr[(size_t)b * TS + k];
+                    const int rowbase = s_cnnz[s] + s_cp[s * TS + r];
+                    const unsigned cmr = __brev(cm) >> 16;
+                    do {
+                        const unsigned low = bm & (0u - bm);
+                        const int o = rowbase + __popc(cmr & (low - 1));
+                        bm ^= low;
+                        s_out[o] = fma(av, bvals[ib++], s_out[o]);
+                    } while (bm);
+                }
+                __syncwarp();
             }
         }
-        __syncwarp(hm);
     }
     __syncthreads();
     if (!has_dense) {
@@ -759,8 +811,9 @@ int numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, int tro
         CK_LAUNCH();
     }
     if (n_staged > 0) {
-        S3Rows P{trow0, nb.dense_th, A->tile_ptr, A->tile_nnz, A->ptr, A->mask, A->col, A->val, B->tile_nnz, B->ptr, B->mask, B->col,
-                 B->val, C->tile_ptr, C->tile_nnz, C->ptr, C->mask, C->col, C->val, wptr, pl.ptr, pl.end, pl.a, pl.b, nb.row_kind};
+        S3Rows P{trow0, nb.dense_th, A->tile_ptr, A->tile_columnidx, A->tile_nnz, A->ptr, A->mask, A->col, A->val,
+                 B->tile_ptr, B->tile_columnidx, B->rm2csc, B->tile_nnz, B->ptr, B->mask, B->col, B->val,
+                 C->tile_ptr, C->tile_columnidx, C->tile_nnz, C->ptr, C->mask, C->col, C->val, wptr, pl.ptr, pl.end, pl.a, pl.b, nb.row_kind};
         const size_t smem = ((size_t)h_ns[NS_MAXNEED] + 1023) & ~(size_t)1023;
         // 128-thread CTAs when a tile-row has few (tile, row) slots (2D meshes): fewer idle threads, more CTAs per SM
         const bool narrow = numblkC * TS < (long long)ntr * 192;

@@ -16,7 +16,8 @@ EXPORTS = [
     "csr2tile_row_major", "csr2tile_col_major", "tilespgemm", "tile2csr", "matrix_destroy", "matrix_transposition",
     "tilespgemm_last_error", "tilespgemm_last_error_string", "tilespgemm_clear_error",
     "tsg_init", "tsg_shutdown", "tsg_stream", "tsg_sync", "tsg_launch_count", "tsg_timer_start", "tsg_timer_stop",
-    "tsg_csr_upload", "tsg_csr_wrap", "tsg_csr_download", "tsg_csr_free", "tsg_csr_validate",
+    "tsg_csr_upload", "tsg_csr_wrap", "tsg_csr_download", "tsg_csr_free", "tsg_csr_validate", "tsg_csr_row_slice",
+    "tsg_csr_canonicalize",
     "tsg_transpose", "tsg_nnzcub", "tsg_csr2tile", "tsg_tile_upload", "tsg_tile_download", "tsg_tile_alloc",
     "tsg_tile_free", "tsg_tilerow_weights", "tsg_spgemm", "tsg_tile2csr", "tsg_tile_rowsums", "tsg_spgemm_csr_host",
     "tsg_spgemm_to_host", "tsg_spgemm_csr_host_into", "tsg_plan_slabs",
