@@ -154,9 +154,10 @@ k_s3_classify_rows(int ntr, int trow0, const int *__restrict__ a_tile_ptr, const
 //      warp-uniform). Tiles are handed out in descending order of their pair count from a shared counter.
 //   G  the other non-empty C tiles: lane = C NONZERO, over a compacted list, register accumulation (the gather
 //      formulation, but with A, C's structure and the pair lists in shared memory).
-//   S  A tiles with <= S3R_SPARSE_MAX entries, for all C tiles at once, in Gustavson order: for an entry (r, k, v) of
-//      such a tile (I,K), lane = one B tile of tile-row K; the lanes update different C tiles, so nothing conflicts,
-//      and the pair lists are not even read. Entries are spread over the warps by r (equal r never runs concurrently).
+//   S  A tiles with <= S3R_SPARSE_MAX entries are left to k_step3_sparse, a second kernel that adds their contributions
+//      for all C tiles of a tile-row in Gustavson order: for an entry (r, k, v) of such a tile (I,K), lane = one B tile
+//      of tile-row K; the lanes update different C tiles, so nothing conflicts, and the pair lists are not even read.
+//      (Inside this kernel the same loop kept two of eight warps busy behind a CTA barrier: 42 % of the stall samples.)
 // The order in which a C entry's contributions are added is fixed (R/G in pair order, then S in ascending A tile), so
 // results are reproducible run to run; for entries fed by both it is not the serial SPA's order (values agree to
 // rounding, and exactly for integer-valued inputs).
@@ -192,7 +193,7 @@ __device__ __forceinline__ int s3_row_of(const uint4 q0, const uint4 q1, int j)
 }
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 3 * 256 / THREADS)
+__global__ void __launch_bounds__(THREADS, 4 * 256 / THREADS)
 k_step3_rows(const __grid_constant__ S3Rows P)
 {
     extern __shared__ __align__(128) unsigned char s3r_smem[];
@@ -405,50 +406,6 @@ k_step3_rows(const __grid_constant__ S3Rows P)
     }
     __syncthreads();
 
-    // ---------------- phase S: sparse A tiles in Gustavson order, lane = one B tile of tile-row K ----------------
-    {
-        constexpr int NW = THREADS / 32;
-        const int warp = tid >> 5;
-        for (int a = 0; a < nA; a++) {
-            const int e1 = s_annz[a + 1];
-            if (e1 - s_annz[a] > S3R_SPARSE_MAX) continue;
-            for (int e = s_annz[a]; e < e1; e++) {
-                const unsigned col = s_acol[e];
-                const int r = col >> 4, k = col & 15;
-                if ((r & (NW - 1)) != warp) continue;  // equal rows never run concurrently: no two warps update the same C entry
-                const double av = s_aval[e];
-                const int K = P.a_tile_col[a0 + a];
-                const int t1 = P.b_tile_ptr[K + 1];
-                for (int tb = P.b_tile_ptr[K] + lane; tb < t1; tb += 32) {
-                    const int J = P.b_tile_col[tb];
-                    int lo = 0, hi = numJ - 1;  // C tile (I, J) is listed: find its slot
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if (s_ccol[mid] < J) lo = mid + 1; else hi = mid;
-                    }
-                    const int s = lo;
-                    const int cnt = s_cnnz[s + 1] - s_cnnz[s];
-                    if (cnt == 0 || cnt >= P.dense_th) continue;  // empty, or the dense accumulator's
-                    const unsigned cm = s_cm[s * TS + r];
-                    if (!cm) continue;
-                    const int b = P.b_rm2csc[tb];
-                    unsigned bm = __brev((unsigned)P.b_mask[(size_t)b * TS + k]) >> 16;
-                    if (!bm) continue;
-                    int ib = P.b_tile_nnz[b] + P.b_ptr[(size_t)b * TS + k];
-                    const int rowbase = s_cnnz[s] + s_cp[s * TS + r];
-                    const unsigned cmr = __brev(cm) >> 16;
-                    do {
-                        const unsigned low = bm & (0u - bm);
-                        const int o = rowbase + __popc(cmr & (low - 1));
-                        bm ^= low;
-                        s_out[o] = fma(av, bvals[ib++], s_out[o]);
-                    } while (bm);
-                }
-                __syncwarp();
-            }
-        }
-    }
-    __syncthreads();
     if (!has_dense) {
         for (int k = tid; k < nnzC; k += THREADS) { P.c_val[n0 + k] = s_out[k]; P.c_col[n0 + k] = s_ocol[k]; }
     } else {  // leave the ranges of the dense tiles alone
@@ -461,6 +418,57 @@ k_step3_rows(const __grid_constant__ S3Rows P)
             if (s_cnnz[lo + 1] - s_cnnz[lo] >= P.dense_th) continue;
             P.c_val[n0 + k] = s_out[k];
             P.c_col[n0 + k] = s_ocol[k];
+        }
+    }
+}
+
+// Phase S of the staged tile-rows (see k_step3_rows): one WARP per C tile-row walks the sparse A tiles of the tile-row
+// in ascending order; for an entry (r, k, v) of A tile (I,K), lane = one B tile (K,J) of B's tile-row K: it finds C tile
+// (I,J) by binary search in the tile-row's column list and adds v * B(k, :) into C's row r, in place (C's values were
+// written by k_step3_rows; tiles of the dense accumulator and gathered tile-rows are skipped: those kernels walk all pairs).
+__global__ void __launch_bounds__(256)
+k_step3_sparse(int ntr, const __grid_constant__ S3Rows P)
+{
+    const int i = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (i >= ntr || P.row_kind[i] != ROW_STAGED) return;
+    const int I = P.trow0 + i;
+    const int c0 = P.c_tile_ptr[i], numJ = P.c_tile_ptr[i + 1] - c0;
+    const int a1 = P.a_tile_ptr[I + 1];
+    for (int a = P.a_tile_ptr[I]; a < a1; a++) {
+        const int e0 = P.a_tile_nnz[a], e1 = P.a_tile_nnz[a + 1];
+        if (e1 - e0 > S3R_SPARSE_MAX) continue;
+        const int K = P.a_tile_col[a];
+        const int t0 = P.b_tile_ptr[K], t1 = P.b_tile_ptr[K + 1];
+        for (int e = e0; e < e1; e++) {
+            const unsigned col = P.a_col[e];  // A stores row*16+col
+            const int r = col >> 4, k = col & 15;
+            const double av = P.a_val[e];
+            for (int tb = t0 + lane; tb < t1; tb += 32) {
+                const int J = P.b_tile_col[tb];
+                int lo = 0, hi = numJ - 1;  // C tile (I, J) is listed: find it
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (P.c_tile_col[c0 + mid] < J) lo = mid + 1; else hi = mid;
+                }
+                const int t = c0 + lo;
+                const int cb = P.c_tile_nnz[t], cnt = P.c_tile_nnz[t + 1] - cb;
+                if (cnt == 0 || cnt >= P.dense_th) continue;
+                const unsigned cm = P.c_mask[(size_t)t * TS + r];
+                if (!cm) continue;
+                const int b = P.b_rm2csc[tb];
+                unsigned bm = __brev((unsigned)P.b_mask[(size_t)b * TS + k]) >> 16;
+                if (!bm) continue;
+                int ib = P.b_tile_nnz[b] + P.b_ptr[(size_t)b * TS + k];
+                const int rowbase = cb + P.c_ptr[(size_t)t * TS + r];
+                const unsigned cmr = __brev(cm) >> 16;
+                do {
+                    const unsigned low = bm & (0u - bm);
+                    const int o = rowbase + __popc(cmr & (low - 1));
+                    bm ^= low;
+                    P.c_val[o] = fma(av, P.b_val[ib++], P.c_val[o]);
+                } while (bm);
+            }
+            __syncwarp();  // the next entry may update the same C entries from other lanes
         }
     }
 }
@@ -823,6 +831,8 @@ int numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, int tro
         }
         if (narrow) k_step3_rows<128><<<ntr, 128, smem, c.stream>>>(P);
         else k_step3_rows<256><<<ntr, 256, smem, c.stream>>>(P);
+        CK_LAUNCH();
+        k_step3_sparse<<<ceil_div((long long)ntr * 32, 256), 256, 0, c.stream>>>(ntr, P);
         CK_LAUNCH();
     }
     if (n_gather > 0) {
