@@ -72,9 +72,8 @@ __host__ __device__ __forceinline__ size_t al16(size_t x) { return (x + 15) & ~(
 __host__ __device__ __forceinline__ size_t s3r_need(int nA, int nnzA, int numJ, int nnzC, int W)
 {
     return 2 * al16((size_t)nA * 32) + al16(((size_t)nnzA + 2) * 8) + 2 * al16((size_t)numJ * 32) + al16((size_t)nnzC * 8) +
-           al16(((size_t)nA + 1) * 4) + al16(((size_t)numJ + 1) * 4) + 3 * al16((size_t)numJ * 4) + 4 * al16((size_t)W * 4) +
-           al16((size_t)nnzC * 2) + al16(((size_t)nnzA + 2) * 2) + al16((size_t)numJ * 2) +
-           al16((size_t)(nnzC < numJ * 15 ? nnzC : numJ * 15) * 2);
+           al16(((size_t)nA + 1) * 4) + al16(((size_t)numJ + 1) * 4) + 2 * al16((size_t)numJ * 4) + 3 * al16((size_t)W * 4) +
+           al16((size_t)nnzC * 2) + al16((size_t)numJ * 2) + al16((size_t)(nnzC < numJ * 15 ? nnzC : numJ * 15) * 2);
 }
 
 __global__ void k_ns_init(int *scal)
@@ -149,22 +148,23 @@ k_s3_classify_rows(int ntr, int trow0, const int *__restrict__ a_tile_ptr, const
 // thirds of a tile's pairs involve a one-entry "corner" tile that touches a single row. So the work of a tile-row is
 // split three ways, each part laid out so that the lanes of a warp do the same thing:
 //   R  well-filled C tiles (>= S3R_ROWS_MIN entries): a HALF-WARP owns the tile, lane = row. It walks the pairs whose
-//      A tile holds more than S3R_SPARSE_MAX entries: A's row mask gives the k's, B's rows k the products, each added
-//      to the row's compact accumulator. Pairs whose B tile is sparse take a short path (B's one or two entries are
-//      warp-uniform). Tiles are handed out in descending order of their pair count from a shared counter.
-//   G  the other non-empty C tiles: lane = C NONZERO, over a compacted list, register accumulation (the gather
-//      formulation, but with A, C's structure and the pair lists in shared memory).
-//   S  A tiles with <= S3R_SPARSE_MAX entries are left to k_step3_sparse, a second kernel that adds their contributions
-//      for all C tiles of a tile-row in Gustavson order: for an entry (r, k, v) of such a tile (I,K), lane = one B tile
-//      of tile-row K; the lanes update different C tiles, so nothing conflicts, and the pair lists are not even read.
-//      (Inside this kernel the same loop kept two of eight warps busy behind a CTA barrier: 42 % of the stall samples.)
+//      A and B tiles both hold more than S3R_SPARSE_MAX entries: A's row mask gives the k's, B's rows k the products,
+//      each added to the row's compact accumulator. Tiles are handed out in descending order of their pair count from
+//      a shared counter, so the two half-warps of a warp mostly run tiles of the same shape in lockstep.
+//   G  the other non-empty C tiles that have such a pair at all: lane = C NONZERO, over a compacted list, register
+//      accumulation (the gather formulation, but with A, C's structure and the pair lists in shared memory).
+//   S  pairs with a sparse tile on either side are left to k_step3_sparse, a second kernel that adds their contributions
+//      for all C tiles of a tile-row in Gustavson order (lane = one B tile of B's tile-row K; the lanes update different
+//      C tiles, so nothing conflicts, and the pair lists are not even read). Inside this kernel the same loop kept two
+//      of eight warps busy behind a CTA barrier (42 % of the stall samples), and walking the pair lists of a stencil's
+//      small C tiles -- fed by sparse pairs only -- cost more than all the products of the well-filled ones.
 // The order in which a C entry's contributions are added is fixed (R/G in pair order, then S in ascending A tile), so
 // results are reproducible run to run; for entries fed by both it is not the serial SPA's order (values agree to
 // rounding, and exactly for integer-valued inputs).
 // ---------------------------------------------------------------------------------------------
 constexpr int S3R_SPARSE_MAX = 2;   // tiles with at most this many entries are "sparse" (phase S / short path)
 constexpr int S3R_ROWS_MIN = 16;    // C tiles with at least this many entries run lane-per-row (phase R)
-constexpr unsigned PF_ASPARSE = 0x80000000u, PF_BSPARSE = 0x40000000u, PF_INDEX = 0x3fffffffu;
+constexpr unsigned PF_SPARSE = 0x80000000u, PF_INDEX = 0x7fffffffu;
 constexpr int S3R_BUCKETS = 64;
 
 struct S3Rows {
@@ -223,13 +223,10 @@ k_step3_rows(const __grid_constant__ S3Rows P)
     int *s_cnnz = (int *)carve(((size_t)numJ + 1) * 4);
     int *s_pp = (int *)carve((size_t)numJ * 4);
     int *s_pe = (int *)carve((size_t)numJ * 4);
-    int *s_ccol = (int *)carve((size_t)numJ * 4);
     int *s_pa = (int *)carve((size_t)W * 4);
     int *s_pb = (int *)carve((size_t)W * 4);
     int *s_pbn = (int *)carve((size_t)W * 4);
-    int *s_pd = (int *)carve((size_t)W * 4);
     uint16_t *s_ocol = (uint16_t *)carve((size_t)nnzC * 2);
-    uint16_t *s_acol = (uint16_t *)carve(((size_t)(av1 - av0) + 2) * 2);
     uint16_t *s_order = (uint16_t *)carve((size_t)numJ * 2);
     uint16_t *s_gitem = (uint16_t *)carve((size_t)min(nnzC, numJ * (S3R_ROWS_MIN - 1)) * 2);
 
@@ -244,9 +241,8 @@ k_step3_rows(const __grid_constant__ S3Rows P)
         bulk_g2s(s_cm, P.c_mask + (size_t)c0 * TS, (uint32_t)numJ * 32, &s_bar);
         bulk_g2s(s_cp, P.c_ptr + (size_t)c0 * TS, (uint32_t)numJ * 32, &s_bar);
     }
-    // everything whose source is only 2/4-byte aligned: plain coalesced loads, overlapping the bulk copies
+    // everything whose source is only 4-byte aligned: plain coalesced loads, overlapping the bulk copies
     for (int k = tid; k <= nA; k += THREADS) s_annz[k] = P.a_tile_nnz[a0 + k] - av0a;
-    for (int k = tid; k < av1 - av0a; k += THREADS) s_acol[k] = P.a_col[av0a + k];
     int dense_here = 0;
     for (int k = tid; k <= numJ; k += THREADS) {
         const int v = P.c_tile_nnz[c0 + k] - n0;
@@ -255,33 +251,19 @@ k_step3_rows(const __grid_constant__ S3Rows P)
             const int pp = P.pair_ptr[c0 + k] - w0, pe = P.pair_end[c0 + k] - w0;
             s_pp[k] = pp;
             s_pe[k] = pe;
-            s_ccol[k] = P.c_tile_col[c0 + k];
             const int cnt = P.c_tile_nnz[c0 + k + 1] - n0 - v;
             if (cnt >= P.dense_th) dense_here = 1;
             else if (cnt >= S3R_ROWS_MIN) atomicAdd(&s_hist[S3R_BUCKETS - 1 - min(pe - pp, S3R_BUCKETS - 1)], 1);  // most pairs first
-            else if (cnt > 0) {  // phase G: its nonzeros join the compacted list
-                const int base = atomicAdd(&s_ngather, cnt);
-                for (int j = 0; j < cnt; j++) s_gitem[base + j] = (uint16_t)(v + j);
-            }
         }
     }
-    for (int k = tid; k < W; k += THREADS) {
+    for (int k = tid; k < W; k += THREADS) {  // pairs with a sparse tile on either side belong to k_step3_sparse
         const int ta = P.pair_a[w0 + k], b = P.pair_b[w0 + k];
-        const int bn0 = P.b_tile_nnz[b], bn = P.b_tile_nnz[b + 1] - bn0;
+        const int bn0 = P.b_tile_nnz[b];
         unsigned f = (unsigned)(ta - a0);
-        int desc = 0;
-        if (P.a_tile_nnz[ta + 1] - P.a_tile_nnz[ta] <= S3R_SPARSE_MAX) f |= PF_ASPARSE;
-        else if (bn <= S3R_SPARSE_MAX) {  // B's one or two entries as (k, c) pairs: n | k0 << 2 | c0 << 6 | k1 << 10 | c1 << 14
-            f |= PF_BSPARSE;
-            const uint4 *pq = reinterpret_cast<const uint4 *>(P.b_ptr + (size_t)b * TS);
-            const uint4 q0 = pq[0], q1 = pq[1];
-            desc = bn;
-            for (int j = 0; j < bn; j++) desc |= (s3_row_of(q0, q1, j) | ((int)P.b_col[bn0 + j] << 4)) << (2 + 8 * j);
-        }
+        if (P.a_tile_nnz[ta + 1] - P.a_tile_nnz[ta] <= S3R_SPARSE_MAX || P.b_tile_nnz[b + 1] - bn0 <= S3R_SPARSE_MAX) f |= PF_SPARSE;
         s_pa[k] = (int)f;
         s_pb[k] = b;
         s_pbn[k] = bn0;
-        s_pd[k] = desc;
     }
     for (int k = tid; k < nnzC; k += THREADS) s_out[k] = 0.0;
     const int has_dense = __syncthreads_or(dense_here);
@@ -297,14 +279,30 @@ k_step3_rows(const __grid_constant__ S3Rows P)
         s_hist[2 * tid + 1] = incl - v1;
         if (tid == 31) s_nord = incl;
     }
+    mbar_wait(&s_bar, 0);
     __syncthreads();
-    for (int k = tid; k < numJ; k += THREADS) {  // counting sort of the phase-R tiles by pair count, descending
-        const int cnt = s_cnnz[k + 1] - s_cnnz[k];
-        if (cnt >= S3R_ROWS_MIN && cnt < P.dense_th)
+    for (int k = tid; k < numJ; k += THREADS) {
+        const int tb = s_cnnz[k], cnt = s_cnnz[k + 1] - tb;
+        if (cnt == 0 || cnt >= P.dense_th) continue;
+        if (cnt >= S3R_ROWS_MIN) {  // counting sort of the phase-R tiles by pair count, descending
             s_order[atomicAdd(&s_hist[S3R_BUCKETS - 1 - min(s_pe[k] - s_pp[k], S3R_BUCKETS - 1)], 1)] = (uint16_t)k;
+            continue;
+        }
+        // a sparsely filled tile: its columns are written here; its nonzeros join phase G's list if any of its pairs
+        // is left to this kernel (a stencil's small C tiles are fed by sparse pairs only)
+        int o = tb;
+        for (int r = 0; r < TS && o < tb + cnt; r++) {
+            unsigned m = s_cm[k * TS + r];
+            while (m) { const int c = __clz(m) - 16; m ^= 0x8000u >> c; s_ocol[o++] = (uint16_t)c; }
+        }
+        bool work = false;
+        for (int p = s_pp[k]; p < s_pe[k] && !work; p++) work = !((unsigned)s_pa[p] & PF_SPARSE);
+        if (work) {
+            const int base = atomicAdd(&s_ngather, cnt);
+            for (int j = 0; j < cnt; j++) s_gitem[base + j] = (uint16_t)(tb + j);
+        }
     }
     __syncthreads();
-    mbar_wait(&s_bar, 0);
 
     const int lane = tid & 31, l16 = tid & 15;
     const unsigned hm = 0xFFFFu << (lane & 16);
@@ -331,24 +329,12 @@ k_step3_rows(const __grid_constant__ S3Rows P)
         const int pe = s_pe[s];
         for (int p = s_pp[s]; p < pe; p++) {
             const unsigned fa = (unsigned)s_pa[p];
-            if (fa & PF_ASPARSE) continue;  // phase S
-            const int a = (int)(fa & PF_INDEX);
+            if (fa & PF_SPARSE) continue;  // k_step3_sparse
+            const int a = (int)fa;
             unsigned am = s_am[a * TS + r];
             if (!am) continue;  // the pair does not touch this row
             const int bbase = s_pbn[p];
             int ia = s_annz[a] + s_ap[a * TS + r];
-            if (fa & PF_BSPARSE) {  // B holds one or two entries (k, c): at most that many products for this row
-                int d = s_pd[p];
-                for (int j = 0, nj = d & 3; j < nj; j++) {
-                    const int k = (d >> 2) & 15, c = (d >> 6) & 15;
-                    d >>= 8;
-                    if (am & (0x8000u >> k)) {
-                        const int o = rowbase + __popc(cmr & ((1u << c) - 1));
-                        s_out[o] = fma(s_aval[ia + __popc(am >> (16 - k))], bvals[bbase + j], s_out[o]);
-                    }
-                }
-                continue;
-            }
             const int b = s_pb[p];
             const uint16_t *bmk = P.b_mask + (size_t)b * TS, *bpt = P.b_ptr + (size_t)b * TS;
             do {  // the bits of A's row mask are the k's of the row, ascending
@@ -383,13 +369,12 @@ k_step3_rows(const __grid_constant__ S3Rows P)
         for (int n = o - s_cnnz[s] - (int)s_cp[s * TS + r]; n > 0; n--) cmr &= cmr - 1;  // drop the n smaller columns
         const int c = __ffs(cmr) - 1;
         const unsigned cbit = 0x8000u >> c;
-        s_ocol[o] = (uint16_t)c;
         double acc = 0.0;
         const int pe = s_pe[s];
         for (int p = s_pp[s]; p < pe; p++) {
             const unsigned fa = (unsigned)s_pa[p];
-            if (fa & PF_ASPARSE) continue;  // phase S
-            const int a = (int)(fa & PF_INDEX);
+            if (fa & PF_SPARSE) continue;  // k_step3_sparse
+            const int a = (int)fa;
             unsigned am = s_am[a * TS + r];
             if (!am) continue;
             const int b = s_pb[p], bbase = s_pbn[p];
@@ -422,10 +407,15 @@ k_step3_rows(const __grid_constant__ S3Rows P)
     }
 }
 
-// Phase S of the staged tile-rows (see k_step3_rows): one WARP per C tile-row walks the sparse A tiles of the tile-row
-// in ascending order; for an entry (r, k, v) of A tile (I,K), lane = one B tile (K,J) of B's tile-row K: it finds C tile
-// (I,J) by binary search in the tile-row's column list and adds v * B(k, :) into C's row r, in place (C's values were
-// written by k_step3_rows; tiles of the dense accumulator and gathered tile-rows are skipped: those kernels walk all pairs).
+// Phase S of the staged tile-rows (see k_step3_rows): every pair with a sparse tile (<= S3R_SPARSE_MAX entries) on either
+// side, in Gustavson order. One WARP per C tile-row walks the A tiles (I,K) of the tile-row in ascending order; lane = one
+// B tile (K,J) of B's tile-row K, which finds C tile (I,J) by binary search in the tile-row's column list:
+//   * A tile sparse: for each of its entries (r, k, v), v * B(k, :) is added into C's row r;
+//   * A tile not sparse, B tile sparse: for each entry (k, c, v) of the B tile, A(r, k) * v is added into C(r, c) for the
+//     rows r of A that hold column k.
+// The lanes of a warp update different C tiles, so nothing conflicts; C's values (written by k_step3_rows) are updated
+// in place, in a fixed order. Tiles of the dense accumulator and gathered tile-rows are skipped: those kernels walk all
+// pairs themselves.
 __global__ void __launch_bounds__(256)
 k_step3_sparse(int ntr, const __grid_constant__ S3Rows P)
 {
@@ -436,39 +426,72 @@ k_step3_sparse(int ntr, const __grid_constant__ S3Rows P)
     const int a1 = P.a_tile_ptr[I + 1];
     for (int a = P.a_tile_ptr[I]; a < a1; a++) {
         const int e0 = P.a_tile_nnz[a], e1 = P.a_tile_nnz[a + 1];
-        if (e1 - e0 > S3R_SPARSE_MAX) continue;
+        const bool a_sparse = e1 - e0 <= S3R_SPARSE_MAX;
         const int K = P.a_tile_col[a];
         const int t0 = P.b_tile_ptr[K], t1 = P.b_tile_ptr[K + 1];
-        for (int e = e0; e < e1; e++) {
-            const unsigned col = P.a_col[e];  // A stores row*16+col
-            const int r = col >> 4, k = col & 15;
-            const double av = P.a_val[e];
-            for (int tb = t0 + lane; tb < t1; tb += 32) {
+        for (int tb0 = t0; tb0 < t1; tb0 += 32) {
+            const int tb = tb0 + lane;
+            // this lane's pair: B tile and C tile (skipped if the C tile is empty or belongs to the dense accumulator)
+            int b = 0, bn0 = 0, bn = 0, t = 0, cb = 0;
+            bool live = tb < t1;
+            if (live) {
+                b = P.b_rm2csc[tb];
+                bn0 = P.b_tile_nnz[b];
+                bn = P.b_tile_nnz[b + 1] - bn0;
+                live = a_sparse || bn <= S3R_SPARSE_MAX;
+            }
+            if (live) {
                 const int J = P.b_tile_col[tb];
                 int lo = 0, hi = numJ - 1;  // C tile (I, J) is listed: find it
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
                     if (P.c_tile_col[c0 + mid] < J) lo = mid + 1; else hi = mid;
                 }
-                const int t = c0 + lo;
-                const int cb = P.c_tile_nnz[t], cnt = P.c_tile_nnz[t + 1] - cb;
-                if (cnt == 0 || cnt >= P.dense_th) continue;
-                const unsigned cm = P.c_mask[(size_t)t * TS + r];
-                if (!cm) continue;
-                const int b = P.b_rm2csc[tb];
-                unsigned bm = __brev((unsigned)P.b_mask[(size_t)b * TS + k]) >> 16;
-                if (!bm) continue;
-                int ib = P.b_tile_nnz[b] + P.b_ptr[(size_t)b * TS + k];
-                const int rowbase = cb + P.c_ptr[(size_t)t * TS + r];
-                const unsigned cmr = __brev(cm) >> 16;
-                do {
-                    const unsigned low = bm & (0u - bm);
-                    const int o = rowbase + __popc(cmr & (low - 1));
-                    bm ^= low;
-                    P.c_val[o] = fma(av, P.b_val[ib++], P.c_val[o]);
-                } while (bm);
+                t = c0 + lo;
+                cb = P.c_tile_nnz[t];
+                const int cnt = P.c_tile_nnz[t + 1] - cb;
+                live = cnt > 0 && cnt < P.dense_th;
             }
-            __syncwarp();  // the next entry may update the same C entries from other lanes
+            if (a_sparse) {
+                for (int e = e0; e < e1; e++) {  // warp-uniform: A's entries (r, k, v)
+                    const unsigned col = P.a_col[e];  // A stores row*16+col
+                    const int r = col >> 4, k = col & 15;
+                    const double av = P.a_val[e];
+                    if (live) {
+                        const unsigned cm = P.c_mask[(size_t)t * TS + r];
+                        unsigned bm = cm ? __brev((unsigned)P.b_mask[(size_t)b * TS + k]) >> 16 : 0u;
+                        if (bm) {
+                            int ib = bn0 + P.b_ptr[(size_t)b * TS + k];
+                            const int rowbase = cb + P.c_ptr[(size_t)t * TS + r];
+                            const unsigned cmr = __brev(cm) >> 16;
+                            do {
+                                const unsigned low = bm & (0u - bm);
+                                const int o = rowbase + __popc(cmr & (low - 1));
+                                bm ^= low;
+                                P.c_val[o] = fma(av, P.b_val[ib++], P.c_val[o]);
+                            } while (bm);
+                        }
+                    }
+                }
+            } else if (live) {  // B's one or two entries (k, c, v) against the rows of A that hold column k
+                const uint4 *pq = reinterpret_cast<const uint4 *>(P.b_ptr + (size_t)b * TS);
+                const uint4 q0 = pq[0], q1 = pq[1];
+                const int abase = e0;
+                for (int j = 0; j < bn; j++) {
+                    const int k = s3_row_of(q0, q1, j), c = P.b_col[bn0 + j];
+                    const double bv = P.b_val[bn0 + j];
+                    const unsigned kbit = 0x8000u >> k;
+                    for (int r = 0; r < TS; r++) {
+                        const unsigned am = P.a_mask[(size_t)a * TS + r];
+                        if (!(am & kbit)) continue;
+                        const unsigned cmr = __brev((unsigned)P.c_mask[(size_t)t * TS + r]) >> 16;
+                        const int o = cb + P.c_ptr[(size_t)t * TS + r] + __popc(cmr & ((1u << c) - 1));
+                        const double av = P.a_val[abase + P.a_ptr[(size_t)a * TS + r] + __popc(am >> (16 - k))];
+                        P.c_val[o] = fma(av, bv, P.c_val[o]);
+                    }
+                }
+            }
+            __syncwarp();  // the next pass may update the same C entries from other lanes
         }
     }
 }
