@@ -21,14 +21,18 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
 int build_rm2csc_device(tsg_dtile *B);
 
 // numeric.cu (step 3)
-struct PairLists { const int *ptr, *end, *a, *b; };  // pairs of C tile t: (a[p], b[p]) for p in [ptr[t], end[t]); b = storage id of the B tile
+// pairs of C tile t: (a[p], b[p]) for p in [ptr[t], end[t]); b = storage id of the B tile. slot (light tile-rows only):
+// for the pairs of a tile-row enumerated in A-major order (A tiles ascending, then the B tiles of B's tile-row K),
+// starting at wptr[row], the position of the pair's C tile within the tile-row.
+struct PairLists { const int *ptr, *end, *a, *b; const uint16_t *slot; };
 struct NumericBufs {
     uint8_t *row_kind;  // [ntr]     which kernel computes the (non-dense) tiles of each C tile-row
     int *dense_list;    // [numblkC] C tiles that take the dense accumulator
     int dense_th, smem_cap;
 };
 size_t numeric_scratch_bytes(int ntr, long long numblkC);
-int numeric_classify_device(const tsg_dtile *A, const tsg_dtile *C, int trow0, int ntr, const int *wptr, NumericBufs *nb, int *d_ns);
+int numeric_classify_device(const tsg_dtile *A, const tsg_dtile *C, int trow0, int ntr, const int *wptr, const uint8_t *light, NumericBufs *nb,
+                            int *d_ns);
 int numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, int trow0, int ntr, const int *wptr, const PairLists &pl,
                    const NumericBufs &nb, const int *h_ns, bool heavy_rows, tsg_stats *stats);
 

@@ -104,7 +104,8 @@ k_s3_classify_tiles(int numblkC, int trow0, const int *__restrict__ c_tile_nnz, 
 __global__ void __launch_bounds__(256)
 k_s3_classify_rows(int ntr, int trow0, const int *__restrict__ a_tile_ptr, const int *__restrict__ a_tile_nnz,
                    const int *__restrict__ c_tile_ptr, const int *__restrict__ c_tile_nnz, const int *__restrict__ wptr,
-                   int smem_cap, int min_fill, int force_kind, uint8_t *__restrict__ row_kind, int *__restrict__ scal)
+                   const uint8_t *__restrict__ light, int smem_cap, int min_fill, int force_kind, uint8_t *__restrict__ row_kind,
+                   int *__restrict__ scal)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -118,9 +119,10 @@ k_s3_classify_rows(int ntr, int trow0, const int *__restrict__ a_tile_ptr, const
             if (nnzC > 0) {
                 const int a0 = a_tile_ptr[trow0 + i], a1 = a_tile_ptr[trow0 + i + 1];
                 const size_t nb = s3r_need(a1 - a0, a_tile_nnz[a1] - a_tile_nnz[a0], numJ, nnzC, wptr[i + 1] - wptr[i]);
-                const bool fits = nb <= (size_t)smem_cap && (long long)nnzC >= (long long)min_fill * numJ;
-                kind = force_kind ? (uint8_t)force_kind : (fits ? ROW_STAGED : ROW_GATHER);
-                if (kind == ROW_STAGED && nb > (size_t)smem_cap) kind = ROW_GATHER;  // a forced choice still has to fit
+                // staged rows need the A-major pair slots, which only the light step-1 path emits
+                const bool fits = nb <= (size_t)smem_cap && light[i];
+                kind = force_kind ? (uint8_t)force_kind : (fits && (long long)nnzC >= (long long)min_fill * numJ ? ROW_STAGED : ROW_GATHER);
+                if (kind == ROW_STAGED && !fits) kind = ROW_GATHER;  // a forced choice still has to fit
                 need = kind == ROW_STAGED ? (int)nb : 0;
             }
         }
@@ -180,6 +182,7 @@ struct S3Rows {
     uint16_t *c_col;
     double *c_val;
     const int *wptr, *pair_ptr, *pair_end, *pair_a, *pair_b;
+    const uint16_t *pair_slot;
     const uint8_t *row_kind;
 };
 
@@ -409,7 +412,7 @@ k_step3_rows(const __grid_constant__ S3Rows P)
 
 // Phase S of the staged tile-rows (see k_step3_rows): every pair with a sparse tile (<= S3R_SPARSE_MAX entries) on either
 // side, in Gustavson order. One WARP per C tile-row walks the A tiles (I,K) of the tile-row in ascending order; lane = one
-// B tile (K,J) of B's tile-row K, which finds C tile (I,J) by binary search in the tile-row's column list:
+// B tile (K,J) of B's tile-row K; the slot of C tile (I,J) in the tile-row comes from step 1 (pair_slot, A-major order):
 //   * A tile sparse: for each of its entries (r, k, v), v * B(k, :) is added into C's row r;
 //   * A tile not sparse, B tile sparse: for each entry (k, c, v) of the B tile, A(r, k) * v is added into C(r, c) for the
 //     rows r of A that hold column k.
@@ -422,13 +425,16 @@ k_step3_sparse(int ntr, const __grid_constant__ S3Rows P)
     const int i = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (i >= ntr || P.row_kind[i] != ROW_STAGED) return;
     const int I = P.trow0 + i;
-    const int c0 = P.c_tile_ptr[i], numJ = P.c_tile_ptr[i + 1] - c0;
+    const int c0 = P.c_tile_ptr[i];
     const int a1 = P.a_tile_ptr[I + 1];
+    int widx = P.wptr[i];  // A-major index of the first pair of the current A tile (the order step 1 enumerated them in)
     for (int a = P.a_tile_ptr[I]; a < a1; a++) {
         const int e0 = P.a_tile_nnz[a], e1 = P.a_tile_nnz[a + 1];
         const bool a_sparse = e1 - e0 <= S3R_SPARSE_MAX;
         const int K = P.a_tile_col[a];
         const int t0 = P.b_tile_ptr[K], t1 = P.b_tile_ptr[K + 1];
+        const int wa = widx;
+        widx += t1 - t0;
         for (int tb0 = t0; tb0 < t1; tb0 += 32) {
             const int tb = tb0 + lane;
             // this lane's pair: B tile and C tile (skipped if the C tile is empty or belongs to the dense accumulator)
@@ -441,13 +447,7 @@ k_step3_sparse(int ntr, const __grid_constant__ S3Rows P)
                 live = a_sparse || bn <= S3R_SPARSE_MAX;
             }
             if (live) {
-                const int J = P.b_tile_col[tb];
-                int lo = 0, hi = numJ - 1;  // C tile (I, J) is listed: find it
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (P.c_tile_col[c0 + mid] < J) lo = mid + 1; else hi = mid;
-                }
-                t = c0 + lo;
+                t = c0 + P.pair_slot[wa + (tb - t0)];  // C tile (I, J) of this pair, as step 1 ranked it
                 cb = P.c_tile_nnz[t];
                 const int cnt = P.c_tile_nnz[t + 1] - cb;
                 live = cnt > 0 && cnt < P.dense_th;
@@ -795,7 +795,8 @@ size_t numeric_scratch_bytes(int ntr, long long numblkC)
 
 // Enqueue the classification of the slab's tile-rows and tiles (after C's tile_nnz has been scanned). Results: row_kind,
 // dense_list and the NS_* counters in d_ns (device ints), which the caller reads back together with nnz(C).
-int numeric_classify_device(const tsg_dtile *A, const tsg_dtile *C, int trow0, int ntr, const int *wptr, NumericBufs *nb, int *d_ns)
+int numeric_classify_device(const tsg_dtile *A, const tsg_dtile *C, int trow0, int ntr, const int *wptr, const uint8_t *light, NumericBufs *nb,
+                            int *d_ns)
 {
     Ctx &c = ctx();
     const char *mode = s3_mode();
@@ -816,7 +817,7 @@ int numeric_classify_device(const tsg_dtile *A, const tsg_dtile *C, int trow0, i
                                                                          nb->dense_list, nb->row_kind, d_ns);
         CK_LAUNCH();
         k_s3_classify_rows<<<ceil_div(ntr, 256), 256, 0, c.stream>>>(ntr, trow0, A->tile_ptr, A->tile_nnz, C->tile_ptr, C->tile_nnz, wptr,
-                                                                      (int)cap, env_int("TSG_ROWS_MIN_FILL", 8), force_kind,
+                                                                      light, (int)cap, env_int("TSG_ROWS_MIN_FILL", 8), force_kind,
                                                                       nb->row_kind, d_ns);
         CK_LAUNCH();
     }
@@ -844,7 +845,8 @@ int numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, int tro
     if (n_staged > 0) {
         S3Rows P{trow0, nb.dense_th, A->tile_ptr, A->tile_columnidx, A->tile_nnz, A->ptr, A->mask, A->col, A->val,
                  B->tile_ptr, B->tile_columnidx, B->rm2csc, B->tile_nnz, B->ptr, B->mask, B->col, B->val,
-                 C->tile_ptr, C->tile_columnidx, C->tile_nnz, C->ptr, C->mask, C->col, C->val, wptr, pl.ptr, pl.end, pl.a, pl.b, nb.row_kind};
+                 C->tile_ptr, C->tile_columnidx, C->tile_nnz, C->ptr, C->mask, C->col, C->val, wptr, pl.ptr, pl.end, pl.a, pl.b, pl.slot,
+                 nb.row_kind};
         const size_t smem = ((size_t)h_ns[NS_MAXNEED] + 1023) & ~(size_t)1023;
         // 128-thread CTAs when a tile-row has few (tile, row) slots (2D meshes): fewer idle threads, more CTAs per SM
         const bool narrow = numblkC * TS < (long long)ntr * 192;

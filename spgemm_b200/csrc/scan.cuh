@@ -27,7 +27,7 @@ __device__ __forceinline__ unsigned long long scan_ld_state(const unsigned long 
 
 template <typename OutT>
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_lookback_kernel(const int *in, OutT *out, long long n, unsigned long long *state, int *ticket)
+scan_lookback_kernel(const int *in, OutT *out, long long n, unsigned long long *state, int *ticket, long long *total)
 {
     __shared__ int s_tile;
     __shared__ long long s_warp[SCAN_THREADS / 32];
@@ -95,13 +95,16 @@ scan_lookback_kernel(const int *in, OutT *out, long long n, unsigned long long *
     for (int k = 0; k < SCAN_ITEMS; k++) {
         long long idx = base + k;
         if (idx <= n) out[idx] = (OutT)run;
+        if (idx == n && total) *total = run;  // the 64-bit total next to narrowed 32-bit offsets
         run += v[k];
     }
 }
 
 // Host wrapper; enqueues on the library stream. Returns TSG_OK or an error code.
+// total64 (optional, device pointer): receives the sum as a 64-bit value even when OutT is int, so that one scan gives
+// 32-bit offsets for the kernels and an overflow-proof total for the host (the reference scans int totals).
 template <typename OutT>
-static int exclusive_scan(const int *in, OutT *out, long long n)
+static int exclusive_scan(const int *in, OutT *out, long long n, long long *total64 = nullptr)
 {
     Ctx &c = ctx();
     long long ntiles = (n + 1 + SCAN_TILE - 1) / SCAN_TILE;
@@ -114,7 +117,7 @@ static int exclusive_scan(const int *in, OutT *out, long long n)
     }
     CK(cudaMemsetAsync(c.scan_state, 0, (size_t)ntiles * sizeof(unsigned long long), c.stream));
     CK(cudaMemsetAsync(c.scan_ticket, 0, sizeof(int), c.stream));
-    scan_lookback_kernel<OutT><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(in, out, n, c.scan_state, c.scan_ticket);
+    scan_lookback_kernel<OutT><<<(unsigned)ntiles, SCAN_THREADS, 0, c.stream>>>(in, out, n, c.scan_state, c.scan_ticket, total64);
     CK_LAUNCH();
     return TSG_OK;
 }

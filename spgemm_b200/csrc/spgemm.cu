@@ -1,35 +1,33 @@
-// spgemm.cu -- TileSpGEMM steps 1-3 on B200, for a slab [trow0, trow1) of C tile-rows.
-// Replaces reference src/tilespgemm-cuda.h:2220-2844 (host) and its kernels:
+// spgemm.cu -- TileSpGEMM steps 1 and 2 on B200 and the host orchestration of all three steps, for a slab
+// [trow0, trow1) of C tile-rows. Replaces reference src/tilespgemm-cuda.h:2220-2844 (host) and its kernels:
 //   step 1  tile_spgemm_step1_cuda_spa_kernel / _numeric_ (:279-392) and the nsparse hash path
 //           (src/spgemm_nsparse_kernel.h:221-311,1171-1438)
 //   step 2  tile_spgemm_step3_cuda_kernel_2level_halfwarp (:394-773)
-//   step 3  tile_spgemm_step4_cuda_kernel_smem_v3[_halfwarp] (:1273-1952)
+//   step 3  tile_spgemm_step4_cuda_kernel_smem_v3[_halfwarp] (:1273-1952)  -> numeric.cu
 //
 // What is different from the reference (same results):
-//   * Step 1 is a Gustavson expansion at tile level over a WINDOWED shared-memory bitmap
-//     [Jmin, Jmax] of the tile-row (the reference's bitmap spans all tile columns and only exists
-//     for tilen <= 16384, else it falls back to a hash path). Besides C's tile list it emits, per C
-//     tile, the list of matched (A tile, B tile) pairs, so the later steps never intersect index
-//     lists (the reference re-intersects A's tile-row with B's tile-column by binary search in both
-//     of its later steps and caches at most one pair, :538-547).
-//   * Step 2 (C's row masks, Ptr, tile nnz) is FUSED into step 1 on the one-warp path: while the warp
-//     enumerates the B tiles paired with one A tile, A's row masks are warp-uniform, so the 16x16x16
-//     boolean product of up to 32 pairs costs one shared-memory load + OR per A entry. Tile-rows on
-//     the multi-warp path (and matrices whose B tile-rows are too short to fill a warp) use k_step2
-//     (half-warp per C tile, lane r ORs B's row masks, fetched by shuffle, selected by A's row mask r) or,
-//     for hypersparse tiles, k_step2_thread (one thread per C tile).
-//   * Step 3 has two kernels, chosen per call from the average fill of A's tiles: a GATHER (one lane per C
-//     nonzero, register accumulation in the serial SPA's summation order, no accumulator memory, coalesced
-//     stores) for sparse tiles, and a DENSE ACCUMULATOR (warp per C tile, 8 register accumulators per lane,
-//     the B tile expanded in shared memory) for well-filled tiles (block-FEM). Neither uses atomics; the
-//     reference does one global atomicAdd per product plus a binary search (:1450,1558,1795,1900).
-//     k_step3_dmma is the FP64 tensor-core (mma.sync m8n8k4) variant of the dense kernel, opt-in.
-//   * Empty C tiles are kept with Ptr = mask = 0 and nnz 0 (the reference leaves them
-//     uninitialised).
-//   * Scratch lives in grow-only arenas; sizes are read back three times (pairs/window, numblkC, nnzC).
-// Superseded kernels measured on the way (half-warp-per-tile numeric with a shared-memory accumulator,
-// "rounds" numeric, flattened / half-warp-per-pair symbolic, tile-row-per-warp numeric, prefetching variants)
-// are described in profiles/README.md; some are kept as text under scratch/.
+//   * Step 1 is a Gustavson expansion at tile level over a WINDOWED shared-memory bitmap [Jmin, Jmax] of the tile-row
+//     (the reference's bitmap spans all tile columns and only exists for tilen <= 16384, else it falls back to a hash
+//     path). Besides C's tile list it emits, per C tile, the list of matched (A tile, B tile) pairs, so the later
+//     steps never intersect index lists (the reference re-intersects A's tile-row with B's tile-column by binary
+//     search in both of its later steps and caches at most one pair, :538-547).
+//   * Two kernels on the light path (tile-rows of <= S1_LIGHT_MAX pairs whose window fits a per-warp bitmap), a WARP
+//     per tile-row and S1_WARPS tile-rows per CTA, each warp with its own slice of shared memory:
+//       k_s1_count  weight (pairs), window and C tile count of every tile-row in one pass; everything else goes to
+//                   the heavy list;
+//       k_s1_fill   bitmap -> per-word prefix (rank of a tile column = two loads and a popcount) -> C's tile columns ->
+//                   pair counts and cursors in shared memory -> pair lists, plus the slot of every pair in A-major order
+//                   (what k_step3_sparse indexes by), plus the FUSED bitmask symbolic (step 2).
+//   * Step 2 (C's row masks, Ptr, tile nnz) fused into k_s1_fill: while the warp enumerates the B tiles paired with
+//     one A tile, A's row masks are warp-uniform, so the 16x16x16 boolean product of up to 32 pairs costs one
+//     shared-memory load + OR per A entry. Heavy tile-rows (and matrices whose B tile-rows are too short to fill a
+//     warp) use k_step2 (half-warp per C tile) or, for hypersparse tiles, k_step2_thread (one thread per C tile).
+//   * Heavy tile-rows (R-MAT hubs): one 1024-thread CTA per row over a compacted list, bitmap in up to all of the
+//     SM's shared memory, one global atomic per pair.
+//   * Empty C tiles are kept with Ptr = mask = 0 and nnz 0 (the reference leaves them uninitialised).
+//   * One scan per array (64-bit total next to 32-bit offsets), scratch in grow-only arenas, two host read-backs per
+//     call on the light path (sizes of the two allocations), one more when heavy tile-rows exist.
+// Superseded kernels measured on the way are described in profiles/README.md; some are kept as text under scratch/.
 #include "common.cuh"
 #include "scan.cuh"
 #include "kernels.h"
@@ -120,45 +118,295 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Step 1b/1c: one CTA per C tile-row. MODE 0 counts the distinct tile columns. MODE 1 emits the
-// sorted tile-column list, and per C tile the matched (A tile, B tile) pair list.
-// THREADS = 32 handles rows with w in (0, S1_LIGHT_MAX]; THREADS = S1_HEAVY_THREADS the heavier ones.
-// Dynamic smem: bitmap[nw_max] | pre8[nw_max/8 + 1] | (fused symbolic) bmT[8][32] u32 | cm[16][numJ_pad] u16.
-//
-// Fused bitmask symbolic (step 2) on the one-warp path: while the warp enumerates the pairs of A tile
-// (I,K) with the B tiles of tile-row K (one B tile per lane), A's 16 row masks are WARP-UNIFORM, so the
-// 16x16x16 boolean product of the pair costs one shared-memory load + OR per A entry for all <= 32
-// pairs at once, instead of a per-pair pass over a half-warp (k_step2). The C row masks of the whole
-// tile-row live in shared memory as cm[row][slot]; Ptr / mask / tile nnz are written at the end.
+// Light path. S1_WARPS tile-rows per CTA, one warp each, each warp with its own slice of dynamic shared memory.
 // ---------------------------------------------------------------------------------------------
-struct S1Fuse {
+constexpr int S1_WARPS = 8;
+enum { SC_NW_HEAVY = 0, SC_ERR = 1, SC_WMAX = 2, SC_MAXJ = 3, SC_NHEAVY = 4, SC_NW_LIGHT = 5, SC_NLIGHT = 6 };
+
+// k_s1_count: per tile-row the weight w (matched tile pairs; also the multi-GPU / slab balancing weight, nsparse
+// set_intprod_num, src/spgemm_nsparse_kernel.h:135-151), the window [jlo, jhi] of tile columns the row can produce, and
+// -- for rows that fit the light path -- the number of distinct tile columns (C tiles). The others join heavy_list.
+__global__ void __launch_bounds__(S1_WARPS * 32)
+k_s1_count(int trow0, int ntr, int bmw, const int *__restrict__ a_tile_ptr, const int *__restrict__ a_tile_col,
+           const int *__restrict__ b_tile_ptr, const int *__restrict__ b_tile_col, int *__restrict__ w, int *__restrict__ jlo,
+           int *__restrict__ jhi, int *__restrict__ cnt, uint8_t *__restrict__ light, int *__restrict__ heavy_list,
+           int *__restrict__ scal)
+{
+    extern __shared__ unsigned s1c_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * S1_WARPS + warp;
+    if (i >= ntr) return;
+    unsigned *bitmap = s1c_smem + (size_t)warp * bmw;
+    const int I = trow0 + i;
+    const int a0 = a_tile_ptr[I], a1 = a_tile_ptr[I + 1];
+    long long s = 0;
+    int lo = 0x7fffffff, hi = -1;
+    for (int ta = a0 + lane; ta < a1; ta += 32) {
+        const int K = a_tile_col[ta];
+        const int b0 = b_tile_ptr[K], b1 = b_tile_ptr[K + 1];
+        if (b1 > b0) {
+            s += b1 - b0;
+            lo = min(lo, b_tile_col[b0]);
+            hi = max(hi, b_tile_col[b1 - 1]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        s += __shfl_xor_sync(FULL_MASK, s, o);
+        lo = min(lo, __shfl_xor_sync(FULL_MASK, lo, o));
+        hi = max(hi, __shfl_xor_sync(FULL_MASK, hi, o));
+    }
+    if (s > 0x7fffffffll) {
+        if (lane == 0) atomicOr(&scal[SC_ERR], 1);
+        s = 0x7fffffff;
+    }
+    if (lane == 0) { w[i] = (int)s; jlo[i] = lo; jhi[i] = hi; }
+    if (s == 0) {
+        if (lane == 0) { cnt[i] = 0; light[i] = 0; }
+        return;
+    }
+    const int lo32 = lo & ~31, nw = ((hi - lo32) >> 5) + 1;
+    if (s > S1_LIGHT_MAX || nw > bmw) {  // heavy: more pairs than one warp should walk, or a window wider than its bitmap
+        if (lane == 0) {
+            cnt[i] = 0;
+            light[i] = 0;
+            heavy_list[atomicAdd(&scal[SC_NHEAVY], 1)] = i;
+            atomicMax(&scal[SC_NW_HEAVY], nw);
+            atomicMax(&scal[SC_WMAX], (int)s);
+        }
+        return;
+    }
+    for (int k = lane; k < nw; k += 32) bitmap[k] = 0;
+    __syncwarp();
+    for (int ta = a0; ta < a1; ta++) {
+        const int K = a_tile_col[ta];
+        const int b1 = b_tile_ptr[K + 1];
+        for (int tb = b_tile_ptr[K] + lane; tb < b1; tb += 32) {
+            const int d = b_tile_col[tb] - lo32;
+            atomicOr(&bitmap[d >> 5], 1u << (d & 31));
+        }
+    }
+    __syncwarp();
+    int n = 0;
+    for (int k = lane; k < nw; k += 32) n += __popc(bitmap[k]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(FULL_MASK, n, o);
+    if (lane == 0) {
+        cnt[i] = n;
+        light[i] = 1;
+        atomicMax(&scal[SC_MAXJ], n);
+        atomicMax(&scal[SC_NW_LIGHT], nw);
+        atomicMax(&scal[SC_WMAX], (int)s);
+        atomicAdd(&scal[SC_NLIGHT], 1);
+    }
+}
+
+// k_s1_fill: everything else of steps 1 and 2 for a light tile-row (see the file header).
+// Per-warp shared memory (32-bit words): bitmap[bmw] | pre[bmw] u16 | cur[nj] | (FUSE) bmT[16][32] u16 | cm[16][njpad] u16.
+struct S1Fill {
+    int trow0, ntr, bmw, nj, njpad, warp_words;
+    const int *a_tile_ptr, *a_tile_col, *b_tile_ptr, *b_tile_col, *b_rm2csc;
+    const int *jlo, *jhi, *wptr, *c_tile_ptr;
+    const uint8_t *light;
+    int *c_tile_col, *c_tile_row, *pair_ptr, *pair_end, *pair_a, *pair_b;
+    uint16_t *pair_slot;
     const uint16_t *a_mask, *b_mask;
     uint16_t *c_ptr, *c_mask;
     int *c_cnt;
-    int numJ_pad;  // 0: not fused (k_step2 computes the masks from the pair lists)
-    int4 *tmp;     // multi-warp path: one (slot, rank in slot, A tile, B tile) record per pair of the slab, or nullptr
 };
 
-template <int THREADS, int MODE>
-__global__ void __launch_bounds__(THREADS)
-k_step1(int trow0, int nw_max, int wmin, int wmax, const int *__restrict__ a_tile_ptr,
-        const int *__restrict__ a_tile_col, const int *__restrict__ b_tile_ptr, const int *__restrict__ b_tile_col,
-        const int *__restrict__ b_rm2csc, const int *__restrict__ w, const int *__restrict__ jlo,
-        const int *__restrict__ jhi, int *__restrict__ cnt /*MODE0 out*/, const int *__restrict__ c_tile_ptr,
-        const int *__restrict__ wptr, int *__restrict__ c_tile_col, int *__restrict__ c_tile_row,
-        int *__restrict__ pair_ptr, int *__restrict__ pair_end, int *__restrict__ pair_a, int *__restrict__ pair_b,
-        int *__restrict__ maxJ /*MODE0: max tile count over one-warp rows*/, S1Fuse fz)
+template <bool FUSE>
+__global__ void __launch_bounds__(S1_WARPS * 32, 4)
+k_s1_fill(const __grid_constant__ S1Fill P)
 {
+    extern __shared__ unsigned s1f_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * S1_WARPS + warp;
+    if (i >= P.ntr || !P.light[i]) return;
+    unsigned *bitmap = s1f_smem + (size_t)warp * P.warp_words;
+    uint16_t *pre = reinterpret_cast<uint16_t *>(bitmap + P.bmw);
+    int *cur = reinterpret_cast<int *>(bitmap + P.bmw + P.bmw / 2);
+    uint16_t *bmT = reinterpret_cast<uint16_t *>(cur + P.nj);  // [16][32]: row mask k of lane's B tile
+    uint16_t *cm = bmT + TS * 32;                               // [16][njpad]: C's row masks of the tile-row
+    const int I = P.trow0 + i;
+    const int lo = P.jlo[i] & ~31, nw = ((P.jhi[i] - lo) >> 5) + 1;
+    const int a0 = P.a_tile_ptr[I], a1 = P.a_tile_ptr[I + 1];
+    const int cbase = P.c_tile_ptr[i], numJ = P.c_tile_ptr[i + 1] - cbase, wbase = P.wptr[i];
+
+    // 1. window bitmap of the tile columns the row produces
+    for (int k = lane; k < nw; k += 32) bitmap[k] = 0;
+    __syncwarp();
+    for (int ta = a0; ta < a1; ta++) {
+        const int K = P.a_tile_col[ta];
+        const int b1 = P.b_tile_ptr[K + 1];
+        for (int tb = P.b_tile_ptr[K] + lane; tb < b1; tb += 32) {
+            const int d = P.b_tile_col[tb] - lo;
+            atomicOr(&bitmap[d >> 5], 1u << (d & 31));
+        }
+    }
+    __syncwarp();
+    // 2. per-word exclusive prefix of the popcounts: rank(d) = pre[d / 32] + popc(bitmap[d / 32] below bit d % 32)
+    {
+        const int q = (nw + 31) >> 5, k0 = lane * q, k1 = min(k0 + q, nw);
+        int sum = 0;
+        for (int k = k0; k < k1; k++) sum += __popc(bitmap[k]);
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int run = incl - sum;
+        for (int k = k0; k < k1; k++) { pre[k] = (uint16_t)run; run += __popc(bitmap[k]); }
+    }
+    __syncwarp();
+    // 3. C's tile columns (ascending) and rows; cursors and (fused) C masks start at zero
+    for (int k = lane; k < nw; k += 32) {
+        unsigned bits = bitmap[k];
+        int r = cbase + pre[k];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            P.c_tile_col[r] = lo + k * 32 + b;
+            P.c_tile_row[r] = I;
+            r++;
+        }
+    }
+    for (int k = lane; k < numJ; k += 32) cur[k] = 0;
+    if (FUSE)
+        for (int k = lane; k < TS * P.njpad / 2; k += 32) reinterpret_cast<unsigned *>(cm)[k] = 0;
+    __syncwarp();
+    // 4. second expansion: pairs per C tile, the slot of every pair in A-major order, and the fused bitmask symbolic
+    int aoff = 0;
+    for (int ta = a0; ta < a1; ta++) {
+        const int K = P.a_tile_col[ta];
+        const int b0 = P.b_tile_ptr[K], b1 = P.b_tile_ptr[K + 1];
+        unsigned amw[8];
+        if (FUSE) {  // A's 16 row masks: one 32-byte line, the same for every lane
+            const uint4 *ap = reinterpret_cast<const uint4 *>(P.a_mask + (size_t)ta * TS);
+            const uint4 x = ap[0], y = ap[1];
+            amw[0] = x.x; amw[1] = x.y; amw[2] = x.z; amw[3] = x.w; amw[4] = y.x; amw[5] = y.y; amw[6] = y.z; amw[7] = y.w;
+        }
+        for (int tb0 = b0; tb0 < b1; tb0 += 32) {
+            const int tb = tb0 + lane;
+            const bool valid = tb < b1;
+            int slot = 0;
+            if (valid) {
+                const int d = P.b_tile_col[tb] - lo, wd = d >> 5;
+                slot = pre[wd] + __popc(bitmap[wd] & ((1u << (d & 31)) - 1));
+                cur[slot]++;  // one A tile at a time: the lanes hold distinct slots
+                P.pair_slot[wbase + aoff + (tb - b0)] = (uint16_t)slot;
+            }
+            if (FUSE) {
+                if (valid) {
+                    const uint4 *bp = reinterpret_cast<const uint4 *>(P.b_mask + (size_t)P.b_rm2csc[tb] * TS);
+                    const uint4 x = bp[0], y = bp[1];
+                    const unsigned bw[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {  // little-endian u16 pairs
+                        bmT[(2 * j) * 32 + lane] = (uint16_t)(bw[j] & 0xFFFFu);
+                        bmT[(2 * j + 1) * 32 + lane] = (uint16_t)(bw[j] >> 16);
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < TS; r++) {
+                    unsigned m = (r & 1) ? (amw[r >> 1] >> 16) : (amw[r >> 1] & 0xFFFFu);
+                    if (m) {  // warp-uniform
+                        unsigned acc = 0;
+                        do {
+                            const int k = __clz(m) - 16;
+                            acc |= bmT[k * 32 + lane];
+                            m &= ~(0x8000u >> k);
+                        } while (m);
+                        if (valid) cm[r * P.njpad + slot] |= (uint16_t)acc;  // distinct slots per lane
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        aoff += b1 - b0;
+    }
+    // 5. exclusive scan of the pair counts over the row's slots: pair_ptr; cur becomes the write cursor
+    {
+        int carry = wbase;
+        for (int s0 = 0; s0 < numJ; s0 += 32) {
+            const int sl = s0 + lane;
+            const int v = sl < numJ ? cur[sl] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL_MASK, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (sl < numJ) { P.pair_ptr[cbase + sl] = carry + incl - v; cur[sl] = carry + incl - v; }
+            carry += __shfl_sync(FULL_MASK, incl, 31);
+        }
+    }
+    __syncwarp();
+    // 6. third expansion: the pair lists, A tiles ascending inside every list (the serial SPA's summation order)
+    for (int ta = a0; ta < a1; ta++) {
+        const int K = P.a_tile_col[ta];
+        const int b1 = P.b_tile_ptr[K + 1];
+        for (int tb = P.b_tile_ptr[K] + lane; tb < b1; tb += 32) {
+            const int d = P.b_tile_col[tb] - lo, wd = d >> 5;
+            const int slot = pre[wd] + __popc(bitmap[wd] & ((1u << (d & 31)) - 1));
+            const int pos = cur[slot]++;
+            P.pair_a[pos] = ta;
+            P.pair_b[pos] = P.b_rm2csc[tb];
+        }
+        __syncwarp();
+    }
+    // 7. list ends; Ptr (exclusive row offsets), mask and nnz of each C tile
+    for (int sl = lane; sl < numJ; sl += 32) {
+        P.pair_end[cbase + sl] = cur[sl];
+        if (FUSE) {
+            unsigned pw[8], mw[8];
+            int run = 0;
+#pragma unroll
+            for (int r = 0; r < TS; r += 2) {
+                const unsigned m0 = cm[r * P.njpad + sl], m1 = cm[(r + 1) * P.njpad + sl];
+                const int p0 = run, p1 = run + __popc(m0);
+                run = p1 + __popc(m1);
+                pw[r >> 1] = (unsigned)p0 | ((unsigned)p1 << 16);
+                mw[r >> 1] = m0 | (m1 << 16);
+            }
+            uint4 *dp = reinterpret_cast<uint4 *>(P.c_ptr + (size_t)(cbase + sl) * TS);
+            uint4 *dm = reinterpret_cast<uint4 *>(P.c_mask + (size_t)(cbase + sl) * TS);
+            dp[0] = make_uint4(pw[0], pw[1], pw[2], pw[3]); dp[1] = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+            dm[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]); dm[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+            P.c_cnt[cbase + sl] = run;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Heavy path: one 1024-thread CTA per tile-row of heavy_list (more than S1_LIGHT_MAX pairs, or a window wider than a
+// warp's bitmap: R-MAT hubs). MODE 0 counts the distinct tile columns. MODE 1 emits the sorted tile-column list and,
+// per C tile, the matched (A tile, B tile) pair list: ONE expansion and ONE global atomic per pair -- the atomicAdd
+// that counts the pairs of a C tile also returns the pair's rank inside the tile's list; (slot, rank, A tile, B tile)
+// is parked in a per-row scratch record, the counts are scanned, and the records are then placed.
+// Dynamic smem: bitmap[nw_max] | pre8[nw_max/8 + 1]. The symbolic of these rows is k_step2 / k_step2_thread.
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(S1_HEAVY_THREADS)
+k_s1_heavy(int trow0, int nw_max, const int *__restrict__ heavy_list, const int *__restrict__ a_tile_ptr,
+           const int *__restrict__ a_tile_col, const int *__restrict__ b_tile_ptr, const int *__restrict__ b_tile_col,
+           const int *__restrict__ b_rm2csc, const int *__restrict__ w, const int *__restrict__ jlo,
+           const int *__restrict__ jhi, int *__restrict__ cnt /*MODE0 out*/, const int *__restrict__ c_tile_ptr,
+           const int *__restrict__ wptr, int *__restrict__ c_tile_col, int *__restrict__ c_tile_row,
+           int *__restrict__ pair_ptr, int *__restrict__ pair_end, int *__restrict__ pair_a, int *__restrict__ pair_b,
+           int4 *__restrict__ pair_tmp)
+{
+    constexpr int THREADS = S1_HEAVY_THREADS, NWARPS = THREADS / 32;
     extern __shared__ unsigned s1_smem[];
-    __shared__ int s_warp[THREADS / 32];
+    __shared__ int s_warp[NWARPS];
     __shared__ int s_carry;
     unsigned *bitmap = s1_smem;
     int *pre8 = (int *)(s1_smem + nw_max);
-    const int i = blockIdx.x, I = trow0 + i;
+    const int i = heavy_list[blockIdx.x], I = trow0 + i;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NWARPS = THREADS / 32;
     const int wi = w[i];
-    if (wi <= wmin || wi > wmax) return;  // other launch's row (or nothing to do: MODE 0 output is pre-zeroed)
     const int lo = jlo[i] & ~31;
     const int nw = ((jhi[i] - lo) >> 5) + 1;
     const int a0 = a_tile_ptr[I], a1 = a_tile_ptr[I + 1];
@@ -177,10 +425,7 @@ k_step1(int trow0, int nw_max, int wmin, int wmax, const int *__restrict__ a_til
         int s = 0, total;
         for (int k = tid; k < nw; k += THREADS) s += __popc(bitmap[k]);
         block_excl_scan<THREADS>(s, s_warp, &total);
-        if (tid == 0) {
-            cnt[i] = total;
-            if (THREADS == 32) atomicMax(maxJ, total);
-        }
+        if (tid == 0) cnt[i] = total;
         return;
     }
     // ---- MODE 1 ----
@@ -201,12 +446,6 @@ k_step1(int trow0, int nw_max, int wmin, int wmax, const int *__restrict__ a_til
     }
     const int numJ = s_carry;
     const int cbase = c_tile_ptr[i];
-    const bool fuse = THREADS == 32 && fz.numJ_pad > 0;
-    unsigned *bmT = s1_smem + nw_max + nw_max / 8 + 2;                    // [8][32]: B row masks 2j, 2j+1 of lane's tile
-    uint16_t *cm = reinterpret_cast<uint16_t *>(bmT + 8 * 32);            // [16][numJ_pad]
-    if (fuse) {
-        for (int k = tid; k < (TS * fz.numJ_pad + 1) / 2; k += THREADS) reinterpret_cast<unsigned *>(cm)[k] = 0;
-    }
     for (int k = tid; k < nw; k += THREADS) {
         unsigned bits = bitmap[k];
         if (bits) {
@@ -221,162 +460,59 @@ k_step1(int trow0, int nw_max, int wmin, int wmax, const int *__restrict__ a_til
             }
         }
     }
-    if (THREADS > 32 && fz.tmp) {
-        // Multi-warp path, ONE expansion and ONE global atomic per pair: the atomicAdd that counts the pairs of a C tile
-        // also returns the pair's rank inside the tile's list; (slot, rank, A tile, B tile) is parked in a per-row
-        // scratch record, the counts are scanned, and the records are then placed -- without walking B's structure,
-        // recomputing slots or touching the counters a second time (global atomics bound this path on R-MAT).
-        if (tid == 0) s_carry = 0;
-        __syncthreads();
-        const unsigned lt = (1u << lane) - 1;
-        int4 *tmp = fz.tmp + wptr[i];
-        for (int ta = a0 + warp; ta < a1; ta += NWARPS) {
-            const int K = a_tile_col[ta];
-            const int b0 = b_tile_ptr[K], b1 = b_tile_ptr[K + 1];
-            for (int tb0 = b0; tb0 < b1; tb0 += 32) {
-                const int tb = tb0 + lane;
-                const bool valid = tb < b1;
-                int slot = 0, off = 0;
-                if (valid) {
-                    slot = s1_rank(bitmap, pre8, b_tile_col[tb] - lo);
-                    off = atomicAdd(&pair_end[cbase + slot], 1);
-                }
-                const unsigned mask = __ballot_sync(FULL_MASK, valid);  // lane 0 is always valid
-                const int leader = __ffs(mask) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(&s_carry, __popc(mask));
-                base = __shfl_sync(FULL_MASK, base, leader);
-                if (valid) tmp[base + __popc(mask & lt)] = make_int4(slot, off, ta, b_rm2csc[tb]);
-            }
-        }
-        __syncthreads();
-        if (tid == 0) s_carry = wptr[i];
-        __syncthreads();
-        for (int s0 = 0; s0 < numJ; s0 += THREADS) {  // counts -> [pair_ptr, pair_end)
-            int sidx = s0 + tid;
-            int v = sidx < numJ ? pair_end[cbase + sidx] : 0, total;
-            int ex = block_excl_scan<THREADS>(v, s_warp, &total);
-            int carry = s_carry;
-            if (sidx < numJ) { pair_ptr[cbase + sidx] = carry + ex; pair_end[cbase + sidx] = carry + ex + v; }
-            __syncthreads();
-            if (tid == 0) s_carry = carry + total;
-            __syncthreads();
-        }
-        for (int e = tid; e < wi; e += THREADS) {
-            const int4 rec = tmp[e];
-            const int pos = pair_ptr[cbase + rec.x] + rec.y;
-            pair_a[pos] = rec.z;
-            pair_b[pos] = rec.w;
-        }
-        __syncthreads();
-        for (int sidx = tid; sidx < numJ; sidx += THREADS) {  // arrival order -> ascending A tile for short lists
-            int b = pair_ptr[cbase + sidx], e = pair_end[cbase + sidx], len = e - b;
-            if (len > 1 && len <= S1_SORT_MAX) {
-                for (int x = b + 1; x < e; x++) {
-                    int ka = pair_a[x], kb = pair_b[x], y = x - 1;
-                    while (y >= b && pair_a[y] > ka) { pair_a[y + 1] = pair_a[y]; pair_b[y + 1] = pair_b[y]; y--; }
-                    pair_a[y + 1] = ka; pair_b[y + 1] = kb;
-                }
-            }
-        }
-        return;
-    }
-    // pair counts per C tile (pair_end is zero on entry)
+    __syncthreads();
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    const unsigned lt = (1u << lane) - 1;
+    int4 *tmp = pair_tmp + wptr[i];
     for (int ta = a0 + warp; ta < a1; ta += NWARPS) {
-        int K = a_tile_col[ta];
-        for (int tb = b_tile_ptr[K] + lane; tb < b_tile_ptr[K + 1]; tb += 32) {
-            int slot = s1_rank(bitmap, pre8, b_tile_col[tb] - lo);
-            if (THREADS == 32) pair_end[cbase + slot]++;  // one A tile at a time, distinct slots per lane
-            else atomicAdd(&pair_end[cbase + slot], 1);
+        const int K = a_tile_col[ta];
+        const int b0 = b_tile_ptr[K], b1 = b_tile_ptr[K + 1];
+        for (int tb0 = b0; tb0 < b1; tb0 += 32) {
+            const int tb = tb0 + lane;
+            const bool valid = tb < b1;
+            int slot = 0, off = 0;
+            if (valid) {
+                slot = s1_rank(bitmap, pre8, b_tile_col[tb] - lo);
+                off = atomicAdd(&pair_end[cbase + slot], 1);
+            }
+            const unsigned mask = __ballot_sync(FULL_MASK, valid);  // lane 0 is always valid
+            const int leader = __ffs(mask) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&s_carry, __popc(mask));
+            base = __shfl_sync(FULL_MASK, base, leader);
+            if (valid) tmp[base + __popc(mask & lt)] = make_int4(slot, off, ta, b_rm2csc[tb]);
         }
-        if (THREADS == 32) __syncwarp();
     }
     __syncthreads();
-    // exclusive scan of the counts over the tile-row's slots -> pair_ptr; pair_end becomes the cursor
     if (tid == 0) s_carry = wptr[i];
     __syncthreads();
-    for (int s0 = 0; s0 < numJ; s0 += THREADS) {
-        int s = s0 + tid;
-        int v = s < numJ ? pair_end[cbase + s] : 0, total;
+    for (int s0 = 0; s0 < numJ; s0 += THREADS) {  // counts -> [pair_ptr, pair_end)
+        int sidx = s0 + tid;
+        int v = sidx < numJ ? pair_end[cbase + sidx] : 0, total;
         int ex = block_excl_scan<THREADS>(v, s_warp, &total);
         int carry = s_carry;
-        if (s < numJ) { pair_ptr[cbase + s] = carry + ex; pair_end[cbase + s] = carry + ex; }
+        if (sidx < numJ) { pair_ptr[cbase + sidx] = carry + ex; pair_end[cbase + sidx] = carry + ex + v; }
         __syncthreads();
         if (tid == 0) s_carry = carry + total;
         __syncthreads();
     }
-    // write the pairs (and, fused, OR the pair's boolean product into the tile-row's C masks)
-    for (int ta = a0 + warp; ta < a1; ta += NWARPS) {
-        int K = a_tile_col[ta];
-        unsigned amw[8];
-        if (fuse) {  // A's 16 row masks: one 32-byte line, the same for every lane
-            const uint4 *ap = reinterpret_cast<const uint4 *>(fz.a_mask + (size_t)ta * TS);
-            const uint4 x = ap[0], y = ap[1];
-            amw[0] = x.x; amw[1] = x.y; amw[2] = x.z; amw[3] = x.w; amw[4] = y.x; amw[5] = y.y; amw[6] = y.z; amw[7] = y.w;
-        }
-        for (int tb = b_tile_ptr[K] + lane; tb < b_tile_ptr[K + 1]; tb += 32) {
-            int slot = s1_rank(bitmap, pre8, b_tile_col[tb] - lo);
-            int pos;
-            if (THREADS == 32) pos = pair_end[cbase + slot]++;
-            else pos = atomicAdd(&pair_end[cbase + slot], 1);
-            const int b = b_rm2csc[tb];
-            pair_a[pos] = ta;
-            pair_b[pos] = b;
-            if (fuse) {
-                const uint4 *bp = reinterpret_cast<const uint4 *>(fz.b_mask + (size_t)b * TS);
-                const uint4 x = bp[0], y = bp[1];
-                bmT[0 * 32 + lane] = x.x; bmT[1 * 32 + lane] = x.y; bmT[2 * 32 + lane] = x.z; bmT[3 * 32 + lane] = x.w;
-                bmT[4 * 32 + lane] = y.x; bmT[5 * 32 + lane] = y.y; bmT[6 * 32 + lane] = y.z; bmT[7 * 32 + lane] = y.w;
-#pragma unroll
-                for (int r = 0; r < TS; r++) {
-                    unsigned m = (r & 1) ? (amw[r >> 1] >> 16) : (amw[r >> 1] & 0xFFFFu);  // little-endian u16 pairs
-                    if (m) {                                                            // warp-uniform
-                        unsigned acc = 0;
-                        do {
-                            const int k = __clz(m) - 16;
-                            const unsigned wd = bmT[(k >> 1) * 32 + lane];
-                            acc |= (k & 1) ? (wd >> 16) : (wd & 0xFFFFu);
-                            m &= ~(0x8000u >> k);
-                        } while (m);
-                        cm[r * fz.numJ_pad + slot] |= (uint16_t)acc;  // distinct slots per lane
-                    }
-                }
-            }
-        }
-        if (THREADS == 32) __syncwarp();
+    for (int e = tid; e < wi; e += THREADS) {
+        const int4 rec = tmp[e];
+        const int pos = pair_ptr[cbase + rec.x] + rec.y;
+        pair_a[pos] = rec.z;
+        pair_b[pos] = rec.w;
     }
-    if (fuse) {
-        __syncwarp();
-        for (int sl = lane; sl < numJ; sl += 32) {  // Ptr (exclusive row offsets), mask and nnz of each C tile
-            unsigned pw[8], mw[8];
-            int run = 0;
-#pragma unroll
-            for (int r = 0; r < TS; r += 2) {
-                const unsigned m0 = cm[r * fz.numJ_pad + sl], m1 = cm[(r + 1) * fz.numJ_pad + sl];
-                const int p0 = run, p1 = run + __popc(m0);
-                run = p1 + __popc(m1);
-                pw[r >> 1] = (unsigned)p0 | ((unsigned)p1 << 16);
-                mw[r >> 1] = m0 | (m1 << 16);
-            }
-            uint4 *dp = reinterpret_cast<uint4 *>(fz.c_ptr + (size_t)(cbase + sl) * TS);
-            uint4 *dm = reinterpret_cast<uint4 *>(fz.c_mask + (size_t)(cbase + sl) * TS);
-            dp[0] = make_uint4(pw[0], pw[1], pw[2], pw[3]); dp[1] = make_uint4(pw[4], pw[5], pw[6], pw[7]);
-            dm[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]); dm[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
-            fz.c_cnt[cbase + sl] = run;
-        }
-    }
-    if (THREADS > 32) {
-        // several warps appended concurrently: restore ascending-A-tile order for short lists so the
-        // FP64 summation order is reproducible (lists longer than S1_SORT_MAX keep arrival order).
-        __syncthreads();
-        for (int s = tid; s < numJ; s += THREADS) {
-            int b = pair_ptr[cbase + s], e = pair_end[cbase + s], len = e - b;
-            if (len > 1 && len <= S1_SORT_MAX) {
-                for (int x = b + 1; x < e; x++) {
-                    int ka = pair_a[x], kb = pair_b[x], y = x - 1;
-                    while (y >= b && pair_a[y] > ka) { pair_a[y + 1] = pair_a[y]; pair_b[y + 1] = pair_b[y]; y--; }
-                    pair_a[y + 1] = ka; pair_b[y + 1] = kb;
-                }
+    __syncthreads();
+    // several warps appended concurrently: restore ascending-A-tile order for short lists so the FP64 summation
+    // order is reproducible (lists longer than S1_SORT_MAX keep arrival order; include/tilespgemm.h says so)
+    for (int sidx = tid; sidx < numJ; sidx += THREADS) {
+        int b = pair_ptr[cbase + sidx], e = pair_end[cbase + sidx], len = e - b;
+        if (len > 1 && len <= S1_SORT_MAX) {
+            for (int x = b + 1; x < e; x++) {
+                int ka = pair_a[x], kb = pair_b[x], y = x - 1;
+                while (y >= b && pair_a[y] > ka) { pair_a[y + 1] = pair_a[y]; pair_b[y + 1] = pair_b[y]; y--; }
+                pair_a[y + 1] = ka; pair_b[y + 1] = kb;
             }
         }
     }
@@ -391,13 +527,13 @@ __global__ void __launch_bounds__(128)
 k_step2(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end,
         const int *__restrict__ pair_a, const int *__restrict__ pair_b, const uint16_t *__restrict__ a_mask,
         const uint16_t *__restrict__ b_mask, uint16_t *__restrict__ c_ptr, uint16_t *__restrict__ c_mask,
-        int *__restrict__ c_cnt, const int *__restrict__ c_tile_row, const int *__restrict__ w, int trow0, int light_max)
+        int *__restrict__ c_cnt, const int *__restrict__ c_tile_row, const uint8_t *__restrict__ light, int trow0)
 {
     const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4);
     const int l16 = threadIdx.x & 15;
     const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
     if (t >= numblkC) return;
-    if (w && w[c_tile_row[t] - trow0] <= light_max) return;  // masks already produced by the fused step-1 path
+    if (light && light[c_tile_row[t] - trow0]) return;  // masks already produced by the fused step-1 path
     unsigned cm = 0;
     const int pe = pair_end[t];
     for (int p = pair_ptr[t]; p < pe; p++) {
@@ -435,12 +571,12 @@ k_step2_thread(int numblkC, const int *__restrict__ pair_ptr, const int *__restr
                const int *__restrict__ pair_a, const int *__restrict__ pair_b, const int *__restrict__ a_tile_nnz,
                const uint16_t *__restrict__ a_col, const uint16_t *__restrict__ b_mask, uint16_t *__restrict__ c_ptr,
                uint16_t *__restrict__ c_mask, int *__restrict__ c_cnt, const int *__restrict__ c_tile_row,
-               const int *__restrict__ w, int trow0, int light_max)
+               const uint8_t *__restrict__ light, int trow0)
 {
     __shared__ uint16_t cm[TS][S2T_THREADS];
     const int t = blockIdx.x * S2T_THREADS + threadIdx.x, tid = threadIdx.x;
     if (t >= numblkC) return;
-    if (w && w[c_tile_row[t] - trow0] <= light_max) return;  // masks already produced by the fused step-1 path
+    if (light && light[c_tile_row[t] - trow0]) return;  // masks already produced by the fused step-1 path
 #pragma unroll
     for (int r = 0; r < TS; r++) cm[r][tid] = 0;
     const int p1 = pair_end[t];
@@ -533,35 +669,6 @@ int tilerow_weights_device(const tsg_dtile *A, const tsg_dtile *B, int **d_w, in
     return TSG_OK;
 }
 
-template <int MODE>
-static int launch_step1(int ntr, int trow0, int nw_max, int wmax_seen, const tsg_dtile *A, const tsg_dtile *B, const int *w,
-                        const int *jlo, const int *jhi, int *cnt, const int *c_tile_ptr, const int *wptr, int *c_tile_col,
-                        int *c_tile_row, int *pair_ptr, int *pair_end, int *pair_a, int *pair_b, int *maxJ, S1Fuse fz)
-{
-    Ctx &c = ctx();
-    size_t smem = ((size_t)nw_max + (size_t)nw_max / 8 + 2) * 4;
-    if (fz.numJ_pad > 0) smem += 8 * 32 * 4 + (size_t)fz.numJ_pad * TS * 2 + 4;
-    if (smem > c.smem_optin) {
-        set_error(TSG_ERR_UNSUPPORTED, "step 1: tile-column window of %d words needs %zu B of shared memory (> %zu)", nw_max, smem, c.smem_optin);
-        return last_error();
-    }
-    if (smem > 48 * 1024) {
-        CK(cudaFuncSetAttribute(k_step1<32, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_step1<S1_HEAVY_THREADS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    k_step1<32, MODE><<<ntr, 32, smem, c.stream>>>(trow0, nw_max, 0, S1_LIGHT_MAX, A->tile_ptr, A->tile_columnidx, B->tile_ptr,
-                                                   B->tile_columnidx, B->rm2csc, w, jlo, jhi, cnt, c_tile_ptr, wptr, c_tile_col,
-                                                   c_tile_row, pair_ptr, pair_end, pair_a, pair_b, maxJ, fz);
-    CK_LAUNCH();
-    if (wmax_seen > S1_LIGHT_MAX) {
-        k_step1<S1_HEAVY_THREADS, MODE><<<ntr, S1_HEAVY_THREADS, smem, c.stream>>>(
-            trow0, nw_max, S1_LIGHT_MAX, 0x7fffffff, A->tile_ptr, A->tile_columnidx, B->tile_ptr, B->tile_columnidx, B->rm2csc, w,
-            jlo, jhi, cnt, c_tile_ptr, wptr, c_tile_col, c_tile_row, pair_ptr, pair_end, pair_a, pair_b, maxJ, fz);
-        CK_LAUNCH();
-    }
-    return TSG_OK;
-}
-
 int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, tsg_dtile *C, tsg_stats *stats)
 {
     Ctx &c = ctx();
@@ -586,55 +693,63 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     const cudaEvent_t ev_s2 = evs.e[5], ev_s3 = evs.e[6];
     CK(cudaEventRecord(ev[0], c.stream));
 
-    // ---------------- step 1 ----------------
-    if (!arena_reserve(0, 5 * arena_need((size_t)ntr + 1, 4) + 2 * arena_need((size_t)ntr + 1, 8))) return last_error();
-    int *w = arena_take<int>(0, (size_t)ntr + 1), *jlo = arena_take<int>(0, (size_t)ntr + 1), *jhi = arena_take<int>(0, (size_t)ntr + 1);
-    int *wptr = arena_take<int>(0, (size_t)ntr + 1);
-    int *c_tile_ptr = arena_take<int>(0, (size_t)ntr + 1);
-    long long *wptr64 = arena_take<long long>(0, (size_t)ntr + 1), *numblk64 = arena_take<long long>(0, (size_t)ntr + 1);
-    if (!w || !jlo || !jhi || !wptr || !c_tile_ptr || !wptr64 || !numblk64) return last_error();
-    int *scal = (int *)c.d_scalars;
-    CK(cudaMemsetAsync(scal, 0, 4 * sizeof(int), c.stream));
-    CK(cudaMemsetAsync(c_tile_ptr, 0, ((size_t)ntr + 1) * sizeof(int), c.stream));
+    // ---------------- step 1a: weights, windows, C tile counts ----------------
+    const size_t nr = (size_t)ntr + 1;
+    if (!arena_reserve(0, 7 * arena_need(nr, 4) + arena_need(nr, 1))) return last_error();
+    int *w = arena_take<int>(0, nr), *jlo = arena_take<int>(0, nr), *jhi = arena_take<int>(0, nr);
+    int *wptr = arena_take<int>(0, nr), *cnt = arena_take<int>(0, nr), *c_tile_ptr = arena_take<int>(0, nr);
+    int *heavy_list = arena_take<int>(0, nr);
+    uint8_t *light = arena_take<uint8_t>(0, nr);
+    if (!w || !jlo || !jhi || !wptr || !cnt || !c_tile_ptr || !heavy_list || !light) return last_error();
+    int *scal = (int *)c.d_scalars;                 // SC_* counters (8 ints)
+    long long *tot = c.d_scalars + 4;               // [0] pairs, [1] C tiles (64-bit scan totals)
+    CK(cudaMemsetAsync(scal, 0, 6 * sizeof(long long), c.stream));
+    // a warp's window bitmap in k_s1_count: up to 2048 words (65536 tile columns); wider windows take the heavy path
+    int bmw1 = (B->tilen + 31) / 32 + 1;
+    if (bmw1 > 2048) bmw1 = 2048;
     if (ntr > 0) {
-        k_step1_weights<<<ceil_div((long long)ntr * 32, 128), 128, 0, c.stream>>>(trow0, ntr, A->tile_ptr, A->tile_columnidx, B->tile_ptr,
-                                                                                 B->tile_columnidx, w, jlo, jhi, scal);
+        const size_t smem = (size_t)S1_WARPS * bmw1 * 4;
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_s1_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_s1_count<<<ceil_div(ntr, S1_WARPS), S1_WARPS * 32, smem, c.stream>>>(trow0, ntr, bmw1, A->tile_ptr, A->tile_columnidx, B->tile_ptr,
+                                                                              B->tile_columnidx, w, jlo, jhi, cnt, light, heavy_list, scal);
         CK_LAUNCH();
     }
-    long long *wtot = c.d_scalars + 4;
-    // 64-bit scan output for the total, 32-bit offsets for the kernels (slab planning keeps it < 2^31)
-    int rc = exclusive_scan<long long>(w, wptr64, ntr);
-    if (rc) return rc;
-    rc = exclusive_scan<int>(w, wptr, ntr);
-    if (rc) return rc;
-    rc = copy_words(wtot, wptr64 + ntr, 2);
-    if (rc) return rc;
-    rc = publish_words(c.h_scalars, c.d_scalars, 12);
+    // one scan per array: 32-bit offsets for the kernels, the 64-bit total for the host (slab planning keeps it < 2^31)
+    int rc = exclusive_scan<int>(w, wptr, ntr, tot);
+    if (!rc) rc = exclusive_scan<int>(cnt, c_tile_ptr, ntr, tot + 1);
+    if (!rc) rc = publish_words(c.h_scalars, c.d_scalars, 12);
     if (rc) return rc;
     CK(cudaStreamSynchronize(c.stream));
-    const int *hs = (const int *)c.h_scalars;
-    const int nw_max = hs[0] > 0 ? hs[0] : 1, werr = hs[1], wmax_seen = hs[2];
+    int hs[8];
+    memcpy(hs, (const void *)c.h_scalars, sizeof(hs));
+    const int n_heavy = hs[SC_NHEAVY], n_light = hs[SC_NLIGHT];
     const long long pairs = c.h_scalars[4];
-    if (werr || pairs >= (1ll << 31)) {
+    if (hs[SC_ERR] || pairs >= (1ll << 31)) {
         set_error(TSG_ERR_OVERFLOW, "spgemm: %lld tile pairs in tile-rows [%d,%d) exceed 32-bit indexing; use smaller slabs", pairs, trow0, trow1);
         return last_error();
     }
-    if (ntr > 0 && pairs > 0) {
-        rc = launch_step1<0>(ntr, trow0, nw_max, wmax_seen, A, B, w, jlo, jhi, c_tile_ptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                             nullptr, nullptr, nullptr, scal + 3, S1Fuse{nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr});
+    long long numblkC = c.h_scalars[5];
+    size_t heavy_smem = 0;
+    if (n_heavy > 0) {  // count the C tiles of the heavy tile-rows, scan again (one more read-back; R-MAT only)
+        const int nw_max = hs[SC_NW_HEAVY];
+        heavy_smem = ((size_t)nw_max + (size_t)nw_max / 8 + 2) * 4;
+        if (heavy_smem > c.smem_optin) {
+            set_error(TSG_ERR_UNSUPPORTED, "step 1: a tile-column window of %d words needs %zu B of shared memory (> %zu); matrices wider "
+                      "than ~29 M columns with tile-rows spanning all of them are not supported yet", nw_max, heavy_smem, c.smem_optin);
+            return last_error();
+        }
+        if (heavy_smem > 48 * 1024) {
+            CK(cudaFuncSetAttribute(k_s1_heavy<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem));
+            CK(cudaFuncSetAttribute(k_s1_heavy<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem));
+        }
+        k_s1_heavy<0><<<n_heavy, S1_HEAVY_THREADS, heavy_smem, c.stream>>>(trow0, nw_max, heavy_list, A->tile_ptr, A->tile_columnidx, B->tile_ptr,
+                                                                          B->tile_columnidx, B->rm2csc, w, jlo, jhi, cnt, nullptr, nullptr,
+                                                                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        CK_LAUNCH();
+        rc = exclusive_scan<int>(cnt, c_tile_ptr, ntr, tot + 1);
+        if (!rc) rc = read_back_i64(tot + 1, &numblkC);
         if (rc) return rc;
     }
-    rc = exclusive_scan<long long>(c_tile_ptr, numblk64, ntr);
-    if (rc) return rc;
-    rc = exclusive_scan<int>(c_tile_ptr, c_tile_ptr, ntr);
-    if (rc) return rc;
-    long long numblkC = 0;
-    rc = publish_words(&c.h_scalars[8], numblk64 + ntr, 2);
-    if (!rc) rc = publish_words(&c.h_scalars[9], scal + 3, 1);
-    if (rc) return rc;
-    CK(cudaStreamSynchronize(c.stream));
-    numblkC = c.h_scalars[8];
-    const int maxJ_light = *(const int *)&c.h_scalars[9];
     if (numblkC >= (1ll << 30)) {  // numblkC*16 must index uint16 arrays with int offsets
         set_error(TSG_ERR_OVERFLOW, "spgemm: %lld C tiles in tile-rows [%d,%d); use smaller slabs", numblkC, trow0, trow1);
         return last_error();
@@ -664,63 +779,77 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     }
     rc = copy_words(C->tile_ptr, c_tile_ptr, (size_t)ntr + 1);
     if (rc) return rc;
-    const bool heavy_rows = wmax_seen > S1_LIGHT_MAX;  // tile-rows on the multi-warp path park one 16-byte record per pair
-    if (!arena_reserve(1, 2 * arena_need(nb + 1, 4) + 2 * arena_need(np, 4) + arena_need(nb + 1, 8) + (heavy_rows ? arena_need(np, 16) : 0) +
+    const bool heavy_rows = n_heavy > 0;  // tile-rows on the multi-warp path park one 16-byte record per pair
+    if (!arena_reserve(1, 2 * arena_need(nb + 1, 4) + 2 * arena_need(np, 4) + arena_need(np, 2) + (heavy_rows ? arena_need(np, 16) : 0) +
                               numeric_scratch_bytes(ntr, numblkC)))
         return last_error();
     int *pair_ptr = arena_take<int>(1, nb + 1), *pair_end = arena_take<int>(1, nb + 1), *pair_a = arena_take<int>(1, np), *pair_b = arena_take<int>(1, np);
-    long long *nnz64 = arena_take<long long>(1, nb + 1);
+    uint16_t *pair_slot = arena_take<uint16_t>(1, np);
     int4 *pair_tmp = heavy_rows ? arena_take<int4>(1, np) : nullptr;
     NumericBufs nbufs{arena_take<uint8_t>(1, (size_t)ntr + 1), arena_take<int>(1, nb), 0, 0};
-    if (!pair_ptr || !pair_end || !pair_a || !pair_b || !nnz64 || (heavy_rows && !pair_tmp) || !nbufs.row_kind || !nbufs.dense_list)
+    if (!pair_ptr || !pair_end || !pair_a || !pair_b || !pair_slot || (heavy_rows && !pair_tmp) || !nbufs.row_kind || !nbufs.dense_list)
         return last_error();
-    CK(cudaMemsetAsync(pair_end, 0, nb * 4, c.stream));
+    if (heavy_rows) CK(cudaMemsetAsync(pair_end, 0, nb * 4, c.stream));  // the heavy kernel counts with atomics
     CK(cudaEventRecord(ev[2], c.stream));  // [1..2] = allocation
-    // the one-warp step-1 path also produces C's masks / Ptr / tile nnz (fused step 2) when the tile-row's
-    // masks fit shared memory; TSG_FUSE=0 disables the fusion (A/B measurements)
+
+    // ---------------- step 1b (+ fused step 2): tile columns, pair lists, C masks ----------------
+    // the light path also produces C's masks / Ptr / tile nnz (fused step 2); TSG_FUSE=0 disables the fusion (A/B runs).
+    // Worthwhile only when B's tile-rows are long enough to fill the lanes (>= 4 tiles per tile-row on average;
+    // block-FEM has 3 and is faster through k_step2).
     static const int fuse_env = getenv("TSG_FUSE") ? atoi(getenv("TSG_FUSE")) : -1;
-    S1Fuse fz{A->mask, B->mask, C->ptr, C->mask, C->tile_nnz, 0, pair_tmp};
-    {
-        size_t need = ((size_t)nw_max + (size_t)nw_max / 8 + 2) * 4 + 8 * 32 * 4 + (size_t)(maxJ_light + 1) * TS * 2 + 4;
-        // worthwhile only when B's tile-rows are long enough to fill the lanes (>= 4 tiles per tile-row on average;
-        // block-FEM has 3 and is faster through k_step2)
+    bool fused = false;
+    if (numblkC > 0 && n_light > 0) {
+        const int bmw = (hs[SC_NW_LIGHT] + 1) & ~1, nj = hs[SC_MAXJ], njpad = nj | 1;  // odd row stride: fewer bank conflicts
         const bool want = fuse_env >= 0 ? fuse_env != 0 : (long long)B->numtile >= 4ll * B->tilem;
-        if (want && maxJ_light > 0 && need <= c.smem_optin) fz.numJ_pad = maxJ_light | 1;  // odd row stride: fewer bank conflicts
+        int warp_words = bmw + bmw / 2 + nj + (TS * 32) / 2 + (TS * njpad + 1) / 2;
+        fused = want && (size_t)S1_WARPS * warp_words * 4 <= c.smem_optin;
+        if (!fused) warp_words = bmw + bmw / 2 + nj;
+        S1Fill P{trow0, ntr, bmw, nj, njpad, warp_words, A->tile_ptr, A->tile_columnidx, B->tile_ptr, B->tile_columnidx, B->rm2csc,
+                 jlo, jhi, wptr, C->tile_ptr, light, C->tile_columnidx, C->tile_rowidx, pair_ptr, pair_end, pair_a, pair_b, pair_slot,
+                 A->mask, B->mask, C->ptr, C->mask, C->tile_nnz};
+        const size_t smem = (size_t)S1_WARPS * warp_words * 4;
+        if (fused) {
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_s1_fill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_s1_fill<true><<<ceil_div(ntr, S1_WARPS), S1_WARPS * 32, smem, c.stream>>>(P);
+        } else {
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_s1_fill<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_s1_fill<false><<<ceil_div(ntr, S1_WARPS), S1_WARPS * 32, smem, c.stream>>>(P);
+        }
+        CK_LAUNCH();
     }
-    const bool fused = fz.numJ_pad > 0;
-    if (numblkC > 0) {
-        rc = launch_step1<1>(ntr, trow0, nw_max, wmax_seen, A, B, w, jlo, jhi, nullptr, C->tile_ptr, wptr, C->tile_columnidx,
-                             C->tile_rowidx, pair_ptr, pair_end, pair_a, pair_b, nullptr, fz);
-        if (rc) return rc;
+    if (numblkC > 0 && n_heavy > 0) {
+        k_s1_heavy<1><<<n_heavy, S1_HEAVY_THREADS, heavy_smem, c.stream>>>(trow0, hs[SC_NW_HEAVY], heavy_list, A->tile_ptr, A->tile_columnidx,
+                                                                          B->tile_ptr, B->tile_columnidx, B->rm2csc, w, jlo, jhi, nullptr,
+                                                                          C->tile_ptr, wptr, C->tile_columnidx, C->tile_rowidx, pair_ptr,
+                                                                          pair_end, pair_a, pair_b, pair_tmp);
+        CK_LAUNCH();
     }
 
     // ---------------- step 2 ----------------
     CK(cudaEventRecord(ev_s2, c.stream));
     // pair-based symbolic for the C tiles the fused step-1 path did not cover: half-warp per tile, or thread per
     // tile when the tiles are hypersparse (<= 2 pairs per C tile and <= 2 entries per A tile on average)
-    if (numblkC > 0 && (!fused || wmax_seen > S1_LIGHT_MAX)) {
-        const int *wf = fused ? w : nullptr;
+    if (numblkC > 0 && (!fused || n_heavy > 0)) {
+        const uint8_t *lf = fused ? light : nullptr;
         const bool hypersparse = pairs <= 2 * numblkC && A->nnz <= 2ll * A->numtile;
         if (hypersparse)
             k_step2_thread<<<ceil_div(numblkC, S2T_THREADS), S2T_THREADS, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b,
                                                                                          A->tile_nnz, A->col, B->mask, C->ptr, C->mask,
-                                                                                         C->tile_nnz, C->tile_rowidx, wf, trow0, S1_LIGHT_MAX);
+                                                                                         C->tile_nnz, C->tile_rowidx, lf, trow0);
         else
             k_step2<<<ceil_div(numblkC * 16, 128), 128, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->mask, B->mask,
-                                                                       C->ptr, C->mask, C->tile_nnz, C->tile_rowidx, wf, trow0, S1_LIGHT_MAX);
+                                                                       C->ptr, C->mask, C->tile_nnz, C->tile_rowidx, lf, trow0);
         CK_LAUNCH();
     }
-    rc = exclusive_scan<long long>(C->tile_nnz, nnz64, numblkC);
-    if (rc) return rc;
-    rc = exclusive_scan<int>(C->tile_nnz, C->tile_nnz, numblkC);
+    rc = exclusive_scan<int>(C->tile_nnz, C->tile_nnz, numblkC, tot);
     if (rc) return rc;
     // pick the accumulator per C tile-row / tile (numeric.cu); its counters come back with nnz(C) in one read-back
     int *d_ns = (int *)(c.d_scalars + 16);
-    rc = numeric_classify_device(A, C, trow0, ntr, wptr, &nbufs, d_ns);
+    rc = numeric_classify_device(A, C, trow0, ntr, wptr, light, &nbufs, d_ns);
     if (rc) return rc;
     long long nnzC = 0;
     rc = publish_words(&c.h_scalars[16], d_ns, 8);
-    if (!rc) rc = read_back_i64(nnz64 + numblkC, &nnzC);
+    if (!rc) rc = read_back_i64(tot, &nnzC);
     if (rc) return rc;
     if (nnzC >= (1ll << 31)) {
         set_error(TSG_ERR_OVERFLOW, "spgemm: nnz(C) = %lld in tile-rows [%d,%d) exceeds int32; use smaller slabs", nnzC, trow0, trow1);
@@ -744,7 +873,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     CK(cudaEventRecord(ev_s3, c.stream));
     tsg_stats nst;
     memset(&nst, 0, sizeof(nst));
-    rc = numeric_device(A, B, C, trow0, ntr, wptr, PairLists{pair_ptr, pair_end, pair_a, pair_b}, nbufs, h_ns, heavy_rows, &nst);
+    rc = numeric_device(A, B, C, trow0, ntr, wptr, PairLists{pair_ptr, pair_end, pair_a, pair_b, pair_slot}, nbufs, h_ns, heavy_rows, &nst);
     if (rc) return rc;
     CK(cudaEventRecord(ev[4], c.stream));
     if (stats && ntr != A->tilem) {  // the slab's share of A (tiles, nonzeros) for the byte count below
