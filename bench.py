@@ -10,9 +10,11 @@ through the public API from HOST buffers: H2D of CSR(A) from pinned memory, csr2
 steps 1-3, tile2csr, D2H of CSR(C) into pinned memory, all inside the timed region (C leaves the
 device slab by slab, the copy of one slab overlapping the computation of the next: tsg_spgemm_to_host).
 
-N > 1: C tile-rows are partitioned across the ranks (contiguous ranges balanced by the step-1
-weight); B is tiled once on rank 0 and broadcast as one buffer over NCCL; each rank computes its C
-tile-rows with no further communication. Total work is fixed => "scaling": "strong".
+N > 1 (spgemm_b200.multigpu): B is broadcast once over NCCL (as the CSR it is built from, or tiled with
+--bcast tiled); the step-1 weights are computed in parallel and all-gathered; C tile-rows are partitioned
+across the ranks (contiguous ranges of equal weight); each rank computes its C tile-rows with no further
+communication. Total work is fixed => "scaling": "strong". Every line carries "parity": the run's own
+C*ones and per-row counts, from the device, against the CPU.
 
 --impl reference: the reference's own CPU path (oracle/_ref: unmodified spgemm_spa of
 src/spgemm_serialref_spa_new.h, OpenMP on all host cores) on a bounded row sample of the same
@@ -102,10 +104,11 @@ class ClockSampler:
 
 
 def step3_bytes(tA, tB, st):
-    """Algorithmic HBM bytes of the numeric kernel: A and B tile payloads it reads
-    (Val 8 + Col 2 per nnz, Ptr 32 + tile_nnz 4 per tile), C structure it reads (Ptr 32 + mask 32 +
-    tile_nnz 4 per C tile, pair list 8 per pair) and C payload it writes (Val 8 + Col 2 per nnz)."""
-    return (tA.nnz * 10 + tA.numtile * 36 + tB.nnz * 10 + tB.numtile * 36 + st["numblkC"] * 68 + st["pairs"] * 8
+    """Algorithmic HBM bytes of the numeric step: what it has to read and write once -- A and B tile
+    payloads (Val 8 per nnz, Ptr 32 + mask 32 + tile_nnz 4 per tile), the pair lists (8 per pair), C's structure for
+    the tiles that hold entries (Ptr 32 + mask 32 + tile_nnz 4 each: the empty listed tiles of a hypersparse product are
+    never read by it) and C's payload written (Val 8 + Col 2 per nnz)."""
+    return (tA.nnz * 8 + tA.numtile * 68 + tB.nnz * 8 + tB.numtile * 68 + st["tiles_nonempty"] * 68 + st["pairs"] * 8
             + st["nnzC"] * 10)
 
 
@@ -164,111 +167,115 @@ def run_reference(args):
 
 
 def cpu_baseline(A, B, nB, total_products, budget_products=1.6e9):
-    """Oracle SPA with values ("port") on all host cores, on a bounded sample of the same workload."""
+    """Oracle SPA with values ("port") on all host cores, on a bounded sample of the same workload: whole A when it holds
+    at most `budget_products` products, else a seeded random sample of A's rows (x whole B) holding about that many --
+    rows drawn at random, not the first ones: R-MAT's heavy rows sit at the low indices."""
     from oracle import oracle as orc
-    rp = A[0]
+    orc.set_num_threads()
+    rp, ci, v = A
     m = len(rp) - 1
-    R = m
-    if total_products > budget_products:  # first rows holding ~budget products
-        R = max(int(m * budget_products / total_products), 1)
-    sample = (rp[:R + 1], A[1][:rp[R]], A[2][:rp[R]])
+    if total_products <= budget_products:
+        sample, what = A, f"all {m} rows of A"
+    else:
+        k = max(int(m * budget_products / total_products), 1)
+        rows = np.sort(np.random.default_rng(12345).choice(m, size=k, replace=False))
+        cnt = (rp[rows + 1] - rp[rows]).astype(np.int64)
+        srp = np.concatenate([[0], np.cumsum(cnt)])
+        idx = np.repeat(rp[rows].astype(np.int64) - srp[:-1], cnt) + np.arange(srp[-1])
+        sample, what = (srp, ci[idx], v[idx]), f"{k} of {m} rows of A drawn at random (seed 12345)"
     products = orc.nnzcub(sample[1], B[0])
     t0 = time.perf_counter()
     orc.spgemm_spa(sample, B, nB)
     dt = time.perf_counter() - t0
     return {"value": 2.0 * products / dt / 1e9, "unit": "GFLOP/s", "cores": orc.num_threads(), "kind": "port",
-            "sample": f"rows [0,{R}) of A x whole B, {products} products, {dt:.2f} s wall, OpenMP SPA with values (oracle/spa_ref.c)"}
+            "sample": f"{what} x whole B, {products} products, {dt:.2f} s wall, OpenMP SPA with values (oracle/spa_ref.c)"}
+
+
+def parity_check(A, B, nB, sums, counts, want_counts):
+    """Size-independent check of a whole run against the CPU: C * ones = A * (B * ones) (exact in FP64 for the driver's
+    integer-valued inputs: every partial sum is an integer below 2^53) and, when asked for, nnz of every row of C against
+    the count pass of the serial SPA (oracle; the reference's get_nnzC_only protocol)."""
+    import scipy.sparse as sp
+    mA, mB = len(A[0]) - 1, len(B[0]) - 1
+    SA = sp.csr_matrix((A[2], A[1], A[0]), shape=(mA, mB))
+    SB = sp.csr_matrix((B[2], B[1], B[0]), shape=(mB, nB))
+    exp = SA @ (SB @ np.ones(nB))
+    out = {"rows": int(mA), "rowsums_equal": bool(np.array_equal(sums, exp)),
+           "rowsums_max_rel_err": float(np.max(np.abs(sums - exp) / np.maximum(np.abs(exp), 1.0))) if mA else 0.0,
+           "nnzC": int(counts.sum())}
+    if want_counts:
+        from oracle import oracle as orc
+        orc.set_num_threads()
+        t0 = time.perf_counter()
+        ec = orc.spgemm_rowcounts(A, B, nB)
+        out.update({"rowcounts_equal": bool(np.array_equal(counts, ec)), "oracle_nnzC": int(ec.sum()),
+                    "oracle_count_pass_s": round(time.perf_counter() - t0, 2)})
+    return out
+
+
+def setup_nccl_logging(world):
+    """NCCL's INFO log (topology, NVLS, 'comm ... nranks N') goes to a file per rank under gpurun_out/ so that stdout stays
+    the one JSON line; whatever the caller already set in the environment is left alone."""
+    if world <= 1:
+        return None
+    if "NCCL_DEBUG" in os.environ:
+        return os.environ.get("NCCL_DEBUG_FILE")
+    d = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    os.environ["NCCL_DEBUG"] = "INFO"
+    os.environ["NCCL_DEBUG_SUBSYS"] = "INIT,ENV"
+    os.environ["NCCL_DEBUG_FILE"] = os.path.join(d, f"nccl_{world}gpu_%h_%p.log")  # NCCL expands %h (host) and %p (pid)
+    return os.environ["NCCL_DEBUG_FILE"]
+
+
+def nccl_evidence(path_pattern):
+    """What the NCCL log of this run says about the communicator (rank 0's view): ranks, NVLS, channels."""
+    import glob
+    import re
+    if not path_pattern:
+        return None
+    files = glob.glob(path_pattern.replace("%h", "*").replace("%p", "*"))
+    nranks, nvls, lines = None, False, 0
+    for f in files:
+        try:
+            for ln in open(f, errors="ignore"):
+                lines += 1
+                mo = re.search(r"nranks (\d+)", ln)
+                if mo:
+                    nranks = max(nranks or 0, int(mo.group(1)))
+                if "NVLS" in ln:
+                    nvls = True
+        except OSError:
+            pass
+    return {"log_files": len(files), "log_lines": lines, "nranks": nranks, "nvls_mentioned": nvls}
 
 
 def run_ours(args):
-    import torch
-    from spgemm_b200 import api, multigpu as mg
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    nccl_log = setup_nccl_logging(world)
+    import torch
+    from spgemm_b200 import api, multigpu as mg
+
     dist = None
-    if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG is VERSION/INFO
-        os.environ["NCCL_DEBUG"] = os.environ.get("TSG_NCCL_DEBUG", "WARN")
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     api.init(local)
 
     gen, aat, desc = WORKLOADS[args.workload]
     K, W = args.steps, args.warmup
 
-    # ------------------------------------------------------------------ data (rank 0 generates)
-    bcast_ms = 0.0
-    if rank == 0:
-        m, n, rp, ci, v = gen()
-        dA_full = api.DeviceCSR.upload(m, n, rp, ci, v)
-        dB = api.transpose(dA_full) if aat else dA_full
-        nnzCub = api.nnzcub(dA_full, dB)
-        tB = api.csr2tile(dB, True)
-        nB = dB.n
-    if world == 1:
-        dA, tA = dA_full, api.csr2tile(dA_full, False)
-        part = {"parts": [[0, tA.tilem]], "imbalance": 1.0}
-    else:
-        # sizes of B, partition of A's tile-rows, per-rank CSR sizes
-        if rank == 0:
-            tA_full = api.csr2tile(dA_full, False)
-            w = api.tilerow_weights(tA_full, tB)
-            cuts = mg.partition_tilerows(w, world)
-            tA_full.free()
-            hdr = [tB.m, tB.n, tB.numtile, tB.nnz, m, n, int(nnzCub)] + [int(c) for c in cuts]
-            part = {"parts": [[int(a), int(b)] for a, b in zip(cuts[:-1], cuts[1:])], "imbalance": mg.imbalance(w, cuts)}
-        else:
-            hdr = [0] * (7 + world + 1)
-            part = None
-        h = torch.tensor(hdr, dtype=torch.int64, device=dev)
-        dist.broadcast(h, 0)
-        hdr = [int(x) for x in h.cpu()]
-        bm, bn, bnt, bnnz, m, n, nnzCub = hdr[:7]
-        cuts = hdr[7:]
-        nB = bn
-        if rank != 0:
-            tB = api.tile_alloc(bm, bn, bnt, bnnz, True)
-        # B: one buffer, one NCCL broadcast over NVLink
-        slab = mg.tile_slab_tensor(tB, dev)
-        torch.cuda.synchronize()
-        dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dist.broadcast(slab, 0)
-        e1.record()
-        torch.cuda.synchronize()
-        bcast_ms = e0.elapsed_time(e1)
-        bcast_bytes = slab.numel()
-        # A: CSR rows of each rank's tile-row range (rank 0 slices on the host and sends)
-        r0, r1 = cuts[rank] * 16, min(cuts[rank + 1] * 16, m)
-        if rank == 0:
-            for dst in range(1, world):
-                a0, a1 = cuts[dst] * 16, min(cuts[dst + 1] * 16, m)
-                srp, sci, sv = mg.csr_row_slice(rp, ci, v, a0, a1)
-                dist.send(torch.tensor([len(sci)], dtype=torch.int64, device=dev), dst)
-                for arr in (srp, sci, sv):
-                    dist.send(torch.from_numpy(np.ascontiguousarray(arr)).to(dev), dst)
-            srp, sci, sv = mg.csr_row_slice(rp, ci, v, r0, r1)
-            dA = api.DeviceCSR.upload(r1 - r0, n, srp, sci, sv)
-        else:
-            cnt = torch.zeros(1, dtype=torch.int64, device=dev)
-            dist.recv(cnt, 0)
-            nz = int(cnt.item())
-            t_rp = torch.empty(r1 - r0 + 1, dtype=torch.int32, device=dev)
-            t_ci = torch.empty(max(nz, 1), dtype=torch.int32, device=dev)
-            t_v = torch.empty(max(nz, 1), dtype=torch.float64, device=dev)
-            for t in (t_rp, t_ci[:nz], t_v[:nz]):
-                dist.recv(t, 0)
-            torch.cuda.synchronize()
-            recv_bufs = (t_rp, t_ci, t_v)  # keep the received tensors alive: dA borrows their memory
-            dA = api.DeviceCSR.wrap(r1 - r0, n, nz, t_rp.data_ptr(), t_ci.data_ptr(), t_v.data_ptr())
-        tA = api.csr2tile(dA, False)
+    # ------------------------------------------------------------------ data: rank 0 generates, B is broadcast once
+    A_host = gen() if rank == 0 else None
+    sh = mg.distribute(A_host, aat, dist, dev, mode=args.bcast)
+    m, n, nB, nnzCub = sh.m, sh.n, sh.nB, sh.nnzCub
+    tA, tB, dA = sh.tA, sh.tB, sh.dA
+    part = {"parts": [[int(a), int(b)] for a, b in zip(sh.cuts[:-1], sh.cuts[1:])], "imbalance": sh.imbalance}
 
     # ------------------------------------------------------------------ timed region: steps 1-3, inputs resident
     def barrier():
@@ -280,14 +287,10 @@ def run_ours(args):
     slab_pairs = SLAB_PAIRS.get(args.workload)
     slab_w = api.tilerow_weights(tA, tB) if slab_pairs else None
 
-    def spgemm_step():
+    def spgemm_step(sink=None):
         """One pass of steps 1-3 over this rank's C tile-rows (slab by slab when C cannot be held whole)."""
-        if slab_pairs:
-            tot, _ = api.spgemm_slabs(tA, tB, max_pairs=slab_pairs, weights=slab_w)
-            return None, tot
-        tC_, st_ = api.spgemm(tA, tB)
-        tC_.free()
-        return None, st_
+        tot, _ = mg.spgemm(sh, slab_pairs, sink, weights=slab_w)
+        return tot
 
     stats = []
     for _ in range(W):
@@ -298,22 +301,33 @@ def run_ours(args):
         api.timer_start()
         t0 = time.perf_counter()
         for _ in range(K):
-            _, st = spgemm_step()
-            stats.append(st)
+            stats.append(spgemm_step())
         dev_ms = api.timer_stop()
         wall_ms = (time.perf_counter() - t0) * 1e3
         barrier()
     gpu_launches = api.launch_count() - launches0
     clocks = clk.summary()
 
+    # ------------------------------------------------------------------ parity of this very run (outside the timed region):
+    # per-row sums and counts of C from the device, slab by slab, against the CPU on rank 0
+    rows_local = dA.m
+    sums, cnts = np.zeros(rows_local), np.zeros(rows_local, np.int64)
+    if not args.no_parity:
+        def check_sink(tC, st):
+            r0 = tC.trow0 * 16
+            s_, c_ = api.tile_rowsums(tC)
+            sums[r0:r0 + len(s_)] = s_
+            cnts[r0:r0 + len(c_)] = c_
+        spgemm_step(check_sink)
+
     # ------------------------------------------------------------------ e2e: host CSR in -> host CSR out
     # (per rank: H2D of its CSR(A) rows, csr2tile(A); rank-local csr2tile(B) from its resident CSR is replaced,
     #  for N > 1, by the already broadcast tiled B -- the broadcast time is reported separately)
-    rpA, ciA, vA = dA.download() if world > 1 else (rp, ci, v)
+    rpA, ciA, vA = dA.download()
     pin = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in (rpA, ciA, vA)]
     nnzC_local = stats[-1]["nnzC"]
     if slab_pairs:  # the pinned landing buffer is reused slab after slab: size it for the largest slab
-        _, per = api.spgemm_slabs(tA, tB, max_pairs=slab_pairs, weights=slab_w)
+        _, per = mg.spgemm(sh, slab_pairs, None, weights=slab_w)
         buf_nnz = max(p["nnzC"] for p in per)
     else:
         buf_nnz = nnzC_local
@@ -352,6 +366,8 @@ def run_ours(args):
     t0 = time.perf_counter()
     for _ in range(e2e_K):
         e2e_step()
+    api.sync()
+    e2e_local_ms = (time.perf_counter() - t0) * 1e3 / e2e_K
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_K
     h2d = sum(int(t.numel() * t.element_size()) for t in pin)
@@ -359,15 +375,30 @@ def run_ours(args):
 
     # ------------------------------------------------------------------ reduce over ranks
     ms_step = max(dev_ms, 0.0) / K
-    vec = [ms_step, e2e_ms, float(gpu_launches), float(h2d), float(d2h), float(stats[-1]["nnzC"]), float(stats[-1]["numblkC"]),
-           float(stats[-1]["pairs"]), float(np.mean([s["ms_step1"] for s in stats])), float(np.mean([s["ms_step2"] for s in stats])),
+    last = stats[-1]
+    vec = [ms_step, e2e_ms, float(gpu_launches), float(h2d), float(d2h), float(last["nnzC"]), float(last["numblkC"]),
+           float(last["pairs"]), float(np.mean([s["ms_step1"] for s in stats])), float(np.mean([s["ms_step2"] for s in stats])),
            float(np.mean([s["ms_step3"] for s in stats])), float(np.mean([s["ms_alloc"] for s in stats])),
-           float(stats[-1]["algorithmic_bytes"]), float(step3_bytes(tA, tB, stats[-1])), wall_ms / K]
+           float(last["algorithmic_bytes"]), float(step3_bytes(tA, tB, last)), wall_ms / K, e2e_local_ms,
+           float(last["rows_staged"]), float(last["rows_gather"]), float(last["tiles_dense"]), float(last["rows_smem"])]
     if dist is not None:
         t = torch.tensor(vec, dtype=torch.float64, device=dev)
         allv = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allv, t)
         allv = np.stack([x.cpu().numpy() for x in allv])
+        # the checksums of every rank's rows, on rank 0
+        longest = int(max(b - a for a, b in part["parts"])) * 16
+        ts = torch.zeros(max(longest, 1), dtype=torch.float64, device=dev)
+        tc = torch.zeros(max(longest, 1), dtype=torch.int64, device=dev)
+        ts[:rows_local] = torch.from_numpy(sums).to(dev)
+        tc[:rows_local] = torch.from_numpy(cnts).to(dev)
+        gs, gc = [torch.zeros_like(ts) for _ in range(world)], [torch.zeros_like(tc) for _ in range(world)]
+        dist.all_gather(gs, ts)
+        dist.all_gather(gc, tc)
+        if rank == 0:
+            lens = [min(b * 16, m) - min(a * 16, m) for a, b in part["parts"]]
+            sums = np.concatenate([g.cpu().numpy()[:k] for g, k in zip(gs, lens)])
+            cnts = np.concatenate([g.cpu().numpy()[:k] for g, k in zip(gc, lens)])
     else:
         allv = np.asarray([vec])
     if rank != 0:
@@ -378,32 +409,38 @@ def run_ours(args):
     ms_step_max, e2e_ms_max = float(allv[:, 0].max()), float(allv[:, 1].max())
     value = 2.0 * nnzCub / (ms_step_max * 1e6)
     peak, peak_src = measured_peak_gbs()
-    # dominant kernel = the numeric kernel (step 3); per rank: bytes / its duration; report the slowest rank's kernel
+    # dominant kernel = the numeric step (step 3); per rank: bytes / its duration; report the slowest rank's
     slow = int(np.argmax(allv[:, 10]))
     s3_ms, s3_bytes = float(allv[slow, 10]), float(allv[slow, 13])
     achieved = s3_bytes / (s3_ms * 1e-3) / 1e9 if s3_ms > 0 else 0.0
     alg_total = float(allv[:, 12].sum())  # every rank reads the whole B, so B's bytes count once per rank
+    rp, ci, v = A_host[2], A_host[3], A_host[4]
+    kern_stats = {"rows_staged": int(allv[:, 16].sum()), "rows_gather": int(allv[:, 17].sum()), "tiles_dense": int(allv[:, 18].sum()),
+                  "rows_smem": int(allv[:, 19].max())}
     line = {
         "metric": "spgemm_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "tile": "16x16", "aat": int(aat), "m": m, "n": n,
-                   "nnzA": int(len(ci)) if world == 1 else None, "nnzCub": int(nnzCub), "nnzC": int(allv[:, 5].sum()),
+                   "nnzA": int(len(ci)), "nnzCub": int(nnzCub), "nnzC": int(allv[:, 5].sum()),
                    "C_tiles": int(allv[:, 6].sum()), "tile_pairs": int(allv[:, 7].sum()),
                    "l2": "inputs larger than L2 (tiled A+B+C per step >> 126 MB)" if alg_total > 4 * 126e6 else
                          "working set fits L2: launch-latency-bound correctness config, not a roofline config",
                    "parallelism": f"tile-row partition x{world}", "partition": part,
-                   "b_broadcast_ms": bcast_ms if world > 1 else None,
-                   "b_broadcast_gbs": (bcast_bytes / bcast_ms / 1e6) if world > 1 and bcast_ms > 0 else None,
+                   "b_broadcast": {"mode": sh.mode, "bytes": sh.bcast_bytes, "ms": sh.bcast_ms,
+                                   "gbs": (sh.bcast_bytes / sh.bcast_ms / 1e6) if sh.bcast_ms > 0 else None} if world > 1 else None,
+                   "nccl": nccl_evidence(nccl_log) if world > 1 else None,
                    "steps_ms": {"step1": float(allv[:, 8].max()), "step2": float(allv[:, 9].max()), "step3": float(allv[:, 10].max()),
                                 "alloc_and_sync": float(allv[:, 11].max()), "host_wall_per_step": float(allv[:, 14].max())},
                    "pipeline_roofline": {"algorithmic_bytes": alg_total, "achieved_gbs": alg_total / (ms_step_max * 1e-3) / 1e9,
                                          "frac_of_peak": alg_total / (ms_step_max * 1e-3) / 1e9 / (peak * world), "note": "SURVEY 8(d) bytes(A)+bytes(B)+bytes(C) over the whole step"}},
         "clocks": clocks,
         "e2e": {"value": 2.0 * nnzCub / (e2e_ms_max * 1e6), "unit": "GFLOP/s", "ms_per_step": e2e_ms_max, "steps": e2e_K,
-                "h2d_bytes_per_step": int(allv[:, 3].sum()), "d2h_bytes_per_step": int(allv[:, 4].sum())},
+                "h2d_bytes_per_step": int(allv[:, 3].sum()), "d2h_bytes_per_step": int(allv[:, 4].sum()),
+                "per_rank_ms": [round(float(x), 3) for x in allv[:, 15]],
+                "pcie_gbs_aggregate": (float(allv[:, 3].sum()) + float(allv[:, 4].sum())) / (e2e_ms_max * 1e-3) / 1e9},
         "gpu_launches": int(allv[:, 2].sum()),
-        "roofline": {"bound": "hbm", "kernel": numeric_kernels(stats[-1]), "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "numeric step: " + numeric_kernels(kern_stats), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": s3_ms,
                      "algorithmic_bytes_per_launch": s3_bytes},
     }
@@ -413,15 +450,19 @@ def run_ours(args):
             line["roofline"]["traffic"] = json.load(open(prof)).get(args.workload)
         except Exception:
             pass
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 or not args.no_parity or not args.no_cpu_baseline:
         from oracle import oracle as orc
         A = (rp, ci, v)
         B = A
         if aat:
             cp, ri, cv = orc.transpose(m, n, rp, ci, v)
-            B = (cp.astype(np.int32), ri, cv)
-        line["cpu_baseline"] = cpu_baseline(A, B, nB, nnzCub)
+            B = (cp.astype(np.int64), ri, cv)
+        if not args.no_parity:
+            line["parity"] = parity_check(A, B, nB, sums, cnts, args.parity_counts or nnzCub <= 4e9)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(A, B, nB, nnzCub)
     print(json.dumps(line), flush=True)
+    sh.free()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -438,6 +479,10 @@ def main():
     ap.add_argument("--e2e-slabs", type=int, default=0, help="slabs of the overlapped end-to-end call (0 = library default)")
     ap.add_argument("--ref-rows", type=int, default=1 << 17, help="--impl reference: rows of A in the bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the C*ones / row-count check of the run against the CPU")
+    ap.add_argument("--parity-counts", action="store_true",
+                    help="also compare nnz per row of C with the oracle's count pass on workloads above 4e9 products (minutes of CPU)")
+    ap.add_argument("--bcast", default="csr", choices=["csr", "tiled"], help="N > 1: broadcast B as its CSR (default) or as the tiled matrix")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

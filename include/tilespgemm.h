@@ -175,6 +175,7 @@ typedef struct {
     int rows_gather;          /* C tile-rows computed by k_step3_gather (lane per nonzero)                  */
     int tiles_dense;          /* C tiles computed by k_step3_dense (dense accumulator in registers)         */
     int rows_smem;            /* dynamic shared memory of k_step3_rows, bytes                               */
+    int tiles_nonempty;       /* C tiles holding at least one entry (numblkC counts the empty ones too)     */
 } tsg_stats;
 
 /* Select the device (like the driver's cudaSetDevice, reference src/main.cu:49) and create the
@@ -234,6 +235,15 @@ int tsg_tilerow_weights(const tsg_dtile *a, const tsg_dtile *b, long long *w_hos
 /* SpGEMM steps 1-3 for C tile-rows [trow0, trow1) (trow1 < 0: to the end). C is a slab: a tiled
  * matrix of its own with tilem = trow1-trow0 and m = its row count. stats may be NULL. */
 int tsg_spgemm(const tsg_dtile *a, const tsg_dtile *b, int trow0, int trow1, tsg_dtile *c, tsg_stats *stats);
+
+/* Steps 1-3 over C tile-rows [trow0, trow1) in SLABS of at most max_pairs matched tile pairs each (<= 0: 2^28; a single
+ * tile-row heavier than that is a slab of its own): what C = A*B needs when nnz(C) or its tile count does not fit the
+ * 32-bit sizes of SMatrix or one GPU's memory (R-MAT scale 20 has nnz(C) ~ 1e10). Every slab -- a
+ * tiled matrix of its own, trow0 = its first tile-row -- is handed to sink(slab, stats, user) and freed afterwards; a
+ * non-zero return stops the run. totals (may be NULL) sums the slabs' stats in 64 bits; *nslabs_out = slabs run. */
+typedef int (*tsg_slab_sink)(const tsg_dtile *c_slab, const tsg_stats *stats, void *user);
+int tsg_spgemm_slabs(const tsg_dtile *a, const tsg_dtile *b, int trow0, int trow1, long long max_pairs, tsg_slab_sink sink,
+                     void *user, tsg_stats *totals, int *nslabs_out);
 
 /* tiles -> CSR on the device (reference src/tile2csr.h:72). */
 int tsg_tile2csr(const tsg_dtile *t, tsg_dcsr *out);

@@ -667,6 +667,54 @@ int tsg_plan_slabs(const long long *weights, int trow0, int trow1, int nslabs, i
     return (int)c.size() - 1;
 }
 
+/* ---------------- slab runner: C tile-rows in slabs of bounded size, each handed to a callback ---------------- */
+
+int tsg_spgemm_slabs(const tsg_dtile *a, const tsg_dtile *b, int trow0, int trow1, long long max_pairs, tsg_slab_sink sink, void *user,
+                     tsg_stats *totals, int *nslabs_out)
+{
+    if (ensure_init()) return g_err;
+    if (trow1 < 0) trow1 = a->tilem;
+    if (trow0 < 0 || trow0 > trow1 || trow1 > a->tilem) {
+        set_error(TSG_ERR_INPUT, "spgemm_slabs: tile-row range [%d,%d) outside [0,%d]", trow0, trow1, a->tilem);
+        return g_err;
+    }
+    if (a->n != b->m) { set_error(TSG_ERR_UNSUPPORTED, "spgemm_slabs: inner dimensions differ (%d vs %d)", a->n, b->m); return g_err; }
+    if (max_pairs <= 0 || max_pairs > (1ll << 30)) max_pairs = 1ll << 28;  // what spgemm_device's 32-bit offsets are sized for
+    if (totals) memset(totals, 0, sizeof(*totals));
+    if (nslabs_out) *nslabs_out = 0;
+    std::vector<long long> w((size_t)a->tilem + 1);
+    int rc = tsg_tilerow_weights(a, b, w.data());
+    if (rc) return rc;
+    int nslabs = 0;
+    for (int r0 = trow0; r0 < trow1 && !rc;) {
+        long long acc = 0;
+        int r1 = r0;
+        while (r1 < trow1 && (r1 == r0 || acc + w[r1] <= max_pairs)) acc += w[r1++];  // a heavier single row stands alone
+        tsg_dtile tC;
+        tsg_stats st;
+        memset(&tC, 0, sizeof(tC));
+        rc = spgemm_device(a, b, r0, r1, &tC, &st);
+        if (!rc && totals) {
+            totals->ms_step1 += st.ms_step1; totals->ms_step2 += st.ms_step2; totals->ms_step3 += st.ms_step3;
+            totals->ms_alloc += st.ms_alloc; totals->ms_total += st.ms_total; totals->numblkC += st.numblkC;
+            totals->nnzC += st.nnzC; totals->pairs += st.pairs; totals->launches += st.launches;
+            totals->algorithmic_bytes += st.algorithmic_bytes;
+            totals->rows_staged += st.rows_staged; totals->rows_gather += st.rows_gather; totals->tiles_dense += st.tiles_dense;
+            totals->tiles_nonempty += st.tiles_nonempty;
+            if (st.rows_smem > totals->rows_smem) totals->rows_smem = st.rows_smem;
+        }
+        if (!rc && sink && sink(&tC, &st, user)) {
+            set_error(TSG_ERR_INPUT, "spgemm_slabs: the slab callback stopped the run at tile-rows [%d,%d)", r0, r1);
+            rc = g_err;
+        }
+        tsg_tile_free(&tC);
+        nslabs++;
+        r0 = r1;
+    }
+    if (nslabs_out) *nslabs_out = nslabs;
+    return rc;
+}
+
 static int landing_init()
 {
     Ctx &c = g_ctx;
@@ -717,6 +765,7 @@ int tsg_spgemm_to_host(const tsg_dtile *a, const tsg_dtile *b, int trow0, int tr
             stats->nnzC += st.nnzC; stats->pairs += st.pairs; stats->launches += st.launches;
             stats->algorithmic_bytes += st.algorithmic_bytes;
             stats->rows_staged += st.rows_staged; stats->rows_gather += st.rows_gather; stats->tiles_dense += st.tiles_dense;
+            stats->tiles_nonempty += st.tiles_nonempty;
             if (st.rows_smem > stats->rows_smem) stats->rows_smem = st.rows_smem;
         }
         const long long nz = tC.nnz;

@@ -64,7 +64,7 @@ __device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity)
 // Classification. Row kinds: what computes the (non-dense) tiles of a C tile-row.
 // ---------------------------------------------------------------------------------------------
 enum : uint8_t { ROW_NONE = 0, ROW_STAGED = 1, ROW_GATHER = 2 };
-enum { NS_MAXNEED = 0, NS_ROWS_STAGED = 1, NS_ROWS_GATHER = 2, NS_DENSE = 3, NS_GLO = 4, NS_GHI = 5 };
+enum { NS_MAXNEED = 0, NS_ROWS_STAGED = 1, NS_ROWS_GATHER = 2, NS_DENSE = 3, NS_GLO = 4, NS_GHI = 5, NS_NONEMPTY = 6 };
 
 __host__ __device__ __forceinline__ size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
@@ -93,7 +93,8 @@ k_s3_classify_tiles(int numblkC, int trow0, const int *__restrict__ c_tile_nnz, 
     const int cnt = t < numblkC ? c_tile_nnz[t + 1] - c_tile_nnz[t] : 0;
     const bool dense = cnt >= dense_th;
     if (cnt > 0 && !dense) row_kind[c_tile_row[t] - trow0] = ROW_STAGED;  // benign race: every writer stores the same value
-    const unsigned m = __ballot_sync(FULL_MASK, dense);
+    const unsigned m = __ballot_sync(FULL_MASK, dense), ne = __ballot_sync(FULL_MASK, cnt > 0);
+    if (lane == 0 && ne) atomicAdd(&scal[NS_NONEMPTY], __popc(ne));
     if (!m) return;
     int base = 0;
     if (lane == 0) base = atomicAdd(&scal[NS_DENSE], __popc(m));
@@ -832,7 +833,10 @@ int numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, int tro
     if (nnzC <= 0 || numblkC <= 0) return TSG_OK;
     const char *mode = s3_mode();
     const int n_staged = h_ns[NS_ROWS_STAGED], n_gather = h_ns[NS_ROWS_GATHER], n_dense = h_ns[NS_DENSE];
-    if (stats) { stats->rows_staged = n_staged; stats->rows_gather = n_gather; stats->tiles_dense = n_dense; stats->rows_smem = h_ns[NS_MAXNEED]; }
+    if (stats) {
+        stats->rows_staged = n_staged; stats->rows_gather = n_gather; stats->tiles_dense = n_dense; stats->rows_smem = h_ns[NS_MAXNEED];
+        stats->tiles_nonempty = h_ns[NS_NONEMPTY];
+    }
 
     if (n_dense > 0) {
         S3Dense P{n_dense, nb.dense_list, pl.ptr, pl.end, pl.a, pl.b, A->tile_nnz, A->ptr, A->col, A->val, B->tile_nnz, B->ptr, B->col, B->val,

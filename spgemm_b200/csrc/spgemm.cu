@@ -899,7 +899,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         stats->ms_step1 = s1a + s1b; stats->ms_step2 = s2; stats->ms_step3 = s3; stats->ms_alloc = al + al2; stats->ms_total = tot;
         stats->launches = (int)(c.launches - launches0);
         stats->rows_staged = nst.rows_staged; stats->rows_gather = nst.rows_gather; stats->tiles_dense = nst.tiles_dense;
-        stats->rows_smem = nst.rows_smem;
+        stats->rows_smem = nst.rows_smem; stats->tiles_nonempty = nst.tiles_nonempty;
         // algorithmic bytes, SURVEY.md 8(d). A's share is the slab's tiles; B is read whole.
         long long a_tiles = A->numtile, a_nnz = A->nnz;
         if (ntr != A->tilem) {

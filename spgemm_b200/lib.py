@@ -20,7 +20,7 @@ EXPORTS = [
     "tsg_csr_canonicalize",
     "tsg_transpose", "tsg_nnzcub", "tsg_csr2tile", "tsg_tile_upload", "tsg_tile_download", "tsg_tile_alloc",
     "tsg_tile_free", "tsg_tilerow_weights", "tsg_spgemm", "tsg_tile2csr", "tsg_tile_rowsums", "tsg_spgemm_csr_host",
-    "tsg_spgemm_to_host", "tsg_spgemm_csr_host_into", "tsg_plan_slabs",
+    "tsg_spgemm_to_host", "tsg_spgemm_csr_host_into", "tsg_plan_slabs", "tsg_spgemm_slabs",
 ]
 
 
@@ -60,7 +60,7 @@ class Stats(C.Structure):
                 ("ms_step1", C.c_double), ("ms_step2", C.c_double), ("ms_step3", C.c_double),
                 ("ms_alloc", C.c_double), ("ms_total", C.c_double),
                 ("algorithmic_bytes", C.c_longlong), ("launches", C.c_int),
-                ("rows_staged", C.c_int), ("rows_gather", C.c_int), ("tiles_dense", C.c_int), ("rows_smem", C.c_int)]
+                ("rows_staged", C.c_int), ("rows_gather", C.c_int), ("tiles_dense", C.c_int), ("rows_smem", C.c_int), ("tiles_nonempty", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -298,8 +298,9 @@ def test_config2_stencil27_128_full():
         o.free()
 
 
-def test_config4_blockfem_full_properties():
-    """BASELINE config 4 at full size (2M rows, dense 6x6 blocks): known sizes and size-independent properties."""
+def test_config4_blockfem_full():
+    """BASELINE config 4 at full size (2M rows, dense 6x6 blocks): known sizes, size-independent properties, and every
+    array of the tiled C (tile list incl. the 40 % empty tiles, tile_nnz, Ptr, mask, Col, Val) against the oracle."""
     m, n, rp, ci, v = M.blockfem(333334)
     A = (rp, ci, v)
     assert (m, len(ci)) == (2000004, 36000000)
@@ -314,6 +315,9 @@ def test_config4_blockfem_full_properties():
     csr = api.tile2csr_device(tC)
     back = api.csr2tile(csr, False)
     assert back.numtile == 375001 and back.nnz == st["nnzC"]
+    assert st["tiles_dense"] > 0, st                       # the dense accumulator is what this config is for
+    _, tC_exp = oracle_c(m, n, A, A, n)
+    assert_tiled_equal(tC.download(), tC_exp, "blockfem-2M C")
     for o in (back, csr, tC, tA, tB, d):
         o.free()
 
@@ -369,6 +373,13 @@ def test_c_driver_cli(tmp_path):
         assert len(open(tmp_path / name).read().strip().splitlines()) == 3
     bad = subprocess.run([exe, "-d", "0", "-aat", "0", str(mtx), "32", "32"], capture_output=True, text=True, env=env, timeout=60)
     assert bad.returncode != 0  # unsupported tile size: the driver exits non-zero instead of printing garbage
+    # -slabs: the product slab by slab through tsg_spgemm_slabs (what configs 3 and 5 need), both modes
+    for args in (["-d", "0", "-aat", "1", "gen:rmat:12:16", "16", "16", "-slabs", "100000"],
+                 ["-d", "0", "-aat", "0", "gen:stencil27:12", "16", "16", "-slabs", "20000"]):
+        out = subprocess.run([exe] + args, capture_output=True, text=True, env=env, timeout=180)
+        assert out.returncode == 0 and "[PASSED]" in out.stdout, out.stdout + out.stderr
+        nslabs = int([ln for ln in out.stdout.splitlines() if ln.startswith("slabs = ")][0].split()[2])
+        assert nslabs >= 3, out.stdout
 
 
 def test_hypersparse_rmat_a2_matches_oracle():
@@ -547,3 +558,107 @@ def test_values_reproducible_run_to_run():
     assert np.array_equal(a.download()["val"], b.download()["val"])
     for o in (a, b, tA, tB, d):
         o.free()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Boundary: what enters the library is checked before anything indexes by it; unsorted / duplicate-bearing CSR
+# ---------------------------------------------------------------------------------------------------------------
+def test_out_of_range_input_fails_before_any_kernel_indexes_by_it():
+    """Column indices outside [0, n) and broken row pointers are refused at upload (TSG_ERR_INPUT) -- also on the paths
+    that would otherwise write ptr[column] (csr2tile_col_major, matrix_transposition) -- and the library stays usable."""
+    m, n, rp, ci, v = M.lap2d(12)
+    for bad_col in (n, n + 1000, -1, -2 ** 31):
+        bad = ci.copy()
+        bad[len(bad) // 2] = bad_col
+        with pytest.raises(api.TsgError) as e:
+            api.DeviceCSR.upload(m, n, rp, bad, v)
+        assert e.value.code == 4
+        H = api.HostMatrix.from_csr(m, n, rp, bad, v)
+        with pytest.raises(api.TsgError) as e:
+            api.csr2tile_col_major(H, 16, 16)
+        assert e.value.code == 4
+        with pytest.raises(api.TsgError) as e:
+            api.matrix_transposition(m, n, rp, bad, v)
+        assert e.value.code == 4
+    brp = rp.copy()
+    brp[5], brp[6] = brp[6], brp[5]                      # not monotone
+    with pytest.raises(api.TsgError) as e:
+        api.DeviceCSR.upload(m, n, brp, ci, v)
+    assert e.value.code == 4
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)            # still usable
+    t = api.csr2tile(d, True)
+    assert_tiled_equal(t.download(), orc.csr2tile_col_major(m, n, rp, ci, v), "after the refused uploads")
+    t.free(); d.free()
+
+
+def _scrambled(seed, dups):
+    """A CSR whose rows are in random order, optionally with duplicate entries, and its canonical form (scipy)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    m, n, rp, ci, _ = M.random_sparse(150, 170, 0.06, seed=seed)
+    v = rng.integers(1, 9, len(ci)).astype(np.float64)
+    rows = np.repeat(np.arange(m), np.diff(rp))
+    if dups:
+        extra = rng.choice(len(ci), len(ci) // 5, replace=False)
+        rows, ci, v = np.concatenate([rows, rows[extra]]), np.concatenate([ci, ci[extra]]), np.concatenate([v, v[extra] + 1])
+    order = np.lexsort((rng.random(len(ci)), rows))      # rows stay contiguous, entries inside a row shuffled
+    rows, ci, v = rows[order], ci[order].astype(np.int32), v[order]
+    urp = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=m))]).astype(np.int32)
+    S = sp.csr_matrix((v, ci, urp), shape=(m, n))
+    S.sum_duplicates()
+    S.sort_indices()
+    return (m, n, urp, ci, v), (S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data)
+
+
+@pytest.mark.parametrize("dups", [False, True])
+def test_canonicalize_and_drop_in_on_unsorted_csr(dups):
+    """The reference's loader neither sorts rows nor merges duplicates (src/mmio_highlevel.h:593-759). The device API
+    refuses such input (TSG_ERR_INPUT) and offers tsg_csr_canonicalize; the drop-in csr2tile_* canonicalise by themselves."""
+    (m, n, urp, uci, uv), (crp, cci, cv) = _scrambled(31 + dups, dups)
+    d = api.DeviceCSR.upload(m, n, urp, uci, uv)
+    with pytest.raises(api.TsgError) as e:
+        api.csr2tile(d, False)
+    assert e.value.code == 4
+    c = d.canonicalize("sum")
+    rp, ci, v = c.download()
+    assert np.array_equal(rp, crp) and np.array_equal(ci, cci) and np.array_equal(v, cv)
+    if dups:  # keep-first policy: the first occurrence in the input order
+        f = d.canonicalize("first")
+        frp, fci, fv = f.download()
+        assert np.array_equal(frp, crp) and np.array_equal(fci, cci)
+        first = {}
+        rows = np.repeat(np.arange(m), np.diff(urp))
+        for r_, c_, v_ in zip(rows, uci, uv):
+            first.setdefault((r_, c_), v_)
+        assert np.array_equal(fv, np.array([first[(r_, c_)] for r_, c_ in zip(np.repeat(np.arange(m), np.diff(crp)), cci)]))
+        f.free()
+    c.free(); d.free()
+    # drop-in entry points on the scrambled matrix: same tiles as the canonical matrix gives
+    A = api.HostMatrix.from_csr(m, n, urp, uci, uv)
+    B = api.HostMatrix().alias_csr_of(A)
+    api.csr2tile_row_major(A, 16, 16)
+    api.csr2tile_col_major(B, 16, 16)
+    assert_tiled_equal(A.tiles(), orc.csr2tile_row_major(m, n, crp, cci, cv), "drop-in A from unsorted CSR")
+    assert_tiled_equal(B.tiles(), orc.csr2tile_col_major(m, n, crp, cci, cv), "drop-in B from unsorted CSR")
+    if not dups:
+        from oracle import ref
+        if ref.available():  # the reference's own csr2tile_col_major sorts inside every tile: identical arrays
+            assert_tiled_equal(B.tiles(), ref.csr2tile_col_major(m, n, urp, uci, uv), "drop-in B vs reference on unsorted CSR",
+                               fields=("tile_ptr", "tile_columnidx", "tile_nnz", "val", "col", "ptr", "mask", "csc_tile_ptr", "csc_tile_rowidx"))
+    for x in (A, B):
+        api.matrix_destroy(x)
+
+
+def test_csr_row_slice_is_a_csr_of_its_own():
+    m, n, rp, ci, v = M.stencil27(9, 8, 7)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    for r0, r1 in ((0, m), (16, 80), (100, 100), (m - 5, m)):
+        s_ = d.row_slice(r0, r1)
+        srp, sci, sv = s_.download()
+        assert np.array_equal(srp, rp[r0:r1 + 1] - rp[r0]) and np.array_equal(sci, ci[rp[r0]:rp[r1]]) and np.array_equal(sv, v[rp[r0]:rp[r1]])
+        if r1 > r0:
+            t = api.csr2tile(s_, False)
+            assert_tiled_equal(t.download(), orc.csr2tile_row_major(r1 - r0, n, srp, sci, sv), f"slice [{r0},{r1})")
+            t.free()
+        s_.free()
+    d.free()

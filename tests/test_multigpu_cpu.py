@@ -50,6 +50,10 @@ def _worker(rank, world, port, q):
     sub = mg.csr_row_slice(rp, ci, v, r0, r1)             # this rank's rows of A
     C = orc.spgemm_spa(sub, A, n)                         # this rank's C rows (stand-in for steps 1-3)
     tC = orc.ctiles_from_csr(m, n, tA, tB, orc.spgemm_spa(A, A, n, r0, r1), t0, t1)
+    # the weights as the GPU path computes them: every rank its own equal block of tile-rows, then one all-gather
+    blocks = mg.equal_row_blocks(tA.tilem, world)
+    w2 = mg.exchange_weights(w[blocks[rank]:blocks[rank + 1]], blocks, dist)
+    assert np.array_equal(w2, w)
     counts = mg.gather_counts([tC.numtile, tC.nnz, r1 - r0], dist)
     off = mg.concat_offsets(counts)
     q.put((rank, t0, t1, C[0] + off[rank, 1], C[1], C[2], tC.tile_nnz + off[rank, 1], tC.tile_ptr + off[rank, 0], counts))
