@@ -429,7 +429,8 @@ def run_ours(args):
                    "parallelism": f"tile-row partition x{world}", "partition": part,
                    "b_broadcast": {"mode": sh.mode, "bytes": sh.bcast_bytes, "ms": sh.bcast_ms,
                                    "gbs": (sh.bcast_bytes / sh.bcast_ms / 1e6) if sh.bcast_ms > 0 else None} if world > 1 else None,
-                   "nccl": nccl_evidence(nccl_log) if world > 1 else None,
+                   "nccl": dict(nccl_evidence(nccl_log) or {}, NCCL_DEBUG=os.environ.get("NCCL_DEBUG"),
+                                NCCL_DEBUG_FILE=os.environ.get("NCCL_DEBUG_FILE")) if world > 1 else None,
                    "steps_ms": {"step1": float(allv[:, 8].max()), "step2": float(allv[:, 9].max()), "step3": float(allv[:, 10].max()),
                                 "alloc_and_sync": float(allv[:, 11].max()), "host_wall_per_step": float(allv[:, 14].max())},
                    "pipeline_roofline": {"algorithmic_bytes": alg_total, "achieved_gbs": alg_total / (ms_step_max * 1e-3) / 1e9,

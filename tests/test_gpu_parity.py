@@ -375,7 +375,7 @@ def test_c_driver_cli(tmp_path):
     assert bad.returncode != 0  # unsupported tile size: the driver exits non-zero instead of printing garbage
     # -slabs: the product slab by slab through tsg_spgemm_slabs (what configs 3 and 5 need), both modes
     for args in (["-d", "0", "-aat", "1", "gen:rmat:12:16", "16", "16", "-slabs", "100000"],
-                 ["-d", "0", "-aat", "0", "gen:stencil27:12", "16", "16", "-slabs", "20000"]):
+                 ["-d", "0", "-aat", "0", "gen:stencil27:12", "16", "16", "-slabs", "2000"]):
         out = subprocess.run([exe] + args, capture_output=True, text=True, env=env, timeout=180)
         assert out.returncode == 0 and "[PASSED]" in out.stdout, out.stdout + out.stderr
         nslabs = int([ln for ln in out.stdout.splitlines() if ln.startswith("slabs = ")][0].split()[2])
