@@ -604,7 +604,7 @@ def _scrambled(seed, dups):
     order = np.lexsort((rng.random(len(ci)), rows))      # rows stay contiguous, entries inside a row shuffled
     rows, ci, v = rows[order], ci[order].astype(np.int32), v[order]
     urp = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=m))]).astype(np.int32)
-    S = sp.csr_matrix((v, ci, urp), shape=(m, n))
+    S = sp.csr_matrix((v.copy(), ci.copy(), urp.copy()), shape=(m, n))  # scipy sorts in place: keep the scrambled arrays
     S.sum_duplicates()
     S.sort_indices()
     return (m, n, urp, ci, v), (S.indptr.astype(np.int32), S.indices.astype(np.int32), S.data)
