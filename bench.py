@@ -108,6 +108,9 @@ def step3_bytes(tA, tB, st):
     payloads (Val 8 per nnz, Ptr 32 + mask 32 + tile_nnz 4 per tile), the pair lists (8 per pair), C's structure for
     the tiles that hold entries (Ptr 32 + mask 32 + tile_nnz 4 each: the empty listed tiles of a hypersparse product are
     never read by it) and C's payload written (Val 8 + Col 2 per nnz)."""
+    if st.get("plan_recipes", 0) > 0:  # plan path (csrc/plans.cu): values of A and B, per pair its two value bases (8),
+        # per C tile its recipe id, nnz offset and pair offset (12), C's payload written; the plans themselves stay in L1/L2
+        return tA.nnz * 8 + tB.nnz * 8 + st["pairs"] * 8 + st["numblkC"] * 12 + st["nnzC"] * 10
     return (tA.nnz * 8 + tA.numtile * 68 + tB.nnz * 8 + tB.numtile * 68 + st["tiles_nonempty"] * 68 + st["pairs"] * 8
             + st["nnzC"] * 10)
 
@@ -115,6 +118,8 @@ def step3_bytes(tA, tB, st):
 def numeric_kernels(st):
     """Names of the numeric (step 3) kernels this workload actually launched (tsg_stats)."""
     names = []
+    if st.get("plan_recipes", 0) > 0:
+        return f"k_pair_bases + k_numeric_from_plans ({st['plan_recipes']} recipes)"
     if st.get("rows_staged", 0) > 0:
         names.append(f"k_step3_rows ({st['rows_staged']} tile-rows, {st['rows_smem']} B smem)")
     if st.get("tiles_dense", 0) > 0:
@@ -380,7 +385,8 @@ def run_ours(args):
            float(last["pairs"]), float(np.mean([s["ms_step1"] for s in stats])), float(np.mean([s["ms_step2"] for s in stats])),
            float(np.mean([s["ms_step3"] for s in stats])), float(np.mean([s["ms_alloc"] for s in stats])),
            float(last["algorithmic_bytes"]), float(step3_bytes(tA, tB, last)), wall_ms / K, e2e_local_ms,
-           float(last["rows_staged"]), float(last["rows_gather"]), float(last["tiles_dense"]), float(last["rows_smem"])]
+           float(last["rows_staged"]), float(last["rows_gather"]), float(last["tiles_dense"]), float(last["rows_smem"]),
+           float(last["plan_recipes"])]
     if dist is not None:
         t = torch.tensor(vec, dtype=torch.float64, device=dev)
         allv = [torch.zeros_like(t) for _ in range(world)]
@@ -416,7 +422,7 @@ def run_ours(args):
     alg_total = float(allv[:, 12].sum())  # every rank reads the whole B, so B's bytes count once per rank
     rp, ci, v = A_host[2], A_host[3], A_host[4]
     kern_stats = {"rows_staged": int(allv[:, 16].sum()), "rows_gather": int(allv[:, 17].sum()), "tiles_dense": int(allv[:, 18].sum()),
-                  "rows_smem": int(allv[:, 19].max())}
+                  "rows_smem": int(allv[:, 19].max()), "plan_recipes": int(allv[:, 20].max())}
     line = {
         "metric": "spgemm_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -159,6 +159,10 @@ typedef struct {
     int *csc_tile_ptr;    /* [tilen+1]  col_major only                                         */
     int *csc_tile_rowidx; /* [numtile]  col_major only                                         */
     int *rm2csc;          /* [numtile]  col_major only: row-major tile index -> storage id     */
+    int *pat;             /* [numtile]  pattern id of every tile (storage order): tiles with equal ids have identical
+                             row masks, i.e. the same sparsity pattern. Filled by csr2tile / tile upload. */
+    int npat;             /* number of distinct patterns; -1: not available (too many -- the recipe plans of
+                             csrc/plans.cu are then not attempted for this matrix) */
     void *slab[4];        /* device allocations owned by this object (tsg_tile_free)           */
     size_t slab_bytes[4];
 } tsg_dtile;
@@ -176,6 +180,8 @@ typedef struct {
     int tiles_dense;          /* C tiles computed by k_step3_dense (dense accumulator in registers)         */
     int rows_smem;            /* dynamic shared memory of k_step3_rows, bytes                               */
     int tiles_nonempty;       /* C tiles holding at least one entry (numblkC counts the empty ones too)     */
+    int plan_recipes;         /* > 0: steps 2 and 3 ran from recipe plans (csrc/plans.cu), this many distinct recipes;
+                                 0: generic kernels; -1: plans were attempted and fell back                     */
 } tsg_stats;
 
 /* Select the device (like the driver's cudaSetDevice, reference src/main.cu:49) and create the

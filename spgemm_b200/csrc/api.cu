@@ -265,6 +265,7 @@ void tsg_shutdown(void)
 {
     if (!g_ready) return;
     cudaStreamSynchronize(g_ctx.stream);
+    plans_shutdown();
     if (g_ctx.scan_state) cudaFreeAsync(g_ctx.scan_state, g_ctx.stream);
     for (int k = 0; k < 3; k++)
         if (g_ctx.arena[k].base) cudaFreeAsync(g_ctx.arena[k].base, g_ctx.stream);
@@ -490,6 +491,8 @@ int tsg_tile_upload(const SMatrix *h, int col_major, tsg_dtile *out)
         rc = build_rm2csc_device(out);
         if (rc) return rc;
     }
+    rc = tile_patterns_device(out);
+    if (rc) return rc;
     CK(cudaStreamSynchronize(s));
     return TSG_OK;
 }
@@ -702,6 +705,7 @@ int tsg_spgemm_slabs(const tsg_dtile *a, const tsg_dtile *b, int trow0, int trow
             totals->rows_staged += st.rows_staged; totals->rows_gather += st.rows_gather; totals->tiles_dense += st.tiles_dense;
             totals->tiles_nonempty += st.tiles_nonempty;
             if (st.rows_smem > totals->rows_smem) totals->rows_smem = st.rows_smem;
+            if (st.plan_recipes > totals->plan_recipes) totals->plan_recipes = st.plan_recipes;
         }
         if (!rc && sink && sink(&tC, &st, user)) {
             set_error(TSG_ERR_INPUT, "spgemm_slabs: the slab callback stopped the run at tile-rows [%d,%d)", r0, r1);
@@ -767,6 +771,7 @@ int tsg_spgemm_to_host(const tsg_dtile *a, const tsg_dtile *b, int trow0, int tr
             stats->rows_staged += st.rows_staged; stats->rows_gather += st.rows_gather; stats->tiles_dense += st.tiles_dense;
             stats->tiles_nonempty += st.tiles_nonempty;
             if (st.rows_smem > stats->rows_smem) stats->rows_smem = st.rows_smem;
+            if (st.plan_recipes > stats->plan_recipes) stats->plan_recipes = st.plan_recipes;
         }
         const long long nz = tC.nnz;
         const int rows = tC.m;

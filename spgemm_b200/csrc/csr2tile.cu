@@ -216,6 +216,7 @@ int tile_alloc_layout(int m, int n, int numtile, long long nnz, int col_major, t
     size_t o_col = take(nz * 2);
     size_t o_ptr = take(nt * TS * 2);
     size_t o_mask = take(nt * TS * 2);
+    size_t o_pat = take(nt * 4);
     size_t o_cscp = 0, o_cscr = 0, o_rm2 = 0;
     if (col_major) {
         o_cscp = take(((size_t)out->tilen + 1) * 4);
@@ -233,6 +234,8 @@ int tile_alloc_layout(int m, int n, int numtile, long long nnz, int col_major, t
     out->col = (uint16_t *)(base + o_col);
     out->ptr = (uint16_t *)(base + o_ptr);
     out->mask = (uint16_t *)(base + o_mask);
+    out->pat = (int *)(base + o_pat);
+    out->npat = -1;
     if (col_major) {
         out->csc_tile_ptr = (int *)(base + o_cscp);
         out->csc_tile_rowidx = (int *)(base + o_cscr);
@@ -323,7 +326,7 @@ int csr2tile_device(const tsg_dcsr *A, int col_major, tsg_dtile *out)
         set_error(TSG_ERR_INPUT, "csr2tile: CSR input violates the contract (flags=%d: 1=column out of range, 2=row not sorted/duplicate, 4=internal)", flag);
         return last_error();
     }
-    return TSG_OK;
+    return tile_patterns_device(out);  // pattern ids of the tiles (plans.cu): format metadata, like the masks
 }
 
 int last_input_flags() { return g_input_flags; }

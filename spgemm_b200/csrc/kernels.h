@@ -36,6 +36,18 @@ int numeric_classify_device(const tsg_dtile *A, const tsg_dtile *C, int trow0, i
 int numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, int trow0, int ntr, const int *wptr, const PairLists &pl,
                    const NumericBufs &nb, const int *h_ns, bool heavy_rows, tsg_stats *stats);
 
+// plans.cu (recipe plans: bit-exact fast path of steps 2 and 3 for matrices made of few distinct tiles)
+struct PlanTable;
+int tile_patterns_device(tsg_dtile *T);
+bool plans_wanted(const tsg_dtile *A, const tsg_dtile *B);
+int plans_begin(PlanTable *out);
+int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const int *rslot, int *recipe_id,
+                          const int **d_fail);
+int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, long long pairs, const int *recipe_id,
+                         tsg_stats *stats);
+const int *plans_recipe_count_ptr();
+void plans_shutdown();
+
 // tile2csr.cu
 int tile2csr_device(const tsg_dtile *T, tsg_dcsr *out);
 int tile2csr_into(const tsg_dtile *T, int *rowptr, int *colidx, double *val, int base);

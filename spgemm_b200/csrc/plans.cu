@@ -1,0 +1,417 @@
+// plans.cu -- recipe plans: a bit-exact fast path of steps 2 and 3 for matrices whose tiles repeat themselves.
+//
+// Structured inputs are made of few distinct tiles: the 27-point stencil on a 128^3 grid has 3 distinct tile patterns (the
+// 16 row masks of a tile) and its 13.7 M listed C tiles follow 42 distinct "recipes" (the sequence of (A pattern, B
+// pattern) over a C tile's pairs); lap2d 256^2: 4 / 20; block-FEM 2M: 12 / 22; a 100^3 stencil: 22 / 408. A recipe fixes
+// everything the symbolic step computes (mask, Ptr, nnz of the C tile) and, per C nonzero, the list of sources
+// (pair, position in A's tile, position in B's tile) in the serial SPA's order. So:
+//   * csr2tile gives every tile a pattern id (k_pattern_insert / _verify: device hash table, full-key verification);
+//   * k_s1_fill hashes each C tile's pair sequence while it writes the pair lists (spgemm.cu) and inserts it into the
+//     recipe table; k_recipe_verify compares every tile's sequence with its recipe's representative;
+//   * k_plan_build plans each distinct recipe once, from the representative tile's actual masks;
+//   * the symbolic step becomes a 68-byte copy per C tile (k_symbolic_from_plans) and the numeric step walks an
+//     L1-resident plan, one lane per C nonzero, every iteration a product, in the serial SPA's summation order
+//     (k_numeric_from_plans): bit-identical to the generic kernels' results.
+// Nothing here waits on another thread: insert = one atomicCAS on the key word, owner of a slot = atomicMin of the item
+// indices that landed in it (deterministic), and a true 64-bit hash collision, too many patterns / recipes, or a plan
+// that outgrows its buffer raise the fail flag -- the generic kernels (spgemm.cu step 2, numeric.cu) then run instead.
+// Irregular matrices (R-MAT: 891 020 recipes for 933 730 C tiles at scale 14) never get here: the path is attempted only
+// when both operands hold few patterns (PLANS_MAX_PATTERNS) and no tile-row is heavy. TSG_PLANS=0 switches it off.
+// Replaces, on such inputs, what reference src/tilespgemm-cuda.h:394-773 (symbolic) and :1273-1952 (numeric) compute.
+#include "common.cuh"
+#include "scan.cuh"
+#include "kernels.h"
+#include "plans.cuh"
+
+namespace tsg {
+
+using namespace plans;
+
+// ---------------------------------------------------------------------------------------------
+// Pattern ids (per tiled matrix, at csr2tile / upload time)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pattern_insert(int numtile, const uint16_t *__restrict__ mask, unsigned long long *keys, int *owner, int *count,
+                 int *__restrict__ pat_id, int *fail)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= numtile) return;
+    const uint4 *mp = reinterpret_cast<const uint4 *>(mask + (size_t)t * TS);
+    const uint4 x = mp[0], y = mp[1];
+    unsigned long long h = 0x243F6A8885A308D3ull;
+    h = mix64(h, ((unsigned long long)x.x << 32) | x.y); h = mix64(h, ((unsigned long long)x.z << 32) | x.w);
+    h = mix64(h, ((unsigned long long)y.x << 32) | y.y); h = mix64(h, ((unsigned long long)y.z << 32) | y.w);
+    const int slot = table_insert(keys, PCAP, h, count, PCAP / 2, fail);
+    pat_id[t] = slot;
+    if (slot >= 0 && t < *(volatile int *)&owner[slot]) atomicMin(&owner[slot], t);  // owner only ever decreases
+}
+
+__global__ void __launch_bounds__(256)
+k_pattern_verify(int numtile, const uint16_t *__restrict__ mask, const int *__restrict__ pat_id, const int *__restrict__ owner, int *fail)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= numtile || *(volatile int *)fail) return;
+    const int slot = pat_id[t];
+    if (slot < 0) { *fail = 1; return; }
+    const uint4 *op = reinterpret_cast<const uint4 *>(mask + (size_t)owner[slot] * TS);
+    const uint4 *mp = reinterpret_cast<const uint4 *>(mask + (size_t)t * TS);
+    const uint4 x = mp[0], y = mp[1], a = op[0], b = op[1];
+    if (!(a.x == x.x && a.y == x.y && a.z == x.z && a.w == x.w && b.x == y.x && b.y == y.y && b.z == y.z && b.w == y.w)) *fail = 2;
+}
+
+struct PlanCtx {
+    // pattern table scratch (reused by every csr2tile)
+    unsigned long long *pkeys = nullptr;
+    int *powner = nullptr;
+    // recipe table + plans (reused by every spgemm call)
+    unsigned long long *rkeys = nullptr;
+    int *rowner = nullptr, *rflags = nullptr, *rdense = nullptr, *rep_tile = nullptr;
+    uint16_t *plan_mask = nullptr, *plan_ptr = nullptr;
+    int *plan_nnz = nullptr, *plan_tot = nullptr, *plan_off = nullptr;
+    unsigned *plan_start = nullptr, *plan_ent = nullptr;
+    uint8_t *plan_col = nullptr;
+    int *ctl = nullptr;  // [0] pattern count, [1] pattern fail, [2] recipe count, [3] recipe / plan fail
+    int device = -1;
+};
+static PlanCtx g_plan;
+
+static int plan_ctx_init()
+{
+    Ctx &c = ctx();
+    if (g_plan.device == c.device && g_plan.pkeys) return TSG_OK;
+    g_plan = PlanCtx();
+    PlanCtx &p = g_plan;
+    p.pkeys = dalloc_n<unsigned long long>(PCAP);
+    p.powner = dalloc_n<int>(PCAP);
+    p.rkeys = dalloc_n<unsigned long long>(RCAP);
+    p.rowner = dalloc_n<int>(RCAP);
+    p.rflags = dalloc_n<int>(RCAP + 1);
+    p.rdense = dalloc_n<int>(RCAP + 1);
+    p.rep_tile = dalloc_n<int>(RMAX);
+    p.plan_mask = dalloc_n<uint16_t>((size_t)RMAX * TS);
+    p.plan_ptr = dalloc_n<uint16_t>((size_t)RMAX * TS);
+    p.plan_nnz = dalloc_n<int>(RMAX);
+    p.plan_tot = dalloc_n<int>(RMAX + 1);
+    p.plan_off = dalloc_n<int>(RMAX + 1);
+    p.plan_start = dalloc_n<unsigned>((size_t)RMAX * PLAN_ROWS);
+    p.plan_col = dalloc_n<uint8_t>((size_t)RMAX * 256);
+    p.plan_ent = dalloc_n<unsigned>(PLAN_ENT_CAP);
+    p.ctl = dalloc_n<int>(8);
+    if (!p.pkeys || !p.powner || !p.rkeys || !p.rowner || !p.rflags || !p.rdense || !p.rep_tile || !p.plan_mask || !p.plan_ptr ||
+        !p.plan_nnz || !p.plan_tot || !p.plan_off || !p.plan_start || !p.plan_col || !p.plan_ent || !p.ctl) {
+        g_plan = PlanCtx();
+        return last_error();
+    }
+    p.device = c.device;
+    return TSG_OK;
+}
+
+void plans_shutdown() { g_plan = PlanCtx(); }  // the buffers belong to the stream-ordered pool, which tsg_shutdown releases
+
+static bool plans_env_on()
+{
+    const char *e = getenv("TSG_PLANS");
+    return !(e && *e == '0');
+}
+
+// Pattern id of every tile of T (storage order) into T->pat, the number of distinct patterns into T->npat (-1 when there
+// are more than PCAP/2 or a 64-bit hash collision was detected). One read-back; runs at csr2tile / upload time.
+int tile_patterns_device(tsg_dtile *T)
+{
+    Ctx &c = ctx();
+    T->npat = -1;
+    if (!T->pat || T->numtile <= 0 || !plans_env_on()) return TSG_OK;
+    int rc = plan_ctx_init();
+    if (rc) return rc;
+    PlanCtx &p = g_plan;
+    CK(cudaMemsetAsync(p.pkeys, 0, (size_t)PCAP * 8, c.stream));
+    CK(cudaMemsetAsync(p.powner, 0x7f, (size_t)PCAP * 4, c.stream));
+    CK(cudaMemsetAsync(p.ctl, 0, 2 * sizeof(int), c.stream));
+    const int blocks = ceil_div(T->numtile, 256);
+    k_pattern_insert<<<blocks, 256, 0, c.stream>>>(T->numtile, T->mask, p.pkeys, p.powner, p.ctl, T->pat, p.ctl + 1);
+    CK_LAUNCH();
+    k_pattern_verify<<<blocks, 256, 0, c.stream>>>(T->numtile, T->mask, T->pat, p.powner, p.ctl + 1);
+    CK_LAUNCH();
+    rc = publish_words(&c.h_scalars[13], p.ctl, 2);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c.stream));
+    const int *h = (const int *)&c.h_scalars[13];
+    T->npat = h[1] ? -1 : h[0];
+    return TSG_OK;
+}
+
+bool plans_wanted(const tsg_dtile *A, const tsg_dtile *B)
+{
+    const char *forced = getenv("TSG_STEP3");  // a forced numeric kernel (A/B measurements, tests) means the generic path
+    if (forced && *forced && strcmp(forced, "auto")) return false;
+    return plans_env_on() && A->pat && B->pat && A->npat > 0 && B->npat > 0 && A->npat <= PLANS_MAX_PATTERNS && B->npat <= PLANS_MAX_PATTERNS;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Recipes and plans (per spgemm call, after k_s1_fill has inserted every C tile's recipe hash)
+// ---------------------------------------------------------------------------------------------
+// flags[slot] = 1 where the slot has an owner; scanned into dense recipe numbers (rdense).
+__global__ void __launch_bounds__(256)
+k_recipe_flags(const int *__restrict__ owner, int *__restrict__ flags)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < RCAP) flags[s] = owner[s] != NO_OWNER;
+}
+
+__global__ void __launch_bounds__(256)
+k_recipe_reps(const int *__restrict__ owner, const int *__restrict__ rdense, int *__restrict__ rep_tile)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < RCAP && owner[s] != NO_OWNER && rdense[s] < RMAX) rep_tile[rdense[s]] = owner[s];
+}
+
+// every C tile compares its (A pattern, B pattern) sequence with its recipe's representative: a 64-bit collision fails
+__global__ void __launch_bounds__(256)
+k_recipe_verify(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end, const int *__restrict__ pair_a,
+                const int *__restrict__ pair_b, const int *__restrict__ patA, const int *__restrict__ patB,
+                const int *__restrict__ rslot, const int *__restrict__ owner, const int *__restrict__ rdense,
+                int *__restrict__ recipe_id, int *fail)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= numblkC) return;
+    recipe_id[t] = 0;
+    if (*(volatile int *)fail) return;
+    const int slot = rslot[t];
+    if (slot < 0 || slot >= RCAP) { *fail = 1; return; }
+    const int u = owner[slot];
+    if (u < 0 || u >= numblkC || rdense[slot] >= RMAX) { *fail = 1; return; }
+    const int p0 = pair_ptr[t], n = pair_end[t] - p0, q0 = pair_ptr[u];
+    bool same = pair_end[u] - q0 == n;
+    if (u != t)
+        for (int i = 0; i < n && same; i++)
+            same = patA[pair_a[p0 + i]] == patA[pair_a[q0 + i]] && patB[pair_b[p0 + i]] == patB[pair_b[q0 + i]];
+    if (!same) *fail = 2;
+    recipe_id[t] = rdense[slot];
+}
+
+// One thread per distinct recipe. FILL = false: masks / Ptr / nnz of the recipe's C tile and the number of plan entries
+// (plan_tot). FILL = true: plan_off = exclusive scan of plan_tot; writes plan_start, plan_col and the entries
+// (pair index << 16 | position in B's tile << 8 | position in A's tile), in the serial SPA's order.
+template <bool FILL>
+__global__ void __launch_bounds__(64)
+k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, const int *__restrict__ pair_ptr,
+             const int *__restrict__ pair_end, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
+             const uint16_t *__restrict__ a_mask, const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ b_mask,
+             const uint16_t *__restrict__ b_ptr, uint16_t *plan_mask, uint16_t *plan_ptr, int *plan_nnz, int *plan_tot,
+             const int *__restrict__ plan_off, unsigned *plan_start, uint8_t *plan_col, unsigned *plan_ent, int *fail)
+{
+    const int R = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nrec = *nrec_p;
+    if (*(volatile int *)fail) return;
+    if (nrec > RMAX) { if (R == 0) *fail = 1; return; }
+    if (R >= nrec) return;
+    if (FILL && plan_off[nrec] > PLAN_ENT_CAP) { if (R == 0) *fail = 3; return; }
+    const int t = rep_tile[R];
+    const int p0 = pair_ptr[t], p1 = pair_end[t];
+    if (p1 - p0 > 0xFFFF) { *fail = 1; return; }  // the plan entry keeps the pair index in 16 bits
+    unsigned cm[TS];
+    for (int r = 0; r < TS; r++) cm[r] = 0;
+    for (int p = p0; p < p1; p++) {
+        const int a = pair_a[p], b = pair_b[p];
+        for (int r = 0; r < TS; r++) {
+            unsigned am = a_mask[(size_t)a * TS + r];
+            while (am) {
+                const int k = __clz(am) - 16;
+                am ^= 0x8000u >> k;
+                cm[r] |= b_mask[(size_t)b * TS + k];
+            }
+        }
+    }
+    if (!FILL) {
+        int run = 0;
+        for (int r = 0; r < TS; r++) {
+            plan_ptr[R * TS + r] = (uint16_t)run;
+            plan_mask[R * TS + r] = (uint16_t)cm[r];
+            run += __popc(cm[r]);
+        }
+        plan_nnz[R] = run;
+    }
+    unsigned e = FILL ? (unsigned)plan_off[R] : 0u;
+    int j = 0;
+    for (int r = 0; r < TS; r++) {
+        unsigned rowm = cm[r];
+        while (rowm) {
+            const int c = __clz(rowm) - 16;
+            rowm ^= 0x8000u >> c;
+            const unsigned cbit = 0x8000u >> c;
+            if (FILL) { plan_start[(size_t)R * PLAN_ROWS + j] = e; plan_col[(size_t)R * 256 + j] = (uint8_t)c; }
+            for (int p = p0; p < p1; p++) {
+                const int a = pair_a[p], b = pair_b[p];
+                unsigned am = a_mask[(size_t)a * TS + r];
+                unsigned ia = a_ptr[(size_t)a * TS + r];
+                while (am) {
+                    const int k = __clz(am) - 16;
+                    am ^= 0x8000u >> k;
+                    const unsigned bm = b_mask[(size_t)b * TS + k];
+                    if (bm & cbit) {
+                        if (FILL) {
+                            const unsigned posb = (unsigned)b_ptr[(size_t)b * TS + k] + __popc(bm >> (16 - c));
+                            plan_ent[e] = ((unsigned)(p - p0) << 16) | (posb << 8) | ia;
+                        }
+                        e++;
+                    }
+                    ia++;
+                }
+            }
+            j++;
+        }
+    }
+    if (FILL) plan_start[(size_t)R * PLAN_ROWS + j] = e;
+    else plan_tot[R] = (int)e;
+}
+
+// C tile metadata from the plan: thread per (tile, row).
+__global__ void __launch_bounds__(256)
+k_symbolic_from_plans(int numblkC, const int *__restrict__ recipe_id, const uint16_t *__restrict__ plan_mask,
+                      const uint16_t *__restrict__ plan_ptr, const int *__restrict__ plan_nnz, uint16_t *__restrict__ c_mask,
+                      uint16_t *__restrict__ c_ptr, int *__restrict__ c_cnt, const int *__restrict__ fail)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = (int)(gid >> 4), r = (int)(gid & 15);
+    if (t >= numblkC) return;
+    if (*fail) { if (r == 0) c_cnt[t] = 0; return; }  // the generic symbolic step will overwrite everything
+    const int R = recipe_id[t];
+    c_mask[(size_t)t * TS + r] = plan_mask[R * TS + r];
+    c_ptr[(size_t)t * TS + r] = plan_ptr[R * TS + r];
+    if (r == 0) c_cnt[t] = plan_nnz[R];
+}
+
+// Value bases of a pair's two tiles, looked up once per pair by a streaming kernel instead of twice per product.
+__global__ void __launch_bounds__(256)
+k_pair_bases(long long npairs, const int *__restrict__ pair_a, const int *__restrict__ pair_b, const int *__restrict__ a_tile_nnz,
+             const int *__restrict__ b_tile_nnz, int2 *__restrict__ pair_base)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    pair_base[p] = make_int2(a_tile_nnz[pair_a[p]], b_tile_nnz[pair_b[p]]);
+}
+
+__global__ void k_blk2tile_p(int numblkC, const int *__restrict__ c_tile_nnz, int *__restrict__ blk2tile)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= numblkC) return;
+    const int s = c_tile_nnz[t], e = c_tile_nnz[t + 1];
+    for (int blk = (s + 31) >> 5; (blk << 5) < e; blk++) blk2tile[blk] = t;
+}
+
+// One lane per C nonzero g: find its tile (blk2tile gives the tile holding nonzero 32*(g/32)), then walk its plan entries:
+// every iteration is a product, added in the serial SPA's order.
+__global__ void __launch_bounds__(256)
+k_numeric_from_plans(int numblkC, int nnzC, const int *__restrict__ blk2tile, const int *__restrict__ c_tile_nnz,
+                     const int *__restrict__ recipe_id, const unsigned *__restrict__ plan_start,
+                     const uint8_t *__restrict__ plan_col, const unsigned *__restrict__ plan_ent,
+                     const int *__restrict__ pair_ptr, const int2 *__restrict__ pair_base, const double *__restrict__ a_val,
+                     const double *__restrict__ b_val, uint16_t *__restrict__ c_col, double *__restrict__ c_val)
+{
+    const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gl >= nnzC) return;
+    const int g = (int)gl;
+    const int blk = g >> 5, nblk = (nnzC + 31) >> 5;
+    int lo = blk2tile[blk], hi = blk + 1 < nblk ? blk2tile[blk + 1] : numblkC - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (c_tile_nnz[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    const int t = lo, off = g - c_tile_nnz[t];
+    const int R = recipe_id[t];
+    const unsigned s1 = plan_start[(size_t)R * PLAN_ROWS + off + 1];
+    const int2 *pb = pair_base + pair_ptr[t];
+    double acc = 0.0;
+    for (unsigned s = plan_start[(size_t)R * PLAN_ROWS + off]; s < s1; s++) {
+        const unsigned e = plan_ent[s];
+        const int2 base = pb[e >> 16];
+        acc = fma(a_val[base.x + (int)(e & 255u)], b_val[base.y + (int)((e >> 8) & 255u)], acc);
+    }
+    c_val[g] = acc;
+    c_col[g] = plan_col[(size_t)R * 256 + off];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+// Before k_s1_fill<HASH>: clear the recipe table and hand its pointers to the fill kernel.
+int plans_begin(PlanTable *out)
+{
+    Ctx &c = ctx();
+    int rc = plan_ctx_init();
+    if (rc) return rc;
+    PlanCtx &p = g_plan;
+    CK(cudaMemsetAsync(p.rkeys, 0, (size_t)RCAP * 8, c.stream));
+    CK(cudaMemsetAsync(p.rowner, 0x7f, (size_t)RCAP * 4, c.stream));
+    CK(cudaMemsetAsync(p.ctl + 2, 0, 2 * sizeof(int), c.stream));
+    CK(cudaMemsetAsync(p.plan_tot, 0, ((size_t)RMAX + 1) * 4, c.stream));
+    out->keys = p.rkeys; out->owner = p.rowner; out->count = p.ctl + 2; out->fail = p.ctl + 3;
+    return TSG_OK;
+}
+
+// After k_s1_fill<HASH>: dense recipe numbers, verification, the plans, and C's masks / Ptr / tile nnz counts from them.
+// Everything is enqueued; *d_fail is the device flag the caller reads back with nnz(C).
+int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const int *rslot, int *recipe_id,
+                          const int **d_fail)
+{
+    Ctx &c = ctx();
+    PlanCtx &p = g_plan;
+    const int numblkC = C->numtile;
+    int *fail = p.ctl + 3;
+    *d_fail = fail;
+    k_recipe_flags<<<ceil_div(RCAP, 256), 256, 0, c.stream>>>(p.rowner, p.rflags);
+    CK_LAUNCH();
+    int rc = exclusive_scan<int>(p.rflags, p.rdense, RCAP);
+    if (rc) return rc;
+    k_recipe_reps<<<ceil_div(RCAP, 256), 256, 0, c.stream>>>(p.rowner, p.rdense, p.rep_tile);
+    CK_LAUNCH();
+    k_recipe_verify<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>(numblkC, pl.ptr, pl.end, pl.a, pl.b, A->pat, B->pat, rslot, p.rowner,
+                                                                  p.rdense, recipe_id, fail);
+    CK_LAUNCH();
+    const int *nrec = p.rdense + RCAP;
+    k_plan_build<false><<<ceil_div(RMAX, 64), 64, 0, c.stream>>>(nrec, p.rep_tile, pl.ptr, pl.end, pl.a, pl.b, A->mask, A->ptr, B->mask, B->ptr,
+                                                                 p.plan_mask, p.plan_ptr, p.plan_nnz, p.plan_tot, nullptr, nullptr, nullptr,
+                                                                 nullptr, fail);
+    CK_LAUNCH();
+    rc = exclusive_scan<int>(p.plan_tot, p.plan_off, RMAX);
+    if (rc) return rc;
+    k_plan_build<true><<<ceil_div(RMAX, 64), 64, 0, c.stream>>>(nrec, p.rep_tile, pl.ptr, pl.end, pl.a, pl.b, A->mask, A->ptr, B->mask, B->ptr,
+                                                                p.plan_mask, p.plan_ptr, p.plan_nnz, p.plan_tot, p.plan_off, p.plan_start,
+                                                                p.plan_col, p.plan_ent, fail);
+    CK_LAUNCH();
+    k_symbolic_from_plans<<<ceil_div((long long)numblkC * 16, 256), 256, 0, c.stream>>>(numblkC, recipe_id, p.plan_mask, p.plan_ptr, p.plan_nnz,
+                                                                                       C->mask, C->ptr, C->tile_nnz, fail);
+    CK_LAUNCH();
+    return TSG_OK;
+}
+
+size_t plans_numeric_scratch_bytes(long long pairs, long long nnzC)
+{
+    return arena_need((size_t)(pairs > 0 ? pairs : 1), 8) + arena_need((size_t)((nnzC + 31) >> 5) + 1, 4);
+}
+
+int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, long long pairs, const int *recipe_id,
+                         tsg_stats *stats)
+{
+    Ctx &c = ctx();
+    PlanCtx &p = g_plan;
+    const long long numblkC = C->numtile, nnzC = C->nnz;
+    if (nnzC <= 0 || numblkC <= 0) return TSG_OK;
+    if (!arena_reserve(2, plans_numeric_scratch_bytes(pairs, nnzC))) return last_error();
+    int2 *pair_base = arena_take<int2>(2, (size_t)(pairs > 0 ? pairs : 1));
+    int *blk2tile = arena_take<int>(2, (size_t)((nnzC + 31) >> 5) + 1);
+    if (!pair_base || !blk2tile) return last_error();
+    k_pair_bases<<<ceil_div(pairs, 256), 256, 0, c.stream>>>(pairs, pl.a, pl.b, A->tile_nnz, B->tile_nnz, pair_base);
+    CK_LAUNCH();
+    k_blk2tile_p<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>((int)numblkC, C->tile_nnz, blk2tile);
+    CK_LAUNCH();
+    k_numeric_from_plans<<<ceil_div(nnzC, 256), 256, 0, c.stream>>>((int)numblkC, (int)nnzC, blk2tile, C->tile_nnz, recipe_id, p.plan_start,
+                                                                    p.plan_col, p.plan_ent, pl.ptr, pair_base, A->val, B->val, C->col, C->val);
+    CK_LAUNCH();
+    if (stats) stats->plan_recipes = 1;  // the caller fills in the count it read back
+    return TSG_OK;
+}
+
+const int *plans_recipe_count_ptr() { return g_plan.rdense ? g_plan.rdense + RCAP : nullptr; }
+
+}  // namespace tsg

@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "scan.cuh"
 #include "kernels.h"
+#include "plans.cuh"
 
 namespace tsg {
 
@@ -204,7 +205,7 @@ k_s1_count(int trow0, int ntr, int bmw, const int *__restrict__ a_tile_ptr, cons
 // k_s1_fill: everything else of steps 1 and 2 for a light tile-row (see the file header).
 // Per-warp shared memory (32-bit words): bitmap[bmw] | pre[bmw] u16 | cur[nj] | (FUSE) bmT[16][32] u16 | cm[16][njpad] u16.
 struct S1Fill {
-    int trow0, ntr, bmw, nj, njpad, warp_words;
+    int trow0, ntr, bmw, nj, njpad, warp_words, hoff;
     const int *a_tile_ptr, *a_tile_col, *b_tile_ptr, *b_tile_col, *b_rm2csc;
     const int *jlo, *jhi, *wptr, *c_tile_ptr;
     const uint8_t *light;
@@ -213,13 +214,19 @@ struct S1Fill {
     const uint16_t *a_mask, *b_mask;
     uint16_t *c_ptr, *c_mask;
     int *c_cnt;
+    // HASH: the recipe of every C tile (plans.cu) -- pattern ids of A's and B's tiles, the recipe table, the slot per C tile
+    const int *pat_a, *pat_b;
+    PlanTable table;
+    int *rslot;
 };
 
-template <bool FUSE>
+// FUSE: fused bitmask symbolic. HASH: instead, hash every C tile's (A pattern, B pattern) sequence into the recipe table
+// (per-warp shared memory then holds hh[nj] 64-bit running hashes in place of bmT / cm).
+template <bool FUSE, bool HASH>
 __global__ void __launch_bounds__(S1_WARPS * 32, 4)
 k_s1_fill(const __grid_constant__ S1Fill P)
 {
-    extern __shared__ unsigned s1f_smem[];
+    extern __shared__ __align__(16) unsigned s1f_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * S1_WARPS + warp;
     if (i >= P.ntr || !P.light[i]) return;
@@ -228,6 +235,7 @@ k_s1_fill(const __grid_constant__ S1Fill P)
     int *cur = reinterpret_cast<int *>(bitmap + P.bmw + P.bmw / 2);
     uint16_t *bmT = reinterpret_cast<uint16_t *>(cur + P.nj);  // [16][32]: row mask k of lane's B tile
     uint16_t *cm = bmT + TS * 32;                               // [16][njpad]: C's row masks of the tile-row
+    unsigned long long *hh = reinterpret_cast<unsigned long long *>(bitmap + P.hoff);  // HASH: [nj], 8-byte aligned (warp_words, hoff even)
     const int I = P.trow0 + i;
     const int lo = P.jlo[i] & ~31, nw = ((P.jhi[i] - lo) >> 5) + 1;
     const int a0 = P.a_tile_ptr[I], a1 = P.a_tile_ptr[I + 1];
@@ -273,6 +281,8 @@ k_s1_fill(const __grid_constant__ S1Fill P)
         }
     }
     for (int k = lane; k < numJ; k += 32) cur[k] = 0;
+    if (HASH)
+        for (int k = lane; k < numJ; k += 32) hh[k] = 0x13198A2E03707344ull;
     if (FUSE)
         for (int k = lane; k < TS * P.njpad / 2; k += 32) reinterpret_cast<unsigned *>(cm)[k] = 0;
     __syncwarp();
@@ -352,14 +362,22 @@ k_s1_fill(const __grid_constant__ S1Fill P)
             const int d = P.b_tile_col[tb] - lo, wd = d >> 5;
             const int slot = pre[wd] + __popc(bitmap[wd] & ((1u << (d & 31)) - 1));
             const int pos = cur[slot]++;
+            const int b = P.b_rm2csc[tb];
             P.pair_a[pos] = ta;
-            P.pair_b[pos] = P.b_rm2csc[tb];
+            P.pair_b[pos] = b;
+            if (HASH) hh[slot] = plans::mix64(hh[slot], ((unsigned long long)(unsigned)P.pat_a[ta] << 32) | (unsigned)P.pat_b[b]);
         }
         __syncwarp();
     }
     // 7. list ends; Ptr (exclusive row offsets), mask and nnz of each C tile
     for (int sl = lane; sl < numJ; sl += 32) {
         P.pair_end[cbase + sl] = cur[sl];
+        if (HASH) {  // the recipe of C tile cbase + sl: its slot in the table; the smallest tile index owns the slot
+            const int t = cbase + sl;
+            const int slot = plans::table_insert(P.table.keys, plans::RCAP, hh[sl], P.table.count, plans::RMAX, P.table.fail);
+            P.rslot[t] = slot;
+            if (slot >= 0 && t < *(volatile int *)&P.table.owner[slot]) atomicMin(&P.table.owner[slot], t);
+        }
         if (FUSE) {
             unsigned pw[8], mw[8];
             int run = 0;
@@ -780,14 +798,18 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     rc = copy_words(C->tile_ptr, c_tile_ptr, (size_t)ntr + 1);
     if (rc) return rc;
     const bool heavy_rows = n_heavy > 0;  // tile-rows on the multi-warp path park one 16-byte record per pair
-    if (!arena_reserve(1, 2 * arena_need(nb + 1, 4) + 2 * arena_need(np, 4) + arena_need(np, 2) + (heavy_rows ? arena_need(np, 16) : 0) +
+    if (!arena_reserve(1, 4 * arena_need(nb + 1, 4) + 2 * arena_need(np, 4) + arena_need(np, 2) + (heavy_rows ? arena_need(np, 16) : 0) +
                               numeric_scratch_bytes(ntr, numblkC)))
         return last_error();
     int *pair_ptr = arena_take<int>(1, nb + 1), *pair_end = arena_take<int>(1, nb + 1), *pair_a = arena_take<int>(1, np), *pair_b = arena_take<int>(1, np);
     uint16_t *pair_slot = arena_take<uint16_t>(1, np);
     int4 *pair_tmp = heavy_rows ? arena_take<int4>(1, np) : nullptr;
     NumericBufs nbufs{arena_take<uint8_t>(1, (size_t)ntr + 1), arena_take<int>(1, nb), 0, 0};
-    if (!pair_ptr || !pair_end || !pair_a || !pair_b || !pair_slot || (heavy_rows && !pair_tmp) || !nbufs.row_kind || !nbufs.dense_list)
+    // recipe plans (plans.cu): attempted when both operands are made of few distinct tile patterns and no tile-row is heavy
+    bool plans_on = plans_wanted(A, B) && !heavy_rows && numblkC > 0 && pairs > 0;
+    int *rslot = plans_on ? arena_take<int>(1, nb) : nullptr, *recipe_id = plans_on ? arena_take<int>(1, nb) : nullptr;
+    if (!pair_ptr || !pair_end || !pair_a || !pair_b || !pair_slot || (heavy_rows && !pair_tmp) || !nbufs.row_kind || !nbufs.dense_list ||
+        (plans_on && (!rslot || !recipe_id)))
         return last_error();
     if (heavy_rows) CK(cudaMemsetAsync(pair_end, 0, nb * 4, c.stream));  // the heavy kernel counts with atomics
     CK(cudaEventRecord(ev[2], c.stream));  // [1..2] = allocation
@@ -798,22 +820,34 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     // block-FEM has 3 and is faster through k_step2).
     static const int fuse_env = getenv("TSG_FUSE") ? atoi(getenv("TSG_FUSE")) : -1;
     bool fused = false;
+    PlanTable ptab{nullptr, nullptr, nullptr, nullptr};
+    if (plans_on) {
+        rc = plans_begin(&ptab);
+        if (rc) return rc;
+    }
     if (numblkC > 0 && n_light > 0) {
         const int bmw = (hs[SC_NW_LIGHT] + 1) & ~1, nj = hs[SC_MAXJ], njpad = nj | 1;  // odd row stride: fewer bank conflicts
-        const bool want = fuse_env >= 0 ? fuse_env != 0 : (long long)B->numtile >= 4ll * B->tilem;
+        const bool want = !plans_on && (fuse_env >= 0 ? fuse_env != 0 : (long long)B->numtile >= 4ll * B->tilem);
         int warp_words = bmw + bmw / 2 + nj + (TS * 32) / 2 + (TS * njpad + 1) / 2;
         fused = want && (size_t)S1_WARPS * warp_words * 4 <= c.smem_optin;
-        if (!fused) warp_words = bmw + bmw / 2 + nj;
-        S1Fill P{trow0, ntr, bmw, nj, njpad, warp_words, A->tile_ptr, A->tile_columnidx, B->tile_ptr, B->tile_columnidx, B->rm2csc,
+        const int hoff = (bmw + bmw / 2 + nj + 1) & ~1;
+        if (!fused) warp_words = plans_on ? hoff + 2 * nj : bmw + bmw / 2 + nj;
+        warp_words = (warp_words + 1) & ~1;
+        S1Fill P{trow0, ntr, bmw, nj, njpad, warp_words, hoff, A->tile_ptr, A->tile_columnidx, B->tile_ptr, B->tile_columnidx, B->rm2csc,
                  jlo, jhi, wptr, C->tile_ptr, light, C->tile_columnidx, C->tile_rowidx, pair_ptr, pair_end, pair_a, pair_b, pair_slot,
-                 A->mask, B->mask, C->ptr, C->mask, C->tile_nnz};
+                 A->mask, B->mask, C->ptr, C->mask, C->tile_nnz, A->pat, B->pat, ptab, rslot};
         const size_t smem = (size_t)S1_WARPS * warp_words * 4;
+        if (smem > c.smem_optin) { set_error(TSG_ERR_UNSUPPORTED, "step 1: %zu B of shared memory per CTA needed (> %zu)", smem, c.smem_optin); return last_error(); }
+        const int blocks = ceil_div(ntr, S1_WARPS);
         if (fused) {
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_s1_fill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_s1_fill<true><<<ceil_div(ntr, S1_WARPS), S1_WARPS * 32, smem, c.stream>>>(P);
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_s1_fill<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_s1_fill<true, false><<<blocks, S1_WARPS * 32, smem, c.stream>>>(P);
+        } else if (plans_on) {
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_s1_fill<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_s1_fill<false, true><<<blocks, S1_WARPS * 32, smem, c.stream>>>(P);
         } else {
-            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_s1_fill<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_s1_fill<false><<<ceil_div(ntr, S1_WARPS), S1_WARPS * 32, smem, c.stream>>>(P);
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_s1_fill<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_s1_fill<false, false><<<blocks, S1_WARPS * 32, smem, c.stream>>>(P);
         }
         CK_LAUNCH();
     }
@@ -827,10 +861,12 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
 
     // ---------------- step 2 ----------------
     CK(cudaEventRecord(ev_s2, c.stream));
+    const PairLists plists{pair_ptr, pair_end, pair_a, pair_b, pair_slot};
+    const int *d_plan_fail = nullptr;
     // pair-based symbolic for the C tiles the fused step-1 path did not cover: half-warp per tile, or thread per
     // tile when the tiles are hypersparse (<= 2 pairs per C tile and <= 2 entries per A tile on average)
-    if (numblkC > 0 && (!fused || n_heavy > 0)) {
-        const uint8_t *lf = fused ? light : nullptr;
+    auto generic_symbolic = [&](bool skip_light) -> int {
+        const uint8_t *lf = skip_light ? light : nullptr;
         const bool hypersparse = pairs <= 2 * numblkC && A->nnz <= 2ll * A->numtile;
         if (hypersparse)
             k_step2_thread<<<ceil_div(numblkC, S2T_THREADS), S2T_THREADS, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b,
@@ -840,17 +876,42 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
             k_step2<<<ceil_div(numblkC * 16, 128), 128, 0, c.stream>>>((int)numblkC, pair_ptr, pair_end, pair_a, pair_b, A->mask, B->mask,
                                                                        C->ptr, C->mask, C->tile_nnz, C->tile_rowidx, lf, trow0);
         CK_LAUNCH();
+        return TSG_OK;
+    };
+    if (plans_on) {  // C's masks / Ptr / tile nnz from the recipe plans (or nothing useful, if the fail flag comes up)
+        rc = plans_symbolic_device(A, B, C, plists, rslot, recipe_id, &d_plan_fail);
+        if (rc) return rc;
+    } else if (numblkC > 0 && (!fused || n_heavy > 0)) {
+        rc = generic_symbolic(fused);
+        if (rc) return rc;
     }
     rc = exclusive_scan<int>(C->tile_nnz, C->tile_nnz, numblkC, tot);
     if (rc) return rc;
     // pick the accumulator per C tile-row / tile (numeric.cu); its counters come back with nnz(C) in one read-back
     int *d_ns = (int *)(c.d_scalars + 16);
-    rc = numeric_classify_device(A, C, trow0, ntr, wptr, light, &nbufs, d_ns);
-    if (rc) return rc;
     long long nnzC = 0;
-    rc = publish_words(&c.h_scalars[16], d_ns, 8);
-    if (!rc) rc = read_back_i64(tot, &nnzC);
-    if (rc) return rc;
+    int plan_recipes = 0;
+    if (plans_on) {
+        rc = publish_words(&c.h_scalars[20], d_plan_fail, 1);
+        if (!rc) rc = publish_words(&c.h_scalars[21], plans_recipe_count_ptr(), 1);
+        if (!rc) rc = read_back_i64(tot, &nnzC);
+        if (rc) return rc;
+        if (*(const volatile int *)&c.h_scalars[20]) {  // a collision or too many recipes: the generic kernels run instead
+            plans_on = false;
+            plan_recipes = -1;
+            rc = generic_symbolic(false);
+            if (!rc) rc = exclusive_scan<int>(C->tile_nnz, C->tile_nnz, numblkC, tot);
+            if (rc) return rc;
+        } else {
+            plan_recipes = *(const volatile int *)&c.h_scalars[21];
+        }
+    }
+    if (!plans_on) {
+        rc = numeric_classify_device(A, C, trow0, ntr, wptr, light, &nbufs, d_ns);
+        if (!rc) rc = publish_words(&c.h_scalars[16], d_ns, 8);
+        if (!rc) rc = read_back_i64(tot, &nnzC);
+        if (rc) return rc;
+    }
     if (nnzC >= (1ll << 31)) {
         set_error(TSG_ERR_OVERFLOW, "spgemm: nnz(C) = %lld in tile-rows [%d,%d) exceeds int32; use smaller slabs", nnzC, trow0, trow1);
         return last_error();
@@ -873,7 +934,8 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     CK(cudaEventRecord(ev_s3, c.stream));
     tsg_stats nst;
     memset(&nst, 0, sizeof(nst));
-    rc = numeric_device(A, B, C, trow0, ntr, wptr, PairLists{pair_ptr, pair_end, pair_a, pair_b, pair_slot}, nbufs, h_ns, heavy_rows, &nst);
+    if (plans_on) rc = plans_numeric_device(A, B, C, plists, pairs, recipe_id, &nst);
+    else rc = numeric_device(A, B, C, trow0, ntr, wptr, plists, nbufs, h_ns, heavy_rows, &nst);
     if (rc) return rc;
     CK(cudaEventRecord(ev[4], c.stream));
     if (stats && ntr != A->tilem) {  // the slab's share of A (tiles, nonzeros) for the byte count below
@@ -900,6 +962,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         stats->launches = (int)(c.launches - launches0);
         stats->rows_staged = nst.rows_staged; stats->rows_gather = nst.rows_gather; stats->tiles_dense = nst.tiles_dense;
         stats->rows_smem = nst.rows_smem; stats->tiles_nonempty = nst.tiles_nonempty;
+        stats->plan_recipes = plan_recipes;
         // algorithmic bytes, SURVEY.md 8(d). A's share is the slab's tiles; B is read whole.
         long long a_tiles = A->numtile, a_nnz = A->nnz;
         if (ntr != A->tilem) {

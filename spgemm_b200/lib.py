@@ -51,6 +51,7 @@ class DTile(C.Structure):
         ("tile_ptr", C.c_void_p), ("tile_columnidx", C.c_void_p), ("tile_rowidx", C.c_void_p), ("tile_nnz", C.c_void_p),
         ("val", C.c_void_p), ("col", C.c_void_p), ("ptr", C.c_void_p), ("mask", C.c_void_p),
         ("csc_tile_ptr", C.c_void_p), ("csc_tile_rowidx", C.c_void_p), ("rm2csc", C.c_void_p),
+        ("pat", C.c_void_p), ("npat", C.c_int),
         ("slab", C.c_void_p * 4), ("slab_bytes", C.c_size_t * 4),
     ]
 
@@ -60,7 +61,7 @@ class Stats(C.Structure):
                 ("ms_step1", C.c_double), ("ms_step2", C.c_double), ("ms_step3", C.c_double),
                 ("ms_alloc", C.c_double), ("ms_total", C.c_double),
                 ("algorithmic_bytes", C.c_longlong), ("launches", C.c_int),
-                ("rows_staged", C.c_int), ("rows_gather", C.c_int), ("tiles_dense", C.c_int), ("rows_smem", C.c_int), ("tiles_nonempty", C.c_int)]
+                ("rows_staged", C.c_int), ("rows_gather", C.c_int), ("tiles_dense", C.c_int), ("rows_smem", C.c_int), ("tiles_nonempty", C.c_int), ("plan_recipes", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -228,13 +228,14 @@ def distribute(A_host, aat: bool, dist=None, device=None, mode: str = "csr") -> 
     if mode == "csr" or world == 1:
         tB = api.csr2tile(dB, True)
     else:  # rank 0 tiles B and broadcasts the tiled matrix as one buffer
-        sizes = torch.zeros(2, dtype=torch.int64, device=device)
+        sizes = torch.zeros(3, dtype=torch.int64, device=device)
         if rank == 0:
             tB = api.csr2tile(dB, True)
-            sizes = torch.tensor([tB.numtile, tB.nnz], dtype=torch.int64, device=device)
-        nt, bnnz = (int(x) for x in bcast(sizes).cpu())
+            sizes = torch.tensor([tB.numtile, tB.nnz, tB.d.npat], dtype=torch.int64, device=device)
+        nt, bnnz, npat = (int(x) for x in bcast(sizes).cpu())
         if rank != 0:
             tB = api.tile_alloc(dB.m, dB.n, nt, bnnz, True)
+            tB.d.npat = npat  # the pattern ids travel inside the slab; their count does not
         slab = tile_slab_tensor(tB, device)
         torch.cuda.synchronize(device)
         dist.barrier()

@@ -662,3 +662,75 @@ def test_csr_row_slice_is_a_csr_of_its_own():
             t.free()
         s_.free()
     d.free()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Recipe plans (csrc/plans.cu): a fast path of steps 2 and 3 for matrices made of few distinct tiles; same results
+# ---------------------------------------------------------------------------------------------------------------
+STRUCTURED = {
+    "stencil27_12x9x8": lambda: M.stencil27(12, 9, 8),
+    "stencil27_17": lambda: M.stencil27(17),          # edge not a multiple of 16: many more patterns and recipes
+    "lap2d_70x33": lambda: M.lap2d(70, 33),
+    "blockfem_200": lambda: M.blockfem(200),
+    "blockfem_band2": lambda: M.blockfem(60, dof=6, band=2),
+}
+
+
+@pytest.mark.parametrize("plans", ["1", "0"])
+@pytest.mark.parametrize("values", ["mod10", "hash"])
+@pytest.mark.parametrize("name", sorted(STRUCTURED))
+def test_recipe_plans_same_result(monkeypatch, name, values, plans):
+    monkeypatch.setenv("TSG_PLANS", plans)
+    m, n, rp, ci, _ = STRUCTURED[name]()
+    v = M.set_values(len(ci), values)
+    A = (rp, ci, v)
+    csrC, tC_exp = oracle_c(m, n, A, A, n)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
+    tC, st = api.spgemm(tA, tB)
+    assert (st["plan_recipes"] > 0) == (plans == "1"), st
+    # the plans add every C entry's products in the serial SPA's order: bit-exact for integer values, 1e-12 otherwise
+    assert_tiled_equal(tC.download(), tC_exp, f"{name}/{values}/plans={plans}", val_rtol=0.0 if values == "mod10" else VAL_RTOL)
+    r, c, vv = (x for x in api.tile2csr_device(tC).download())
+    assert np.array_equal(r, csrC[0]) and np.array_equal(c, csrC[1])
+    # slabs share the recipe machinery: a sub-range of tile-rows through the plans
+    t0, t1 = 1, max(2, tA.tilem - 1)
+    sub = orc.spgemm_spa(A, A, n, t0 * 16, min(t1 * 16, m))
+    tS, st2 = api.spgemm(tA, tB, t0, t1)
+    exp = orc.ctiles_from_csr(m, n, orc.csr2tile_row_major(m, n, *A), orc.csr2tile_col_major(m, n, *A), sub, t0, t1)
+    assert_tiled_equal(tS.download(), exp, f"{name} slab, plans={plans}", val_rtol=0.0 if values == "mod10" else VAL_RTOL)
+    for o in (tS, tC, tA, tB, d):
+        o.free()
+
+
+def test_recipe_plans_fall_back_when_recipes_do_not_repeat(monkeypatch):
+    """Few tile patterns but tens of thousands of distinct pair sequences: the recipe table overflows, the fail flag
+    comes up and the generic kernels produce the result (stats say -1)."""
+    monkeypatch.setenv("TSG_PLANS", "1")
+    import scipy.sparse as sp
+    rng = np.random.default_rng(7)
+    T = 256                                             # tiles per side, n = 4096
+    pats = [sp.random(16, 16, density=0.04, random_state=s, format="coo") for s in range(4)]
+    tiles = sp.random(T, T, density=0.06, random_state=11, format="coo")
+    rows, cols = [], []
+    for I, J in zip(tiles.row, tiles.col):
+        pm = pats[rng.integers(0, 4)]
+        rows.append(I * 16 + pm.row)
+        cols.append(J * 16 + pm.col)
+    S = sp.csr_matrix((np.ones(sum(len(r_) for r_ in rows)), (np.concatenate(rows), np.concatenate(cols))), shape=(T * 16, T * 16))
+    S.sum_duplicates(); S.sort_indices()
+    m = n = T * 16
+    rp, ci = S.indptr.astype(np.int32), S.indices.astype(np.int32)
+    v = M.set_values(len(ci), "mod10")
+    A = (rp, ci, v)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
+    assert 0 < tA.d.npat <= 16 and 0 < tB.d.npat <= 16
+    tC, st = api.spgemm(tA, tB)
+    assert st["plan_recipes"] == -1, st
+    csr = api.tile2csr_device(tC)
+    r, c, vv = csr.download()
+    er, ec, ev = orc.spgemm_spa(A, A, n)
+    assert np.array_equal(r, er) and np.array_equal(c, ec) and np.array_equal(vv, ev)
+    for o in (csr, tC, tA, tB, d):
+        o.free()
