@@ -42,8 +42,8 @@ int tile_patterns_device(tsg_dtile *T);
 bool plans_wanted(const tsg_dtile *A, const tsg_dtile *B);
 int plans_begin(PlanTable *out);
 int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const int *rslot, int *recipe_id,
-                          const int **d_fail);
-int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, long long pairs, const int *recipe_id,
+                          void *pair_base, const int **d_fail);
+int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const void *pair_base, const int *recipe_id,
                          tsg_stats *stats);
 const int *plans_recipe_count_ptr();
 void plans_shutdown();

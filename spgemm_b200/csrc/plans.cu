@@ -68,7 +68,8 @@ struct PlanCtx {
     int *rowner = nullptr, *rflags = nullptr, *rdense = nullptr, *rep_tile = nullptr;
     uint16_t *plan_mask = nullptr, *plan_ptr = nullptr;
     int *plan_nnz = nullptr, *plan_tot = nullptr, *plan_off = nullptr;
-    unsigned *plan_start = nullptr, *plan_ent = nullptr;
+    unsigned *plan_ent = nullptr;
+    uint16_t *plan_cnt = nullptr;
     uint8_t *plan_col = nullptr;
     int *ctl = nullptr;  // [0] pattern count, [1] pattern fail, [2] recipe count, [3] recipe / plan fail
     int device = -1;
@@ -93,12 +94,12 @@ static int plan_ctx_init()
     p.plan_nnz = dalloc_n<int>(RMAX);
     p.plan_tot = dalloc_n<int>(RMAX + 1);
     p.plan_off = dalloc_n<int>(RMAX + 1);
-    p.plan_start = dalloc_n<unsigned>((size_t)RMAX * PLAN_ROWS);
+    p.plan_cnt = dalloc_n<uint16_t>((size_t)RMAX * 256);
     p.plan_col = dalloc_n<uint8_t>((size_t)RMAX * 256);
     p.plan_ent = dalloc_n<unsigned>(PLAN_ENT_CAP);
     p.ctl = dalloc_n<int>(8);
     if (!p.pkeys || !p.powner || !p.rkeys || !p.rowner || !p.rflags || !p.rdense || !p.rep_tile || !p.plan_mask || !p.plan_ptr ||
-        !p.plan_nnz || !p.plan_tot || !p.plan_off || !p.plan_start || !p.plan_col || !p.plan_ent || !p.ctl) {
+        !p.plan_nnz || !p.plan_tot || !p.plan_off || !p.plan_cnt || !p.plan_col || !p.plan_ent || !p.ctl) {
         g_plan = PlanCtx();
         return last_error();
     }
@@ -165,11 +166,14 @@ k_recipe_reps(const int *__restrict__ owner, const int *__restrict__ rdense, int
     if (s < RCAP && owner[s] != NO_OWNER && rdense[s] < RMAX) rep_tile[rdense[s]] = owner[s];
 }
 
-// every C tile compares its (A pattern, B pattern) sequence with its recipe's representative: a 64-bit collision fails
+// every C tile compares its (A pattern, B pattern) sequence with its recipe's representative: a 64-bit collision fails.
+// While the pair list is in hand, the value bases of each pair's two tiles are written out (pair_base): the numeric
+// kernel then needs one 8-byte load per product instead of two index loads and two gathers.
 __global__ void __launch_bounds__(256)
 k_recipe_verify(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end, const int *__restrict__ pair_a,
                 const int *__restrict__ pair_b, const int *__restrict__ patA, const int *__restrict__ patB,
                 const int *__restrict__ rslot, const int *__restrict__ owner, const int *__restrict__ rdense,
+                const int *__restrict__ a_tile_nnz, const int *__restrict__ b_tile_nnz, int2 *__restrict__ pair_base,
                 int *__restrict__ recipe_id, int *fail)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,113 +186,118 @@ k_recipe_verify(int numblkC, const int *__restrict__ pair_ptr, const int *__rest
     if (u < 0 || u >= numblkC || rdense[slot] >= RMAX) { *fail = 1; return; }
     const int p0 = pair_ptr[t], n = pair_end[t] - p0, q0 = pair_ptr[u];
     bool same = pair_end[u] - q0 == n;
-    if (u != t)
-        for (int i = 0; i < n && same; i++)
-            same = patA[pair_a[p0 + i]] == patA[pair_a[q0 + i]] && patB[pair_b[p0 + i]] == patB[pair_b[q0 + i]];
+    for (int i = 0; i < n; i++) {
+        const int a = pair_a[p0 + i], b = pair_b[p0 + i];
+        pair_base[p0 + i] = make_int2(a_tile_nnz[a], b_tile_nnz[b]);
+        if (same && u != t) same = patA[a] == patA[pair_a[q0 + i]] && patB[b] == patB[pair_b[q0 + i]];
+    }
     if (!same) *fail = 2;
     recipe_id[t] = rdense[slot];
 }
 
-// One thread per distinct recipe. FILL = false: masks / Ptr / nnz of the recipe's C tile and the number of plan entries
-// (plan_tot). FILL = true: plan_off = exclusive scan of plan_tot; writes plan_start, plan_col and the entries
-// (pair index << 16 | position in B's tile << 8 | position in A's tile), in the serial SPA's order.
+// A HALF-WARP per distinct recipe, lane = row r of the recipe's representative C tile. FILL = false: masks / Ptr / nnz of
+// the tile, the number of products of every C nonzero (plan_cnt) and the space the recipe's entries take (plan_tot =
+// nnz * the longest product list). FILL = true: plan_off = exclusive scan of plan_tot; writes the entries
+// (pair index << 16 | position in B's tile << 8 | position in A's tile), in the serial SPA's order, ITERATION-MAJOR:
+// product i of nonzero j lives at plan_off[R] + i * nnz + j, so the lanes of the numeric kernel -- consecutive nonzeros of a
+// tile, all at iteration i -- read consecutive words.
 template <bool FILL>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128)
 k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, const int *__restrict__ pair_ptr,
              const int *__restrict__ pair_end, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
              const uint16_t *__restrict__ a_mask, const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ b_mask,
              const uint16_t *__restrict__ b_ptr, uint16_t *plan_mask, uint16_t *plan_ptr, int *plan_nnz, int *plan_tot,
-             const int *__restrict__ plan_off, unsigned *plan_start, uint8_t *plan_col, unsigned *plan_ent, int *fail)
+             const int *__restrict__ plan_off, uint16_t *plan_cnt, uint8_t *plan_col, unsigned *plan_ent, int *fail)
 {
-    const int R = blockIdx.x * blockDim.x + threadIdx.x;
+    const int R = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, r = threadIdx.x & 15;
+    const unsigned hm = 0xFFFFu << (threadIdx.x & 16);
     const int nrec = *nrec_p;
     if (*(volatile int *)fail) return;
-    if (nrec > RMAX) { if (R == 0) *fail = 1; return; }
-    if (R >= nrec) return;
-    if (FILL && plan_off[nrec] > PLAN_ENT_CAP) { if (R == 0) *fail = 3; return; }
+    if (nrec > RMAX) { if (R == 0 && r == 0) *fail = 1; return; }
+    if (R >= nrec) return;  // whole half-warps leave together
+    if (FILL && plan_off[nrec] > PLAN_ENT_CAP) { if (R == 0 && r == 0) *fail = 3; return; }
     const int t = rep_tile[R];
     const int p0 = pair_ptr[t], p1 = pair_end[t];
     if (p1 - p0 > 0xFFFF) { *fail = 1; return; }  // the plan entry keeps the pair index in 16 bits
-    unsigned cm[TS];
-    for (int r = 0; r < TS; r++) cm[r] = 0;
+    unsigned cm = 0;
     for (int p = p0; p < p1; p++) {
         const int a = pair_a[p], b = pair_b[p];
-        for (int r = 0; r < TS; r++) {
+        unsigned am = a_mask[(size_t)a * TS + r];
+        while (am) {
+            const int k = __clz(am) - 16;
+            am ^= 0x8000u >> k;
+            cm |= b_mask[(size_t)b * TS + k];
+        }
+    }
+    const int n = __popc(cm);
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int v = __shfl_up_sync(hm, incl, o, 16);
+        if (r >= o) incl += v;
+    }
+    const int rowbase = incl - n, nnz = __shfl_sync(hm, incl, 15, 16);
+    if (!FILL) {
+        plan_ptr[R * TS + r] = (uint16_t)rowbase;
+        plan_mask[R * TS + r] = (uint16_t)cm;
+        if (r == 0) plan_nnz[R] = nnz;
+    }
+    const unsigned base = FILL ? (unsigned)plan_off[R] : 0u;
+    int longest = 0, j = rowbase;
+    unsigned rowm = cm;
+    while (rowm) {
+        const int c = __clz(rowm) - 16;
+        rowm ^= 0x8000u >> c;
+        const unsigned cbit = 0x8000u >> c;
+        int i = 0;
+        for (int p = p0; p < p1; p++) {
+            const int a = pair_a[p], b = pair_b[p];
             unsigned am = a_mask[(size_t)a * TS + r];
+            unsigned ia = a_ptr[(size_t)a * TS + r];
             while (am) {
                 const int k = __clz(am) - 16;
                 am ^= 0x8000u >> k;
-                cm[r] |= b_mask[(size_t)b * TS + k];
+                const unsigned bm = b_mask[(size_t)b * TS + k];
+                if (bm & cbit) {
+                    if (FILL) {
+                        const unsigned posb = (unsigned)b_ptr[(size_t)b * TS + k] + __popc(bm >> (16 - c));
+                        plan_ent[base + (unsigned)i * (unsigned)nnz + (unsigned)j] = ((unsigned)(p - p0) << 16) | (posb << 8) | ia;
+                    }
+                    i++;
+                }
+                ia++;
             }
         }
+        if (!FILL) {
+            if (i > 0xFFFF) *fail = 1;
+            plan_cnt[(size_t)R * 256 + j] = (uint16_t)i;
+            plan_col[(size_t)R * 256 + j] = (uint8_t)c;
+        }
+        longest = max(longest, i);
+        j++;
     }
     if (!FILL) {
-        int run = 0;
-        for (int r = 0; r < TS; r++) {
-            plan_ptr[R * TS + r] = (uint16_t)run;
-            plan_mask[R * TS + r] = (uint16_t)cm[r];
-            run += __popc(cm[r]);
-        }
-        plan_nnz[R] = run;
+#pragma unroll
+        for (int o = 8; o; o >>= 1) longest = max(longest, __shfl_xor_sync(hm, longest, o, 16));
+        if (r == 0) plan_tot[R] = longest * nnz;
     }
-    unsigned e = FILL ? (unsigned)plan_off[R] : 0u;
-    int j = 0;
-    for (int r = 0; r < TS; r++) {
-        unsigned rowm = cm[r];
-        while (rowm) {
-            const int c = __clz(rowm) - 16;
-            rowm ^= 0x8000u >> c;
-            const unsigned cbit = 0x8000u >> c;
-            if (FILL) { plan_start[(size_t)R * PLAN_ROWS + j] = e; plan_col[(size_t)R * 256 + j] = (uint8_t)c; }
-            for (int p = p0; p < p1; p++) {
-                const int a = pair_a[p], b = pair_b[p];
-                unsigned am = a_mask[(size_t)a * TS + r];
-                unsigned ia = a_ptr[(size_t)a * TS + r];
-                while (am) {
-                    const int k = __clz(am) - 16;
-                    am ^= 0x8000u >> k;
-                    const unsigned bm = b_mask[(size_t)b * TS + k];
-                    if (bm & cbit) {
-                        if (FILL) {
-                            const unsigned posb = (unsigned)b_ptr[(size_t)b * TS + k] + __popc(bm >> (16 - c));
-                            plan_ent[e] = ((unsigned)(p - p0) << 16) | (posb << 8) | ia;
-                        }
-                        e++;
-                    }
-                    ia++;
-                }
-            }
-            j++;
-        }
-    }
-    if (FILL) plan_start[(size_t)R * PLAN_ROWS + j] = e;
-    else plan_tot[R] = (int)e;
 }
 
-// C tile metadata from the plan: thread per (tile, row).
+// C tile metadata from the plan: one thread per C tile copies its recipe's 32 + 32 bytes and its nnz.
 __global__ void __launch_bounds__(256)
 k_symbolic_from_plans(int numblkC, const int *__restrict__ recipe_id, const uint16_t *__restrict__ plan_mask,
                       const uint16_t *__restrict__ plan_ptr, const int *__restrict__ plan_nnz, uint16_t *__restrict__ c_mask,
                       uint16_t *__restrict__ c_ptr, int *__restrict__ c_cnt, const int *__restrict__ fail)
 {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = (int)(gid >> 4), r = (int)(gid & 15);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= numblkC) return;
-    if (*fail) { if (r == 0) c_cnt[t] = 0; return; }  // the generic symbolic step will overwrite everything
+    if (*fail) { c_cnt[t] = 0; return; }  // the generic symbolic step will overwrite everything
     const int R = recipe_id[t];
-    c_mask[(size_t)t * TS + r] = plan_mask[R * TS + r];
-    c_ptr[(size_t)t * TS + r] = plan_ptr[R * TS + r];
-    if (r == 0) c_cnt[t] = plan_nnz[R];
-}
-
-// Value bases of a pair's two tiles, looked up once per pair by a streaming kernel instead of twice per product.
-__global__ void __launch_bounds__(256)
-k_pair_bases(long long npairs, const int *__restrict__ pair_a, const int *__restrict__ pair_b, const int *__restrict__ a_tile_nnz,
-             const int *__restrict__ b_tile_nnz, int2 *__restrict__ pair_base)
-{
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npairs) return;
-    pair_base[p] = make_int2(a_tile_nnz[pair_a[p]], b_tile_nnz[pair_b[p]]);
+    const uint4 *sm = reinterpret_cast<const uint4 *>(plan_mask + (size_t)R * TS), *sp = reinterpret_cast<const uint4 *>(plan_ptr + (size_t)R * TS);
+    uint4 *dm = reinterpret_cast<uint4 *>(c_mask + (size_t)t * TS), *dp = reinterpret_cast<uint4 *>(c_ptr + (size_t)t * TS);
+    dm[0] = sm[0]; dm[1] = sm[1];
+    dp[0] = sp[0]; dp[1] = sp[1];
+    c_cnt[t] = plan_nnz[R];
 }
 
 __global__ void k_blk2tile_p(int numblkC, const int *__restrict__ c_tile_nnz, int *__restrict__ blk2tile)
@@ -300,11 +309,12 @@ __global__ void k_blk2tile_p(int numblkC, const int *__restrict__ c_tile_nnz, in
 }
 
 // One lane per C nonzero g: find its tile (blk2tile gives the tile holding nonzero 32*(g/32)), then walk its plan entries:
-// every iteration is a product, added in the serial SPA's order.
+// every iteration is a product, added in the serial SPA's order. The lanes of a warp are consecutive nonzeros of (mostly)
+// one tile: at iteration i they read consecutive plan words.
 __global__ void __launch_bounds__(256)
 k_numeric_from_plans(int numblkC, int nnzC, const int *__restrict__ blk2tile, const int *__restrict__ c_tile_nnz,
-                     const int *__restrict__ recipe_id, const unsigned *__restrict__ plan_start,
-                     const uint8_t *__restrict__ plan_col, const unsigned *__restrict__ plan_ent,
+                     const int *__restrict__ recipe_id, const int *__restrict__ plan_off, const int *__restrict__ plan_nnz,
+                     const uint16_t *__restrict__ plan_cnt, const uint8_t *__restrict__ plan_col, const unsigned *__restrict__ plan_ent,
                      const int *__restrict__ pair_ptr, const int2 *__restrict__ pair_base, const double *__restrict__ a_val,
                      const double *__restrict__ b_val, uint16_t *__restrict__ c_col, double *__restrict__ c_val)
 {
@@ -319,11 +329,12 @@ k_numeric_from_plans(int numblkC, int nnzC, const int *__restrict__ blk2tile, co
     }
     const int t = lo, off = g - c_tile_nnz[t];
     const int R = recipe_id[t];
-    const unsigned s1 = plan_start[(size_t)R * PLAN_ROWS + off + 1];
+    const int n = plan_cnt[(size_t)R * 256 + off], stride = plan_nnz[R];
+    const unsigned *ent = plan_ent + plan_off[R] + off;
     const int2 *pb = pair_base + pair_ptr[t];
     double acc = 0.0;
-    for (unsigned s = plan_start[(size_t)R * PLAN_ROWS + off]; s < s1; s++) {
-        const unsigned e = plan_ent[s];
+    for (int i = 0; i < n; i++, ent += stride) {
+        const unsigned e = *ent;
         const int2 base = pb[e >> 16];
         acc = fma(a_val[base.x + (int)(e & 255u)], b_val[base.y + (int)((e >> 8) & 255u)], acc);
     }
@@ -352,7 +363,7 @@ int plans_begin(PlanTable *out)
 // After k_s1_fill<HASH>: dense recipe numbers, verification, the plans, and C's masks / Ptr / tile nnz counts from them.
 // Everything is enqueued; *d_fail is the device flag the caller reads back with nnz(C).
 int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const int *rslot, int *recipe_id,
-                          const int **d_fail)
+                          void *pair_base, const int **d_fail)
 {
     Ctx &c = ctx();
     PlanCtx &p = g_plan;
@@ -366,47 +377,40 @@ int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, 
     k_recipe_reps<<<ceil_div(RCAP, 256), 256, 0, c.stream>>>(p.rowner, p.rdense, p.rep_tile);
     CK_LAUNCH();
     k_recipe_verify<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>(numblkC, pl.ptr, pl.end, pl.a, pl.b, A->pat, B->pat, rslot, p.rowner,
-                                                                  p.rdense, recipe_id, fail);
+                                                                  p.rdense, A->tile_nnz, B->tile_nnz, (int2 *)pair_base, recipe_id, fail);
     CK_LAUNCH();
     const int *nrec = p.rdense + RCAP;
-    k_plan_build<false><<<ceil_div(RMAX, 64), 64, 0, c.stream>>>(nrec, p.rep_tile, pl.ptr, pl.end, pl.a, pl.b, A->mask, A->ptr, B->mask, B->ptr,
-                                                                 p.plan_mask, p.plan_ptr, p.plan_nnz, p.plan_tot, nullptr, nullptr, nullptr,
-                                                                 nullptr, fail);
+    k_plan_build<false><<<ceil_div(RMAX * 16, 128), 128, 0, c.stream>>>(nrec, p.rep_tile, pl.ptr, pl.end, pl.a, pl.b, A->mask, A->ptr, B->mask,
+                                                                        B->ptr, p.plan_mask, p.plan_ptr, p.plan_nnz, p.plan_tot, nullptr,
+                                                                        p.plan_cnt, p.plan_col, nullptr, fail);
     CK_LAUNCH();
     rc = exclusive_scan<int>(p.plan_tot, p.plan_off, RMAX);
     if (rc) return rc;
-    k_plan_build<true><<<ceil_div(RMAX, 64), 64, 0, c.stream>>>(nrec, p.rep_tile, pl.ptr, pl.end, pl.a, pl.b, A->mask, A->ptr, B->mask, B->ptr,
-                                                                p.plan_mask, p.plan_ptr, p.plan_nnz, p.plan_tot, p.plan_off, p.plan_start,
-                                                                p.plan_col, p.plan_ent, fail);
+    k_plan_build<true><<<ceil_div(RMAX * 16, 128), 128, 0, c.stream>>>(nrec, p.rep_tile, pl.ptr, pl.end, pl.a, pl.b, A->mask, A->ptr, B->mask,
+                                                                       B->ptr, p.plan_mask, p.plan_ptr, p.plan_nnz, p.plan_tot, p.plan_off,
+                                                                       p.plan_cnt, p.plan_col, p.plan_ent, fail);
     CK_LAUNCH();
-    k_symbolic_from_plans<<<ceil_div((long long)numblkC * 16, 256), 256, 0, c.stream>>>(numblkC, recipe_id, p.plan_mask, p.plan_ptr, p.plan_nnz,
-                                                                                       C->mask, C->ptr, C->tile_nnz, fail);
+    k_symbolic_from_plans<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>(numblkC, recipe_id, p.plan_mask, p.plan_ptr, p.plan_nnz, C->mask, C->ptr,
+                                                                        C->tile_nnz, fail);
     CK_LAUNCH();
     return TSG_OK;
 }
 
-size_t plans_numeric_scratch_bytes(long long pairs, long long nnzC)
-{
-    return arena_need((size_t)(pairs > 0 ? pairs : 1), 8) + arena_need((size_t)((nnzC + 31) >> 5) + 1, 4);
-}
-
-int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, long long pairs, const int *recipe_id,
+int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const void *pair_base, const int *recipe_id,
                          tsg_stats *stats)
 {
     Ctx &c = ctx();
     PlanCtx &p = g_plan;
     const long long numblkC = C->numtile, nnzC = C->nnz;
     if (nnzC <= 0 || numblkC <= 0) return TSG_OK;
-    if (!arena_reserve(2, plans_numeric_scratch_bytes(pairs, nnzC))) return last_error();
-    int2 *pair_base = arena_take<int2>(2, (size_t)(pairs > 0 ? pairs : 1));
+    if (!arena_reserve(2, arena_need((size_t)((nnzC + 31) >> 5) + 1, 4))) return last_error();
     int *blk2tile = arena_take<int>(2, (size_t)((nnzC + 31) >> 5) + 1);
-    if (!pair_base || !blk2tile) return last_error();
-    k_pair_bases<<<ceil_div(pairs, 256), 256, 0, c.stream>>>(pairs, pl.a, pl.b, A->tile_nnz, B->tile_nnz, pair_base);
-    CK_LAUNCH();
+    if (!blk2tile) return last_error();
     k_blk2tile_p<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>((int)numblkC, C->tile_nnz, blk2tile);
     CK_LAUNCH();
-    k_numeric_from_plans<<<ceil_div(nnzC, 256), 256, 0, c.stream>>>((int)numblkC, (int)nnzC, blk2tile, C->tile_nnz, recipe_id, p.plan_start,
-                                                                    p.plan_col, p.plan_ent, pl.ptr, pair_base, A->val, B->val, C->col, C->val);
+    k_numeric_from_plans<<<ceil_div(nnzC, 256), 256, 0, c.stream>>>((int)numblkC, (int)nnzC, blk2tile, C->tile_nnz, recipe_id, p.plan_off,
+                                                                    p.plan_nnz, p.plan_cnt, p.plan_col, p.plan_ent, pl.ptr,
+                                                                    (const int2 *)pair_base, A->val, B->val, C->col, C->val);
     CK_LAUNCH();
     if (stats) stats->plan_recipes = 1;  // the caller fills in the count it read back
     return TSG_OK;

@@ -9,7 +9,6 @@ constexpr int PCAP = 1 << 13;            // pattern table slots; more than PCAP/
 constexpr int PLANS_MAX_PATTERNS = 1024; // the plan path is attempted only when both operands hold at most this many patterns
 constexpr int RCAP = 1 << 14;            // recipe table slots
 constexpr int RMAX = RCAP / 2;           // more distinct recipes than this => fail (generic kernels run)
-constexpr int PLAN_ROWS = 257;           // plan_start entries per recipe (<= 256 nonzeros per C tile, plus the end)
 constexpr int PLAN_ENT_CAP = 1 << 24;    // plan entries (products of all distinct recipes) the buffer holds
 constexpr int NO_OWNER = 0x7f7f7f7f;     // what cudaMemset(0x7f) leaves; item indices stay below it
 

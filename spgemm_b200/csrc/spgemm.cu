@@ -798,8 +798,8 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     rc = copy_words(C->tile_ptr, c_tile_ptr, (size_t)ntr + 1);
     if (rc) return rc;
     const bool heavy_rows = n_heavy > 0;  // tile-rows on the multi-warp path park one 16-byte record per pair
-    if (!arena_reserve(1, 4 * arena_need(nb + 1, 4) + 2 * arena_need(np, 4) + arena_need(np, 2) + (heavy_rows ? arena_need(np, 16) : 0) +
-                              numeric_scratch_bytes(ntr, numblkC)))
+    if (!arena_reserve(1, 4 * arena_need(nb + 1, 4) + 2 * arena_need(np, 4) + arena_need(np, 2) + arena_need(np, 8) +
+                              (heavy_rows ? arena_need(np, 16) : 0) + numeric_scratch_bytes(ntr, numblkC)))
         return last_error();
     int *pair_ptr = arena_take<int>(1, nb + 1), *pair_end = arena_take<int>(1, nb + 1), *pair_a = arena_take<int>(1, np), *pair_b = arena_take<int>(1, np);
     uint16_t *pair_slot = arena_take<uint16_t>(1, np);
@@ -808,8 +808,9 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     // recipe plans (plans.cu): attempted when both operands are made of few distinct tile patterns and no tile-row is heavy
     bool plans_on = plans_wanted(A, B) && !heavy_rows && numblkC > 0 && pairs > 0;
     int *rslot = plans_on ? arena_take<int>(1, nb) : nullptr, *recipe_id = plans_on ? arena_take<int>(1, nb) : nullptr;
+    void *pair_base = plans_on ? (void *)arena_take<long long>(1, np) : nullptr;  // (A value base, B value base) per pair
     if (!pair_ptr || !pair_end || !pair_a || !pair_b || !pair_slot || (heavy_rows && !pair_tmp) || !nbufs.row_kind || !nbufs.dense_list ||
-        (plans_on && (!rslot || !recipe_id)))
+        (plans_on && (!rslot || !recipe_id || !pair_base)))
         return last_error();
     if (heavy_rows) CK(cudaMemsetAsync(pair_end, 0, nb * 4, c.stream));  // the heavy kernel counts with atomics
     CK(cudaEventRecord(ev[2], c.stream));  // [1..2] = allocation
@@ -879,7 +880,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         return TSG_OK;
     };
     if (plans_on) {  // C's masks / Ptr / tile nnz from the recipe plans (or nothing useful, if the fail flag comes up)
-        rc = plans_symbolic_device(A, B, C, plists, rslot, recipe_id, &d_plan_fail);
+        rc = plans_symbolic_device(A, B, C, plists, rslot, recipe_id, pair_base, &d_plan_fail);
         if (rc) return rc;
     } else if (numblkC > 0 && (!fused || n_heavy > 0)) {
         rc = generic_symbolic(fused);
@@ -934,7 +935,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     CK(cudaEventRecord(ev_s3, c.stream));
     tsg_stats nst;
     memset(&nst, 0, sizeof(nst));
-    if (plans_on) rc = plans_numeric_device(A, B, C, plists, pairs, recipe_id, &nst);
+    if (plans_on) rc = plans_numeric_device(A, B, C, plists, pair_base, recipe_id, &nst);
     else rc = numeric_device(A, B, C, trow0, ntr, wptr, plists, nbufs, h_ns, heavy_rows, &nst);
     if (rc) return rc;
     CK(cudaEventRecord(ev[4], c.stream));
