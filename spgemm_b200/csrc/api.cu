@@ -857,7 +857,7 @@ static void csr2tile_host(SMatrix *mat, int tm, int tn, int col_major)
     memset(&t, 0, sizeof(t)); memset(&An, 0, sizeof(An));
     if (tsg_csr_upload(mat->m, mat->n, mat->rowpointer, mat->columnindex, mat->value, &A)) return;
     int rc = tsg_csr2tile(&A, col_major, &t);
-    if (rc == TSG_ERR_INPUT && last_input_flags() == 2) {
+    if (rc == TSG_ERR_INPUT && (last_input_flags() & 2) && !(last_input_flags() & 1)) {  // unsorted rows (which also derail the tile search: flag 4)
         // The reference's loader neither sorts rows nor merges duplicates (src/mmio_highlevel.h:593-759) and its csr2tile
         // takes whatever order it is given (src/csr2tile.h:152-168). The kernels here need sorted, duplicate-free rows:
         // bring the matrix into that form on the device (duplicates summed; TSG_DUP_POLICY=first keeps the first) and retry.

@@ -311,7 +311,7 @@ __global__ void k_blk2tile_p(int numblkC, const int *__restrict__ c_tile_nnz, in
 // One lane per C nonzero g: find its tile (blk2tile gives the tile holding nonzero 32*(g/32)), then walk its plan entries:
 // every iteration is a product, added in the serial SPA's order. The lanes of a warp are consecutive nonzeros of (mostly)
 // one tile: at iteration i they read consecutive plan words.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 k_numeric_from_plans(int numblkC, int nnzC, const int *__restrict__ blk2tile, const int *__restrict__ c_tile_nnz,
                      const int *__restrict__ recipe_id, const int *__restrict__ plan_off, const int *__restrict__ plan_nnz,
                      const uint16_t *__restrict__ plan_cnt, const uint8_t *__restrict__ plan_col, const unsigned *__restrict__ plan_ent,
