@@ -44,7 +44,8 @@ int plans_begin(PlanTable *out);
 int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const int *rslot, int *recipe_id,
                           void *pair_base, const int **d_fail);
 int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const void *pair_base, const int *recipe_id,
-                         tsg_stats *stats);
+                         int trow0, int ntr, const int *wptr, int max_need, tsg_stats *stats);
+size_t plans_rows_need_bound(int max_nnzA_row, int maxJ, int wmax);
 const int *plans_recipe_count_ptr();
 void plans_shutdown();
 

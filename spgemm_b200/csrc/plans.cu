@@ -191,7 +191,7 @@ k_recipe_verify(int numblkC, const int *__restrict__ pair_ptr, const int *__rest
     bool same = pair_end[u] - q0 == n;
     for (int i = 0; i < n; i++) {
         const int a = pair_a[p0 + i], b = pair_b[p0 + i];
-        pair_base[p0 + i] = make_int2(a_tile_nnz[a], b_tile_nnz[b]);
+        if (pair_base) pair_base[p0 + i] = make_int2(a_tile_nnz[a], b_tile_nnz[b]);
         if (same && u != t) same = patA[a] == patA[pair_a[q0 + i]] && patB[b] == patB[pair_b[q0 + i]];
     }
     if (!same) *fail = 2;
@@ -345,6 +345,97 @@ k_numeric_from_plans(int numblkC, int nnzC, const int *__restrict__ blk2tile, co
     c_col[g] = plan_col[(size_t)R * 256 + off];
 }
 
+// The same walk with a CTA per C TILE-ROW: the tile-row's share of A's values (contiguous in row-major tile order), the
+// offsets / recipes / pair ranges of its C tiles and, per pair, the position of the A tile's values in that staged copy and
+// the base of the B tile's values are put into shared memory first. Per product that leaves two global loads (the plan
+// word and B's value) instead of four, and the pair_base array is not needed. Rows that do not fit `smem_cap` read
+// everything from global memory (same results).
+struct PlanRows {
+    int trow0, smem_cap;
+    const int *a_tile_ptr, *a_tile_nnz;
+    const double *a_val;
+    const int *b_tile_nnz;
+    const double *b_val;
+    const int *c_tile_ptr, *c_tile_nnz, *wptr, *pair_ptr, *pair_a, *pair_b, *recipe_id;
+    const int *plan_off, *plan_nnz;
+    const uint16_t *plan_cnt;
+    const uint8_t *plan_col;
+    const unsigned *plan_ent;
+    uint16_t *c_col;
+    double *c_val;
+};
+
+__host__ __device__ __forceinline__ size_t plan_rows_need(int nnzA, int numJ, int W)
+{
+    return (((size_t)nnzA * 8 + 15) & ~(size_t)15) + (((size_t)(numJ + 1) * 4 + 15) & ~(size_t)15) + 2 * (((size_t)numJ * 4 + 15) & ~(size_t)15) +
+           2 * (((size_t)W * 4 + 15) & ~(size_t)15);
+}
+
+__global__ void __launch_bounds__(256)
+k_numeric_from_plans_rows(const __grid_constant__ PlanRows P)
+{
+    extern __shared__ __align__(16) unsigned char pr_smem[];
+    const int i = blockIdx.x, tid = threadIdx.x, I = P.trow0 + i;
+    const int c0 = P.c_tile_ptr[i], numJ = P.c_tile_ptr[i + 1] - c0;
+    if (numJ == 0) return;
+    const int n0 = P.c_tile_nnz[c0], nnzC = P.c_tile_nnz[c0 + numJ] - n0;
+    if (nnzC == 0) return;
+    const int a0 = P.a_tile_ptr[I], a1 = P.a_tile_ptr[I + 1];
+    const int av0 = P.a_tile_nnz[a0], nnzA = P.a_tile_nnz[a1] - av0;
+    const int w0 = P.wptr[i], W = P.wptr[i + 1] - w0;
+    const bool staged = plan_rows_need(nnzA, numJ, W) <= (size_t)P.smem_cap;  // uniform over the CTA
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { unsigned char *p = pr_smem + off; off += (bytes + 15) & ~(size_t)15; return p; };
+    double *s_aval = (double *)carve((size_t)nnzA * 8);
+    int *s_cnnz = (int *)carve((size_t)(numJ + 1) * 4);
+    int *s_rec = (int *)carve((size_t)numJ * 4);
+    int *s_pp = (int *)carve((size_t)numJ * 4);
+    int *s_abase = (int *)carve((size_t)W * 4);
+    int *s_bbase = (int *)carve((size_t)W * 4);
+    if (staged) {
+        for (int k = tid; k < nnzA; k += 256) s_aval[k] = P.a_val[av0 + k];
+        for (int k = tid; k <= numJ; k += 256) {
+            s_cnnz[k] = P.c_tile_nnz[c0 + k] - n0;
+            if (k < numJ) { s_rec[k] = P.recipe_id[c0 + k]; s_pp[k] = P.pair_ptr[c0 + k] - w0; }
+        }
+        for (int k = tid; k < W; k += 256) {
+            s_abase[k] = P.a_tile_nnz[P.pair_a[w0 + k]] - av0;
+            s_bbase[k] = P.b_tile_nnz[P.pair_b[w0 + k]];
+        }
+        __syncthreads();
+    }
+    for (int g = tid; g < nnzC; g += 256) {
+        int lo = 0, hi = numJ - 1;  // the tile holding nonzero g of the tile-row: largest s with nnz offset <= g
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((staged ? s_cnnz[mid] : P.c_tile_nnz[c0 + mid] - n0) <= g) lo = mid; else hi = mid - 1;
+        }
+        const int sidx = lo;
+        const int off_in_tile = g - (staged ? s_cnnz[sidx] : P.c_tile_nnz[c0 + sidx] - n0);
+        const int R = staged ? s_rec[sidx] : P.recipe_id[c0 + sidx];
+        const int n = P.plan_cnt[(size_t)R * 256 + off_in_tile], stride = P.plan_nnz[R];
+        const unsigned *ent = P.plan_ent + P.plan_off[R] + off_in_tile;
+        double acc = 0.0;
+        if (staged) {
+            const int pp = s_pp[sidx];
+            for (int it = 0; it < n; it++, ent += stride) {
+                const unsigned e = *ent;
+                const int p = pp + (int)(e >> 16);
+                acc = fma(s_aval[s_abase[p] + (int)(e & 255u)], P.b_val[s_bbase[p] + (int)((e >> 8) & 255u)], acc);
+            }
+        } else {
+            const int pp = P.pair_ptr[c0 + sidx];
+            for (int it = 0; it < n; it++, ent += stride) {
+                const unsigned e = *ent;
+                const int p = pp + (int)(e >> 16);
+                acc = fma(P.a_val[P.a_tile_nnz[P.pair_a[p]] + (int)(e & 255u)], P.b_val[P.b_tile_nnz[P.pair_b[p]] + (int)((e >> 8) & 255u)], acc);
+            }
+        }
+        P.c_val[n0 + g] = acc;
+        P.c_col[n0 + g] = P.plan_col[(size_t)R * 256 + off_in_tile];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
@@ -400,12 +491,25 @@ int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, 
 }
 
 int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const void *pair_base, const int *recipe_id,
-                         tsg_stats *stats)
+                         int trow0, int ntr, const int *wptr, int max_need, tsg_stats *stats)
 {
     Ctx &c = ctx();
     PlanCtx &p = g_plan;
     const long long numblkC = C->numtile, nnzC = C->nnz;
     if (nnzC <= 0 || numblkC <= 0) return TSG_OK;
+    if (!pair_base) {  // CTA per tile-row, A's values and the per-pair bases staged in shared memory
+        const char *kb = getenv("TSG_PLANS_SMEM_KB");  // tests: a small budget sends tile-rows down the unstaged branch
+        const size_t cap = kb && *kb ? (size_t)atoi(kb) * 1024 : (size_t)64 * 1024;
+        size_t smem = (size_t)max_need < cap ? (size_t)max_need : cap;
+        smem = (smem + 1023) & ~(size_t)1023;
+        PlanRows P{trow0, (int)smem, A->tile_ptr, A->tile_nnz, A->val, B->tile_nnz, B->val, C->tile_ptr, C->tile_nnz, wptr, pl.ptr, pl.a, pl.b,
+                   recipe_id, p.plan_off, p.plan_nnz, p.plan_cnt, p.plan_col, p.plan_ent, C->col, C->val};
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_numeric_from_plans_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_numeric_from_plans_rows<<<ntr, 256, smem, c.stream>>>(P);
+        CK_LAUNCH();
+        if (stats) stats->plan_recipes = 1;
+        return TSG_OK;
+    }
     if (!arena_reserve(2, arena_need((size_t)((nnzC + 31) >> 5) + 1, 4))) return last_error();
     int *blk2tile = arena_take<int>(2, (size_t)((nnzC + 31) >> 5) + 1);
     if (!blk2tile) return last_error();
@@ -418,6 +522,9 @@ int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, c
     if (stats) stats->plan_recipes = 1;  // the caller fills in the count it read back
     return TSG_OK;
 }
+
+// largest shared-memory need of k_numeric_from_plans_rows over the slab's tile-rows (host side, from sizes known after step 1)
+size_t plans_rows_need_bound(int max_nnzA_row, int maxJ, int wmax) { return plan_rows_need(max_nnzA_row, maxJ, wmax); }
 
 const int *plans_recipe_count_ptr() { return g_plan.rdense ? g_plan.rdense + RCAP : nullptr; }
 

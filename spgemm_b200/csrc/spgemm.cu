@@ -122,14 +122,14 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total)
 // Light path. S1_WARPS tile-rows per CTA, one warp each, each warp with its own slice of dynamic shared memory.
 // ---------------------------------------------------------------------------------------------
 constexpr int S1_WARPS = 8;
-enum { SC_NW_HEAVY = 0, SC_ERR = 1, SC_WMAX = 2, SC_MAXJ = 3, SC_NHEAVY = 4, SC_NW_LIGHT = 5, SC_NLIGHT = 6 };
+enum { SC_NW_HEAVY = 0, SC_ERR = 1, SC_WMAX = 2, SC_MAXJ = 3, SC_NHEAVY = 4, SC_NW_LIGHT = 5, SC_NLIGHT = 6, SC_MAXNNZA = 7 };
 
 // k_s1_count: per tile-row the weight w (matched tile pairs; also the multi-GPU / slab balancing weight, nsparse
 // set_intprod_num, src/spgemm_nsparse_kernel.h:135-151), the window [jlo, jhi] of tile columns the row can produce, and
 // -- for rows that fit the light path -- the number of distinct tile columns (C tiles). The others join heavy_list.
 __global__ void __launch_bounds__(S1_WARPS * 32)
 k_s1_count(int trow0, int ntr, int bmw, const int *__restrict__ a_tile_ptr, const int *__restrict__ a_tile_col,
-           const int *__restrict__ b_tile_ptr, const int *__restrict__ b_tile_col, int *__restrict__ w, int *__restrict__ jlo,
+           const int *__restrict__ a_tile_nnz, const int *__restrict__ b_tile_ptr, const int *__restrict__ b_tile_col, int *__restrict__ w, int *__restrict__ jlo,
            int *__restrict__ jhi, int *__restrict__ cnt, uint8_t *__restrict__ light, int *__restrict__ heavy_list,
            int *__restrict__ scal)
 {
@@ -199,6 +199,7 @@ k_s1_count(int trow0, int ntr, int bmw, const int *__restrict__ a_tile_ptr, cons
         atomicMax(&scal[SC_NW_LIGHT], nw);
         atomicMax(&scal[SC_WMAX], (int)s);
         atomicAdd(&scal[SC_NLIGHT], 1);
+        atomicMax(&scal[SC_MAXNNZA], a_tile_nnz[a1] - a_tile_nnz[a0]);  // sizes the staged kernels' shared memory
     }
 }
 
@@ -728,8 +729,9 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     if (ntr > 0) {
         const size_t smem = (size_t)S1_WARPS * bmw1 * 4;
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_s1_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_s1_count<<<ceil_div(ntr, S1_WARPS), S1_WARPS * 32, smem, c.stream>>>(trow0, ntr, bmw1, A->tile_ptr, A->tile_columnidx, B->tile_ptr,
-                                                                              B->tile_columnidx, w, jlo, jhi, cnt, light, heavy_list, scal);
+        k_s1_count<<<ceil_div(ntr, S1_WARPS), S1_WARPS * 32, smem, c.stream>>>(trow0, ntr, bmw1, A->tile_ptr, A->tile_columnidx, A->tile_nnz,
+                                                                              B->tile_ptr, B->tile_columnidx, w, jlo, jhi, cnt, light, heavy_list,
+                                                                              scal);
         CK_LAUNCH();
     }
     // one scan per array: 32-bit offsets for the kernels, the 64-bit total for the host (slab planning keeps it < 2^31)
@@ -808,9 +810,12 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     // recipe plans (plans.cu): attempted when both operands are made of few distinct tile patterns and no tile-row is heavy
     bool plans_on = plans_wanted(A, B) && !heavy_rows && numblkC > 0 && pairs > 0;
     int *rslot = plans_on ? arena_take<int>(1, nb) : nullptr, *recipe_id = plans_on ? arena_take<int>(1, nb) : nullptr;
-    void *pair_base = plans_on ? (void *)arena_take<long long>(1, np) : nullptr;  // (A value base, B value base) per pair
+    // TSG_PLANS_NUMERIC=flat: lane per C nonzero over the whole slab, value bases per pair in an array of their own
+    // (default: CTA per tile-row with A's values and the bases in shared memory)
+    const bool plans_flat = getenv("TSG_PLANS_NUMERIC") && !strcmp(getenv("TSG_PLANS_NUMERIC"), "flat");
+    void *pair_base = plans_on && plans_flat ? (void *)arena_take<long long>(1, np) : nullptr;  // (A value base, B value base) per pair
     if (!pair_ptr || !pair_end || !pair_a || !pair_b || !pair_slot || (heavy_rows && !pair_tmp) || !nbufs.row_kind || !nbufs.dense_list ||
-        (plans_on && (!rslot || !recipe_id || !pair_base)))
+        (plans_on && (!rslot || !recipe_id || (plans_flat && !pair_base))))
         return last_error();
     if (heavy_rows) CK(cudaMemsetAsync(pair_end, 0, nb * 4, c.stream));  // the heavy kernel counts with atomics
     CK(cudaEventRecord(ev[2], c.stream));  // [1..2] = allocation
@@ -935,7 +940,11 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     CK(cudaEventRecord(ev_s3, c.stream));
     tsg_stats nst;
     memset(&nst, 0, sizeof(nst));
-    if (plans_on) rc = plans_numeric_device(A, B, C, plists, pair_base, recipe_id, &nst);
+    if (plans_on) {
+        // the largest tile-row: A values, C tiles and pairs as k_s1_count saw them (every tile-row is light on this path)
+        const size_t need = plans_rows_need_bound(hs[SC_MAXNNZA], hs[SC_MAXJ], hs[SC_WMAX]);
+        rc = plans_numeric_device(A, B, C, plists, pair_base, recipe_id, trow0, ntr, wptr, need > (1u << 30) ? (1 << 30) : (int)need, &nst);
+    }
     else rc = numeric_device(A, B, C, trow0, ntr, wptr, plists, nbufs, h_ns, heavy_rows, &nst);
     if (rc) return rc;
     CK(cudaEventRecord(ev[4], c.stream));

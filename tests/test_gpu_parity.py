@@ -704,6 +704,33 @@ def test_recipe_plans_same_result(monkeypatch, name, values, plans):
         o.free()
 
 
+@pytest.mark.parametrize("variant", ["flat", "rows_unstaged"])
+def test_recipe_plans_numeric_variants(monkeypatch, variant):
+    """The plan-driven numeric step has two kernels (CTA per tile-row with A's values staged in shared memory -- the
+    default, covered above -- and lane per nonzero over the whole slab) and the staged one has an unstaged branch for
+    tile-rows that do not fit: all give the serial SPA's values."""
+    monkeypatch.setenv("TSG_PLANS", "1")
+    if variant == "flat":
+        monkeypatch.setenv("TSG_PLANS_NUMERIC", "flat")
+    else:
+        monkeypatch.setenv("TSG_PLANS_SMEM_KB", "2")
+    m, n, rp, ci, _ = M.stencil27(13, 10, 9)
+    v = M.set_values(len(ci), "hash")
+    A = (rp, ci, v)
+    _, tC_exp = oracle_c(m, n, A, A, n)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
+    tC, st = api.spgemm(tA, tB)
+    assert st["plan_recipes"] > 0, st
+    assert_tiled_equal(tC.download(), tC_exp, f"plans numeric {variant}", val_rtol=VAL_RTOL)
+    monkeypatch.delenv("TSG_PLANS_NUMERIC", raising=False)
+    monkeypatch.delenv("TSG_PLANS_SMEM_KB", raising=False)
+    tD, _ = api.spgemm(tA, tB)                      # the default kernel adds in the same order: bit-identical values
+    assert np.array_equal(tC.download()["val"], tD.download()["val"])
+    for o in (tD, tC, tA, tB, d):
+        o.free()
+
+
 def test_recipe_plans_fall_back_when_recipes_do_not_repeat(monkeypatch):
     """Few tile patterns but tens of thousands of distinct pair sequences: the recipe table overflows, the fail flag
     comes up and the generic kernels produce the result (stats say -1)."""
