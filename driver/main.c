@@ -97,32 +97,103 @@ static void coo_to_csr(int m, int n, long long cnt, coo_t *e, SMatrix *A)
     for (int i = 0; i < m; i++) A->rowpointer[i + 1] += A->rowpointer[i];
 }
 
+/* File-order CSR, exactly what the reference's mmio_allinone builds (src/mmio_highlevel.h:593-759): rows in the order
+ * the entries appear in the file, symmetric entries mirrored on the spot, nothing sorted, duplicates kept. Selected with
+ * TSG_MTX_RAW=1: the library's drop-in csr2tile_* then canonicalise on the device (tsg_csr_canonicalize). */
+static void coo_to_csr_file_order(int m, int n, long long cnt, const coo_t *e, SMatrix *A)
+{
+    A->m = m; A->n = n; A->nnz = (int)cnt; A->isSymmetric = 0;
+    A->rowpointer = (int *)calloc((size_t)m + 2, sizeof(int));
+    A->columnindex = (int *)malloc((size_t)(cnt ? cnt : 1) * sizeof(int));
+    A->value = (double *)malloc((size_t)(cnt ? cnt : 1) * sizeof(double));
+    for (long long i = 0; i < cnt; i++) A->rowpointer[e[i].key / n + 2]++;
+    for (int i = 0; i < m; i++) A->rowpointer[i + 2] += A->rowpointer[i + 1];
+    for (long long i = 0; i < cnt; i++) {
+        const int r = (int)(e[i].key / n), at = A->rowpointer[r + 1]++;
+        A->columnindex[at] = (int)(e[i].key % n);
+        A->value[at] = e[i].v;
+    }
+}
+
+/* Binary cache next to the .mtx file (text parsing of a 57M-entry file takes minutes): the CSR exactly
+ * as load_mtx built it. "<file>.tsgcsr" (".tsgraw" for TSG_MTX_RAW=1); ignored when older than the .mtx; TSG_MTX_CACHE=0 disables. */
+typedef struct { char magic[8]; int m, n, nnz, sym; } cache_hdr_t;
+#include <sys/stat.h>
+
+static int cache_load(const char *cpath, const char *mtx, SMatrix *A)
+{
+    struct stat sc, sm;
+    if (stat(cpath, &sc) || stat(mtx, &sm) || sc.st_mtime < sm.st_mtime) return -1;
+    FILE *f = fopen(cpath, "rb");
+    if (!f) return -1;
+    cache_hdr_t h;
+    int ok = fread(&h, sizeof h, 1, f) == 1 && !memcmp(h.magic, "TSGCSR1", 8) && h.m >= 0 && h.n >= 0 && h.nnz >= 0;
+    if (ok) {
+        A->m = h.m; A->n = h.n; A->nnz = h.nnz; A->isSymmetric = h.sym;
+        A->rowpointer = (int *)malloc(((size_t)h.m + 1) * sizeof(int));
+        A->columnindex = (int *)malloc((size_t)(h.nnz ? h.nnz : 1) * sizeof(int));
+        A->value = (double *)malloc((size_t)(h.nnz ? h.nnz : 1) * sizeof(double));
+        ok = fread(A->rowpointer, sizeof(int), (size_t)h.m + 1, f) == (size_t)h.m + 1 &&
+             fread(A->columnindex, sizeof(int), (size_t)h.nnz, f) == (size_t)h.nnz &&
+             fread(A->value, sizeof(double), (size_t)h.nnz, f) == (size_t)h.nnz && A->rowpointer[h.m] == h.nnz;
+        if (!ok) { free(A->rowpointer); free(A->columnindex); free(A->value); }
+    }
+    fclose(f);
+    return ok ? 0 : -1;
+}
+
+static void cache_store(const char *cpath, const SMatrix *A)
+{
+    FILE *f = fopen(cpath, "wb");
+    if (!f) return;  /* read-only directory: no cache */
+    cache_hdr_t h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "TSGCSR1", 8);
+    h.m = A->m; h.n = A->n; h.nnz = A->nnz; h.sym = A->isSymmetric;
+    int ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(A->rowpointer, sizeof(int), (size_t)A->m + 1, f) == (size_t)A->m + 1 &&
+             fwrite(A->columnindex, sizeof(int), (size_t)A->nnz, f) == (size_t)A->nnz &&
+             fwrite(A->value, sizeof(double), (size_t)A->nnz, f) == (size_t)A->nnz;
+    fclose(f);
+    if (!ok) remove(cpath);
+}
+
+/* MatrixMarket coordinate files: real, integer, pattern (value 1) and complex (real part kept, like mmio_allinone's
+ * "%lg %lg" read, src/mmio_highlevel.h:662-666); general, symmetric and hermitian (mirrored, :636-640, :701-723). */
 static int load_mtx(const char *path, SMatrix *A)
 {
+    const int raw = getenv("TSG_MTX_RAW") && atoi(getenv("TSG_MTX_RAW"));
+    const int use_cache = !(getenv("TSG_MTX_CACHE") && !atoi(getenv("TSG_MTX_CACHE")));
+    char cpath[1100];
+    snprintf(cpath, sizeof cpath, "%s.%s", path, raw ? "tsgraw" : "tsgcsr");
+    if (use_cache && cache_load(cpath, path, A) == 0) { printf("(binary cache %s)\n", cpath); return 0; }
     FILE *f = fopen(path, "r");
     if (!f) return -1;
     char line[1024];
     if (!fgets(line, sizeof line, f)) { fclose(f); return -1; }
+    if (strncmp(line, "%%MatrixMarket", 14) || !strstr(line, "coordinate")) { fclose(f); fprintf(stderr, "%s: not a MatrixMarket coordinate file\n", path); return -1; }
     int pattern = strstr(line, "pattern") != NULL;
     int symmetric = strstr(line, "symmetric") != NULL || strstr(line, "hermitian") != NULL;
     do { if (!fgets(line, sizeof line, f)) { fclose(f); return -1; } } while (line[0] == '%');
     int m, n;
     long long nz;
-    if (sscanf(line, "%d %d %lld", &m, &n, &nz) != 3) { fclose(f); return -1; }
+    if (sscanf(line, "%d %d %lld", &m, &n, &nz) != 3 || m < 0 || n < 0 || nz < 0) { fclose(f); return -1; }
     coo_t *e = (coo_t *)malloc(sizeof(coo_t) * (size_t)(2 * nz + 1));
     long long cnt = 0;
     for (long long i = 0; i < nz; i++) {
         int r, c;
         double v = 1.0;
         if (!fgets(line, sizeof line, f)) break;
-        if (pattern) sscanf(line, "%d %d", &r, &c); else sscanf(line, "%d %d %lf", &r, &c, &v);
+        /* "%lf" reads a real, an integer, or the real part of a complex entry alike */
+        if ((pattern ? sscanf(line, "%d %d", &r, &c) : sscanf(line, "%d %d %lf", &r, &c, &v)) < 2) continue;
+        if (r < 1 || r > m || c < 1 || c > n) { fprintf(stderr, "%s: entry (%d,%d) outside %dx%d\n", path, r, c, m, n); free(e); fclose(f); return -1; }
         e[cnt].key = (long long)(r - 1) * n + (c - 1); e[cnt++].v = v;
         if (symmetric && r != c) { e[cnt].key = (long long)(c - 1) * n + (r - 1); e[cnt++].v = v; }
     }
     fclose(f);
-    coo_to_csr(m, n, cnt, e, A);
+    if (raw) coo_to_csr_file_order(m, n, cnt, e, A); else coo_to_csr(m, n, cnt, e, A);
     A->isSymmetric = symmetric;  /* like mmio_allinone (src/mmio_highlevel.h) */
     free(e);
+    if (use_cache) cache_store(cpath, A);
     return 0;
 }
 
@@ -236,10 +307,21 @@ int main(int argc, char **argv)
     if (strcmp(argv[1], "-d") != 0 || strcmp(argv[3], "-aat") != 0) return 0;
     int device_id = atoi(argv[2]), aat = atoi(argv[4]);
     char *filename = argv[5];
+    /* -aat 2 A B tile_m tile_n: the general product C = A*B of two files, the CLI shape of the reference's cuSPARSE harness
+     * (src/external/cusparse/main.cu:83-126) */
+    char *filenameB = NULL;
+    if (aat == 2) {
+        if (argc < 9) { printf("-aat 2 needs two matrices: ./test_b200 -d 0 -aat 2 A.mtx B.mtx tile_size_m tile_size_n\n"); return 0; }
+        filenameB = argv[6];
+        argv++; argc--;
+    }
     int tile_size_m = atoi(argv[6]), tile_size_n = argc > 7 ? atoi(argv[7]) : tile_size_m;
     printf("device_id = %i\n", device_id);
     /* the reference calls cudaSetDevice(device_id) (main.cu:49); the library owns its CUDA runtime, so select there */
-    if (tsg_init(device_id) != TSG_OK) { fprintf(stderr, "tsg_init(%d) failed: %s\n", device_id, tilespgemm_last_error_string()); return 2; }
+    if (!getenv("TSG_DRIVER_PARSE_ONLY") && tsg_init(device_id) != TSG_OK) {
+        fprintf(stderr, "tsg_init(%d) failed: %s\n", device_id, tilespgemm_last_error_string());
+        return 2;
+    }
 
     SMatrix *matrixA = (SMatrix *)calloc(1, sizeof(SMatrix));
     SMatrix *matrixB = (SMatrix *)calloc(1, sizeof(SMatrix));
@@ -251,6 +333,18 @@ int main(int argc, char **argv)
     printf("input matrix A: ( %i, %i ) nnz = %i\n loadfile time    = %4.5f sec\n", matrixA->m, matrixA->n, matrixA->nnz,
            (now_ms() - t0) / 1000.0);
     if (!aat && matrixA->m != matrixA->n) { printf("matrix squaring must have rowA == colA. Exit.\n"); return 0; }
+    if (getenv("TSG_DRIVER_PARSE_ONLY")) {  /* loader check without a device (tests/test_driver_loader.py) */
+        long long s0 = 0; double s1 = 0;
+        int sorted = 1;
+        for (int i = 0; i < matrixA->m; i++)
+            for (int p = matrixA->rowpointer[i]; p < matrixA->rowpointer[i + 1]; p++) {
+                s0 += (long long)(i + 1) * (matrixA->columnindex[p] + 1); s1 += matrixA->value[p];
+                if (p > matrixA->rowpointer[i] && matrixA->columnindex[p - 1] >= matrixA->columnindex[p]) sorted = 0;
+            }
+        printf("parsed: m=%d n=%d nnz=%d symmetric=%d sorted=%d index_checksum=%lld value_sum=%.6f\n", matrixA->m, matrixA->n, matrixA->nnz,
+               matrixA->isSymmetric, sorted, s0, s1);
+        return 0;
+    }
     printf("the tile_size_m = %d\nthe tile_size_n = %d\n", tile_size_m, tile_size_n);
     for (int i = 0; i < matrixA->nnz; i++) matrixA->value[i] = i % 10;       /* main.cu:111-112 */
 
@@ -258,7 +352,13 @@ int main(int argc, char **argv)
         printf("matrix AAT does not do symmetric matrix. Exit.\n");
         return 0;
     }
-    if (aat) {                                                               /* main.cu:114-142 */
+    if (aat == 2) {                                                          /* general C = A*B: B from its own file */
+        int rcb = strncmp(filenameB, "gen:", 4) == 0 ? generate(filenameB, matrixB) : load_mtx(filenameB, matrixB);
+        if (rcb) { fprintf(stderr, "cannot load %s\n", filenameB); return 2; }
+        printf("input matrix B: ( %i, %i ) nnz = %i\n", matrixB->m, matrixB->n, matrixB->nnz);
+        if (matrixA->n != matrixB->m) { printf("C = A*B needs colA == rowB. Exit.\n"); return 0; }
+        for (int i = 0; i < matrixB->nnz; i++) matrixB->value[i] = i % 10;
+    } else if (aat) {                                                        /* main.cu:114-142 */
         matrixB->m = matrixA->n; matrixB->n = matrixA->m; matrixB->nnz = matrixA->nnz;
         matrixB->rowpointer = (int *)malloc(((size_t)matrixA->n + 1) * sizeof(int));
         matrixB->columnindex = (int *)malloc((size_t)(matrixA->nnz ? matrixA->nnz : 1) * sizeof(int));

@@ -367,11 +367,28 @@ def test_c_driver_cli(tmp_path):
         assert out.returncode == 0, out.stdout + out.stderr
         assert "[PASSED]" in out.stdout and "CUDA  TileSpGEMM runtime is" in out.stdout
     rows = open(tmp_path / "results_tile.csv").read().strip().splitlines()
-    assert len(rows) == 3 and rows[0].split(",")[1:4] == ["120", "120", str(len(ci))]
+    assert len(rows) >= 3 and rows[0].split(",")[1:4] == ["120", "120", str(len(ci))]
     for name in ("step_runtime.csv", "mem-cost.csv", "preprocessing.csv"):
         assert len(open(tmp_path / name).read().strip().splitlines()) == 3
     bad = subprocess.run([exe, "-d", "0", "-aat", "0", str(mtx), "32", "32"], capture_output=True, text=True, env=env, timeout=60)
     assert bad.returncode != 0  # unsupported tile size: the driver exits non-zero instead of printing garbage
+    # the reference's loader keeps file order and duplicates (TSG_MTX_RAW=1 does the same): the drop-in csr2tile_* canonicalise
+    scr = tmp_path / "scrambled.mtx"
+    rng = np.random.default_rng(2)
+    S = [(r + 1, c + 1) for r in range(m) for c in ci[rp[r]:rp[r + 1]]]
+    rng.shuffle(S)
+    S += S[:25]
+    with open(scr, "w") as f:
+        f.write(f"%%MatrixMarket matrix coordinate pattern general\n{m} {n} {len(S)}\n" + "".join(f"{r} {c}\n" for r, c in S))
+    out = subprocess.run([exe, "-d", "0", "-aat", "0", str(scr), "16", "16"], capture_output=True, text=True,
+                         env=dict(env, TSG_MTX_RAW="1", TSG_MTX_CACHE="0"), timeout=120)
+    assert out.returncode == 0 and "[PASSED]" in out.stdout and "canonicalised on the device" in out.stderr, out.stdout + out.stderr
+    # -aat 2 A B: the general product of two files (the CLI shape of the reference's cuSPARSE harness)
+    mb, nb, rpb, cib, vb = M.random_sparse(120, 75, 0.07, seed=8)
+    mtxb = tmp_path / "rand120x75.mtx"
+    M.write_mtx(str(mtxb), mb, nb, rpb, cib, vb)
+    out = subprocess.run([exe, "-d", "0", "-aat", "2", str(mtx), str(mtxb), "16", "16"], capture_output=True, text=True, env=env, timeout=120)
+    assert out.returncode == 0 and "[PASSED]" in out.stdout and "input matrix B: ( 120, 75 )" in out.stdout, out.stdout + out.stderr
     # -slabs: the product slab by slab through tsg_spgemm_slabs (what configs 3 and 5 need), both modes
     for args in (["-d", "0", "-aat", "1", "gen:rmat:12:16", "16", "16", "-slabs", "100000"],
                  ["-d", "0", "-aat", "0", "gen:stencil27:12", "16", "16", "-slabs", "2000"]):
