@@ -405,11 +405,15 @@ k_s1_fill(const __grid_constant__ S1Fill P)
 // per C tile, the matched (A tile, B tile) pair list: ONE expansion and ONE global atomic per pair -- the atomicAdd
 // that counts the pairs of a C tile also returns the pair's rank inside the tile's list; (slot, rank, A tile, B tile)
 // is parked in a per-row scratch record, the counts are scanned, and the records are then placed.
-// Dynamic smem: bitmap[nw_max] | pre8[nw_max/8 + 1]. The symbolic of these rows is k_step2 / k_step2_thread.
+// Dynamic smem: bitmap[nw_max] | pre8[nw_max/8 + 1] -- or, when a window does not fit shared memory (matrices wider than
+// ~29 M columns whose hub tile-rows span all of them; the reference falls back to a global-memory hash there,
+// src/spgemm_nsparse_kernel.h:1253-1283), the same two arrays in a per-CTA slice of GLOBAL memory (gscratch): the grid is then
+// a few CTAs per SM that walk heavy_list in a loop. The symbolic of these rows is k_step2 / k_step2_thread.
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(S1_HEAVY_THREADS)
-k_s1_heavy(int trow0, int nw_max, const int *__restrict__ heavy_list, const int *__restrict__ a_tile_ptr,
+k_s1_heavy(int trow0, int nw_max, int n_heavy, unsigned *__restrict__ gscratch, const int *__restrict__ heavy_list,
+           const int *__restrict__ a_tile_ptr,
            const int *__restrict__ a_tile_col, const int *__restrict__ b_tile_ptr, const int *__restrict__ b_tile_col,
            const int *__restrict__ b_rm2csc, const int *__restrict__ w, const int *__restrict__ jlo,
            const int *__restrict__ jhi, int *__restrict__ cnt /*MODE0 out*/, const int *__restrict__ c_tile_ptr,
@@ -421,10 +425,12 @@ k_s1_heavy(int trow0, int nw_max, const int *__restrict__ heavy_list, const int 
     extern __shared__ unsigned s1_smem[];
     __shared__ int s_warp[NWARPS];
     __shared__ int s_carry;
-    unsigned *bitmap = s1_smem;
-    int *pre8 = (int *)(s1_smem + nw_max);
-    const int i = heavy_list[blockIdx.x], I = trow0 + i;
+    unsigned *bitmap = gscratch ? gscratch + (size_t)blockIdx.x * ((size_t)nw_max + nw_max / 8 + 2) : s1_smem;
+    int *pre8 = (int *)(bitmap + nw_max);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+    __syncthreads();  // the previous row of this CTA is done with the bitmap
+    const int i = heavy_list[h], I = trow0 + i;
     const int wi = w[i];
     const int lo = jlo[i] & ~31;
     const int nw = ((jhi[i] - lo) >> 5) + 1;
@@ -445,7 +451,7 @@ k_s1_heavy(int trow0, int nw_max, const int *__restrict__ heavy_list, const int 
         for (int k = tid; k < nw; k += THREADS) s += __popc(bitmap[k]);
         block_excl_scan<THREADS>(s, s_warp, &total);
         if (tid == 0) cnt[i] = total;
-        return;
+        continue;
     }
     // ---- MODE 1 ----
     const int ngroups = (nw + 7) >> 3;
@@ -535,6 +541,7 @@ k_s1_heavy(int trow0, int nw_max, const int *__restrict__ heavy_list, const int 
             }
         }
     }
+    }  // heavy_list loop
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -750,19 +757,27 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     }
     long long numblkC = c.h_scalars[5];
     size_t heavy_smem = 0;
+    int heavy_grid = 0;
+    unsigned *heavy_gscratch = nullptr;
+    struct Scratch { unsigned *&p; ~Scratch() { if (p) dfree(p); } } heavy_guard{heavy_gscratch};  // released on every return path
     if (n_heavy > 0) {  // count the C tiles of the heavy tile-rows, scan again (one more read-back; R-MAT only)
         const int nw_max = hs[SC_NW_HEAVY];
         heavy_smem = ((size_t)nw_max + (size_t)nw_max / 8 + 2) * 4;
-        if (heavy_smem > c.smem_optin) {
-            set_error(TSG_ERR_UNSUPPORTED, "step 1: a tile-column window of %d words needs %zu B of shared memory (> %zu); matrices wider "
-                      "than ~29 M columns with tile-rows spanning all of them are not supported yet", nw_max, heavy_smem, c.smem_optin);
-            return last_error();
+        const char *kb = getenv("TSG_S1_SMEM_KB");  // tests: a small budget forces the global-memory bitmap
+        if (heavy_smem > (kb && *kb ? (size_t)atoi(kb) * 1024 : c.smem_optin)) {
+            // the window does not fit shared memory: bitmap + prefix in a per-CTA slice of global memory, 2 CTAs per SM walk the list
+            heavy_grid = n_heavy < 2 * c.num_sms ? n_heavy : 2 * c.num_sms;
+            heavy_gscratch = dalloc_n<unsigned>((size_t)heavy_grid * (heavy_smem / 4));
+            if (!heavy_gscratch) return last_error();
+            heavy_smem = 0;
+        } else {
+            heavy_grid = n_heavy;
         }
         if (heavy_smem > 48 * 1024) {
             CK(cudaFuncSetAttribute(k_s1_heavy<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem));
             CK(cudaFuncSetAttribute(k_s1_heavy<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem));
         }
-        k_s1_heavy<0><<<n_heavy, S1_HEAVY_THREADS, heavy_smem, c.stream>>>(trow0, nw_max, heavy_list, A->tile_ptr, A->tile_columnidx, B->tile_ptr,
+        k_s1_heavy<0><<<heavy_grid, S1_HEAVY_THREADS, heavy_smem, c.stream>>>(trow0, nw_max, n_heavy, heavy_gscratch, heavy_list, A->tile_ptr, A->tile_columnidx, B->tile_ptr,
                                                                           B->tile_columnidx, B->rm2csc, w, jlo, jhi, cnt, nullptr, nullptr,
                                                                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
         CK_LAUNCH();
@@ -858,7 +873,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         CK_LAUNCH();
     }
     if (numblkC > 0 && n_heavy > 0) {
-        k_s1_heavy<1><<<n_heavy, S1_HEAVY_THREADS, heavy_smem, c.stream>>>(trow0, hs[SC_NW_HEAVY], heavy_list, A->tile_ptr, A->tile_columnidx,
+        k_s1_heavy<1><<<heavy_grid, S1_HEAVY_THREADS, heavy_smem, c.stream>>>(trow0, hs[SC_NW_HEAVY], n_heavy, heavy_gscratch, heavy_list, A->tile_ptr, A->tile_columnidx,
                                                                           B->tile_ptr, B->tile_columnidx, B->rm2csc, w, jlo, jhi, nullptr,
                                                                           C->tile_ptr, wptr, C->tile_columnidx, C->tile_rowidx, pair_ptr,
                                                                           pair_end, pair_a, pair_b, pair_tmp);

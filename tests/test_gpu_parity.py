@@ -780,3 +780,22 @@ def test_recipe_plans_fall_back_when_recipes_do_not_repeat(monkeypatch):
     assert np.array_equal(r, er) and np.array_equal(c, ec) and np.array_equal(vv, ev)
     for o in (csr, tC, tA, tB, d):
         o.free()
+
+
+def test_heavy_tile_rows_with_global_memory_bitmap(monkeypatch):
+    """Hub tile-rows whose tile-column window does not fit shared memory (forced here with a 1 KB budget; for real from
+    ~29 M columns up) keep their step-1 bitmap in global memory, a few CTAs per SM walking the heavy list: same C."""
+    monkeypatch.setenv("TSG_S1_SMEM_KB", "1")
+    m, n, rp, ci, v = M.rmat(13, 16, seed=3)
+    A = (rp, ci, v)
+    cp, ri, cv = orc.transpose(m, n, rp, ci, v)
+    B = (cp, ri, cv)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    dT = api.transpose(d)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(dT, True)
+    assert api.tilerow_weights(tA, tB).max() > 2048          # heavy tile-rows exist
+    csrC, tC_exp = oracle_c(m, n, A, B, m)
+    tC, st = api.spgemm(tA, tB)
+    assert_tiled_equal(tC.download(), tC_exp, "global-bitmap C")
+    for o in (tC, tA, tB, d, dT):
+        o.free()
