@@ -49,7 +49,21 @@ WORKLOADS = {
     "rmat-s24": (lambda: M.rmat(24, 16, a=0.30, b=0.25, c=0.25, d=0.20, seed=1), False,
                  "C=A^2, R-MAT scale 24, edge factor 16, mild skew (0.30,0.25,0.25,0.20), slab-wise (config 5)"),
     "blockfem-2M": (lambda: M.blockfem(333334), False, "C=A^2, block-FEM 2M rows, dense 6x6 blocks, band 1 (config 4)"),
+    "mixed-fem-stencil": (lambda: mixed_fem_stencil(), False,
+                          "C=A^2, block-diagonal [block-FEM 1M rows | 27-point stencil 100^3]: well-filled and sparse tiles in one matrix "
+                          "(per-tile accumulator selection; not a BASELINE config)"),
 }
+
+
+def mixed_fem_stencil():
+    """Block-diagonal of a block-FEM matrix and a 27-point stencil: half of the C tiles want the dense accumulator, half the sparse one."""
+    import scipy.sparse as sp
+    parts = []
+    for m, n, rp, ci, v in (M.blockfem(166667), M.stencil27(100)):
+        parts.append(sp.csr_matrix((np.ones(len(ci)), ci, rp), shape=(m, n)))
+    S = sp.block_diag(parts, format="csr")
+    S.sort_indices()
+    return S.shape[0], S.shape[1], S.indptr.astype(np.int32), S.indices.astype(np.int32), M.set_values(S.nnz, "mod10")
 # workloads whose C does not fit one GPU / int32 offsets whole: executed as slabs of at most this many tile pairs
 SLAB_PAIRS = {"rmat-s16-aat": 1 << 26, "rmat-s18-aat": 1 << 28, "rmat-s20-aat": 1 << 28, "rmat-s22": 1 << 28, "rmat-s24": 1 << 28}
 DEFAULT_WORKLOAD = "stencil27-128"   # BASELINE.json configs[1]: the configuration the metric is quoted on
