@@ -726,7 +726,7 @@ def test_recipe_plans_numeric_variants(monkeypatch, variant):
     """The plan-driven numeric step has two kernels (CTA per tile-row with A's values staged in shared memory -- the
     default, covered above -- and lane per nonzero over the whole slab) and the staged one has an unstaged branch for
     tile-rows that do not fit: all give the serial SPA's values."""
-    monkeypatch.setenv("TSG_PLANS", "1")
+    monkeypatch.setenv("TSG_PLANS", "2")            # 2 = also on well-filled tiles (this small stencil has > 24 entries per tile)
     if variant == "flat":
         monkeypatch.setenv("TSG_PLANS_NUMERIC", "flat")
     else:
