@@ -122,7 +122,7 @@ def step3_bytes(tA, tB, st):
     payloads (Val 8 per nnz, Ptr 32 + mask 32 + tile_nnz 4 per tile), the pair lists (8 per pair), C's structure for
     the tiles that hold entries (Ptr 32 + mask 32 + tile_nnz 4 each: the empty listed tiles of a hypersparse product are
     never read by it) and C's payload written (Val 8 + Col 2 per nnz)."""
-    if st.get("plan_recipes", 0) > 0:  # plan path (csrc/plans.cu): values of A and B, per pair its two value bases (8),
+    if st.get("plan_recipes", 0) > 0:  # plan path (csrc/plans.cu): values of A and B, per pair its two tile indices (8),
         # per C tile its recipe id, nnz offset and pair offset (12), C's payload written; the plans themselves stay in L1/L2
         return tA.nnz * 8 + tB.nnz * 8 + st["pairs"] * 8 + st["numblkC"] * 12 + st["nnzC"] * 10
     return (tA.nnz * 8 + tA.numtile * 68 + tB.nnz * 8 + tB.numtile * 68 + st["tiles_nonempty"] * 68 + st["pairs"] * 8
@@ -133,7 +133,7 @@ def numeric_kernels(st):
     """Names of the numeric (step 3) kernels this workload actually launched (tsg_stats)."""
     names = []
     if st.get("plan_recipes", 0) > 0:
-        return f"k_pair_bases + k_numeric_from_plans ({st['plan_recipes']} recipes)"
+        return f"k_numeric_from_plans_rows ({st['plan_recipes']} recipes)"
     if st.get("rows_staged", 0) > 0:
         names.append(f"k_step3_rows ({st['rows_staged']} tile-rows, {st['rows_smem']} B smem)")
     if st.get("tiles_dense", 0) > 0:

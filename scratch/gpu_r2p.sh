@@ -1,0 +1,11 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+make -s -C driver
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/r2p_pytest.txt; tail -6 gpurun_out/r2p_pytest.txt
+timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/r2p_bench_stencil27-128.json 2> gpurun_out/r2p_bench.err; tail -c 1000 gpurun_out/r2p_bench_stencil27-128.json
+TSG_PLANS_OCC=5 timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/r2p_bench_stencil27-128_occ5.json 2>> gpurun_out/r2p_bench.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 250 --csv --log-file gpurun_out/r2p_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity --e2e-steps 1 > gpurun_out/r2p_ncu1.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_numeric_from_plans_rows -c 1 -o gpurun_out/r2p_plans_rows python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity --e2e-steps 1 > gpurun_out/r2p_ncu2.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_s1_fill -c 1 -o gpurun_out/r2p_s1_fill python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity --e2e-steps 1 > gpurun_out/r2p_ncu3.log 2>&1
+tail -5 gpurun_out/r2p_bench.err

@@ -9,9 +9,11 @@
 //   * k_s1_fill hashes each C tile's pair sequence while it writes the pair lists (spgemm.cu) and inserts it into the
 //     recipe table; k_recipe_verify compares every tile's sequence with its recipe's representative;
 //   * k_plan_build plans each distinct recipe once, from the representative tile's actual masks;
+//   * k_plan_slots pairs each recipe's C nonzeros, the one with the most products with the one with the fewest and so
+//     on inwards, into "slots" of nearly equal length;
 //   * the symbolic step becomes a 68-byte copy per C tile (k_symbolic_from_plans) and the numeric step walks an
-//     L1-resident plan, one lane per C nonzero, every iteration a product, in the serial SPA's summation order
-//     (k_numeric_from_plans): bit-identical to the generic kernels' results.
+//     L1-resident plan, one lane per slot, every iteration a product, each nonzero summed in the serial SPA's order
+//     (k_numeric_from_plans_rows): bit-identical to the generic kernels' results.
 // Nothing here waits on another thread: insert = one atomicCAS on the key word, owner of a slot = atomicMin of the item
 // indices that landed in it (deterministic), and a true 64-bit hash collision, too many patterns / recipes, or a plan
 // that outgrows its buffer raise the fail flag -- the generic kernels (spgemm.cu step 2, numeric.cu) then run instead.
@@ -71,6 +73,8 @@ struct PlanCtx {
     unsigned *plan_ent = nullptr;
     uint16_t *plan_cnt = nullptr;
     uint8_t *plan_col = nullptr;
+    uint2 *plan_slot = nullptr;      // per recipe, 128 slots: (n | nx << 16, X | Y << 8)
+    unsigned *plan_jslot = nullptr;  // per recipe, 256 nonzeros: slot | first iteration << 8
     int *ctl = nullptr;  // [0] pattern count, [1] pattern fail, [2] recipe count, [3] recipe / plan fail
     int device = -1;
 };
@@ -96,10 +100,12 @@ static int plan_ctx_init()
     p.plan_off = dalloc_n<int>(RMAX + 1);
     p.plan_cnt = dalloc_n<uint16_t>((size_t)RMAX * 256);
     p.plan_col = dalloc_n<uint8_t>((size_t)RMAX * 256);
+    p.plan_slot = dalloc_n<uint2>((size_t)RMAX * 128);
+    p.plan_jslot = dalloc_n<unsigned>((size_t)RMAX * 256);
     p.plan_ent = dalloc_n<unsigned>(PLAN_ENT_CAP);
     p.ctl = dalloc_n<int>(8);
     if (!p.pkeys || !p.powner || !p.rkeys || !p.rowner || !p.rflags || !p.rdense || !p.rep_tile || !p.plan_mask || !p.plan_ptr ||
-        !p.plan_nnz || !p.plan_tot || !p.plan_off || !p.plan_cnt || !p.plan_col || !p.plan_ent || !p.ctl) {
+        !p.plan_nnz || !p.plan_tot || !p.plan_off || !p.plan_cnt || !p.plan_col || !p.plan_slot || !p.plan_jslot || !p.plan_ent || !p.ctl) {
         g_plan = PlanCtx();
         return last_error();
     }
@@ -170,13 +176,10 @@ k_recipe_reps(const int *__restrict__ owner, const int *__restrict__ rdense, int
 }
 
 // every C tile compares its (A pattern, B pattern) sequence with its recipe's representative: a 64-bit collision fails.
-// While the pair list is in hand, the value bases of each pair's two tiles are written out (pair_base): the numeric
-// kernel then needs one 8-byte load per product instead of two index loads and two gathers.
 __global__ void __launch_bounds__(256)
 k_recipe_verify(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end, const int *__restrict__ pair_a,
                 const int *__restrict__ pair_b, const int *__restrict__ patA, const int *__restrict__ patB,
                 const int *__restrict__ rslot, const int *__restrict__ owner, const int *__restrict__ rdense,
-                const int *__restrict__ a_tile_nnz, const int *__restrict__ b_tile_nnz, int2 *__restrict__ pair_base,
                 int *__restrict__ recipe_id, int *fail)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,28 +192,28 @@ k_recipe_verify(int numblkC, const int *__restrict__ pair_ptr, const int *__rest
     if (u < 0 || u >= numblkC || rdense[slot] >= RMAX) { *fail = 1; return; }
     const int p0 = pair_ptr[t], n = pair_end[t] - p0, q0 = pair_ptr[u];
     bool same = pair_end[u] - q0 == n;
-    for (int i = 0; i < n; i++) {
-        const int a = pair_a[p0 + i], b = pair_b[p0 + i];
-        if (pair_base) pair_base[p0 + i] = make_int2(a_tile_nnz[a], b_tile_nnz[b]);
-        if (same && u != t) same = patA[a] == patA[pair_a[q0 + i]] && patB[b] == patB[pair_b[q0 + i]];
-    }
+    if (u != t)
+        for (int i = 0; i < n && same; i++)
+            same = patA[pair_a[p0 + i]] == patA[pair_a[q0 + i]] && patB[pair_b[p0 + i]] == patB[pair_b[q0 + i]];
     if (!same) *fail = 2;
     recipe_id[t] = rdense[slot];
 }
 
 // A HALF-WARP per distinct recipe, lane = row r of the recipe's representative C tile. FILL = false: masks / Ptr / nnz of
-// the tile, the number of products of every C nonzero (plan_cnt) and the space the recipe's entries take (plan_tot =
-// nnz * the longest product list). FILL = true: plan_off = exclusive scan of plan_tot; writes the entries
-// (pair index << 16 | position in B's tile << 8 | position in A's tile), in the serial SPA's order, ITERATION-MAJOR:
-// product i of nonzero j lives at plan_off[R] + i * nnz + j, so the lanes of the numeric kernel -- consecutive nonzeros of a
-// tile, all at iteration i -- read consecutive words.
+// the tile and the number of products of every C nonzero (plan_cnt). k_plan_slots then pairs the nonzeros into slots and
+// sizes the recipe's entries (plan_tot). FILL = true: plan_off = exclusive scan of plan_tot; writes the entries
+// (pair index << 16 | position in B's tile << 8 | position in A's tile), each nonzero's in the serial SPA's order,
+// ITERATION-MAJOR over slots: product i of the nonzero that starts at iteration `start` of slot v lives at
+// plan_off[R] + (start + i) * nslots + v, so the lanes of the numeric kernel -- consecutive slots of a tile, all at the
+// same iteration -- read consecutive words.
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, const int *__restrict__ pair_ptr,
              const int *__restrict__ pair_end, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
              const uint16_t *__restrict__ a_mask, const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ b_mask,
-             const uint16_t *__restrict__ b_ptr, uint16_t *plan_mask, uint16_t *plan_ptr, int *plan_nnz, int *plan_tot,
-             const int *__restrict__ plan_off, uint16_t *plan_cnt, uint8_t *plan_col, unsigned *plan_ent, int *fail)
+             const uint16_t *__restrict__ b_ptr, uint16_t *plan_mask, uint16_t *plan_ptr, int *plan_nnz,
+             const int *__restrict__ plan_off, uint16_t *plan_cnt, uint8_t *plan_col, const unsigned *__restrict__ plan_jslot,
+             unsigned *plan_ent, int *fail)
 {
     const int R = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, r = threadIdx.x & 15;
     const unsigned hm = 0xFFFFu << (threadIdx.x & 16);
@@ -245,14 +248,16 @@ k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, c
         plan_mask[R * TS + r] = (uint16_t)cm;
         if (r == 0) plan_nnz[R] = nnz;
     }
-    const unsigned base = FILL ? (unsigned)plan_off[R] : 0u;
-    int longest = 0, j = rowbase;
+    const unsigned base = FILL ? (unsigned)plan_off[R] : 0u, nslots = (unsigned)(nnz + 1) >> 1;
+    int j = rowbase;
     unsigned rowm = cm;
     while (rowm) {
         const int c = __clz(rowm) - 16;
         rowm ^= 0x8000u >> c;
         const unsigned cbit = 0x8000u >> c;
-        int i = 0;
+        const unsigned js = FILL ? plan_jslot[(size_t)R * 256 + j] : 0u;  // slot | first iteration << 8
+        unsigned i = js >> 8;
+        const unsigned i0 = i;
         for (int p = p0; p < p1; p++) {
             const int a = pair_a[p], b = pair_b[p];
             unsigned am = a_mask[(size_t)a * TS + r];
@@ -264,7 +269,7 @@ k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, c
                 if (bm & cbit) {
                     if (FILL) {
                         const unsigned posb = (unsigned)b_ptr[(size_t)b * TS + k] + __popc(bm >> (16 - c));
-                        plan_ent[base + (unsigned)i * (unsigned)nnz + (unsigned)j] = ((unsigned)(p - p0) << 16) | (posb << 8) | ia;
+                        plan_ent[base + i * nslots + (js & 255u)] = ((unsigned)(p - p0) << 16) | (posb << 8) | ia;
                     }
                     i++;
                 }
@@ -272,18 +277,59 @@ k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, c
             }
         }
         if (!FILL) {
-            if (i > 0xFFFF) *fail = 1;
-            plan_cnt[(size_t)R * 256 + j] = (uint16_t)i;
+            if (i - i0 > 0xFFFFu) *fail = 1;
+            plan_cnt[(size_t)R * 256 + j] = (uint16_t)(i - i0);
             plan_col[(size_t)R * 256 + j] = (uint8_t)c;
         }
-        longest = max(longest, i);
         j++;
     }
-    if (!FILL) {
-#pragma unroll
-        for (int o = 8; o; o >>= 1) longest = max(longest, __shfl_xor_sync(hm, longest, o, 16));
-        if (r == 0) plan_tot[R] = longest * nnz;
+}
+
+// A WARP per distinct recipe: the C nonzeros of the tile differ in how many products they sum (1 ... 27 on the 27-point
+// stencil), and a warp whose lanes each walked one nonzero would run as long as its longest list with, measured, 15 of 32
+// lanes busy. So the nonzeros are ranked by product count and paired from the two ends -- most with fewest, and so on
+// inwards -- into ceil(nnz / 2) SLOTS of nearly equal total length; a lane of the numeric kernel walks a slot: nonzero X's
+// products, then nonzero Y's. Per slot: plan_slot = (n | nx << 16, X | Y << 8) with nx = X's count, n = nx + Y's count
+// (n == nx: the odd one in the middle, alone). Per nonzero: plan_jslot = slot | first iteration << 8.
+// plan_tot = nslots * the longest slot = the words the recipe's entries take.
+__global__ void __launch_bounds__(128)
+k_plan_slots(const int *__restrict__ nrec_p, const int *__restrict__ plan_nnz, const uint16_t *__restrict__ plan_cnt,
+             unsigned *__restrict__ plan_jslot, uint2 *__restrict__ plan_slot, int *__restrict__ plan_tot, int *fail)
+{
+    __shared__ uint16_t s_cnt[4][256];
+    __shared__ uint8_t s_sorted[4][256];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, R = blockIdx.x * 4 + w;
+    const int nrec = *nrec_p;
+    if (*(volatile int *)fail || nrec > RMAX || R >= nrec) return;  // whole warps leave together
+    const int nnz = plan_nnz[R];
+    for (int j = lane; j < nnz; j += 32) s_cnt[w][j] = plan_cnt[(size_t)R * 256 + j];
+    __syncwarp();
+    for (int j = lane; j < nnz; j += 32) {  // rank = how many nonzeros come before j in (count descending, index ascending) order
+        const int cj = s_cnt[w][j];
+        int rank = 0;
+        for (int k = 0; k < nnz; k++) {
+            const int ck = s_cnt[w][k];
+            rank += (ck > cj) || (ck == cj && k < j);
+        }
+        s_sorted[w][rank] = (uint8_t)j;
     }
+    __syncwarp();
+    const int nslots = (nnz + 1) >> 1;
+    int longest = 0;
+    for (int v = lane; v < nslots; v += 32) {
+        const int ky = nnz - 1 - v;
+        const bool has_y = ky > v;
+        const unsigned X = s_sorted[w][v], Y = has_y ? s_sorted[w][ky] : X;
+        const unsigned nx = s_cnt[w][X], n = nx + (has_y ? s_cnt[w][Y] : 0u);
+        if (n > 0xFFFFu) *fail = 1;
+        plan_slot[(size_t)R * 128 + v] = make_uint2(n | (nx << 16), X | (Y << 8));
+        plan_jslot[(size_t)R * 256 + X] = (unsigned)v;
+        if (has_y) plan_jslot[(size_t)R * 256 + Y] = (unsigned)v | (nx << 8);
+        longest = max(longest, (int)n);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) longest = max(longest, __shfl_xor_sync(0xFFFFFFFFu, longest, o));
+    if (lane == 0) plan_tot[R] = longest * nslots;
 }
 
 // C tile metadata from the plan: one thread per C tile copies its recipe's 32 + 32 bytes and its nnz.
@@ -303,53 +349,13 @@ k_symbolic_from_plans(int numblkC, const int *__restrict__ recipe_id, const uint
     c_cnt[t] = plan_nnz[R];
 }
 
-__global__ void k_blk2tile_p(int numblkC, const int *__restrict__ c_tile_nnz, int *__restrict__ blk2tile)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= numblkC) return;
-    const int s = c_tile_nnz[t], e = c_tile_nnz[t + 1];
-    for (int blk = (s + 31) >> 5; (blk << 5) < e; blk++) blk2tile[blk] = t;
-}
-
-// One lane per C nonzero g: find its tile (blk2tile gives the tile holding nonzero 32*(g/32)), then walk its plan entries:
-// every iteration is a product, added in the serial SPA's order. The lanes of a warp are consecutive nonzeros of (mostly)
-// one tile: at iteration i they read consecutive plan words.
-__global__ void __launch_bounds__(256, 8)
-k_numeric_from_plans(int numblkC, int nnzC, const int *__restrict__ blk2tile, const int *__restrict__ c_tile_nnz,
-                     const int *__restrict__ recipe_id, const int *__restrict__ plan_off, const int *__restrict__ plan_nnz,
-                     const uint16_t *__restrict__ plan_cnt, const uint8_t *__restrict__ plan_col, const unsigned *__restrict__ plan_ent,
-                     const int *__restrict__ pair_ptr, const int2 *__restrict__ pair_base, const double *__restrict__ a_val,
-                     const double *__restrict__ b_val, uint16_t *__restrict__ c_col, double *__restrict__ c_val)
-{
-    const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gl >= nnzC) return;
-    const int g = (int)gl;
-    const int blk = g >> 5, nblk = (nnzC + 31) >> 5;
-    int lo = blk2tile[blk], hi = blk + 1 < nblk ? blk2tile[blk + 1] : numblkC - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (c_tile_nnz[mid] <= g) lo = mid; else hi = mid - 1;
-    }
-    const int t = lo, off = g - c_tile_nnz[t];
-    const int R = recipe_id[t];
-    const int n = plan_cnt[(size_t)R * 256 + off], stride = plan_nnz[R];
-    const unsigned *ent = plan_ent + plan_off[R] + off;
-    const int2 *pb = pair_base + pair_ptr[t];
-    double acc = 0.0;
-    for (int i = 0; i < n; i++, ent += stride) {
-        const unsigned e = *ent;
-        const int2 base = pb[e >> 16];
-        acc = fma(a_val[base.x + (int)(e & 255u)], b_val[base.y + (int)((e >> 8) & 255u)], acc);
-    }
-    c_val[g] = acc;
-    c_col[g] = plan_col[(size_t)R * 256 + off];
-}
-
-// The same walk with a CTA per C TILE-ROW: the tile-row's share of A's values (contiguous in row-major tile order), the
-// offsets / recipes / pair ranges of its C tiles and, per pair, the position of the A tile's values in that staged copy and
-// the base of the B tile's values are put into shared memory first. Per product that leaves two global loads (the plan
-// word and B's value) instead of four, and the pair_base array is not needed. Rows that do not fit `smem_cap` read
-// everything from global memory (same results).
+// The numeric step: a CTA per C TILE-ROW. The tile-row's share of A's values (contiguous in row-major tile order), the
+// offsets / recipes / pair ranges / slot ranges of its C tiles and, per pair, the position of the A tile's values in that
+// staged copy and the base of the B tile's values are put into shared memory first. Then one lane per SLOT of the
+// tile-row (k_plan_slots: two C nonzeros of one tile, the second's products after the first's): every iteration is a
+// product -- two global loads (the plan word, coalesced, and B's value) and two shared ones (the pair's bases, A's value).
+// Each nonzero is summed in the serial SPA's order, so the values are bit-identical to the generic kernels'.
+// Tile-rows that do not fit `smem_cap` take one lane per nonzero and read everything from global memory (same results).
 struct PlanRows {
     int trow0, smem_cap;
     const int *a_tile_ptr, *a_tile_nnz;
@@ -360,18 +366,20 @@ struct PlanRows {
     const int *plan_off, *plan_nnz;
     const uint16_t *plan_cnt;
     const uint8_t *plan_col;
-    const unsigned *plan_ent;
+    const uint2 *plan_slot;
+    const unsigned *plan_jslot, *plan_ent;
     uint16_t *c_col;
     double *c_val;
 };
 
 __host__ __device__ __forceinline__ size_t plan_rows_need(int nnzA, int numJ, int W)
 {
-    return (((size_t)nnzA * 8 + 15) & ~(size_t)15) + (((size_t)(numJ + 1) * 4 + 15) & ~(size_t)15) + 2 * (((size_t)numJ * 4 + 15) & ~(size_t)15) +
-           2 * (((size_t)W * 4 + 15) & ~(size_t)15);
+    return (((size_t)nnzA * 8 + 15) & ~(size_t)15) + 2 * (((size_t)(numJ + 1) * 4 + 15) & ~(size_t)15) + 2 * (((size_t)numJ * 4 + 15) & ~(size_t)15) +
+           (((size_t)W * 8 + 15) & ~(size_t)15);
 }
 
-__global__ void __launch_bounds__(256)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_numeric_from_plans_rows(const __grid_constant__ PlanRows P)
 {
     extern __shared__ __align__(16) unsigned char pr_smem[];
@@ -383,56 +391,88 @@ k_numeric_from_plans_rows(const __grid_constant__ PlanRows P)
     const int a0 = P.a_tile_ptr[I], a1 = P.a_tile_ptr[I + 1];
     const int av0 = P.a_tile_nnz[a0], nnzA = P.a_tile_nnz[a1] - av0;
     const int w0 = P.wptr[i], W = P.wptr[i + 1] - w0;
-    const bool staged = plan_rows_need(nnzA, numJ, W) <= (size_t)P.smem_cap;  // uniform over the CTA
-    size_t off = 0;
-    auto carve = [&](size_t bytes) { unsigned char *p = pr_smem + off; off += (bytes + 15) & ~(size_t)15; return p; };
-    double *s_aval = (double *)carve((size_t)nnzA * 8);
-    int *s_cnnz = (int *)carve((size_t)(numJ + 1) * 4);
-    int *s_rec = (int *)carve((size_t)numJ * 4);
-    int *s_pp = (int *)carve((size_t)numJ * 4);
-    int *s_abase = (int *)carve((size_t)W * 4);
-    int *s_bbase = (int *)carve((size_t)W * 4);
-    if (staged) {
-        for (int k = tid; k < nnzA; k += 256) s_aval[k] = P.a_val[av0 + k];
-        for (int k = tid; k <= numJ; k += 256) {
-            s_cnnz[k] = P.c_tile_nnz[c0 + k] - n0;
-            if (k < numJ) { s_rec[k] = P.recipe_id[c0 + k]; s_pp[k] = P.pair_ptr[c0 + k] - w0; }
-        }
-        for (int k = tid; k < W; k += 256) {
-            s_abase[k] = P.a_tile_nnz[P.pair_a[w0 + k]] - av0;
-            s_bbase[k] = P.b_tile_nnz[P.pair_b[w0 + k]];
-        }
-        __syncthreads();
-    }
-    for (int g = tid; g < nnzC; g += 256) {
-        int lo = 0, hi = numJ - 1;  // the tile holding nonzero g of the tile-row: largest s with nnz offset <= g
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if ((staged ? s_cnnz[mid] : P.c_tile_nnz[c0 + mid] - n0) <= g) lo = mid; else hi = mid - 1;
-        }
-        const int sidx = lo;
-        const int off_in_tile = g - (staged ? s_cnnz[sidx] : P.c_tile_nnz[c0 + sidx] - n0);
-        const int R = staged ? s_rec[sidx] : P.recipe_id[c0 + sidx];
-        const int n = P.plan_cnt[(size_t)R * 256 + off_in_tile], stride = P.plan_nnz[R];
-        const unsigned *ent = P.plan_ent + P.plan_off[R] + off_in_tile;
-        double acc = 0.0;
-        if (staged) {
-            const int pp = s_pp[sidx];
-            for (int it = 0; it < n; it++, ent += stride) {
-                const unsigned e = *ent;
-                const int p = pp + (int)(e >> 16);
-                acc = fma(s_aval[s_abase[p] + (int)(e & 255u)], P.b_val[s_bbase[p] + (int)((e >> 8) & 255u)], acc);
+    if (plan_rows_need(nnzA, numJ, W) > (size_t)P.smem_cap) {  // uniform over the CTA: lane per nonzero, nothing staged
+        for (int g = tid; g < nnzC; g += 256) {
+            int lo = 0, hi = numJ - 1;  // the tile holding nonzero g of the tile-row: largest s with nnz offset <= g
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (P.c_tile_nnz[c0 + mid] - n0 <= g) lo = mid; else hi = mid - 1;
             }
-        } else {
-            const int pp = P.pair_ptr[c0 + sidx];
-            for (int it = 0; it < n; it++, ent += stride) {
+            const int off = g - (P.c_tile_nnz[c0 + lo] - n0), R = P.recipe_id[c0 + lo];
+            const unsigned js = P.plan_jslot[(size_t)R * 256 + off];
+            const int n = P.plan_cnt[(size_t)R * 256 + off], nsl = (P.plan_nnz[R] + 1) >> 1, pp = P.pair_ptr[c0 + lo];
+            const unsigned *ent = P.plan_ent + P.plan_off[R] + (size_t)(js >> 8) * nsl + (js & 255u);
+            double acc = 0.0;
+            for (int it = 0; it < n; it++, ent += nsl) {
                 const unsigned e = *ent;
                 const int p = pp + (int)(e >> 16);
                 acc = fma(P.a_val[P.a_tile_nnz[P.pair_a[p]] + (int)(e & 255u)], P.b_val[P.b_tile_nnz[P.pair_b[p]] + (int)((e >> 8) & 255u)], acc);
             }
+            P.c_val[n0 + g] = acc;
+            P.c_col[n0 + g] = P.plan_col[(size_t)R * 256 + off];
         }
-        P.c_val[n0 + g] = acc;
-        P.c_col[n0 + g] = P.plan_col[(size_t)R * 256 + off_in_tile];
+        return;
+    }
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { unsigned char *p = pr_smem + off; off += (bytes + 15) & ~(size_t)15; return p; };
+    double *s_aval = (double *)carve((size_t)nnzA * 8);
+    int *s_cnnz = (int *)carve((size_t)(numJ + 1) * 4);
+    int *s_slot0 = (int *)carve((size_t)(numJ + 1) * 4);
+    int *s_rec = (int *)carve((size_t)numJ * 4);
+    int *s_pp = (int *)carve((size_t)numJ * 4);
+    int2 *s_base = (int2 *)carve((size_t)W * 8);
+    for (int k = tid; k < nnzA; k += 256) s_aval[k] = P.a_val[av0 + k];
+    for (int k = tid; k <= numJ; k += 256) {
+        s_cnnz[k] = P.c_tile_nnz[c0 + k] - n0;
+        if (k < numJ) { s_rec[k] = P.recipe_id[c0 + k]; s_pp[k] = P.pair_ptr[c0 + k] - w0; }
+    }
+    for (int k = tid; k < W; k += 256) s_base[k] = make_int2(P.a_tile_nnz[P.pair_a[w0 + k]] - av0, P.b_tile_nnz[P.pair_b[w0 + k]]);
+    __syncthreads();
+    if (tid < 32) {  // first slot of every tile: exclusive scan of ceil(nnz / 2) over the tile-row's tiles
+        int carry = 0;
+        for (int k0 = 0; k0 < numJ; k0 += 32) {
+            const int k = k0 + tid, v = k < numJ ? (s_cnnz[k + 1] - s_cnnz[k] + 1) >> 1 : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (tid >= o) incl += u;
+            }
+            if (k < numJ) s_slot0[k] = carry + incl - v;
+            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        if (tid == 0) s_slot0[numJ] = carry;
+    }
+    __syncthreads();
+    const int nslot_row = s_slot0[numJ];
+    for (int q = tid; q < nslot_row; q += 256) {
+        int lo = 0, hi = numJ - 1;  // the tile holding slot q of the tile-row: largest s with first slot <= q
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_slot0[mid] <= q) lo = mid; else hi = mid - 1;
+        }
+        const int sidx = lo, v = q - s_slot0[sidx], R = s_rec[sidx];
+        const int cb = s_cnnz[sidx], nsl = (s_cnnz[sidx + 1] - cb + 1) >> 1, pp = s_pp[sidx];
+        const uint2 si = P.plan_slot[(size_t)R * 128 + v];
+        const int n = (int)(si.x & 0xFFFFu), nx = (int)(si.x >> 16);
+        const unsigned *ent = P.plan_ent + P.plan_off[R] + v;
+        double acc = 0.0, first = 0.0;
+        for (int it = 0; it < n; it++, ent += nsl) {
+            const unsigned e = *ent;
+            const int2 base = s_base[pp + (int)(e >> 16)];
+            if (it == nx) { first = acc; acc = 0.0; }
+            acc = fma(s_aval[base.x + (int)(e & 255u)], P.b_val[base.y + (int)((e >> 8) & 255u)], acc);
+        }
+        const int ox = (int)(si.y & 255u), oy = (int)((si.y >> 8) & 255u);
+        const uint8_t *colp = P.plan_col + (size_t)R * 256;
+        const size_t out = (size_t)n0 + cb;
+        if (nx < n) {
+            P.c_val[out + oy] = acc;
+            P.c_col[out + oy] = colp[oy];
+            acc = first;
+        }
+        P.c_val[out + ox] = acc;
+        P.c_col[out + ox] = colp[ox];
     }
 }
 
@@ -457,7 +497,7 @@ int plans_begin(PlanTable *out)
 // After k_s1_fill<HASH>: dense recipe numbers, verification, the plans, and C's masks / Ptr / tile nnz counts from them.
 // Everything is enqueued; *d_fail is the device flag the caller reads back with nnz(C).
 int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const int *rslot, int *recipe_id,
-                          void *pair_base, const int **d_fail)
+                          const int **d_fail)
 {
     Ctx &c = ctx();
     PlanCtx &p = g_plan;
@@ -471,18 +511,20 @@ int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, 
     k_recipe_reps<<<ceil_div(RCAP, 256), 256, 0, c.stream>>>(p.rowner, p.rdense, p.rep_tile);
     CK_LAUNCH();
     k_recipe_verify<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>(numblkC, pl.ptr, pl.end, pl.a, pl.b, A->pat, B->pat, rslot, p.rowner,
-                                                                  p.rdense, A->tile_nnz, B->tile_nnz, (int2 *)pair_base, recipe_id, fail);
+                                                                  p.rdense, recipe_id, fail);
     CK_LAUNCH();
     const int *nrec = p.rdense + RCAP;
     k_plan_build<false><<<ceil_div(RMAX * 16, 128), 128, 0, c.stream>>>(nrec, p.rep_tile, pl.ptr, pl.end, pl.a, pl.b, A->mask, A->ptr, B->mask,
-                                                                        B->ptr, p.plan_mask, p.plan_ptr, p.plan_nnz, p.plan_tot, nullptr,
-                                                                        p.plan_cnt, p.plan_col, nullptr, fail);
+                                                                        B->ptr, p.plan_mask, p.plan_ptr, p.plan_nnz, nullptr, p.plan_cnt,
+                                                                        p.plan_col, nullptr, nullptr, fail);
+    CK_LAUNCH();
+    k_plan_slots<<<ceil_div(RMAX, 4), 128, 0, c.stream>>>(nrec, p.plan_nnz, p.plan_cnt, p.plan_jslot, p.plan_slot, p.plan_tot, fail);
     CK_LAUNCH();
     rc = exclusive_scan<int>(p.plan_tot, p.plan_off, RMAX);
     if (rc) return rc;
     k_plan_build<true><<<ceil_div(RMAX * 16, 128), 128, 0, c.stream>>>(nrec, p.rep_tile, pl.ptr, pl.end, pl.a, pl.b, A->mask, A->ptr, B->mask,
-                                                                       B->ptr, p.plan_mask, p.plan_ptr, p.plan_nnz, p.plan_tot, p.plan_off,
-                                                                       p.plan_cnt, p.plan_col, p.plan_ent, fail);
+                                                                       B->ptr, p.plan_mask, p.plan_ptr, p.plan_nnz, p.plan_off, p.plan_cnt,
+                                                                       p.plan_col, p.plan_jslot, p.plan_ent, fail);
     CK_LAUNCH();
     k_symbolic_from_plans<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>(numblkC, recipe_id, p.plan_mask, p.plan_ptr, p.plan_nnz, C->mask, C->ptr,
                                                                         C->tile_nnz, fail);
@@ -490,34 +532,26 @@ int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, 
     return TSG_OK;
 }
 
-int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const void *pair_base, const int *recipe_id,
-                         int trow0, int ntr, const int *wptr, int max_need, tsg_stats *stats)
+int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const int *recipe_id, int trow0, int ntr,
+                         const int *wptr, int max_need, tsg_stats *stats)
 {
     Ctx &c = ctx();
     PlanCtx &p = g_plan;
-    const long long numblkC = C->numtile, nnzC = C->nnz;
-    if (nnzC <= 0 || numblkC <= 0) return TSG_OK;
-    if (!pair_base) {  // CTA per tile-row, A's values and the per-pair bases staged in shared memory
-        const char *kb = getenv("TSG_PLANS_SMEM_KB");  // tests: a small budget sends tile-rows down the unstaged branch
-        const size_t cap = kb && *kb ? (size_t)atoi(kb) * 1024 : (size_t)64 * 1024;
-        size_t smem = (size_t)max_need < cap ? (size_t)max_need : cap;
-        smem = (smem + 1023) & ~(size_t)1023;
-        PlanRows P{trow0, (int)smem, A->tile_ptr, A->tile_nnz, A->val, B->tile_nnz, B->val, C->tile_ptr, C->tile_nnz, wptr, pl.ptr, pl.a, pl.b,
-                   recipe_id, p.plan_off, p.plan_nnz, p.plan_cnt, p.plan_col, p.plan_ent, C->col, C->val};
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_numeric_from_plans_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_numeric_from_plans_rows<<<ntr, 256, smem, c.stream>>>(P);
-        CK_LAUNCH();
-        if (stats) stats->plan_recipes = 1;
-        return TSG_OK;
+    if (C->nnz <= 0 || C->numtile <= 0) return TSG_OK;
+    const char *kb = getenv("TSG_PLANS_SMEM_KB");  // tests: a small budget sends tile-rows down the unstaged branch
+    const size_t cap = kb && *kb ? (size_t)atoi(kb) * 1024 : (size_t)64 * 1024;
+    size_t smem = (size_t)max_need < cap ? (size_t)max_need : cap;
+    smem = (smem + 1023) & ~(size_t)1023;
+    PlanRows P{trow0, (int)smem, A->tile_ptr, A->tile_nnz, A->val, B->tile_nnz, B->val, C->tile_ptr, C->tile_nnz, wptr, pl.ptr, pl.a, pl.b,
+               recipe_id, p.plan_off, p.plan_nnz, p.plan_cnt, p.plan_col, p.plan_slot, p.plan_jslot, p.plan_ent, C->col, C->val};
+    const char *occ = getenv("TSG_PLANS_OCC");  // A/B: 5 CTAs per SM (48 registers) instead of 6 (40)
+    if (occ && *occ == '5') {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_numeric_from_plans_rows<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_numeric_from_plans_rows<5><<<ntr, 256, smem, c.stream>>>(P);
+    } else {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_numeric_from_plans_rows<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_numeric_from_plans_rows<6><<<ntr, 256, smem, c.stream>>>(P);
     }
-    if (!arena_reserve(2, arena_need((size_t)((nnzC + 31) >> 5) + 1, 4))) return last_error();
-    int *blk2tile = arena_take<int>(2, (size_t)((nnzC + 31) >> 5) + 1);
-    if (!blk2tile) return last_error();
-    k_blk2tile_p<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>((int)numblkC, C->tile_nnz, blk2tile);
-    CK_LAUNCH();
-    k_numeric_from_plans<<<ceil_div(nnzC, 256), 256, 0, c.stream>>>((int)numblkC, (int)nnzC, blk2tile, C->tile_nnz, recipe_id, p.plan_off,
-                                                                    p.plan_nnz, p.plan_cnt, p.plan_col, p.plan_ent, pl.ptr,
-                                                                    (const int2 *)pair_base, A->val, B->val, C->col, C->val);
     CK_LAUNCH();
     if (stats) stats->plan_recipes = 1;  // the caller fills in the count it read back
     return TSG_OK;

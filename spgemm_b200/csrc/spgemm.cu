@@ -825,12 +825,8 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     // recipe plans (plans.cu): attempted when both operands are made of few distinct tile patterns and no tile-row is heavy
     bool plans_on = plans_wanted(A, B) && !heavy_rows && numblkC > 0 && pairs > 0;
     int *rslot = plans_on ? arena_take<int>(1, nb) : nullptr, *recipe_id = plans_on ? arena_take<int>(1, nb) : nullptr;
-    // TSG_PLANS_NUMERIC=flat: lane per C nonzero over the whole slab, value bases per pair in an array of their own
-    // (default: CTA per tile-row with A's values and the bases in shared memory)
-    const bool plans_flat = getenv("TSG_PLANS_NUMERIC") && !strcmp(getenv("TSG_PLANS_NUMERIC"), "flat");
-    void *pair_base = plans_on && plans_flat ? (void *)arena_take<long long>(1, np) : nullptr;  // (A value base, B value base) per pair
     if (!pair_ptr || !pair_end || !pair_a || !pair_b || !pair_slot || (heavy_rows && !pair_tmp) || !nbufs.row_kind || !nbufs.dense_list ||
-        (plans_on && (!rslot || !recipe_id || (plans_flat && !pair_base))))
+        (plans_on && (!rslot || !recipe_id)))
         return last_error();
     if (heavy_rows) CK(cudaMemsetAsync(pair_end, 0, nb * 4, c.stream));  // the heavy kernel counts with atomics
     CK(cudaEventRecord(ev[2], c.stream));  // [1..2] = allocation
@@ -900,7 +896,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         return TSG_OK;
     };
     if (plans_on) {  // C's masks / Ptr / tile nnz from the recipe plans (or nothing useful, if the fail flag comes up)
-        rc = plans_symbolic_device(A, B, C, plists, rslot, recipe_id, pair_base, &d_plan_fail);
+        rc = plans_symbolic_device(A, B, C, plists, rslot, recipe_id, &d_plan_fail);
         if (rc) return rc;
     } else if (numblkC > 0 && (!fused || n_heavy > 0)) {
         rc = generic_symbolic(fused);
@@ -958,7 +954,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     if (plans_on) {
         // the largest tile-row: A values, C tiles and pairs as k_s1_count saw them (every tile-row is light on this path)
         const size_t need = plans_rows_need_bound(hs[SC_MAXNNZA], hs[SC_MAXJ], hs[SC_WMAX]);
-        rc = plans_numeric_device(A, B, C, plists, pair_base, recipe_id, trow0, ntr, wptr, need > (1u << 30) ? (1 << 30) : (int)need, &nst);
+        rc = plans_numeric_device(A, B, C, plists, recipe_id, trow0, ntr, wptr, need > (1u << 30) ? (1 << 30) : (int)need, &nst);
     }
     else rc = numeric_device(A, B, C, trow0, ntr, wptr, plists, nbufs, h_ns, heavy_rows, &nst);
     if (rc) return rc;

@@ -721,16 +721,12 @@ def test_recipe_plans_same_result(monkeypatch, name, values, plans):
         o.free()
 
 
-@pytest.mark.parametrize("variant", ["flat", "rows_unstaged"])
-def test_recipe_plans_numeric_variants(monkeypatch, variant):
-    """The plan-driven numeric step has two kernels (CTA per tile-row with A's values staged in shared memory -- the
-    default, covered above -- and lane per nonzero over the whole slab) and the staged one has an unstaged branch for
-    tile-rows that do not fit: all give the serial SPA's values."""
+def test_recipe_plans_numeric_unstaged_rows(monkeypatch):
+    """The plan-driven numeric kernel (CTA per tile-row, A's values staged in shared memory, lane per SLOT of two C
+    nonzeros) has a branch for tile-rows that do not fit its shared memory (lane per nonzero, nothing staged): both
+    give the serial SPA's values, bit for bit the same."""
     monkeypatch.setenv("TSG_PLANS", "2")            # 2 = also on well-filled tiles (this small stencil has > 24 entries per tile)
-    if variant == "flat":
-        monkeypatch.setenv("TSG_PLANS_NUMERIC", "flat")
-    else:
-        monkeypatch.setenv("TSG_PLANS_SMEM_KB", "2")
+    monkeypatch.setenv("TSG_PLANS_SMEM_KB", "2")
     m, n, rp, ci, _ = M.stencil27(13, 10, 9)
     v = M.set_values(len(ci), "hash")
     A = (rp, ci, v)
@@ -739,12 +735,37 @@ def test_recipe_plans_numeric_variants(monkeypatch, variant):
     tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
     tC, st = api.spgemm(tA, tB)
     assert st["plan_recipes"] > 0, st
-    assert_tiled_equal(tC.download(), tC_exp, f"plans numeric {variant}", val_rtol=VAL_RTOL)
-    monkeypatch.delenv("TSG_PLANS_NUMERIC", raising=False)
+    assert_tiled_equal(tC.download(), tC_exp, "plans numeric, unstaged rows", val_rtol=VAL_RTOL)
     monkeypatch.delenv("TSG_PLANS_SMEM_KB", raising=False)
-    tD, _ = api.spgemm(tA, tB)                      # the default kernel adds in the same order: bit-identical values
+    tD, st2 = api.spgemm(tA, tB)                    # the staged branch adds in the same order: bit-identical values
+    assert st2["plan_recipes"] > 0, st2
+    assert_tiled_equal(tD.download(), tC_exp, "plans numeric, staged rows", val_rtol=VAL_RTOL)
     assert np.array_equal(tC.download()["val"], tD.download()["val"])
     for o in (tD, tC, tA, tB, d):
+        o.free()
+
+
+@pytest.mark.parametrize("density", [0.02, 0.3, 1.0])
+def test_recipe_plans_slot_pairing_odd_and_full_tiles(monkeypatch, density):
+    """Slots pair a tile's C nonzeros from the two ends of their product-count ranking: tiles with one nonzero (a slot
+    with no partner), odd counts (the middle one alone) and full 256-entry tiles (128 slots) all come out exact."""
+    monkeypatch.setenv("TSG_PLANS", "2")
+    import scipy.sparse as sp
+    pat = sp.random(16, 16, density=density, random_state=3, format="csr")
+    pat.data[:] = 1.0
+    S = sp.kron(sp.diags([1.0, 1.0, 1.0], [-1, 0, 2], shape=(9, 9)), pat, format="csr")   # 3 tile diagonals of one pattern
+    S.sort_indices()
+    m = n = S.shape[0]
+    rp, ci = S.indptr.astype(np.int32), S.indices.astype(np.int32)
+    v = M.set_values(len(ci), "mod10")
+    A = (rp, ci, v)
+    _, tC_exp = oracle_c(m, n, A, A, n)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
+    tC, st = api.spgemm(tA, tB)
+    assert st["plan_recipes"] > 0, st
+    assert_tiled_equal(tC.download(), tC_exp, f"plans slots, density {density}", val_rtol=0.0)
+    for o in (tC, tA, tB, d):
         o.free()
 
 
