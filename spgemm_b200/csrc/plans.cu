@@ -9,8 +9,7 @@
 //   * k_s1_fill hashes each C tile's pair sequence while it writes the pair lists (spgemm.cu) and inserts it into the
 //     recipe table; k_recipe_verify compares every tile's sequence with its recipe's representative;
 //   * k_plan_build plans each distinct recipe once, from the representative tile's actual masks;
-//   * k_plan_slots pairs each recipe's C nonzeros, the one with the most products with the one with the fewest and so
-//     on inwards, into "slots" of nearly equal length;
+//   * k_plan_slots packs each recipe's C nonzeros into "slots" (chains of nonzeros) of nearly equal product count;
 //   * the symbolic step becomes a 68-byte copy per C tile (k_symbolic_from_plans) and the numeric step walks an
 //     L1-resident plan, one lane per slot, every iteration a product, each nonzero summed in the serial SPA's order
 //     (k_numeric_from_plans_rows): bit-identical to the generic kernels' results.
@@ -73,8 +72,10 @@ struct PlanCtx {
     unsigned *plan_ent = nullptr;
     uint16_t *plan_cnt = nullptr;
     uint8_t *plan_col = nullptr;
-    uint2 *plan_slot = nullptr;      // per recipe, 128 slots: (n | nx << 16, X | Y << 8)
+    unsigned *plan_slot = nullptr;   // per recipe, 128 slots: products | first chain entry << 16
     unsigned *plan_jslot = nullptr;  // per recipe, 256 nonzeros: slot | first iteration << 8
+    uint16_t *plan_chain = nullptr;  // per recipe, 256 chain entries: position in the tile | column << 8
+    int *plan_nslots = nullptr;
     int *ctl = nullptr;  // [0] pattern count, [1] pattern fail, [2] recipe count, [3] recipe / plan fail
     int device = -1;
 };
@@ -100,12 +101,14 @@ static int plan_ctx_init()
     p.plan_off = dalloc_n<int>(RMAX + 1);
     p.plan_cnt = dalloc_n<uint16_t>((size_t)RMAX * 256);
     p.plan_col = dalloc_n<uint8_t>((size_t)RMAX * 256);
-    p.plan_slot = dalloc_n<uint2>((size_t)RMAX * 128);
+    p.plan_slot = dalloc_n<unsigned>((size_t)RMAX * 128);
     p.plan_jslot = dalloc_n<unsigned>((size_t)RMAX * 256);
+    p.plan_chain = dalloc_n<uint16_t>((size_t)RMAX * 256);
+    p.plan_nslots = dalloc_n<int>(RMAX);
     p.plan_ent = dalloc_n<unsigned>(PLAN_ENT_CAP);
     p.ctl = dalloc_n<int>(8);
     if (!p.pkeys || !p.powner || !p.rkeys || !p.rowner || !p.rflags || !p.rdense || !p.rep_tile || !p.plan_mask || !p.plan_ptr ||
-        !p.plan_nnz || !p.plan_tot || !p.plan_off || !p.plan_cnt || !p.plan_col || !p.plan_slot || !p.plan_jslot || !p.plan_ent || !p.ctl) {
+        !p.plan_nnz || !p.plan_tot || !p.plan_off || !p.plan_cnt || !p.plan_col || !p.plan_slot || !p.plan_jslot || !p.plan_chain || !p.plan_nslots || !p.plan_ent || !p.ctl) {
         g_plan = PlanCtx();
         return last_error();
     }
@@ -202,10 +205,10 @@ k_recipe_verify(int numblkC, const int *__restrict__ pair_ptr, const int *__rest
 // A HALF-WARP per distinct recipe, lane = row r of the recipe's representative C tile. FILL = false: masks / Ptr / nnz of
 // the tile and the number of products of every C nonzero (plan_cnt). k_plan_slots then pairs the nonzeros into slots and
 // sizes the recipe's entries (plan_tot). FILL = true: plan_off = exclusive scan of plan_tot; writes the entries
-// (pair index << 16 | position in B's tile << 8 | position in A's tile), each nonzero's in the serial SPA's order,
-// ITERATION-MAJOR over slots: product i of the nonzero that starts at iteration `start` of slot v lives at
-// plan_off[R] + (start + i) * nslots + v, so the lanes of the numeric kernel -- consecutive slots of a tile, all at the
-// same iteration -- read consecutive words.
+// (last product of its nonzero << 31 | pair index << 16 | position in B's tile << 8 | position in A's tile), each
+// nonzero's in the serial SPA's order, ITERATION-MAJOR over slots: product i of the nonzero that starts at iteration
+// `start` of slot v lives at plan_off[R] + (start + i) * nslots + v, so the lanes of the numeric kernel -- consecutive
+// slots of a tile, all at the same iteration -- read consecutive words.
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, const int *__restrict__ pair_ptr,
@@ -213,7 +216,7 @@ k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, c
              const uint16_t *__restrict__ a_mask, const uint16_t *__restrict__ a_ptr, const uint16_t *__restrict__ b_mask,
              const uint16_t *__restrict__ b_ptr, uint16_t *plan_mask, uint16_t *plan_ptr, int *plan_nnz,
              const int *__restrict__ plan_off, uint16_t *plan_cnt, uint8_t *plan_col, const unsigned *__restrict__ plan_jslot,
-             unsigned *plan_ent, int *fail)
+             const int *__restrict__ plan_nslots, unsigned *plan_ent, int *fail)
 {
     const int R = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, r = threadIdx.x & 15;
     const unsigned hm = 0xFFFFu << (threadIdx.x & 16);
@@ -224,7 +227,7 @@ k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, c
     if (FILL && plan_off[nrec] > PLAN_ENT_CAP) { if (R == 0 && r == 0) *fail = 3; return; }
     const int t = rep_tile[R];
     const int p0 = pair_ptr[t], p1 = pair_end[t];
-    if (p1 - p0 > 0xFFFF) { *fail = 1; return; }  // the plan entry keeps the pair index in 16 bits
+    if (p1 - p0 > 0x7FFF) { *fail = 1; return; }  // the plan entry keeps the pair index in 15 bits
     unsigned cm = 0;
     for (int p = p0; p < p1; p++) {
         const int a = pair_a[p], b = pair_b[p];
@@ -248,7 +251,7 @@ k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, c
         plan_mask[R * TS + r] = (uint16_t)cm;
         if (r == 0) plan_nnz[R] = nnz;
     }
-    const unsigned base = FILL ? (unsigned)plan_off[R] : 0u, nslots = (unsigned)(nnz + 1) >> 1;
+    const unsigned base = FILL ? (unsigned)plan_off[R] : 0u, nslots = FILL ? (unsigned)plan_nslots[R] : 0u;
     int j = rowbase;
     unsigned rowm = cm;
     while (rowm) {
@@ -257,7 +260,7 @@ k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, c
         const unsigned cbit = 0x8000u >> c;
         const unsigned js = FILL ? plan_jslot[(size_t)R * 256 + j] : 0u;  // slot | first iteration << 8
         unsigned i = js >> 8;
-        const unsigned i0 = i;
+        const unsigned i0 = i, ilast = FILL ? i0 + plan_cnt[(size_t)R * 256 + j] - 1u : 0u;
         for (int p = p0; p < p1; p++) {
             const int a = pair_a[p], b = pair_b[p];
             unsigned am = a_mask[(size_t)a * TS + r];
@@ -269,7 +272,7 @@ k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, c
                 if (bm & cbit) {
                     if (FILL) {
                         const unsigned posb = (unsigned)b_ptr[(size_t)b * TS + k] + __popc(bm >> (16 - c));
-                        plan_ent[base + i * nslots + (js & 255u)] = ((unsigned)(p - p0) << 16) | (posb << 8) | ia;
+                        plan_ent[base + i * nslots + (js & 255u)] = ((unsigned)(i == ilast) << 31) | ((unsigned)(p - p0) << 16) | (posb << 8) | ia;
                     }
                     i++;
                 }
@@ -287,22 +290,27 @@ k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, c
 
 // A WARP per distinct recipe: the C nonzeros of the tile differ in how many products they sum (1 ... 27 on the 27-point
 // stencil), and a warp whose lanes each walked one nonzero would run as long as its longest list with, measured, 15 of 32
-// lanes busy. So the nonzeros are ranked by product count and paired from the two ends -- most with fewest, and so on
-// inwards -- into ceil(nnz / 2) SLOTS of nearly equal total length; a lane of the numeric kernel walks a slot: nonzero X's
-// products, then nonzero Y's. Per slot: plan_slot = (n | nx << 16, X | Y << 8) with nx = X's count, n = nx + Y's count
-// (n == nx: the odd one in the middle, alone). Per nonzero: plan_jslot = slot | first iteration << 8.
-// plan_tot = nslots * the longest slot = the words the recipe's entries take.
+// lanes busy. So the nonzeros are packed into SLOTS -- chains of nonzeros walked one after the other by one lane of the
+// numeric kernel -- of nearly equal total length: nslots = ceil(all products / T) with T = max(the longest list, tmin),
+// filled longest-first into the slot with the least so far (LPT). Per slot: plan_slot = products | first chain entry << 16.
+// Per chain entry (slot after slot, in walking order): plan_chain = position of the nonzero in the tile | its column << 8.
+// Per nonzero: plan_jslot = slot | first iteration << 8. plan_tot = nslots * the longest slot = words of plan entries.
 __global__ void __launch_bounds__(128)
-k_plan_slots(const int *__restrict__ nrec_p, const int *__restrict__ plan_nnz, const uint16_t *__restrict__ plan_cnt,
-             unsigned *__restrict__ plan_jslot, uint2 *__restrict__ plan_slot, int *__restrict__ plan_tot, int *fail)
+k_plan_slots(const int *__restrict__ nrec_p, int tmin, const int *__restrict__ plan_nnz, const uint16_t *__restrict__ plan_cnt,
+             const uint8_t *__restrict__ plan_col, unsigned *__restrict__ plan_jslot, unsigned *__restrict__ plan_slot,
+             uint16_t *__restrict__ plan_chain, int *__restrict__ plan_nslots, int *__restrict__ plan_tot, int *fail)
 {
-    __shared__ uint16_t s_cnt[4][256];
-    __shared__ uint8_t s_sorted[4][256];
+    __shared__ uint16_t s_cnt[4][256], s_start[4][256];
+    __shared__ uint8_t s_sorted[4][256], s_bin[4][256], s_k[4][256];
+    __shared__ int s_load[4][128], s_len[4][128];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, R = blockIdx.x * 4 + w;
     const int nrec = *nrec_p;
     if (*(volatile int *)fail || nrec > RMAX || R >= nrec) return;  // whole warps leave together
     const int nnz = plan_nnz[R];
-    for (int j = lane; j < nnz; j += 32) s_cnt[w][j] = plan_cnt[(size_t)R * 256 + j];
+    int total = 0;
+    for (int j = lane; j < nnz; j += 32) { const int cj = plan_cnt[(size_t)R * 256 + j]; s_cnt[w][j] = (uint16_t)cj; total += cj; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(FULL_MASK, total, o);
     __syncwarp();
     for (int j = lane; j < nnz; j += 32) {  // rank = how many nonzeros come before j in (count descending, index ascending) order
         const int cj = s_cnt[w][j];
@@ -313,23 +321,55 @@ k_plan_slots(const int *__restrict__ nrec_p, const int *__restrict__ plan_nnz, c
         }
         s_sorted[w][rank] = (uint8_t)j;
     }
+    for (int b = lane; b < 128; b += 32) { s_load[w][b] = 0; s_len[w][b] = 0; }
     __syncwarp();
-    const int nslots = (nnz + 1) >> 1;
-    int longest = 0;
-    for (int v = lane; v < nslots; v += 32) {
-        const int ky = nnz - 1 - v;
-        const bool has_y = ky > v;
-        const unsigned X = s_sorted[w][v], Y = has_y ? s_sorted[w][ky] : X;
-        const unsigned nx = s_cnt[w][X], n = nx + (has_y ? s_cnt[w][Y] : 0u);
-        if (n > 0xFFFFu) *fail = 1;
-        plan_slot[(size_t)R * 128 + v] = make_uint2(n | (nx << 16), X | (Y << 8));
-        plan_jslot[(size_t)R * 256 + X] = (unsigned)v;
-        if (has_y) plan_jslot[(size_t)R * 256 + Y] = (unsigned)v | (nx << 8);
-        longest = max(longest, (int)n);
+    int nslots = 0;
+    if (nnz > 0) {
+        const int T = max((int)s_cnt[w][s_sorted[w][0]], tmin);
+        nslots = min(128, (total + T - 1) / T);  // <= nnz: every list holds at least one product
+    }
+    for (int r = 0; r < nnz; r++) {  // LPT: the next-longest list goes to the slot with the fewest products so far
+        unsigned best = 0xFFFFFFFFu;
+        for (int b = lane; b < nslots; b += 32) best = min(best, ((unsigned)s_load[w][b] << 8) | (unsigned)b);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(FULL_MASK, best, o));
+        if (lane == 0) {
+            const int j = s_sorted[w][r], b = (int)(best & 255u), ld = s_load[w][b];
+            if (ld + (int)s_cnt[w][j] > 0xFFFF) *fail = 1;
+            s_bin[w][j] = (uint8_t)b;
+            s_start[w][j] = (uint16_t)ld;
+            s_k[w][j] = (uint8_t)s_len[w][b];
+            s_load[w][b] = ld + s_cnt[w][j];
+            s_len[w][b]++;
+        }
+        __syncwarp();
+    }
+    int longest = 0, carry = 0;
+    for (int b0 = 0; b0 < nslots; b0 += 32) {  // first chain entry of every slot: exclusive scan of the chain lengths
+        const int b = b0 + lane, len = b < nslots ? s_len[w][b] : 0;
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (b < nslots) {
+            const int first = carry + incl - len;
+            plan_slot[(size_t)R * 128 + b] = (unsigned)s_load[w][b] | ((unsigned)first << 16);
+            longest = max(longest, s_load[w][b]);
+            s_len[w][b] = first;
+        }
+        carry += __shfl_sync(FULL_MASK, incl, 31);
+    }
+    __syncwarp();
+    for (int j = lane; j < nnz; j += 32) {
+        const int b = s_bin[w][j];
+        plan_jslot[(size_t)R * 256 + j] = (unsigned)b | ((unsigned)s_start[w][j] << 8);
+        plan_chain[(size_t)R * 256 + s_len[w][b] + s_k[w][j]] = (uint16_t)(j | ((int)plan_col[(size_t)R * 256 + j] << 8));
     }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) longest = max(longest, __shfl_xor_sync(0xFFFFFFFFu, longest, o));
-    if (lane == 0) plan_tot[R] = longest * nslots;
+    for (int o = 16; o; o >>= 1) longest = max(longest, __shfl_xor_sync(FULL_MASK, longest, o));
+    if (lane == 0) { plan_nslots[R] = nslots; plan_tot[R] = longest * nslots; }
 }
 
 // C tile metadata from the plan: one thread per C tile copies its recipe's 32 + 32 bytes and its nnz.
@@ -352,9 +392,10 @@ k_symbolic_from_plans(int numblkC, const int *__restrict__ recipe_id, const uint
 // The numeric step: a CTA per C TILE-ROW. The tile-row's share of A's values (contiguous in row-major tile order), the
 // offsets / recipes / pair ranges / slot ranges of its C tiles and, per pair, the position of the A tile's values in that
 // staged copy and the base of the B tile's values are put into shared memory first. Then one lane per SLOT of the
-// tile-row (k_plan_slots: two C nonzeros of one tile, the second's products after the first's): every iteration is a
-// product -- two global loads (the plan word, coalesced, and B's value) and two shared ones (the pair's bases, A's value).
-// Each nonzero is summed in the serial SPA's order, so the values are bit-identical to the generic kernels'.
+// tile-row (k_plan_slots: a chain of C nonzeros of one tile): every iteration is a product -- two global loads (the plan
+// word, coalesced, and B's value) and two shared ones (the pair's bases, A's value) -- and the product that ends a
+// nonzero's list (bit 31 of the plan word) stores the sum and moves on to the chain's next nonzero. Each nonzero is summed
+// in the serial SPA's order, so the values are bit-identical to the generic kernels'.
 // Tile-rows that do not fit `smem_cap` take one lane per nonzero and read everything from global memory (same results).
 struct PlanRows {
     int trow0, smem_cap;
@@ -363,11 +404,10 @@ struct PlanRows {
     const int *b_tile_nnz;
     const double *b_val;
     const int *c_tile_ptr, *c_tile_nnz, *wptr, *pair_ptr, *pair_a, *pair_b, *recipe_id;
-    const int *plan_off, *plan_nnz;
-    const uint16_t *plan_cnt;
+    const int *plan_off, *plan_nslots;
+    const uint16_t *plan_cnt, *plan_chain;
     const uint8_t *plan_col;
-    const uint2 *plan_slot;
-    const unsigned *plan_jslot, *plan_ent;
+    const unsigned *plan_slot, *plan_jslot, *plan_ent;
     uint16_t *c_col;
     double *c_val;
 };
@@ -378,8 +418,8 @@ __host__ __device__ __forceinline__ size_t plan_rows_need(int nnzA, int numJ, in
            (((size_t)W * 8 + 15) & ~(size_t)15);
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB)
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_numeric_from_plans_rows(const __grid_constant__ PlanRows P)
 {
     extern __shared__ __align__(16) unsigned char pr_smem[];
@@ -392,7 +432,7 @@ k_numeric_from_plans_rows(const __grid_constant__ PlanRows P)
     const int av0 = P.a_tile_nnz[a0], nnzA = P.a_tile_nnz[a1] - av0;
     const int w0 = P.wptr[i], W = P.wptr[i + 1] - w0;
     if (plan_rows_need(nnzA, numJ, W) > (size_t)P.smem_cap) {  // uniform over the CTA: lane per nonzero, nothing staged
-        for (int g = tid; g < nnzC; g += 256) {
+        for (int g = tid; g < nnzC; g += THREADS) {
             int lo = 0, hi = numJ - 1;  // the tile holding nonzero g of the tile-row: largest s with nnz offset <= g
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
@@ -400,12 +440,12 @@ k_numeric_from_plans_rows(const __grid_constant__ PlanRows P)
             }
             const int off = g - (P.c_tile_nnz[c0 + lo] - n0), R = P.recipe_id[c0 + lo];
             const unsigned js = P.plan_jslot[(size_t)R * 256 + off];
-            const int n = P.plan_cnt[(size_t)R * 256 + off], nsl = (P.plan_nnz[R] + 1) >> 1, pp = P.pair_ptr[c0 + lo];
+            const int n = P.plan_cnt[(size_t)R * 256 + off], nsl = P.plan_nslots[R], pp = P.pair_ptr[c0 + lo];
             const unsigned *ent = P.plan_ent + P.plan_off[R] + (size_t)(js >> 8) * nsl + (js & 255u);
             double acc = 0.0;
             for (int it = 0; it < n; it++, ent += nsl) {
                 const unsigned e = *ent;
-                const int p = pp + (int)(e >> 16);
+                const int p = pp + (int)((e >> 16) & 0x7FFFu);
                 acc = fma(P.a_val[P.a_tile_nnz[P.pair_a[p]] + (int)(e & 255u)], P.b_val[P.b_tile_nnz[P.pair_b[p]] + (int)((e >> 8) & 255u)], acc);
             }
             P.c_val[n0 + g] = acc;
@@ -421,58 +461,71 @@ k_numeric_from_plans_rows(const __grid_constant__ PlanRows P)
     int *s_rec = (int *)carve((size_t)numJ * 4);
     int *s_pp = (int *)carve((size_t)numJ * 4);
     int2 *s_base = (int2 *)carve((size_t)W * 8);
-    for (int k = tid; k < nnzA; k += 256) s_aval[k] = P.a_val[av0 + k];
-    for (int k = tid; k <= numJ; k += 256) {
+    for (int k = tid; k < nnzA; k += THREADS) s_aval[k] = P.a_val[av0 + k];
+    for (int k = tid; k <= numJ; k += THREADS) {
         s_cnnz[k] = P.c_tile_nnz[c0 + k] - n0;
-        if (k < numJ) { s_rec[k] = P.recipe_id[c0 + k]; s_pp[k] = P.pair_ptr[c0 + k] - w0; }
+        if (k < numJ) {
+            const int R = P.recipe_id[c0 + k];
+            s_rec[k] = R;
+            s_slot0[k] = P.plan_nslots[R];
+            s_pp[k] = P.pair_ptr[c0 + k] - w0;
+        }
     }
-    for (int k = tid; k < W; k += 256) s_base[k] = make_int2(P.a_tile_nnz[P.pair_a[w0 + k]] - av0, P.b_tile_nnz[P.pair_b[w0 + k]]);
+    for (int k = tid; k < W; k += THREADS) s_base[k] = make_int2(P.a_tile_nnz[P.pair_a[w0 + k]] - av0, P.b_tile_nnz[P.pair_b[w0 + k]]);
     __syncthreads();
-    if (tid < 32) {  // first slot of every tile: exclusive scan of ceil(nnz / 2) over the tile-row's tiles
+    if (tid < 32) {  // first slot of every tile: exclusive scan of the slot counts over the tile-row's tiles
         int carry = 0;
         for (int k0 = 0; k0 < numJ; k0 += 32) {
-            const int k = k0 + tid, v = k < numJ ? (s_cnnz[k + 1] - s_cnnz[k] + 1) >> 1 : 0;
+            const int k = k0 + tid, v = k < numJ ? s_slot0[k] : 0;
             int incl = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                const int u = __shfl_up_sync(FULL_MASK, incl, o);
                 if (tid >= o) incl += u;
             }
             if (k < numJ) s_slot0[k] = carry + incl - v;
-            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            carry += __shfl_sync(FULL_MASK, incl, 31);
         }
         if (tid == 0) s_slot0[numJ] = carry;
     }
     __syncthreads();
     const int nslot_row = s_slot0[numJ];
-    for (int q = tid; q < nslot_row; q += 256) {
+    for (int q = tid; q < nslot_row; q += THREADS) {
         int lo = 0, hi = numJ - 1;  // the tile holding slot q of the tile-row: largest s with first slot <= q
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
             if (s_slot0[mid] <= q) lo = mid; else hi = mid - 1;
         }
         const int sidx = lo, v = q - s_slot0[sidx], R = s_rec[sidx];
-        const int cb = s_cnnz[sidx], nsl = (s_cnnz[sidx + 1] - cb + 1) >> 1, pp = s_pp[sidx];
-        const uint2 si = P.plan_slot[(size_t)R * 128 + v];
-        const int n = (int)(si.x & 0xFFFFu), nx = (int)(si.x >> 16);
-        const unsigned *ent = P.plan_ent + P.plan_off[R] + v;
-        double acc = 0.0, first = 0.0;
-        for (int it = 0; it < n; it++, ent += nsl) {
-            const unsigned e = *ent;
-            const int2 base = s_base[pp + (int)(e >> 16)];
-            if (it == nx) { first = acc; acc = 0.0; }
-            acc = fma(s_aval[base.x + (int)(e & 255u)], P.b_val[base.y + (int)((e >> 8) & 255u)], acc);
+        const int nsl = s_slot0[sidx + 1] - s_slot0[sidx], pp = s_pp[sidx];
+        const unsigned si = __ldg(P.plan_slot + R * 128 + v);
+        const int n = (int)(si & 0xFFFFu), out = n0 + s_cnnz[sidx];  // nnz(C) of a slab fits int32 (spgemm_device checks)
+        int ch = R * 256 + (int)(si >> 16), eo = P.plan_off[R] + v;   // next chain entry, next plan word
+        unsigned oc = __ldg(P.plan_chain + ch);  // position of the chain's current nonzero in the tile | its column << 8
+        double acc = 0.0;
+        for (int it = 0; it < n; it += 4, eo += 4 * nsl) {  // four products at a time: all their loads first, then the sums in order
+            unsigned e[4];
+            double av[4], bv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) e[u] = it + u < n ? __ldg(P.plan_ent + (eo + u * nsl)) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int2 base = s_base[pp + (int)((e[u] >> 16) & 0x7FFFu)];
+                av[u] = s_aval[base.x + (int)(e[u] & 255u)];
+                bv[u] = it + u < n ? __ldg(P.b_val + (base.y + (int)((e[u] >> 8) & 255u))) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (it + u < n) acc = fma(av[u], bv[u], acc);
+                if (e[u] >> 31) {  // the nonzero's last product
+                    const int o = out + (int)(oc & 255u);
+                    P.c_val[o] = acc;
+                    P.c_col[o] = (uint16_t)(oc >> 8);
+                    acc = 0.0;
+                    if (it + u + 1 < n) oc = __ldg(P.plan_chain + ++ch);
+                }
+            }
         }
-        const int ox = (int)(si.y & 255u), oy = (int)((si.y >> 8) & 255u);
-        const uint8_t *colp = P.plan_col + (size_t)R * 256;
-        const size_t out = (size_t)n0 + cb;
-        if (nx < n) {
-            P.c_val[out + oy] = acc;
-            P.c_col[out + oy] = colp[oy];
-            acc = first;
-        }
-        P.c_val[out + ox] = acc;
-        P.c_col[out + ox] = colp[ox];
     }
 }
 
@@ -516,15 +569,18 @@ int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, 
     const int *nrec = p.rdense + RCAP;
     k_plan_build<false><<<ceil_div(RMAX * 16, 128), 128, 0, c.stream>>>(nrec, p.rep_tile, pl.ptr, pl.end, pl.a, pl.b, A->mask, A->ptr, B->mask,
                                                                         B->ptr, p.plan_mask, p.plan_ptr, p.plan_nnz, nullptr, p.plan_cnt,
-                                                                        p.plan_col, nullptr, nullptr, fail);
+                                                                        p.plan_col, nullptr, nullptr, nullptr, fail);
     CK_LAUNCH();
-    k_plan_slots<<<ceil_div(RMAX, 4), 128, 0, c.stream>>>(nrec, p.plan_nnz, p.plan_cnt, p.plan_jslot, p.plan_slot, p.plan_tot, fail);
+    const char *ch = getenv("TSG_PLANS_CHAIN");  // shortest slot length aimed at (the longest product list of the recipe if that is more)
+    const int tmin = ch && *ch ? atoi(ch) : PLANS_CHAIN_MIN;
+    k_plan_slots<<<ceil_div(RMAX, 4), 128, 0, c.stream>>>(nrec, tmin, p.plan_nnz, p.plan_cnt, p.plan_col, p.plan_jslot, p.plan_slot, p.plan_chain,
+                                                          p.plan_nslots, p.plan_tot, fail);
     CK_LAUNCH();
     rc = exclusive_scan<int>(p.plan_tot, p.plan_off, RMAX);
     if (rc) return rc;
     k_plan_build<true><<<ceil_div(RMAX * 16, 128), 128, 0, c.stream>>>(nrec, p.rep_tile, pl.ptr, pl.end, pl.a, pl.b, A->mask, A->ptr, B->mask,
                                                                        B->ptr, p.plan_mask, p.plan_ptr, p.plan_nnz, p.plan_off, p.plan_cnt,
-                                                                       p.plan_col, p.plan_jslot, p.plan_ent, fail);
+                                                                       p.plan_col, p.plan_jslot, p.plan_nslots, p.plan_ent, fail);
     CK_LAUNCH();
     k_symbolic_from_plans<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>(numblkC, recipe_id, p.plan_mask, p.plan_ptr, p.plan_nnz, C->mask, C->ptr,
                                                                         C->tile_nnz, fail);
@@ -543,15 +599,9 @@ int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, c
     size_t smem = (size_t)max_need < cap ? (size_t)max_need : cap;
     smem = (smem + 1023) & ~(size_t)1023;
     PlanRows P{trow0, (int)smem, A->tile_ptr, A->tile_nnz, A->val, B->tile_nnz, B->val, C->tile_ptr, C->tile_nnz, wptr, pl.ptr, pl.a, pl.b,
-               recipe_id, p.plan_off, p.plan_nnz, p.plan_cnt, p.plan_col, p.plan_slot, p.plan_jslot, p.plan_ent, C->col, C->val};
-    const char *occ = getenv("TSG_PLANS_OCC");  // A/B: 5 CTAs per SM (48 registers) instead of 6 (40)
-    if (occ && *occ == '5') {
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_numeric_from_plans_rows<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_numeric_from_plans_rows<5><<<ntr, 256, smem, c.stream>>>(P);
-    } else {
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_numeric_from_plans_rows<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_numeric_from_plans_rows<6><<<ntr, 256, smem, c.stream>>>(P);
-    }
+               recipe_id, p.plan_off, p.plan_nslots, p.plan_cnt, p.plan_chain, p.plan_col, p.plan_slot, p.plan_jslot, p.plan_ent, C->col, C->val};
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_numeric_from_plans_rows<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_numeric_from_plans_rows<256, 6><<<ntr, 256, smem, c.stream>>>(P);
     CK_LAUNCH();
     if (stats) stats->plan_recipes = 1;  // the caller fills in the count it read back
     return TSG_OK;

@@ -722,7 +722,7 @@ def test_recipe_plans_same_result(monkeypatch, name, values, plans):
 
 
 def test_recipe_plans_numeric_unstaged_rows(monkeypatch):
-    """The plan-driven numeric kernel (CTA per tile-row, A's values staged in shared memory, lane per SLOT of two C
+    """The plan-driven numeric kernel (CTA per tile-row, A's values staged in shared memory, lane per slot -- a chain of C
     nonzeros) has a branch for tile-rows that do not fit its shared memory (lane per nonzero, nothing staged): both
     give the serial SPA's values, bit for bit the same."""
     monkeypatch.setenv("TSG_PLANS", "2")            # 2 = also on well-filled tiles (this small stencil has > 24 entries per tile)
@@ -745,11 +745,14 @@ def test_recipe_plans_numeric_unstaged_rows(monkeypatch):
         o.free()
 
 
+@pytest.mark.parametrize("chain", ["1", "16", "4000"])
 @pytest.mark.parametrize("density", [0.02, 0.3, 1.0])
-def test_recipe_plans_slot_pairing_odd_and_full_tiles(monkeypatch, density):
-    """Slots pair a tile's C nonzeros from the two ends of their product-count ranking: tiles with one nonzero (a slot
-    with no partner), odd counts (the middle one alone) and full 256-entry tiles (128 slots) all come out exact."""
+def test_recipe_plans_slot_chains(monkeypatch, density, chain):
+    """A lane of the plan-driven numeric kernel walks a SLOT: a chain of C nonzeros of one tile packed (longest list
+    first, into the emptiest slot) to about TSG_PLANS_CHAIN products. Tiles with one nonzero, full 256-entry tiles (up to
+    128 slots), chains of one nonzero each (1) and one chain holding the whole tile (4000) all come out exact."""
     monkeypatch.setenv("TSG_PLANS", "2")
+    monkeypatch.setenv("TSG_PLANS_CHAIN", chain)
     import scipy.sparse as sp
     pat = sp.random(16, 16, density=density, random_state=3, format="csr")
     pat.data[:] = 1.0
@@ -764,7 +767,7 @@ def test_recipe_plans_slot_pairing_odd_and_full_tiles(monkeypatch, density):
     tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
     tC, st = api.spgemm(tA, tB)
     assert st["plan_recipes"] > 0, st
-    assert_tiled_equal(tC.download(), tC_exp, f"plans slots, density {density}", val_rtol=0.0)
+    assert_tiled_equal(tC.download(), tC_exp, f"plans slots, density {density}, chain {chain}", val_rtol=0.0)
     for o in (tC, tA, tB, d):
         o.free()
 
