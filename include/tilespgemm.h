@@ -159,7 +159,8 @@ typedef struct {
     int *csc_tile_ptr;    /* [tilen+1]  col_major only                                         */
     int *csc_tile_rowidx; /* [numtile]  col_major only                                         */
     int *rm2csc;          /* [numtile]  col_major only: row-major tile index -> storage id     */
-    int *pat;             /* [numtile]  pattern id of every tile (storage order): tiles with equal ids have identical
+    int *pat;             /* [numtile]  pattern id of every tile, in ROW-MAJOR tile order (storage order for a row-major
+                             matrix, the order of rm2csc for a column-major one): tiles with equal ids have identical
                              row masks, i.e. the same sparsity pattern. Filled by csr2tile / tile upload. */
     int npat;             /* number of distinct patterns; -1: not available (too many -- the recipe plans of
                              csrc/plans.cu are then not attempted for this matrix) */

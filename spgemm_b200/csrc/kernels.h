@@ -41,7 +41,7 @@ struct PlanTable;
 int tile_patterns_device(tsg_dtile *T);
 bool plans_wanted(const tsg_dtile *A, const tsg_dtile *B);
 int plans_begin(PlanTable *out);
-int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const int *rslot, int *recipe_id,
+int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const unsigned *pair_pat, const int *rslot, int *recipe_id,
                           const int **d_fail);
 int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const int *recipe_id,
                          int trow0, int ntr, const int *wptr, int max_need, tsg_stats *stats);

@@ -44,7 +44,7 @@ k_pattern_insert(int numtile, const uint16_t *__restrict__ mask, unsigned long l
     h = mix64(h, ((unsigned long long)y.x << 32) | y.y); h = mix64(h, ((unsigned long long)y.z << 32) | y.w);
     const int slot = table_insert(keys, PCAP, h, count, PCAP / 2, fail);
     pat_id[t] = slot;
-    if (slot >= 0 && t < *(volatile int *)&owner[slot]) atomicMin(&owner[slot], t);  // owner only ever decreases
+    if (slot >= 0 && t < owner[slot]) atomicMin(&owner[slot], t);  // owner only ever decreases: a stale read costs one atomic
 }
 
 __global__ void __launch_bounds__(256)
@@ -124,8 +124,16 @@ static bool plans_env_on()
     return !(e && *e == '0');
 }
 
-// Pattern id of every tile of T (storage order) into T->pat, the number of distinct patterns into T->npat (-1 when there
-// are more than PCAP/2 or a 64-bit hash collision was detected). One read-back; runs at csr2tile / upload time.
+__global__ void k_gather_int(int n, const int *__restrict__ idx, const int *__restrict__ src, int *__restrict__ dst)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) dst[t] = src[idx[t]];
+}
+
+// Pattern id of every tile of T into T->pat -- in ROW-MAJOR tile order (for a column-major T that is the order of
+// rm2csc, the order step 1 walks B's tile-rows in: k_s1_fill reads the ids beside B's tile columns, coalesced) -- and the
+// number of distinct patterns into T->npat (-1 when there are more than PCAP/2 or a 64-bit hash collision was detected).
+// One read-back; runs at csr2tile / upload time.
 int tile_patterns_device(tsg_dtile *T)
 {
     Ctx &c = ctx();
@@ -138,9 +146,15 @@ int tile_patterns_device(tsg_dtile *T)
     CK(cudaMemsetAsync(p.powner, 0x7f, (size_t)PCAP * 4, c.stream));
     CK(cudaMemsetAsync(p.ctl, 0, 2 * sizeof(int), c.stream));
     const int blocks = ceil_div(T->numtile, 256);
-    k_pattern_insert<<<blocks, 256, 0, c.stream>>>(T->numtile, T->mask, p.pkeys, p.powner, p.ctl, T->pat, p.ctl + 1);
-    CK_LAUNCH();
-    k_pattern_verify<<<blocks, 256, 0, c.stream>>>(T->numtile, T->mask, T->pat, p.powner, p.ctl + 1);
+    const bool permute = T->col_major && T->rm2csc;
+    int *ids = permute ? dalloc_n<int>((size_t)T->numtile) : T->pat;  // storage order first
+    if (!ids) return last_error();
+    k_pattern_insert<<<blocks, 256, 0, c.stream>>>(T->numtile, T->mask, p.pkeys, p.powner, p.ctl, ids, p.ctl + 1);
+    k_pattern_verify<<<blocks, 256, 0, c.stream>>>(T->numtile, T->mask, ids, p.powner, p.ctl + 1);
+    if (permute) {
+        k_gather_int<<<blocks, 256, 0, c.stream>>>(T->numtile, T->rm2csc, ids, T->pat);
+        dfree(ids);  // stream-ordered: released after the gather
+    }
     CK_LAUNCH();
     rc = publish_words(&c.h_scalars[13], p.ctl, 2);
     if (rc) return rc;
@@ -178,10 +192,10 @@ k_recipe_reps(const int *__restrict__ owner, const int *__restrict__ rdense, int
     if (s < RCAP && owner[s] != NO_OWNER && rdense[s] < RMAX) rep_tile[rdense[s]] = owner[s];
 }
 
-// every C tile compares its (A pattern, B pattern) sequence with its recipe's representative: a 64-bit collision fails.
+// every C tile compares its (A pattern, B pattern) sequence (pair_pat, written by k_s1_fill beside the pair lists) with
+// its recipe's representative: a 64-bit collision fails.
 __global__ void __launch_bounds__(256)
-k_recipe_verify(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end, const int *__restrict__ pair_a,
-                const int *__restrict__ pair_b, const int *__restrict__ patA, const int *__restrict__ patB,
+k_recipe_verify(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end, const unsigned *__restrict__ pair_pat,
                 const int *__restrict__ rslot, const int *__restrict__ owner, const int *__restrict__ rdense,
                 int *__restrict__ recipe_id, int *fail)
 {
@@ -196,8 +210,7 @@ k_recipe_verify(int numblkC, const int *__restrict__ pair_ptr, const int *__rest
     const int p0 = pair_ptr[t], n = pair_end[t] - p0, q0 = pair_ptr[u];
     bool same = pair_end[u] - q0 == n;
     if (u != t)
-        for (int i = 0; i < n && same; i++)
-            same = patA[pair_a[p0 + i]] == patA[pair_a[q0 + i]] && patB[pair_b[p0 + i]] == patB[pair_b[q0 + i]];
+        for (int i = 0; i < n && same; i++) same = pair_pat[p0 + i] == pair_pat[q0 + i];
     if (!same) *fail = 2;
     recipe_id[t] = rdense[slot];
 }
@@ -549,8 +562,8 @@ int plans_begin(PlanTable *out)
 
 // After k_s1_fill<HASH>: dense recipe numbers, verification, the plans, and C's masks / Ptr / tile nnz counts from them.
 // Everything is enqueued; *d_fail is the device flag the caller reads back with nnz(C).
-int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const int *rslot, int *recipe_id,
-                          const int **d_fail)
+int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const unsigned *pair_pat, const int *rslot,
+                          int *recipe_id, const int **d_fail)
 {
     Ctx &c = ctx();
     PlanCtx &p = g_plan;
@@ -563,8 +576,8 @@ int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, 
     if (rc) return rc;
     k_recipe_reps<<<ceil_div(RCAP, 256), 256, 0, c.stream>>>(p.rowner, p.rdense, p.rep_tile);
     CK_LAUNCH();
-    k_recipe_verify<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>(numblkC, pl.ptr, pl.end, pl.a, pl.b, A->pat, B->pat, rslot, p.rowner,
-                                                                  p.rdense, recipe_id, fail);
+    k_recipe_verify<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>(numblkC, pl.ptr, pl.end, pair_pat, rslot, p.rowner, p.rdense, recipe_id,
+                                                                  fail);
     CK_LAUNCH();
     const int *nrec = p.rdense + RCAP;
     k_plan_build<false><<<ceil_div(RMAX * 16, 128), 128, 0, c.stream>>>(nrec, p.rep_tile, pl.ptr, pl.end, pl.a, pl.b, A->mask, A->ptr, B->mask,

@@ -24,13 +24,15 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long h, unsign
 // Deduplication without waiting: insert the 64-bit hash with one atomicCAS on the key word; the smallest item index
 // that lands in a slot becomes its owner (atomicMin, done by the caller: deterministic); every item later compares its
 // full key with the owner's. Returns the slot, or -1 after raising *fail (table full / too many distinct keys).
+// Millions of items, a few dozen hot slots: the key is read with a plain (L1-cached) load first. A slot only ever goes
+// from empty to one key, so a stale read can only show "empty" -- and then the atomicCAS returns the truth.
 __device__ __forceinline__ int table_insert(unsigned long long *keys, int cap, unsigned long long h, int *count, int limit, int *fail)
 {
     if (h == 0ull) h = 1ull;  // 0 marks an empty slot
     unsigned slot = (unsigned)(h >> 20) & (unsigned)(cap - 1);
     for (int probe = 0; probe < cap; probe++, slot = (slot + 1) & (unsigned)(cap - 1)) {
-        if (*(volatile int *)fail) return -1;
-        unsigned long long old = *(volatile unsigned long long *)&keys[slot];  // millions of items, a few dozen hot slots: read first
+        if (probe && *(volatile int *)fail) return -1;  // a table that overflowed is not worth probing to the end
+        unsigned long long old = keys[slot];
         if (old == 0ull) old = atomicCAS(&keys[slot], 0ull, h);
         if (old == 0ull) {
             if (atomicAdd(count, 1) >= limit) *fail = 1;

@@ -124,14 +124,27 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total)
 constexpr int S1_WARPS = 8;
 enum { SC_NW_HEAVY = 0, SC_ERR = 1, SC_WMAX = 2, SC_MAXJ = 3, SC_NHEAVY = 4, SC_NW_LIGHT = 5, SC_NLIGHT = 6, SC_MAXNNZA = 7 };
 
+// The B tile-rows a C tile-row expands: A tile ta pairs with B's tile-row K = a_tile_col[ta], tiles [b0, b1). The expansion
+// loops below take them 32 A tiles at a time -- one per lane, handed out by shuffle -- and load the first 32 tile columns of
+// the NEXT B tile-row while the current one is processed: a warp then waits for one load per A tile instead of a chain of
+// three (a_tile_col -> b_tile_ptr -> b_tile_col). Measured on config 2: k_s1_fill is bound by exactly that latency.
+struct BRange {
+    int b0, b1;
+    __device__ __forceinline__ BRange(const int *__restrict__ a_tile_col, const int *__restrict__ b_tile_ptr, int ta, int a1) : b0(0), b1(0)
+    {
+        if (ta < a1) { const int K = a_tile_col[ta]; b0 = b_tile_ptr[K]; b1 = b_tile_ptr[K + 1]; }
+    }
+};
+
 // k_s1_count: per tile-row the weight w (matched tile pairs; also the multi-GPU / slab balancing weight, nsparse
 // set_intprod_num, src/spgemm_nsparse_kernel.h:135-151), the window [jlo, jhi] of tile columns the row can produce, and
-// -- for rows that fit the light path -- the number of distinct tile columns (C tiles). The others join heavy_list.
+// -- for rows that fit the light path -- the number of distinct tile columns (C tiles) and, when bm_save is given and the
+// window is at most bm_stride words, the window bitmap itself. The others join heavy_list.
 __global__ void __launch_bounds__(S1_WARPS * 32)
 k_s1_count(int trow0, int ntr, int bmw, const int *__restrict__ a_tile_ptr, const int *__restrict__ a_tile_col,
            const int *__restrict__ a_tile_nnz, const int *__restrict__ b_tile_ptr, const int *__restrict__ b_tile_col, int *__restrict__ w, int *__restrict__ jlo,
            int *__restrict__ jhi, int *__restrict__ cnt, uint8_t *__restrict__ light, int *__restrict__ heavy_list,
-           int *__restrict__ scal)
+           int *__restrict__ scal, unsigned *__restrict__ bm_save, int bm_stride)
 {
     extern __shared__ unsigned s1c_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -179,17 +192,32 @@ k_s1_count(int trow0, int ntr, int bmw, const int *__restrict__ a_tile_ptr, cons
     }
     for (int k = lane; k < nw; k += 32) bitmap[k] = 0;
     __syncwarp();
-    for (int ta = a0; ta < a1; ta++) {
-        const int K = a_tile_col[ta];
-        const int b1 = b_tile_ptr[K + 1];
-        for (int tb = b_tile_ptr[K] + lane; tb < b1; tb += 32) {
-            const int d = b_tile_col[tb] - lo32;
-            atomicOr(&bitmap[d >> 5], 1u << (d & 31));
+    for (int tc = a0; tc < a1; tc += 32) {
+        const BRange br(a_tile_col, b_tile_ptr, tc + lane, a1);
+        const int nt = min(32, a1 - tc);
+        int nb0 = __shfl_sync(FULL_MASK, br.b0, 0), nb1 = __shfl_sync(FULL_MASK, br.b1, 0);
+        int ncol = nb0 + lane < nb1 ? b_tile_col[nb0 + lane] : -1;
+        for (int j = 0; j < nt; j++) {
+            const int b0 = nb0, b1 = nb1, col = ncol;
+            if (j + 1 < nt) {
+                nb0 = __shfl_sync(FULL_MASK, br.b0, j + 1); nb1 = __shfl_sync(FULL_MASK, br.b1, j + 1);
+                ncol = nb0 + lane < nb1 ? b_tile_col[nb0 + lane] : -1;
+            }
+            if (col >= 0) atomicOr(&bitmap[(col - lo32) >> 5], 1u << ((col - lo32) & 31));
+            for (int tb = b0 + 32 + lane; tb < b1; tb += 32) {
+                const int d = b_tile_col[tb] - lo32;
+                atomicOr(&bitmap[d >> 5], 1u << (d & 31));
+            }
         }
     }
     __syncwarp();
     int n = 0;
-    for (int k = lane; k < nw; k += 32) n += __popc(bitmap[k]);
+    const bool save = bm_save && nw <= bm_stride;
+    for (int k = lane; k < nw; k += 32) {
+        const unsigned word = bitmap[k];
+        n += __popc(word);
+        if (save) bm_save[(size_t)i * bm_stride + k] = word;  // k_s1_fill starts from it instead of expanding the row again
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(FULL_MASK, n, o);
     if (lane == 0) {
@@ -219,12 +247,15 @@ struct S1Fill {
     const int *pat_a, *pat_b;
     PlanTable table;
     int *rslot;
+    unsigned *pair_pat;        // HASH: (A pattern << 16 | B pattern) of every pair, beside pair_a / pair_b (k_recipe_verify reads it)
+    const unsigned *bm_saved;  // the window bitmaps k_s1_count saved (bm_stride words per tile-row), or null
+    int bm_stride;
 };
 
 // FUSE: fused bitmask symbolic. HASH: instead, hash every C tile's (A pattern, B pattern) sequence into the recipe table
 // (per-warp shared memory then holds hh[nj] 64-bit running hashes in place of bmT / cm).
 template <bool FUSE, bool HASH>
-__global__ void __launch_bounds__(S1_WARPS * 32, 4)
+__global__ void __launch_bounds__(S1_WARPS * 32, 5)
 k_s1_fill(const __grid_constant__ S1Fill P)
 {
     extern __shared__ __align__(16) unsigned s1f_smem[];
@@ -242,15 +273,29 @@ k_s1_fill(const __grid_constant__ S1Fill P)
     const int a0 = P.a_tile_ptr[I], a1 = P.a_tile_ptr[I + 1];
     const int cbase = P.c_tile_ptr[i], numJ = P.c_tile_ptr[i + 1] - cbase, wbase = P.wptr[i];
 
-    // 1. window bitmap of the tile columns the row produces
-    for (int k = lane; k < nw; k += 32) bitmap[k] = 0;
-    __syncwarp();
-    for (int ta = a0; ta < a1; ta++) {
-        const int K = P.a_tile_col[ta];
-        const int b1 = P.b_tile_ptr[K + 1];
-        for (int tb = P.b_tile_ptr[K] + lane; tb < b1; tb += 32) {
-            const int d = P.b_tile_col[tb] - lo;
-            atomicOr(&bitmap[d >> 5], 1u << (d & 31));
+    // 1. window bitmap of the tile columns the row produces (as k_s1_count left it, when it was saved)
+    if (P.bm_saved && nw <= P.bm_stride) {
+        for (int k = lane; k < nw; k += 32) bitmap[k] = P.bm_saved[(size_t)i * P.bm_stride + k];
+    } else {
+        for (int k = lane; k < nw; k += 32) bitmap[k] = 0;
+        __syncwarp();
+        for (int tc = a0; tc < a1; tc += 32) {
+            const BRange br(P.a_tile_col, P.b_tile_ptr, tc + lane, a1);
+            const int nt = min(32, a1 - tc);
+            int nb0 = __shfl_sync(FULL_MASK, br.b0, 0), nb1 = __shfl_sync(FULL_MASK, br.b1, 0);
+            int ncol = nb0 + lane < nb1 ? P.b_tile_col[nb0 + lane] : -1;
+            for (int j = 0; j < nt; j++) {
+                const int b0 = nb0, b1 = nb1, col = ncol;
+                if (j + 1 < nt) {
+                    nb0 = __shfl_sync(FULL_MASK, br.b0, j + 1); nb1 = __shfl_sync(FULL_MASK, br.b1, j + 1);
+                    ncol = nb0 + lane < nb1 ? P.b_tile_col[nb0 + lane] : -1;
+                }
+                if (col >= 0) atomicOr(&bitmap[(col - lo) >> 5], 1u << ((col - lo) & 31));
+                for (int tb = b0 + 32 + lane; tb < b1; tb += 32) {
+                    const int d = P.b_tile_col[tb] - lo;
+                    atomicOr(&bitmap[d >> 5], 1u << (d & 31));
+                }
+            }
         }
     }
     __syncwarp();
@@ -289,54 +334,63 @@ k_s1_fill(const __grid_constant__ S1Fill P)
     __syncwarp();
     // 4. second expansion: pairs per C tile, the slot of every pair in A-major order, and the fused bitmask symbolic
     int aoff = 0;
-    for (int ta = a0; ta < a1; ta++) {
-        const int K = P.a_tile_col[ta];
-        const int b0 = P.b_tile_ptr[K], b1 = P.b_tile_ptr[K + 1];
-        unsigned amw[8];
-        if (FUSE) {  // A's 16 row masks: one 32-byte line, the same for every lane
-            const uint4 *ap = reinterpret_cast<const uint4 *>(P.a_mask + (size_t)ta * TS);
-            const uint4 x = ap[0], y = ap[1];
-            amw[0] = x.x; amw[1] = x.y; amw[2] = x.z; amw[3] = x.w; amw[4] = y.x; amw[5] = y.y; amw[6] = y.z; amw[7] = y.w;
-        }
-        for (int tb0 = b0; tb0 < b1; tb0 += 32) {
-            const int tb = tb0 + lane;
-            const bool valid = tb < b1;
-            int slot = 0;
-            if (valid) {
-                const int d = P.b_tile_col[tb] - lo, wd = d >> 5;
-                slot = pre[wd] + __popc(bitmap[wd] & ((1u << (d & 31)) - 1));
-                cur[slot]++;  // one A tile at a time: the lanes hold distinct slots
-                P.pair_slot[wbase + aoff + (tb - b0)] = (uint16_t)slot;
+    for (int tc = a0; tc < a1; tc += 32) {
+        const BRange br(P.a_tile_col, P.b_tile_ptr, tc + lane, a1);
+        const int nt = min(32, a1 - tc);
+        int nb0 = __shfl_sync(FULL_MASK, br.b0, 0), nb1 = __shfl_sync(FULL_MASK, br.b1, 0);
+        int ncol = nb0 + lane < nb1 ? P.b_tile_col[nb0 + lane] : -1;
+        for (int j = 0; j < nt; j++) {
+            const int ta = tc + j, b0 = nb0, b1 = nb1, col0 = ncol;
+            if (j + 1 < nt) {
+                nb0 = __shfl_sync(FULL_MASK, br.b0, j + 1); nb1 = __shfl_sync(FULL_MASK, br.b1, j + 1);
+                ncol = nb0 + lane < nb1 ? P.b_tile_col[nb0 + lane] : -1;
             }
-            if (FUSE) {
+            unsigned amw[8];
+            if (FUSE) {  // A's 16 row masks: one 32-byte line, the same for every lane
+                const uint4 *ap = reinterpret_cast<const uint4 *>(P.a_mask + (size_t)ta * TS);
+                const uint4 x = ap[0], y = ap[1];
+                amw[0] = x.x; amw[1] = x.y; amw[2] = x.z; amw[3] = x.w; amw[4] = y.x; amw[5] = y.y; amw[6] = y.z; amw[7] = y.w;
+            }
+            for (int tb0 = b0; tb0 < b1; tb0 += 32) {
+                const int tb = tb0 + lane;
+                const bool valid = tb < b1;
+                int slot = 0;
                 if (valid) {
-                    const uint4 *bp = reinterpret_cast<const uint4 *>(P.b_mask + (size_t)P.b_rm2csc[tb] * TS);
-                    const uint4 x = bp[0], y = bp[1];
-                    const unsigned bw[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                    const int d = (tb0 == b0 ? col0 : P.b_tile_col[tb]) - lo, wd = d >> 5;
+                    slot = pre[wd] + __popc(bitmap[wd] & ((1u << (d & 31)) - 1));
+                    cur[slot]++;  // one A tile at a time: the lanes hold distinct slots
+                    if (!HASH) P.pair_slot[wbase + aoff + (tb - b0)] = (uint16_t)slot;  // the plan kernels do not use it (k_pair_slots if they fail)
+                }
+                if (FUSE) {
+                    if (valid) {
+                        const uint4 *bp = reinterpret_cast<const uint4 *>(P.b_mask + (size_t)P.b_rm2csc[tb] * TS);
+                        const uint4 x = bp[0], y = bp[1];
+                        const unsigned bw[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {  // little-endian u16 pairs
-                        bmT[(2 * j) * 32 + lane] = (uint16_t)(bw[j] & 0xFFFFu);
-                        bmT[(2 * j + 1) * 32 + lane] = (uint16_t)(bw[j] >> 16);
+                        for (int q = 0; q < 8; q++) {  // little-endian u16 pairs
+                            bmT[(2 * q) * 32 + lane] = (uint16_t)(bw[q] & 0xFFFFu);
+                            bmT[(2 * q + 1) * 32 + lane] = (uint16_t)(bw[q] >> 16);
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int r = 0; r < TS; r++) {
+                        unsigned m = (r & 1) ? (amw[r >> 1] >> 16) : (amw[r >> 1] & 0xFFFFu);
+                        if (m) {  // warp-uniform
+                            unsigned acc = 0;
+                            do {
+                                const int k = __clz(m) - 16;
+                                acc |= bmT[k * 32 + lane];
+                                m &= ~(0x8000u >> k);
+                            } while (m);
+                            if (valid) cm[r * P.njpad + slot] |= (uint16_t)acc;  // distinct slots per lane
+                        }
                     }
                 }
                 __syncwarp();
-#pragma unroll
-                for (int r = 0; r < TS; r++) {
-                    unsigned m = (r & 1) ? (amw[r >> 1] >> 16) : (amw[r >> 1] & 0xFFFFu);
-                    if (m) {  // warp-uniform
-                        unsigned acc = 0;
-                        do {
-                            const int k = __clz(m) - 16;
-                            acc |= bmT[k * 32 + lane];
-                            m &= ~(0x8000u >> k);
-                        } while (m);
-                        if (valid) cm[r * P.njpad + slot] |= (uint16_t)acc;  // distinct slots per lane
-                    }
-                }
             }
-            __syncwarp();
+            aoff += b1 - b0;
         }
-        aoff += b1 - b0;
     }
     // 5. exclusive scan of the pair counts over the row's slots: pair_ptr; cur becomes the write cursor
     {
@@ -356,19 +410,38 @@ k_s1_fill(const __grid_constant__ S1Fill P)
     }
     __syncwarp();
     // 6. third expansion: the pair lists, A tiles ascending inside every list (the serial SPA's summation order)
-    for (int ta = a0; ta < a1; ta++) {
-        const int K = P.a_tile_col[ta];
-        const int b1 = P.b_tile_ptr[K + 1];
-        for (int tb = P.b_tile_ptr[K] + lane; tb < b1; tb += 32) {
-            const int d = P.b_tile_col[tb] - lo, wd = d >> 5;
-            const int slot = pre[wd] + __popc(bitmap[wd] & ((1u << (d & 31)) - 1));
-            const int pos = cur[slot]++;
-            const int b = P.b_rm2csc[tb];
-            P.pair_a[pos] = ta;
-            P.pair_b[pos] = b;
-            if (HASH) hh[slot] = plans::mix64(hh[slot], ((unsigned long long)(unsigned)P.pat_a[ta] << 32) | (unsigned)P.pat_b[b]);
+    for (int tc = a0; tc < a1; tc += 32) {
+        const BRange br(P.a_tile_col, P.b_tile_ptr, tc + lane, a1);
+        const unsigned mypa = HASH && tc + lane < a1 ? (unsigned)P.pat_a[tc + lane] : 0u;
+        const int nt = min(32, a1 - tc);
+        int nb0 = __shfl_sync(FULL_MASK, br.b0, 0), nb1 = __shfl_sync(FULL_MASK, br.b1, 0);
+        int ncol = -1, nrm = 0;
+        unsigned npb = 0;
+        if (nb0 + lane < nb1) { ncol = P.b_tile_col[nb0 + lane]; nrm = P.b_rm2csc[nb0 + lane]; if (HASH) npb = (unsigned)P.pat_b[nb0 + lane]; }
+        for (int j = 0; j < nt; j++) {
+            const int ta = tc + j, b0 = nb0, b1 = nb1, col0 = ncol, rm0 = nrm;
+            const unsigned pb0 = npb, pa = __shfl_sync(FULL_MASK, mypa, j);  // pattern ids (< 2^13); B's are in row-major tile order
+            if (j + 1 < nt) {
+                nb0 = __shfl_sync(FULL_MASK, br.b0, j + 1); nb1 = __shfl_sync(FULL_MASK, br.b1, j + 1);
+                ncol = -1;
+                if (nb0 + lane < nb1) { ncol = P.b_tile_col[nb0 + lane]; nrm = P.b_rm2csc[nb0 + lane]; if (HASH) npb = (unsigned)P.pat_b[nb0 + lane]; }
+            }
+            for (int tb = b0 + lane; tb < b1; tb += 32) {
+                const bool first = tb < b0 + 32;
+                const int d = (first ? col0 : P.b_tile_col[tb]) - lo, wd = d >> 5;
+                const int slot = pre[wd] + __popc(bitmap[wd] & ((1u << (d & 31)) - 1));
+                const int pos = cur[slot]++;
+                const int b = first ? rm0 : P.b_rm2csc[tb];
+                P.pair_a[pos] = ta;
+                P.pair_b[pos] = b;
+                if (HASH) {
+                    const unsigned pb = first ? pb0 : (unsigned)P.pat_b[tb];
+                    hh[slot] = plans::mix64(hh[slot], ((unsigned long long)pa << 32) | pb);
+                    P.pair_pat[pos] = (pa << 16) | pb;
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
     // 7. list ends; Ptr (exclusive row offsets), mask and nnz of each C tile
     for (int sl = lane; sl < numJ; sl += 32) {
@@ -377,7 +450,7 @@ k_s1_fill(const __grid_constant__ S1Fill P)
             const int t = cbase + sl;
             const int slot = plans::table_insert(P.table.keys, plans::RCAP, hh[sl], P.table.count, plans::RMAX, P.table.fail);
             P.rslot[t] = slot;
-            if (slot >= 0 && t < *(volatile int *)&P.table.owner[slot]) atomicMin(&P.table.owner[slot], t);
+            if (slot >= 0 && t < P.table.owner[slot]) atomicMin(&P.table.owner[slot], t);  // owner only decreases: a stale read costs one atomic
         }
         if (FUSE) {
             unsigned pw[8], mw[8];
@@ -396,6 +469,33 @@ k_s1_fill(const __grid_constant__ S1Fill P)
             dm[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]); dm[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
             P.c_cnt[cbase + sl] = run;
         }
+    }
+}
+
+// The A-major slot array k_step3_sparse needs, for the one case k_s1_fill<.., HASH> did not write it: the recipe plans
+// were attempted and failed (a 64-bit collision, too many recipes), so the generic numeric kernels run after all.
+// One warp per light tile-row; the slot of (A tile, B tile) = position of the B tile's column in the row's C tile columns.
+__global__ void __launch_bounds__(S1_WARPS * 32)
+k_pair_slots(int trow0, int ntr, const uint8_t *__restrict__ light, const int *__restrict__ a_tile_ptr, const int *__restrict__ a_tile_col,
+             const int *__restrict__ b_tile_ptr, const int *__restrict__ b_tile_col, const int *__restrict__ c_tile_ptr,
+             const int *__restrict__ c_tile_col, const int *__restrict__ wptr, uint16_t *__restrict__ pair_slot)
+{
+    const int i = blockIdx.x * S1_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= ntr || !light[i]) return;
+    const int I = trow0 + i, cbase = c_tile_ptr[i], numJ = c_tile_ptr[i + 1] - cbase;
+    int out = wptr[i];
+    for (int ta = a_tile_ptr[I]; ta < a_tile_ptr[I + 1]; ta++) {
+        const int K = a_tile_col[ta], b0 = b_tile_ptr[K], b1 = b_tile_ptr[K + 1];
+        for (int tb = b0 + lane; tb < b1; tb += 32) {
+            const int col = b_tile_col[tb];
+            int lo = 0, hi = numJ - 1;  // the column is there: step 1 listed it
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (c_tile_col[cbase + mid] < col) lo = mid + 1; else hi = mid;
+            }
+            pair_slot[out + (tb - b0)] = (uint16_t)lo;
+        }
+        out += b1 - b0;
     }
 }
 
@@ -721,7 +821,16 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
 
     // ---------------- step 1a: weights, windows, C tile counts ----------------
     const size_t nr = (size_t)ntr + 1;
-    if (!arena_reserve(0, 7 * arena_need(nr, 4) + arena_need(nr, 1))) return last_error();
+    // a warp's window bitmap in k_s1_count: up to 2048 words (65536 tile columns); wider windows take the heavy path
+    int bmw1 = (B->tilen + 31) / 32 + 1;
+    if (bmw1 > 2048) bmw1 = 2048;
+    // the bitmaps of windows up to bm_stride words go from k_s1_count to k_s1_fill through global memory (<= 128 MB in all;
+    // config 2: 66-word windows, 64 MB), so that k_s1_fill does not expand the tile-row a fourth time
+    int bm_stride = bmw1 < 128 ? bmw1 : 128;
+    if (ntr > 0 && (size_t)ntr * bm_stride * 4 > ((size_t)128 << 20)) bm_stride = (int)((((size_t)128 << 20) / 4) / (size_t)ntr);
+    const size_t bm_bytes = (size_t)ntr * bm_stride * 4;
+    const bool bm_keep = ntr > 0 && bm_stride >= 8 && !(getenv("TSG_S1_KEEP_BITMAPS") && *getenv("TSG_S1_KEEP_BITMAPS") == '0');
+    if (!arena_reserve(0, 7 * arena_need(nr, 4) + arena_need(nr, 1) + (bm_keep ? arena_need(bm_bytes, 1) : 0))) return last_error();
     int *w = arena_take<int>(0, nr), *jlo = arena_take<int>(0, nr), *jhi = arena_take<int>(0, nr);
     int *wptr = arena_take<int>(0, nr), *cnt = arena_take<int>(0, nr), *c_tile_ptr = arena_take<int>(0, nr);
     int *heavy_list = arena_take<int>(0, nr);
@@ -730,15 +839,14 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     int *scal = (int *)c.d_scalars;                 // SC_* counters (8 ints)
     long long *tot = c.d_scalars + 4;               // [0] pairs, [1] C tiles (64-bit scan totals)
     CK(cudaMemsetAsync(scal, 0, 6 * sizeof(long long), c.stream));
-    // a warp's window bitmap in k_s1_count: up to 2048 words (65536 tile columns); wider windows take the heavy path
-    int bmw1 = (B->tilen + 31) / 32 + 1;
-    if (bmw1 > 2048) bmw1 = 2048;
+    unsigned *bm_save = bm_keep ? (unsigned *)arena_take<uint8_t>(0, bm_bytes) : nullptr;
+    if (bm_keep && !bm_save) return last_error();
     if (ntr > 0) {
         const size_t smem = (size_t)S1_WARPS * bmw1 * 4;
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_s1_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_s1_count<<<ceil_div(ntr, S1_WARPS), S1_WARPS * 32, smem, c.stream>>>(trow0, ntr, bmw1, A->tile_ptr, A->tile_columnidx, A->tile_nnz,
                                                                               B->tile_ptr, B->tile_columnidx, w, jlo, jhi, cnt, light, heavy_list,
-                                                                              scal);
+                                                                              scal, bm_save, bm_stride);
         CK_LAUNCH();
     }
     // one scan per array: 32-bit offsets for the kernels, the 64-bit total for the host (slab planning keeps it < 2^31)
@@ -815,7 +923,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     rc = copy_words(C->tile_ptr, c_tile_ptr, (size_t)ntr + 1);
     if (rc) return rc;
     const bool heavy_rows = n_heavy > 0;  // tile-rows on the multi-warp path park one 16-byte record per pair
-    if (!arena_reserve(1, 4 * arena_need(nb + 1, 4) + 2 * arena_need(np, 4) + arena_need(np, 2) + arena_need(np, 8) +
+    if (!arena_reserve(1, 4 * arena_need(nb + 1, 4) + 3 * arena_need(np, 4) + arena_need(np, 2) +
                               (heavy_rows ? arena_need(np, 16) : 0) + numeric_scratch_bytes(ntr, numblkC)))
         return last_error();
     int *pair_ptr = arena_take<int>(1, nb + 1), *pair_end = arena_take<int>(1, nb + 1), *pair_a = arena_take<int>(1, np), *pair_b = arena_take<int>(1, np);
@@ -825,8 +933,9 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     // recipe plans (plans.cu): attempted when both operands are made of few distinct tile patterns and no tile-row is heavy
     bool plans_on = plans_wanted(A, B) && !heavy_rows && numblkC > 0 && pairs > 0;
     int *rslot = plans_on ? arena_take<int>(1, nb) : nullptr, *recipe_id = plans_on ? arena_take<int>(1, nb) : nullptr;
+    unsigned *pair_pat = plans_on ? arena_take<unsigned>(1, np) : nullptr;  // (A pattern, B pattern) per pair
     if (!pair_ptr || !pair_end || !pair_a || !pair_b || !pair_slot || (heavy_rows && !pair_tmp) || !nbufs.row_kind || !nbufs.dense_list ||
-        (plans_on && (!rslot || !recipe_id)))
+        (plans_on && (!rslot || !recipe_id || !pair_pat)))
         return last_error();
     if (heavy_rows) CK(cudaMemsetAsync(pair_end, 0, nb * 4, c.stream));  // the heavy kernel counts with atomics
     CK(cudaEventRecord(ev[2], c.stream));  // [1..2] = allocation
@@ -852,7 +961,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         warp_words = (warp_words + 1) & ~1;
         S1Fill P{trow0, ntr, bmw, nj, njpad, warp_words, hoff, A->tile_ptr, A->tile_columnidx, B->tile_ptr, B->tile_columnidx, B->rm2csc,
                  jlo, jhi, wptr, C->tile_ptr, light, C->tile_columnidx, C->tile_rowidx, pair_ptr, pair_end, pair_a, pair_b, pair_slot,
-                 A->mask, B->mask, C->ptr, C->mask, C->tile_nnz, A->pat, B->pat, ptab, rslot};
+                 A->mask, B->mask, C->ptr, C->mask, C->tile_nnz, A->pat, B->pat, ptab, rslot, pair_pat, bm_save, bm_stride};
         const size_t smem = (size_t)S1_WARPS * warp_words * 4;
         if (smem > c.smem_optin) { set_error(TSG_ERR_UNSUPPORTED, "step 1: %zu B of shared memory per CTA needed (> %zu)", smem, c.smem_optin); return last_error(); }
         const int blocks = ceil_div(ntr, S1_WARPS);
@@ -896,7 +1005,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         return TSG_OK;
     };
     if (plans_on) {  // C's masks / Ptr / tile nnz from the recipe plans (or nothing useful, if the fail flag comes up)
-        rc = plans_symbolic_device(A, B, C, plists, rslot, recipe_id, &d_plan_fail);
+        rc = plans_symbolic_device(A, B, C, plists, pair_pat, rslot, recipe_id, &d_plan_fail);
         if (rc) return rc;
     } else if (numblkC > 0 && (!fused || n_heavy > 0)) {
         rc = generic_symbolic(fused);
@@ -916,6 +1025,9 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         if (*(const volatile int *)&c.h_scalars[20]) {  // a collision or too many recipes: the generic kernels run instead
             plans_on = false;
             plan_recipes = -1;
+            k_pair_slots<<<ceil_div(ntr, S1_WARPS), S1_WARPS * 32, 0, c.stream>>>(trow0, ntr, light, A->tile_ptr, A->tile_columnidx, B->tile_ptr,
+                                                                                  B->tile_columnidx, C->tile_ptr, C->tile_columnidx, wptr, pair_slot);
+            CK_LAUNCH();
             rc = generic_symbolic(false);
             if (!rc) rc = exclusive_scan<int>(C->tile_nnz, C->tile_nnz, numblkC, tot);
             if (rc) return rc;
