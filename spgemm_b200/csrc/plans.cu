@@ -168,9 +168,10 @@ bool plans_wanted(const tsg_dtile *A, const tsg_dtile *B)
 {
     const char *forced = getenv("TSG_STEP3");  // a forced numeric kernel (A/B measurements, tests) means the generic path
     if (forced && *forced && strcmp(forced, "auto")) return false;
-    // well-filled tiles (block-FEM: 96 entries per A tile) are the dense accumulator's: measured on config 4, the plan
-    // path's lane-per-nonzero numeric is 20 % slower than k_step3_dense there (profiles/README.md, r2k vs r2j)
-    if (!(getenv("TSG_PLANS") && *getenv("TSG_PLANS") == '2') && A->nnz >= 24ll * A->numtile) return false;
+    // matrices made of well-filled tiles only (block-FEM: 96 entries per A tile) are the dense accumulator's: measured on
+    // config 4, the plan path is 4 % slower than k_step3_dense there (552.8 vs 573.8 GFLOP/s, profiles/README.md r2t / r2s);
+    // a half-and-half mix of block-FEM and stencil tiles (45 entries per tile on average) is 2.1x FASTER through the plans
+    if (!(getenv("TSG_PLANS") && *getenv("TSG_PLANS") == '2') && A->nnz >= 64ll * A->numtile) return false;
     return plans_env_on() && A->pat && B->pat && A->npat > 0 && B->npat > 0 && A->npat <= PLANS_MAX_PATTERNS && B->npat <= PLANS_MAX_PATTERNS;
 }
 
