@@ -400,7 +400,7 @@ def run_ours(args):
            float(np.mean([s["ms_step3"] for s in stats])), float(np.mean([s["ms_alloc"] for s in stats])),
            float(last["algorithmic_bytes"]), float(step3_bytes(tA, tB, last)), wall_ms / K, e2e_local_ms,
            float(last["rows_staged"]), float(last["rows_gather"]), float(last["tiles_dense"]), float(last["rows_smem"]),
-           float(last["plan_recipes"])]
+           float(last["plan_recipes"]), float(last.get("row_templates", 0))]
     if dist is not None:
         t = torch.tensor(vec, dtype=torch.float64, device=dev)
         allv = [torch.zeros_like(t) for _ in range(world)]
@@ -436,7 +436,7 @@ def run_ours(args):
     alg_total = float(allv[:, 12].sum())  # every rank reads the whole B, so B's bytes count once per rank
     rp, ci, v = A_host[2], A_host[3], A_host[4]
     kern_stats = {"rows_staged": int(allv[:, 16].sum()), "rows_gather": int(allv[:, 17].sum()), "tiles_dense": int(allv[:, 18].sum()),
-                  "rows_smem": int(allv[:, 19].max()), "plan_recipes": int(allv[:, 20].max())}
+                  "rows_smem": int(allv[:, 19].max()), "plan_recipes": int(allv[:, 20].max()), "row_templates": int(allv[:, 21].max())}
     line = {
         "metric": "spgemm_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -444,6 +444,7 @@ def run_ours(args):
         "config": {"workload": args.workload, "description": desc, "tile": "16x16", "aat": int(aat), "m": m, "n": n,
                    "nnzA": int(len(ci)), "nnzCub": int(nnzCub), "nnzC": int(allv[:, 5].sum()),
                    "C_tiles": int(allv[:, 6].sum()), "tile_pairs": int(allv[:, 7].sum()),
+                   "plan_recipes": kern_stats["plan_recipes"], "row_templates": kern_stats["row_templates"],
                    "l2": "inputs larger than L2 (tiled A+B+C per step >> 126 MB)" if alg_total > 4 * 126e6 else
                          "working set fits L2: launch-latency-bound correctness config, not a roofline config",
                    "parallelism": f"tile-row partition x{world}", "partition": part,

@@ -183,6 +183,8 @@ typedef struct {
     int tiles_nonempty;       /* C tiles holding at least one entry (numblkC counts the empty ones too)     */
     int plan_recipes;         /* > 0: steps 2 and 3 ran from recipe plans (csrc/plans.cu), this many distinct recipes;
                                  0: generic kernels; -1: plans were attempted and fell back                     */
+    int row_templates;        /* > 0: step 1 ran on this many representative tile-rows and the others were instantiated
+                                 from them (csrc/rowplans.cu); 0: every tile-row expanded; -1: attempted, redone without */
 } tsg_stats;
 
 /* Select the device (like the driver's cudaSetDevice, reference src/main.cu:49) and create the

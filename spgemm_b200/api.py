@@ -375,7 +375,7 @@ def spgemm_slabs(a: DeviceTiled, b: DeviceTiled, max_pairs: int = 1 << 28, sink=
     w = tilerow_weights(a, b) if weights is None else weights
     slabs = [(t0 + trow0, t1 + trow0) for t0, t1 in plan_slabs(w[trow0:trow1], max_pairs)]
     tot = dict(numblkC=0, nnzC=0, pairs=0, ms_step1=0.0, ms_step2=0.0, ms_step3=0.0, ms_alloc=0.0, ms_total=0.0,
-               algorithmic_bytes=0, launches=0, rows_staged=0, rows_gather=0, tiles_dense=0, rows_smem=0, tiles_nonempty=0, plan_recipes=0, slabs=len(slabs))
+               algorithmic_bytes=0, launches=0, rows_staged=0, rows_gather=0, tiles_dense=0, rows_smem=0, tiles_nonempty=0, plan_recipes=0, row_templates=0, slabs=len(slabs))
     per = []
     for t0, t1 in slabs:
         c, st = spgemm(a, b, t0, t1)
@@ -383,7 +383,7 @@ def spgemm_slabs(a: DeviceTiled, b: DeviceTiled, max_pairs: int = 1 << 28, sink=
             sink(c, st)
         c.free()
         for k in tot:
-            if k in ("rows_smem", "plan_recipes"):
+            if k in ("rows_smem", "plan_recipes", "row_templates"):
                 tot[k] = max(tot[k], st[k])
             elif k != "slabs":
                 tot[k] += st[k]

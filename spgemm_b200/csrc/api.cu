@@ -266,6 +266,7 @@ void tsg_shutdown(void)
     if (!g_ready) return;
     cudaStreamSynchronize(g_ctx.stream);
     plans_shutdown();
+    rowplans_shutdown();
     if (g_ctx.scan_state) cudaFreeAsync(g_ctx.scan_state, g_ctx.stream);
     for (int k = 0; k < 3; k++)
         if (g_ctx.arena[k].base) cudaFreeAsync(g_ctx.arena[k].base, g_ctx.stream);
@@ -706,6 +707,7 @@ int tsg_spgemm_slabs(const tsg_dtile *a, const tsg_dtile *b, int trow0, int trow
             totals->tiles_nonempty += st.tiles_nonempty;
             if (st.rows_smem > totals->rows_smem) totals->rows_smem = st.rows_smem;
             if (st.plan_recipes > totals->plan_recipes) totals->plan_recipes = st.plan_recipes;
+            if (st.row_templates > totals->row_templates) totals->row_templates = st.row_templates;
         }
         if (!rc && sink && sink(&tC, &st, user)) {
             set_error(TSG_ERR_INPUT, "spgemm_slabs: the slab callback stopped the run at tile-rows [%d,%d)", r0, r1);
@@ -772,6 +774,7 @@ int tsg_spgemm_to_host(const tsg_dtile *a, const tsg_dtile *b, int trow0, int tr
             stats->tiles_nonempty += st.tiles_nonempty;
             if (st.rows_smem > stats->rows_smem) stats->rows_smem = st.rows_smem;
             if (st.plan_recipes > stats->plan_recipes) stats->plan_recipes = st.plan_recipes;
+            if (st.row_templates > stats->row_templates) stats->row_templates = st.row_templates;
         }
         const long long nz = tC.nnz;
         const int rows = tC.m;

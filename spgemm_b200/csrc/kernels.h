@@ -38,11 +38,25 @@ int numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, int tro
 
 // plans.cu (recipe plans: bit-exact fast path of steps 2 and 3 for matrices made of few distinct tiles)
 struct PlanTable;
+// tile-row templates (rowplans.cu): what k_rows_instantiate needs besides the tiled matrices
+struct RowTemplates {
+    int n, trow0, ntr;                    // distinct tile-row signatures; the slab
+    const int *rep_list, *rep_of, *w, *wptr;
+    int *pair_ptr, *pair_end, *pair_a, *pair_b;
+    const uint16_t *pair_dest;            // A-major: where the representative's pair landed in its pair lists
+};
+bool rowplans_env_on();
+int rowplans_signatures(const tsg_dtile *A, const tsg_dtile *B, int trow0, int ntr, int *w, int *sig_slot, int *rep_of, int *sc_err,
+                        const int **rep_list, int *nsig);
+int rowplans_expand_counts(int ntr, const int *rep_of, int *cnt, uint8_t *light);
+int rowplans_instantiate(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const RowTemplates &rt, int *recipe_id);
+int *rowplans_fail_ptr();
+void rowplans_shutdown();
 int tile_patterns_device(tsg_dtile *T);
 bool plans_wanted(const tsg_dtile *A, const tsg_dtile *B);
 int plans_begin(PlanTable *out);
 int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const unsigned *pair_pat, const int *rslot, int *recipe_id,
-                          const int **d_fail);
+                          const RowTemplates *rt, const int **d_fail);
 int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const int *recipe_id,
                          int trow0, int ntr, const int *wptr, int max_need, tsg_stats *stats);
 size_t plans_rows_need_bound(int max_nnzA_row, int maxJ, int wmax);

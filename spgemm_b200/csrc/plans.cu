@@ -198,13 +198,14 @@ k_recipe_reps(const int *__restrict__ owner, const int *__restrict__ rdense, int
 __global__ void __launch_bounds__(256)
 k_recipe_verify(int numblkC, const int *__restrict__ pair_ptr, const int *__restrict__ pair_end, const unsigned *__restrict__ pair_pat,
                 const int *__restrict__ rslot, const int *__restrict__ owner, const int *__restrict__ rdense,
-                int *__restrict__ recipe_id, int *fail)
+                int *__restrict__ recipe_id, int *fail, int skip_unset)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= numblkC) return;
     recipe_id[t] = 0;
     if (*(volatile int *)fail) return;
     const int slot = rslot[t];
+    if (skip_unset && slot == -1) return;  // tile-row templates: this tile's row takes its recipes from its representative
     if (slot < 0 || slot >= RCAP) { *fail = 1; return; }
     const int u = owner[slot];
     if (u < 0 || u >= numblkC || rdense[slot] >= RMAX) { *fail = 1; return; }
@@ -564,7 +565,7 @@ int plans_begin(PlanTable *out)
 // After k_s1_fill<HASH>: dense recipe numbers, verification, the plans, and C's masks / Ptr / tile nnz counts from them.
 // Everything is enqueued; *d_fail is the device flag the caller reads back with nnz(C).
 int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const unsigned *pair_pat, const int *rslot,
-                          int *recipe_id, const int **d_fail)
+                          int *recipe_id, const RowTemplates *rt, const int **d_fail)
 {
     Ctx &c = ctx();
     PlanCtx &p = g_plan;
@@ -578,8 +579,12 @@ int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, 
     k_recipe_reps<<<ceil_div(RCAP, 256), 256, 0, c.stream>>>(p.rowner, p.rdense, p.rep_tile);
     CK_LAUNCH();
     k_recipe_verify<<<ceil_div(numblkC, 256), 256, 0, c.stream>>>(numblkC, pl.ptr, pl.end, pair_pat, rslot, p.rowner, p.rdense, recipe_id,
-                                                                  fail);
+                                                                  fail, rt != nullptr);
     CK_LAUNCH();
+    if (rt) {  // the other tile-rows: C's tile columns, pair lists and recipe ids from their representatives (rowplans.cu)
+        rc = rowplans_instantiate(A, B, C, *rt, recipe_id);
+        if (rc) return rc;
+    }
     const int *nrec = p.rdense + RCAP;
     k_plan_build<false><<<ceil_div(RMAX * 16, 128), 128, 0, c.stream>>>(nrec, p.rep_tile, pl.ptr, pl.end, pl.a, pl.b, A->mask, A->ptr, B->mask,
                                                                         B->ptr, p.plan_mask, p.plan_ptr, p.plan_nnz, nullptr, p.plan_cnt,

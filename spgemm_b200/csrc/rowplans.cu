@@ -1,0 +1,296 @@
+// rowplans.cu -- tile-ROW templates: step 1 for matrices whose tile-rows repeat themselves.
+//
+// The recipe plans (plans.cu) use the fact that a structured matrix is made of few distinct tiles. One level up the same
+// holds for its tile-rows: on the 27-point stencil all interior tile-rows of C = A*B are translates of each other -- the
+// same tile columns relative to the diagonal, the same B tile-rows behind every A tile, the same tile patterns. For such
+// a tile-row everything step 1 computes (C's tile columns, the pair lists, and with the patterns also the recipe of every
+// C tile) is the representative's, shifted. So:
+//   * k_row_sig     one expansion per tile-row: the pair count w (step 1 needs it anyway) and a 64-bit hash of the
+//                   row's SIGNATURE -- per A tile (K - I, pattern, length of B's tile-row K), per B tile behind it
+//                   (J - I, pattern) -- inserted into a table like the recipes (atomicCAS, owner = smallest row index);
+//   * k_s1_count / k_s1_fill (spgemm.cu) then run on the REPRESENTATIVE tile-rows only; fill also records where every
+//     pair of the A-major walk landed in the pair lists (pair_dest);
+//   * k_rows_expand copies the C tile counts to the other rows (before the scans and the allocation);
+//   * k_rows_instantiate walks every other tile-row once more, side by side with its representative: it compares the
+//     two signatures element by element (a hash collision raises the fail flag and the whole call is redone without
+//     templates) and writes the row's C tile columns, pair lists and recipe ids from the representative's.
+// Two expansions per tile-row (hash, instantiate + verify) with no bitmap, no shared-memory atomics, no sorting and no
+// recipe hashing, instead of four. Attempted only together with the recipe plans (both operands made of few patterns, no
+// heavy tile-row) and when the rows repeat at least 4 times on average. TSG_ROWPLANS=0 switches it off.
+// Replaces, on such inputs, what reference src/tilespgemm-cuda.h:10-392 (step 1) computes per tile-row.
+#include "common.cuh"
+#include "scan.cuh"
+#include "kernels.h"
+#include "plans.cuh"
+
+namespace tsg {
+
+using namespace plans;
+
+namespace {
+
+constexpr int RPCAP = 1 << 15;   // signature table slots
+constexpr int RPMAX = RPCAP / 4; // more distinct tile-row signatures than this => the regular path
+
+struct RowPlanCtx {
+    unsigned long long *keys = nullptr;
+    int *owner = nullptr, *flags = nullptr, *dense = nullptr, *rep_row = nullptr;
+    int *ctl = nullptr;  // [0] signatures inserted, [1] fail
+    int device = -1;
+};
+RowPlanCtx g_rp;
+
+int rp_init()
+{
+    Ctx &c = ctx();
+    if (g_rp.device == c.device && g_rp.keys) return TSG_OK;
+    g_rp = RowPlanCtx();
+    g_rp.keys = dalloc_n<unsigned long long>(RPCAP);
+    g_rp.owner = dalloc_n<int>(RPCAP);
+    g_rp.flags = dalloc_n<int>(RPCAP + 1);
+    g_rp.dense = dalloc_n<int>(RPCAP + 1);
+    g_rp.rep_row = dalloc_n<int>(RPMAX);
+    g_rp.ctl = dalloc_n<int>(4);
+    if (!g_rp.keys || !g_rp.owner || !g_rp.flags || !g_rp.dense || !g_rp.rep_row || !g_rp.ctl) {
+        g_rp = RowPlanCtx();
+        return last_error();
+    }
+    g_rp.device = c.device;
+    return TSG_OK;
+}
+
+// position-dependent element hash; the signature hash is the SUM of these, so the lanes can add in any order
+__device__ __forceinline__ unsigned long long sig_elem(unsigned pos, unsigned long long v)
+{
+    unsigned long long x = (v + 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull ^ ((unsigned long long)(pos + 1u) * 0x94D049BB133111EBull);
+    x ^= x >> 29;
+    x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32;
+    return x;
+}
+
+}  // namespace
+
+void rowplans_shutdown() { g_rp = RowPlanCtx(); }
+
+// One warp per tile-row: w[i] and the row's signature slot (sig_slot[i]; -1 for a tile-row without pairs).
+__global__ void __launch_bounds__(256)
+k_row_sig(int trow0, int ntr, const int *__restrict__ a_tile_ptr, const int *__restrict__ a_tile_col, const int *__restrict__ pat_a,
+          const int *__restrict__ b_tile_ptr, const int *__restrict__ b_tile_col, const int *__restrict__ pat_b, int *__restrict__ w,
+          int *__restrict__ sig_slot, unsigned long long *keys, int *owner, int *ctl, int *__restrict__ sc_err)
+{
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= ntr) return;
+    const int I = trow0 + i, a0 = a_tile_ptr[I], a1 = a_tile_ptr[I + 1];
+    unsigned long long acc = 0;
+    long long s = 0;
+    int aoff = 0;  // pairs in front of the current A tile (warp-uniform)
+    for (int tc = a0; tc < a1; tc += 32) {
+        int b0 = 0, b1 = 0;
+        if (tc + lane < a1) {
+            const int K = a_tile_col[tc + lane];
+            b0 = b_tile_ptr[K]; b1 = b_tile_ptr[K + 1];
+            acc += sig_elem(0x40000000u + (unsigned)(tc + lane - a0),
+                            ((unsigned long long)(unsigned)(K - I) << 32) | ((unsigned long long)(unsigned)pat_a[tc + lane] << 16) ^ (unsigned)(b1 - b0));
+            s += b1 - b0;
+        }
+        const int nt = min(32, a1 - tc);
+        int nb0 = __shfl_sync(FULL_MASK, b0, 0), nb1 = __shfl_sync(FULL_MASK, b1, 0);
+        int ncol = 0, npb = 0;
+        if (nb0 + lane < nb1) { ncol = b_tile_col[nb0 + lane]; npb = pat_b[nb0 + lane]; }
+        for (int j = 0; j < nt; j++) {
+            const int cb0 = nb0, cb1 = nb1, col0 = ncol, pb0 = npb;
+            if (j + 1 < nt) {
+                nb0 = __shfl_sync(FULL_MASK, b0, j + 1); nb1 = __shfl_sync(FULL_MASK, b1, j + 1);
+                if (nb0 + lane < nb1) { ncol = b_tile_col[nb0 + lane]; npb = pat_b[nb0 + lane]; }
+            }
+            for (int tb = cb0 + lane; tb < cb1; tb += 32) {
+                const bool first = tb < cb0 + 32;
+                const int col = first ? col0 : b_tile_col[tb], pb = first ? pb0 : pat_b[tb];
+                acc += sig_elem((unsigned)(aoff + (tb - cb0)), ((unsigned long long)(unsigned)(col - I) << 16) ^ (unsigned)pb);
+            }
+            aoff += cb1 - cb0;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        acc += __shfl_xor_sync(FULL_MASK, acc, o);
+        s += __shfl_xor_sync(FULL_MASK, s, o);
+    }
+    if (lane) return;
+    if (s > 0x7fffffffll) { atomicOr(sc_err, 1); s = 0x7fffffff; }
+    w[i] = (int)s;
+    if (s == 0) { sig_slot[i] = -1; return; }
+    const unsigned long long h = mix64(acc, ((unsigned long long)(unsigned)(a1 - a0) << 32) | (unsigned)s);
+    const int slot = table_insert(keys, RPCAP, h, ctl, RPMAX, ctl + 1);
+    sig_slot[i] = slot;
+    if (slot >= 0 && i < owner[slot]) atomicMin(&owner[slot], i);  // owner only decreases: a stale read costs one atomic
+}
+
+__global__ void __launch_bounds__(256)
+k_tab_flags(int cap, const int *__restrict__ owner, int *__restrict__ flags)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < cap) flags[s] = owner[s] != NO_OWNER;
+}
+
+__global__ void __launch_bounds__(256)
+k_tab_reps(int cap, int rmax, const int *__restrict__ owner, const int *__restrict__ dense, int *__restrict__ rep)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < cap && owner[s] != NO_OWNER && dense[s] < rmax) rep[dense[s]] = owner[s];
+}
+
+// rep_of[i] = the representative tile-row of row i (itself for a representative, -1 for a row without pairs).
+__global__ void __launch_bounds__(256)
+k_rows_rep_of(int ntr, const int *__restrict__ sig_slot, const int *__restrict__ owner, int *__restrict__ rep_of)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntr) return;
+    const int slot = sig_slot[i];
+    rep_of[i] = slot < 0 ? -1 : owner[slot];
+}
+
+// After k_s1_count ran on the representatives: every other row takes its representative's C tile count and light flag.
+__global__ void __launch_bounds__(256)
+k_rows_expand(int ntr, const int *__restrict__ rep_of, int *__restrict__ cnt, uint8_t *__restrict__ light)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntr) return;
+    const int r = rep_of[i];
+    if (r < 0) { cnt[i] = 0; light[i] = 0; }
+    else if (r != i) { cnt[i] = cnt[r]; light[i] = light[r]; }
+}
+
+// One warp per tile-row that is not its own representative: verify its signature against the representative's,
+// element by element, and write its share of C's tile lists and of the pair lists from the representative's.
+struct RowInst {
+    int trow0, ntr;
+    const int *rep_of, *w, *wptr, *c_tile_ptr;
+    const int *a_tile_ptr, *a_tile_col, *pat_a, *b_tile_ptr, *b_tile_col, *pat_b, *b_rm2csc;
+    const uint16_t *pair_dest;
+    int *c_tile_col, *c_tile_row, *pair_ptr, *pair_end, *pair_a, *pair_b, *recipe_id;
+    int *fail;
+};
+
+__global__ void __launch_bounds__(256)
+k_rows_instantiate(const __grid_constant__ RowInst P)
+{
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= P.ntr) return;
+    const int r = P.rep_of[i];
+    if (r < 0 || r == i) return;
+    const int I = P.trow0 + i, Ir = P.trow0 + r, shift = I - Ir;
+    const int a0 = P.a_tile_ptr[I], a1 = P.a_tile_ptr[I + 1], ar0 = P.a_tile_ptr[Ir];
+    const int wbase = P.wptr[i], wbr = P.wptr[r];
+    if (a1 - a0 != P.a_tile_ptr[Ir + 1] - ar0 || P.w[i] != P.w[r]) {  // not the same row after all: nothing of it can be trusted
+        if (lane == 0) *P.fail = 1;
+        return;
+    }
+    const int cbase = P.c_tile_ptr[i], numJ = P.c_tile_ptr[i + 1] - cbase, cbr = P.c_tile_ptr[r];
+    for (int s = lane; s < numJ; s += 32) {
+        P.c_tile_col[cbase + s] = P.c_tile_col[cbr + s] + shift;
+        P.c_tile_row[cbase + s] = I;
+        P.pair_ptr[cbase + s] = P.pair_ptr[cbr + s] - wbr + wbase;
+        P.pair_end[cbase + s] = P.pair_end[cbr + s] - wbr + wbase;
+        P.recipe_id[cbase + s] = P.recipe_id[cbr + s];
+    }
+    bool bad = false;
+    int aoff = 0;
+    for (int tc = 0; tc < a1 - a0; tc += 32) {
+        int b0 = 0, b1 = 0, rb0 = 0;
+        if (tc + lane < a1 - a0) {
+            const int K = P.a_tile_col[a0 + tc + lane], Kr = P.a_tile_col[ar0 + tc + lane];
+            b0 = P.b_tile_ptr[K]; b1 = P.b_tile_ptr[K + 1]; rb0 = P.b_tile_ptr[Kr];
+            bad |= K - I != Kr - Ir || P.pat_a[a0 + tc + lane] != P.pat_a[ar0 + tc + lane] || b1 - b0 != P.b_tile_ptr[Kr + 1] - rb0;
+        }
+        const int nt = min(32, a1 - a0 - tc);
+        int nb0 = __shfl_sync(FULL_MASK, b0, 0), nb1 = __shfl_sync(FULL_MASK, b1, 0), nrb0 = __shfl_sync(FULL_MASK, rb0, 0);
+        int ncol = 0, npb = 0, nrm = 0;
+        if (nb0 + lane < nb1) { ncol = P.b_tile_col[nb0 + lane]; npb = P.pat_b[nb0 + lane]; nrm = P.b_rm2csc[nb0 + lane]; }
+        for (int j = 0; j < nt; j++) {
+            const int cb0 = nb0, cb1 = nb1, crb0 = nrb0, col0 = ncol, pb0 = npb, rm0 = nrm, ta = a0 + tc + j;
+            if (j + 1 < nt) {
+                nb0 = __shfl_sync(FULL_MASK, b0, j + 1); nb1 = __shfl_sync(FULL_MASK, b1, j + 1); nrb0 = __shfl_sync(FULL_MASK, rb0, j + 1);
+                if (nb0 + lane < nb1) { ncol = P.b_tile_col[nb0 + lane]; npb = P.pat_b[nb0 + lane]; nrm = P.b_rm2csc[nb0 + lane]; }
+            }
+            for (int tb = cb0 + lane; tb < cb1; tb += 32) {
+                const bool first = tb < cb0 + 32;
+                const int o = tb - cb0;
+                const int col = first ? col0 : P.b_tile_col[tb], pb = first ? pb0 : P.pat_b[tb], rm = first ? rm0 : P.b_rm2csc[tb];
+                bad |= col - I != P.b_tile_col[crb0 + o] - Ir || pb != P.pat_b[crb0 + o];
+                const int dest = wbase + (int)P.pair_dest[wbr + aoff + o];  // < wbase + w: the representative has the same w
+                P.pair_a[dest] = ta;
+                P.pair_b[dest] = rm;
+            }
+            aoff += cb1 - cb0;  // the lengths were compared lane by lane above; a mismatch is already flagged
+        }
+    }
+    if (__any_sync(FULL_MASK, bad) && lane == 0) *P.fail = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+bool rowplans_env_on()
+{
+    const char *e = getenv("TSG_ROWPLANS");
+    return !(e && *e == '0');
+}
+
+// Step 1a with templates: w and the signature of every tile-row, the representatives (dense numbering), rep_of.
+// One read-back (number of signatures, fail). Returns *nsig = 0 when the regular path should run instead.
+int rowplans_signatures(const tsg_dtile *A, const tsg_dtile *B, int trow0, int ntr, int *w, int *sig_slot, int *rep_of, int *sc_err,
+                        const int **rep_list, int *nsig)
+{
+    Ctx &c = ctx();
+    *nsig = 0;
+    int rc = rp_init();
+    if (rc) return rc;
+    RowPlanCtx &p = g_rp;
+    CK(cudaMemsetAsync(p.keys, 0, (size_t)RPCAP * 8, c.stream));
+    CK(cudaMemsetAsync(p.owner, 0x7f, (size_t)RPCAP * 4, c.stream));
+    CK(cudaMemsetAsync(p.ctl, 0, 4 * sizeof(int), c.stream));
+    k_row_sig<<<ceil_div(ntr, 8), 256, 0, c.stream>>>(trow0, ntr, A->tile_ptr, A->tile_columnidx, A->pat, B->tile_ptr, B->tile_columnidx, B->pat, w,
+                                                      sig_slot, p.keys, p.owner, p.ctl, sc_err);
+    CK_LAUNCH();
+    k_tab_flags<<<ceil_div(RPCAP, 256), 256, 0, c.stream>>>(RPCAP, p.owner, p.flags);
+    CK_LAUNCH();
+    rc = exclusive_scan<int>(p.flags, p.dense, RPCAP);
+    if (rc) return rc;
+    k_tab_reps<<<ceil_div(RPCAP, 256), 256, 0, c.stream>>>(RPCAP, RPMAX, p.owner, p.dense, p.rep_row);
+    k_rows_rep_of<<<ceil_div(ntr, 256), 256, 0, c.stream>>>(ntr, sig_slot, p.owner, rep_of);
+    CK_LAUNCH();
+    rc = publish_words(&c.h_scalars[24], p.dense + RPCAP, 1);
+    if (!rc) rc = publish_words(&c.h_scalars[25], p.ctl + 1, 1);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c.stream));
+    const int n = *(const volatile int *)&c.h_scalars[24], fail = *(const volatile int *)&c.h_scalars[25];
+    if (fail || n <= 0 || n > RPMAX || (long long)n * 4 > ntr) return TSG_OK;  // rows do not repeat enough: the regular path
+    *nsig = n;
+    *rep_list = p.rep_row;
+    return TSG_OK;
+}
+
+int rowplans_expand_counts(int ntr, const int *rep_of, int *cnt, uint8_t *light)
+{
+    Ctx &c = ctx();
+    k_rows_expand<<<ceil_div(ntr, 256), 256, 0, c.stream>>>(ntr, rep_of, cnt, light);
+    CK_LAUNCH();
+    return TSG_OK;
+}
+
+int *rowplans_fail_ptr() { return g_rp.ctl ? g_rp.ctl + 1 : nullptr; }
+
+int rowplans_instantiate(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const RowTemplates &rt, int *recipe_id)
+{
+    Ctx &c = ctx();
+    RowInst P{rt.trow0, rt.ntr, rt.rep_of, rt.w, rt.wptr, C->tile_ptr, A->tile_ptr, A->tile_columnidx, A->pat, B->tile_ptr, B->tile_columnidx, B->pat,
+              B->rm2csc, rt.pair_dest, C->tile_columnidx, C->tile_rowidx, rt.pair_ptr, rt.pair_end, rt.pair_a, rt.pair_b, recipe_id, g_rp.ctl + 1};
+    k_rows_instantiate<<<ceil_div(rt.ntr, 8), 256, 0, c.stream>>>(P);
+    CK_LAUNCH();
+    if (getenv("TSG_ROWPLANS_FORCE_FAIL")) CK(cudaMemsetAsync(g_rp.ctl + 1, 1, 1, c.stream));  // tests: the redo-without-templates path
+    return TSG_OK;
+}
+
+}  // namespace tsg

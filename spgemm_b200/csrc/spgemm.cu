@@ -144,12 +144,13 @@ __global__ void __launch_bounds__(S1_WARPS * 32)
 k_s1_count(int trow0, int ntr, int bmw, const int *__restrict__ a_tile_ptr, const int *__restrict__ a_tile_col,
            const int *__restrict__ a_tile_nnz, const int *__restrict__ b_tile_ptr, const int *__restrict__ b_tile_col, int *__restrict__ w, int *__restrict__ jlo,
            int *__restrict__ jhi, int *__restrict__ cnt, uint8_t *__restrict__ light, int *__restrict__ heavy_list,
-           int *__restrict__ scal, unsigned *__restrict__ bm_save, int bm_stride)
+           int *__restrict__ scal, unsigned *__restrict__ bm_save, int bm_stride, const int *__restrict__ row_list, int nlist)
 {
     extern __shared__ unsigned s1c_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = blockIdx.x * S1_WARPS + warp;
-    if (i >= ntr) return;
+    const int idx = blockIdx.x * S1_WARPS + warp;
+    if (idx >= (row_list ? nlist : ntr)) return;
+    const int i = row_list ? row_list[idx] : idx;  // tile-row templates (rowplans.cu): the representatives only
     unsigned *bitmap = s1c_smem + (size_t)warp * bmw;
     const int I = trow0 + i;
     const int a0 = a_tile_ptr[I], a1 = a_tile_ptr[I + 1];
@@ -250,6 +251,9 @@ struct S1Fill {
     unsigned *pair_pat;        // HASH: (A pattern << 16 | B pattern) of every pair, beside pair_a / pair_b (k_recipe_verify reads it)
     const unsigned *bm_saved;  // the window bitmaps k_s1_count saved (bm_stride words per tile-row), or null
     int bm_stride;
+    const int *row_list;       // tile-row templates (rowplans.cu): run on these nlist representatives only ...
+    int nlist;
+    uint16_t *pair_dest;       // ... and record, A-major, where every pair landed in the row's pair lists
 };
 
 // FUSE: fused bitmask symbolic. HASH: instead, hash every C tile's (A pattern, B pattern) sequence into the recipe table
@@ -260,8 +264,10 @@ k_s1_fill(const __grid_constant__ S1Fill P)
 {
     extern __shared__ __align__(16) unsigned s1f_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = blockIdx.x * S1_WARPS + warp;
-    if (i >= P.ntr || !P.light[i]) return;
+    const int idx = blockIdx.x * S1_WARPS + warp;
+    if (idx >= (P.row_list ? P.nlist : P.ntr)) return;
+    const int i = P.row_list ? P.row_list[idx] : idx;
+    if (!P.light[i]) return;
     unsigned *bitmap = s1f_smem + (size_t)warp * P.warp_words;
     uint16_t *pre = reinterpret_cast<uint16_t *>(bitmap + P.bmw);
     int *cur = reinterpret_cast<int *>(bitmap + P.bmw + P.bmw / 2);
@@ -410,6 +416,7 @@ k_s1_fill(const __grid_constant__ S1Fill P)
     }
     __syncwarp();
     // 6. third expansion: the pair lists, A tiles ascending inside every list (the serial SPA's summation order)
+    int aoff3 = 0;
     for (int tc = a0; tc < a1; tc += 32) {
         const BRange br(P.a_tile_col, P.b_tile_ptr, tc + lane, a1);
         const unsigned mypa = HASH && tc + lane < a1 ? (unsigned)P.pat_a[tc + lane] : 0u;
@@ -438,8 +445,10 @@ k_s1_fill(const __grid_constant__ S1Fill P)
                     const unsigned pb = first ? pb0 : (unsigned)P.pat_b[tb];
                     hh[slot] = plans::mix64(hh[slot], ((unsigned long long)pa << 32) | pb);
                     P.pair_pat[pos] = (pa << 16) | pb;
+                    if (P.pair_dest) P.pair_dest[wbase + aoff3 + (tb - b0)] = (uint16_t)(pos - wbase);  // light rows: < 2048 pairs
                 }
             }
+            aoff3 += b1 - b0;
             __syncwarp();
         }
     }
@@ -795,9 +804,26 @@ int tilerow_weights_device(const tsg_dtile *A, const tsg_dtile *B, int **d_w, in
     return TSG_OK;
 }
 
+static int spgemm_device_impl(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, tsg_dtile *C, tsg_stats *stats, bool try_rowplans,
+                              bool *retry);
+
 int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, tsg_dtile *C, tsg_stats *stats)
 {
+    bool retry = false;
+    int rc = spgemm_device_impl(A, B, trow0, trow1, C, stats, rowplans_env_on(), &retry);
+    if (retry) {  // the tile-row templates did not hold (a heavy representative, a 64-bit collision): once more without them
+        tsg_tile_free(C);
+        rc = spgemm_device_impl(A, B, trow0, trow1, C, stats, false, &retry);
+        if (!rc && stats) stats->row_templates = -1;
+    }
+    return rc;
+}
+
+static int spgemm_device_impl(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, tsg_dtile *C, tsg_stats *stats, bool try_rowplans,
+                              bool *retry)
+{
     Ctx &c = ctx();
+    *retry = false;
     memset(C, 0, sizeof(*C));
     if (A->n != B->m) { set_error(TSG_ERR_UNSUPPORTED, "spgemm: A is %dx%d but B is %dx%d", A->m, A->n, B->m, B->n); return last_error(); }
     if (A->col_major || !B->col_major || !B->rm2csc) {
@@ -830,7 +856,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     if (ntr > 0 && (size_t)ntr * bm_stride * 4 > ((size_t)128 << 20)) bm_stride = (int)((((size_t)128 << 20) / 4) / (size_t)ntr);
     const size_t bm_bytes = (size_t)ntr * bm_stride * 4;
     const bool bm_keep = ntr > 0 && bm_stride >= 8 && !(getenv("TSG_S1_KEEP_BITMAPS") && *getenv("TSG_S1_KEEP_BITMAPS") == '0');
-    if (!arena_reserve(0, 7 * arena_need(nr, 4) + arena_need(nr, 1) + (bm_keep ? arena_need(bm_bytes, 1) : 0))) return last_error();
+    if (!arena_reserve(0, 9 * arena_need(nr, 4) + arena_need(nr, 1) + (bm_keep ? arena_need(bm_bytes, 1) : 0))) return last_error();
     int *w = arena_take<int>(0, nr), *jlo = arena_take<int>(0, nr), *jhi = arena_take<int>(0, nr);
     int *wptr = arena_take<int>(0, nr), *cnt = arena_take<int>(0, nr), *c_tile_ptr = arena_take<int>(0, nr);
     int *heavy_list = arena_take<int>(0, nr);
@@ -841,13 +867,28 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     CK(cudaMemsetAsync(scal, 0, 6 * sizeof(long long), c.stream));
     unsigned *bm_save = bm_keep ? (unsigned *)arena_take<uint8_t>(0, bm_bytes) : nullptr;
     if (bm_keep && !bm_save) return last_error();
+    // tile-row templates (rowplans.cu), together with the recipe plans only: hash every tile-row's signature; if the rows
+    // repeat, k_s1_count and k_s1_fill run on the representatives and the other rows are instantiated from them
+    int nsig = 0;
+    const int *rep_list = nullptr;
+    int *sig_slot = arena_take<int>(0, nr), *rep_of = arena_take<int>(0, nr);
+    if (!sig_slot || !rep_of) return last_error();
+    if (try_rowplans && ntr >= 64 && plans_wanted(A, B)) {
+        int rc0 = rowplans_signatures(A, B, trow0, ntr, w, sig_slot, rep_of, scal + SC_ERR, &rep_list, &nsig);
+        if (rc0) return rc0;
+    }
+    const bool rowplans = nsig > 0;
     if (ntr > 0) {
         const size_t smem = (size_t)S1_WARPS * bmw1 * 4;
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_s1_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_s1_count<<<ceil_div(ntr, S1_WARPS), S1_WARPS * 32, smem, c.stream>>>(trow0, ntr, bmw1, A->tile_ptr, A->tile_columnidx, A->tile_nnz,
-                                                                              B->tile_ptr, B->tile_columnidx, w, jlo, jhi, cnt, light, heavy_list,
-                                                                              scal, bm_save, bm_stride);
+        k_s1_count<<<ceil_div(rowplans ? nsig : ntr, S1_WARPS), S1_WARPS * 32, smem, c.stream>>>(
+            trow0, ntr, bmw1, A->tile_ptr, A->tile_columnidx, A->tile_nnz, B->tile_ptr, B->tile_columnidx, w, jlo, jhi, cnt, light, heavy_list, scal,
+            bm_save, bm_stride, rep_list, nsig);
         CK_LAUNCH();
+        if (rowplans) {
+            int rc0 = rowplans_expand_counts(ntr, rep_of, cnt, light);
+            if (rc0) return rc0;
+        }
     }
     // one scan per array: 32-bit offsets for the kernels, the 64-bit total for the host (slab planning keeps it < 2^31)
     int rc = exclusive_scan<int>(w, wptr, ntr, tot);
@@ -858,6 +899,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     int hs[8];
     memcpy(hs, (const void *)c.h_scalars, sizeof(hs));
     const int n_heavy = hs[SC_NHEAVY], n_light = hs[SC_NLIGHT];
+    if (rowplans && n_heavy > 0) { *retry = true; return TSG_OK; }  // a heavy representative: templates are for light rows
     const long long pairs = c.h_scalars[4];
     if (hs[SC_ERR] || pairs >= (1ll << 31)) {
         set_error(TSG_ERR_OVERFLOW, "spgemm: %lld tile pairs in tile-rows [%d,%d) exceed 32-bit indexing; use smaller slabs", pairs, trow0, trow1);
@@ -938,6 +980,8 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         (plans_on && (!rslot || !recipe_id || !pair_pat)))
         return last_error();
     if (heavy_rows) CK(cudaMemsetAsync(pair_end, 0, nb * 4, c.stream));  // the heavy kernel counts with atomics
+    if (rowplans && !plans_on) { *retry = true; return TSG_OK; }
+    if (rowplans) CK(cudaMemsetAsync(rslot, 0xFF, nb * 4, c.stream));  // -1: "this tile's row is not a representative"
     CK(cudaEventRecord(ev[2], c.stream));  // [1..2] = allocation
 
     // ---------------- step 1b (+ fused step 2): tile columns, pair lists, C masks ----------------
@@ -961,10 +1005,10 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         warp_words = (warp_words + 1) & ~1;
         S1Fill P{trow0, ntr, bmw, nj, njpad, warp_words, hoff, A->tile_ptr, A->tile_columnidx, B->tile_ptr, B->tile_columnidx, B->rm2csc,
                  jlo, jhi, wptr, C->tile_ptr, light, C->tile_columnidx, C->tile_rowidx, pair_ptr, pair_end, pair_a, pair_b, pair_slot,
-                 A->mask, B->mask, C->ptr, C->mask, C->tile_nnz, A->pat, B->pat, ptab, rslot, pair_pat, bm_save, bm_stride};
+                 A->mask, B->mask, C->ptr, C->mask, C->tile_nnz, A->pat, B->pat, ptab, rslot, pair_pat, bm_save, bm_stride, rep_list, nsig, rowplans ? pair_slot : nullptr};
         const size_t smem = (size_t)S1_WARPS * warp_words * 4;
         if (smem > c.smem_optin) { set_error(TSG_ERR_UNSUPPORTED, "step 1: %zu B of shared memory per CTA needed (> %zu)", smem, c.smem_optin); return last_error(); }
-        const int blocks = ceil_div(ntr, S1_WARPS);
+        const int blocks = ceil_div(rowplans ? nsig : ntr, S1_WARPS);
         if (fused) {
             if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_s1_fill<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_s1_fill<true, false><<<blocks, S1_WARPS * 32, smem, c.stream>>>(P);
@@ -1004,8 +1048,9 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         CK_LAUNCH();
         return TSG_OK;
     };
+    const RowTemplates rt{nsig, trow0, ntr, rep_list, rep_of, w, wptr, pair_ptr, pair_end, pair_a, pair_b, pair_slot};
     if (plans_on) {  // C's masks / Ptr / tile nnz from the recipe plans (or nothing useful, if the fail flag comes up)
-        rc = plans_symbolic_device(A, B, C, plists, pair_pat, rslot, recipe_id, &d_plan_fail);
+        rc = plans_symbolic_device(A, B, C, plists, pair_pat, rslot, recipe_id, rowplans ? &rt : nullptr, &d_plan_fail);
         if (rc) return rc;
     } else if (numblkC > 0 && (!fused || n_heavy > 0)) {
         rc = generic_symbolic(fused);
@@ -1020,9 +1065,14 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
     if (plans_on) {
         rc = publish_words(&c.h_scalars[20], d_plan_fail, 1);
         if (!rc) rc = publish_words(&c.h_scalars[21], plans_recipe_count_ptr(), 1);
+        if (!rc && rowplans) rc = publish_words(&c.h_scalars[25], rowplans_fail_ptr(), 1);
         if (!rc) rc = read_back_i64(tot, &nnzC);
         if (rc) return rc;
+        if (rowplans && *(const volatile int *)&c.h_scalars[25]) { *retry = true; return TSG_OK; }  // a signature collision
         if (*(const volatile int *)&c.h_scalars[20]) {  // a collision or too many recipes: the generic kernels run instead
+            if (getenv("TSG_DEBUG"))
+                fprintf(stderr, "tsg: recipe plans failed with code %d (%d recipes, %d row templates): generic kernels\n",
+                        *(const volatile int *)&c.h_scalars[20], *(const volatile int *)&c.h_scalars[21], nsig);
             plans_on = false;
             plan_recipes = -1;
             k_pair_slots<<<ceil_div(ntr, S1_WARPS), S1_WARPS * 32, 0, c.stream>>>(trow0, ntr, light, A->tile_ptr, A->tile_columnidx, B->tile_ptr,
@@ -1096,6 +1146,7 @@ int spgemm_device(const tsg_dtile *A, const tsg_dtile *B, int trow0, int trow1, 
         stats->rows_staged = nst.rows_staged; stats->rows_gather = nst.rows_gather; stats->tiles_dense = nst.tiles_dense;
         stats->rows_smem = nst.rows_smem; stats->tiles_nonempty = nst.tiles_nonempty;
         stats->plan_recipes = plan_recipes;
+        stats->row_templates = rowplans ? nsig : 0;
         // algorithmic bytes, SURVEY.md 8(d). A's share is the slab's tiles; B is read whole.
         long long a_tiles = A->numtile, a_nnz = A->nnz;
         if (ntr != A->tilem) {

@@ -61,7 +61,7 @@ class Stats(C.Structure):
                 ("ms_step1", C.c_double), ("ms_step2", C.c_double), ("ms_step3", C.c_double),
                 ("ms_alloc", C.c_double), ("ms_total", C.c_double),
                 ("algorithmic_bytes", C.c_longlong), ("launches", C.c_int),
-                ("rows_staged", C.c_int), ("rows_gather", C.c_int), ("tiles_dense", C.c_int), ("rows_smem", C.c_int), ("tiles_nonempty", C.c_int), ("plan_recipes", C.c_int)]
+                ("rows_staged", C.c_int), ("rows_gather", C.c_int), ("tiles_dense", C.c_int), ("rows_smem", C.c_int), ("tiles_nonempty", C.c_int), ("plan_recipes", C.c_int), ("row_templates", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

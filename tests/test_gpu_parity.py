@@ -772,6 +772,44 @@ def test_recipe_plans_slot_chains(monkeypatch, density, chain):
         o.free()
 
 
+@pytest.mark.parametrize("mode", ["on", "off", "forced_fail"])
+@pytest.mark.parametrize("case", ["stencil27_32x16x16", "lap2d_96", "stencil27_slab"])
+def test_tile_row_templates_same_result(monkeypatch, case, mode):
+    """Tile-row templates (csrc/rowplans.cu): step 1 runs on one representative per distinct tile-row signature and the
+    other tile-rows are instantiated from it (and verified element by element). Same C, bit for bit, with the templates
+    on, off, and when the verification fails (forced) and the call is redone without them."""
+    if mode == "off":
+        monkeypatch.setenv("TSG_ROWPLANS", "0")
+    if mode == "forced_fail":
+        monkeypatch.setenv("TSG_ROWPLANS_FORCE_FAIL", "1")
+    if case == "lap2d_96":
+        m, n, rp, ci, _ = M.lap2d(96)
+    else:
+        m, n, rp, ci, _ = M.stencil27(32, 16, 16)
+    v = M.set_values(len(ci), "hash")
+    A = (rp, ci, v)
+    d = api.DeviceCSR.upload(m, n, rp, ci, v)
+    tA, tB = api.csr2tile(d, False), api.csr2tile(d, True)
+    if case == "stencil27_slab":
+        t0, t1 = 37, tA.tilem - 29
+        sub = orc.spgemm_spa(A, A, n, t0 * 16, min(t1 * 16, m))
+        exp = orc.ctiles_from_csr(m, n, orc.csr2tile_row_major(m, n, *A), orc.csr2tile_col_major(m, n, *A), sub, t0, t1)
+        tC, st = api.spgemm(tA, tB, t0, t1)
+    else:
+        _, exp = oracle_c(m, n, A, A, n)
+        tC, st = api.spgemm(tA, tB)
+    assert st["plan_recipes"] > 0, st
+    if mode == "on":
+        assert 0 < st["row_templates"] <= tA.tilem // 4, st
+    elif mode == "off":
+        assert st["row_templates"] == 0, st
+    else:
+        assert st["row_templates"] == -1, st
+    assert_tiled_equal(tC.download(), exp, f"row templates {case} {mode}", val_rtol=VAL_RTOL)
+    for o in (tC, tA, tB, d):
+        o.free()
+
+
 def test_recipe_plans_fall_back_when_recipes_do_not_repeat(monkeypatch):
     """Few tile patterns but tens of thousands of distinct pair sequences: the recipe table overflows, the fail flag
     comes up and the generic kernels produce the result (stats say -1)."""
