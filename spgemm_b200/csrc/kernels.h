@@ -43,7 +43,7 @@ struct RowTemplates {
     int n, trow0, ntr;                    // distinct tile-row signatures; the slab
     const int *rep_list, *rep_of, *w, *wptr;
     int *pair_ptr, *pair_end, *pair_a, *pair_b;
-    const uint16_t *pair_dest;            // A-major: where the representative's pair landed in its pair lists
+    const unsigned *pair_src;             // beside the representative's pairs: (A tile of the row << 16) | (tile of B's tile-row)
 };
 bool rowplans_env_on();
 int rowplans_signatures(const tsg_dtile *A, const tsg_dtile *B, int trow0, int ntr, int *w, int *sig_slot, int *rep_of, int *sc_err,

@@ -202,10 +202,10 @@ k_recipe_verify(int numblkC, const int *__restrict__ pair_ptr, const int *__rest
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= numblkC) return;
-    recipe_id[t] = 0;
-    if (*(volatile int *)fail) return;
     const int slot = rslot[t];
     if (skip_unset && slot == -1) return;  // tile-row templates: this tile's row takes its recipes from its representative
+    recipe_id[t] = 0;
+    if (*(volatile int *)fail) return;
     if (slot < 0 || slot >= RCAP) { *fail = 1; return; }
     const int u = owner[slot];
     if (u < 0 || u >= numblkC || rdense[slot] >= RMAX) { *fail = 1; return; }

@@ -8,8 +8,8 @@
 //   * k_row_sig     one expansion per tile-row: the pair count w (step 1 needs it anyway) and a 64-bit hash of the
 //                   row's SIGNATURE -- per A tile (K - I, pattern, length of B's tile-row K), per B tile behind it
 //                   (J - I, pattern) -- inserted into a table like the recipes (atomicCAS, owner = smallest row index);
-//   * k_s1_count / k_s1_fill (spgemm.cu) then run on the REPRESENTATIVE tile-rows only; fill also records where every
-//     pair of the A-major walk landed in the pair lists (pair_dest);
+//   * k_s1_count / k_s1_fill (spgemm.cu) then run on the REPRESENTATIVE tile-rows only; fill also records, beside every
+//     pair, which A tile of the row and which tile of B's tile-row it came from (pair_src);
 //   * k_rows_expand copies the C tile counts to the other rows (before the scans and the allocation);
 //   * k_rows_instantiate walks every other tile-row once more, side by side with its representative: it compares the
 //     two signatures element by element (a hash collision raises the fail flag and the whole call is redone without
@@ -163,27 +163,33 @@ k_rows_expand(int ntr, const int *__restrict__ rep_of, int *__restrict__ cnt, ui
 }
 
 // One warp per tile-row that is not its own representative: verify its signature against the representative's,
-// element by element, and write its share of C's tile lists and of the pair lists from the representative's.
+// element by element (an A-major walk: coalesced loads, nothing stored), then write its share of C's tile lists and of the
+// pair lists from the representative's -- in the order of the pair lists, so the stores are coalesced: pair q of the
+// representative came from (A tile ta of the row, tile o of B's tile-row), so pair q of this row is
+// (a0 + ta, rm2csc[first tile of B's tile-row behind a0 + ta, + o]).
 struct RowInst {
     int trow0, ntr;
     const int *rep_of, *w, *wptr, *c_tile_ptr;
     const int *a_tile_ptr, *a_tile_col, *pat_a, *b_tile_ptr, *b_tile_col, *pat_b, *b_rm2csc;
-    const uint16_t *pair_dest;
+    const unsigned *pair_src;
     int *c_tile_col, *c_tile_row, *pair_ptr, *pair_end, *pair_a, *pair_b, *recipe_id;
     int *fail;
 };
 
+constexpr int RI_STAGE = 64;  // first tiles of the B tile-rows behind up to this many A tiles are kept in shared memory
+
 __global__ void __launch_bounds__(256)
 k_rows_instantiate(const __grid_constant__ RowInst P)
 {
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    __shared__ int s_b0[8][RI_STAGE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, i = blockIdx.x * 8 + warp;
     if (i >= P.ntr) return;
     const int r = P.rep_of[i];
     if (r < 0 || r == i) return;
     const int I = P.trow0 + i, Ir = P.trow0 + r, shift = I - Ir;
-    const int a0 = P.a_tile_ptr[I], a1 = P.a_tile_ptr[I + 1], ar0 = P.a_tile_ptr[Ir];
-    const int wbase = P.wptr[i], wbr = P.wptr[r];
-    if (a1 - a0 != P.a_tile_ptr[Ir + 1] - ar0 || P.w[i] != P.w[r]) {  // not the same row after all: nothing of it can be trusted
+    const int a0 = P.a_tile_ptr[I], nA = P.a_tile_ptr[I + 1] - a0, ar0 = P.a_tile_ptr[Ir];
+    const int wbase = P.wptr[i], wbr = P.wptr[r], w = P.w[i];
+    if (nA != P.a_tile_ptr[Ir + 1] - ar0 || w != P.w[r]) {  // not the same row after all: nothing of it can be trusted
         if (lane == 0) *P.fail = 1;
         return;
     }
@@ -196,37 +202,44 @@ k_rows_instantiate(const __grid_constant__ RowInst P)
         P.recipe_id[cbase + s] = P.recipe_id[cbr + s];
     }
     bool bad = false;
-    int aoff = 0;
-    for (int tc = 0; tc < a1 - a0; tc += 32) {
+    for (int tc = 0; tc < nA; tc += 32) {
         int b0 = 0, b1 = 0, rb0 = 0;
-        if (tc + lane < a1 - a0) {
+        if (tc + lane < nA) {
             const int K = P.a_tile_col[a0 + tc + lane], Kr = P.a_tile_col[ar0 + tc + lane];
             b0 = P.b_tile_ptr[K]; b1 = P.b_tile_ptr[K + 1]; rb0 = P.b_tile_ptr[Kr];
             bad |= K - I != Kr - Ir || P.pat_a[a0 + tc + lane] != P.pat_a[ar0 + tc + lane] || b1 - b0 != P.b_tile_ptr[Kr + 1] - rb0;
+            if (tc + lane < RI_STAGE) s_b0[warp][tc + lane] = b0;
         }
-        const int nt = min(32, a1 - a0 - tc);
+        const int nt = min(32, nA - tc);
         int nb0 = __shfl_sync(FULL_MASK, b0, 0), nb1 = __shfl_sync(FULL_MASK, b1, 0), nrb0 = __shfl_sync(FULL_MASK, rb0, 0);
-        int ncol = 0, npb = 0, nrm = 0;
-        if (nb0 + lane < nb1) { ncol = P.b_tile_col[nb0 + lane]; npb = P.pat_b[nb0 + lane]; nrm = P.b_rm2csc[nb0 + lane]; }
+        int ncol = 0, npb = 0;
+        if (nb0 + lane < nb1) { ncol = P.b_tile_col[nb0 + lane]; npb = P.pat_b[nb0 + lane]; }
         for (int j = 0; j < nt; j++) {
-            const int cb0 = nb0, cb1 = nb1, crb0 = nrb0, col0 = ncol, pb0 = npb, rm0 = nrm, ta = a0 + tc + j;
+            const int cb0 = nb0, cb1 = nb1, crb0 = nrb0, col0 = ncol, pb0 = npb;
             if (j + 1 < nt) {
                 nb0 = __shfl_sync(FULL_MASK, b0, j + 1); nb1 = __shfl_sync(FULL_MASK, b1, j + 1); nrb0 = __shfl_sync(FULL_MASK, rb0, j + 1);
-                if (nb0 + lane < nb1) { ncol = P.b_tile_col[nb0 + lane]; npb = P.pat_b[nb0 + lane]; nrm = P.b_rm2csc[nb0 + lane]; }
+                if (nb0 + lane < nb1) { ncol = P.b_tile_col[nb0 + lane]; npb = P.pat_b[nb0 + lane]; }
             }
             for (int tb = cb0 + lane; tb < cb1; tb += 32) {
                 const bool first = tb < cb0 + 32;
                 const int o = tb - cb0;
-                const int col = first ? col0 : P.b_tile_col[tb], pb = first ? pb0 : P.pat_b[tb], rm = first ? rm0 : P.b_rm2csc[tb];
+                const int col = first ? col0 : P.b_tile_col[tb], pb = first ? pb0 : P.pat_b[tb];
                 bad |= col - I != P.b_tile_col[crb0 + o] - Ir || pb != P.pat_b[crb0 + o];
-                const int dest = wbase + (int)P.pair_dest[wbr + aoff + o];  // < wbase + w: the representative has the same w
-                P.pair_a[dest] = ta;
-                P.pair_b[dest] = rm;
             }
-            aoff += cb1 - cb0;  // the lengths were compared lane by lane above; a mismatch is already flagged
         }
     }
-    if (__any_sync(FULL_MASK, bad) && lane == 0) *P.fail = 1;
+    if (__any_sync(FULL_MASK, bad)) {  // a 64-bit collision: the call is redone without templates; write nothing that could run off
+        if (lane == 0) *P.fail = 1;
+        return;
+    }
+    __syncwarp();
+    for (int q = lane; q < w; q += 32) {
+        const unsigned src = P.pair_src[wbr + q];
+        const int ta = (int)(src >> 16), o = (int)(src & 0xFFFFu);
+        const int b0 = ta < RI_STAGE ? s_b0[warp][ta] : P.b_tile_ptr[P.a_tile_col[a0 + ta]];
+        P.pair_a[wbase + q] = a0 + ta;
+        P.pair_b[wbase + q] = P.b_rm2csc[b0 + o];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -286,7 +299,7 @@ int rowplans_instantiate(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, c
 {
     Ctx &c = ctx();
     RowInst P{rt.trow0, rt.ntr, rt.rep_of, rt.w, rt.wptr, C->tile_ptr, A->tile_ptr, A->tile_columnidx, A->pat, B->tile_ptr, B->tile_columnidx, B->pat,
-              B->rm2csc, rt.pair_dest, C->tile_columnidx, C->tile_rowidx, rt.pair_ptr, rt.pair_end, rt.pair_a, rt.pair_b, recipe_id, g_rp.ctl + 1};
+              B->rm2csc, rt.pair_src, C->tile_columnidx, C->tile_rowidx, rt.pair_ptr, rt.pair_end, rt.pair_a, rt.pair_b, recipe_id, g_rp.ctl + 1};
     k_rows_instantiate<<<ceil_div(rt.ntr, 8), 256, 0, c.stream>>>(P);
     CK_LAUNCH();
     if (getenv("TSG_ROWPLANS_FORCE_FAIL")) CK(cudaMemsetAsync(g_rp.ctl + 1, 1, 1, c.stream));  // tests: the redo-without-templates path

@@ -253,7 +253,7 @@ struct S1Fill {
     int bm_stride;
     const int *row_list;       // tile-row templates (rowplans.cu): run on these nlist representatives only ...
     int nlist;
-    uint16_t *pair_dest;       // ... and record, A-major, where every pair landed in the row's pair lists
+    unsigned *pair_src;        // ... and record, beside every pair, where it came from: (A tile of the row << 16) | (tile of B's tile-row)
 };
 
 // FUSE: fused bitmask symbolic. HASH: instead, hash every C tile's (A pattern, B pattern) sequence into the recipe table
@@ -416,7 +416,6 @@ k_s1_fill(const __grid_constant__ S1Fill P)
     }
     __syncwarp();
     // 6. third expansion: the pair lists, A tiles ascending inside every list (the serial SPA's summation order)
-    int aoff3 = 0;
     for (int tc = a0; tc < a1; tc += 32) {
         const BRange br(P.a_tile_col, P.b_tile_ptr, tc + lane, a1);
         const unsigned mypa = HASH && tc + lane < a1 ? (unsigned)P.pat_a[tc + lane] : 0u;
@@ -445,10 +444,9 @@ k_s1_fill(const __grid_constant__ S1Fill P)
                     const unsigned pb = first ? pb0 : (unsigned)P.pat_b[tb];
                     hh[slot] = plans::mix64(hh[slot], ((unsigned long long)pa << 32) | pb);
                     P.pair_pat[pos] = (pa << 16) | pb;
-                    if (P.pair_dest) P.pair_dest[wbase + aoff3 + (tb - b0)] = (uint16_t)(pos - wbase);  // light rows: < 2048 pairs
+                    if (P.pair_src) P.pair_src[pos] = ((unsigned)(ta - a0) << 16) | (unsigned)(tb - b0);  // light rows: both < 2048
                 }
             }
-            aoff3 += b1 - b0;
             __syncwarp();
         }
     }
@@ -965,7 +963,7 @@ static int spgemm_device_impl(const tsg_dtile *A, const tsg_dtile *B, int trow0,
     rc = copy_words(C->tile_ptr, c_tile_ptr, (size_t)ntr + 1);
     if (rc) return rc;
     const bool heavy_rows = n_heavy > 0;  // tile-rows on the multi-warp path park one 16-byte record per pair
-    if (!arena_reserve(1, 4 * arena_need(nb + 1, 4) + 3 * arena_need(np, 4) + arena_need(np, 2) +
+    if (!arena_reserve(1, 4 * arena_need(nb + 1, 4) + 4 * arena_need(np, 4) + arena_need(np, 2) +
                               (heavy_rows ? arena_need(np, 16) : 0) + numeric_scratch_bytes(ntr, numblkC)))
         return last_error();
     int *pair_ptr = arena_take<int>(1, nb + 1), *pair_end = arena_take<int>(1, nb + 1), *pair_a = arena_take<int>(1, np), *pair_b = arena_take<int>(1, np);
@@ -976,8 +974,9 @@ static int spgemm_device_impl(const tsg_dtile *A, const tsg_dtile *B, int trow0,
     bool plans_on = plans_wanted(A, B) && !heavy_rows && numblkC > 0 && pairs > 0;
     int *rslot = plans_on ? arena_take<int>(1, nb) : nullptr, *recipe_id = plans_on ? arena_take<int>(1, nb) : nullptr;
     unsigned *pair_pat = plans_on ? arena_take<unsigned>(1, np) : nullptr;  // (A pattern, B pattern) per pair
+    unsigned *pair_src = rowplans ? arena_take<unsigned>(1, np) : nullptr;  // tile-row templates: where every pair of a representative came from
     if (!pair_ptr || !pair_end || !pair_a || !pair_b || !pair_slot || (heavy_rows && !pair_tmp) || !nbufs.row_kind || !nbufs.dense_list ||
-        (plans_on && (!rslot || !recipe_id || !pair_pat)))
+        (plans_on && (!rslot || !recipe_id || !pair_pat)) || (rowplans && !pair_src))
         return last_error();
     if (heavy_rows) CK(cudaMemsetAsync(pair_end, 0, nb * 4, c.stream));  // the heavy kernel counts with atomics
     if (rowplans && !plans_on) { *retry = true; return TSG_OK; }
@@ -1005,7 +1004,7 @@ static int spgemm_device_impl(const tsg_dtile *A, const tsg_dtile *B, int trow0,
         warp_words = (warp_words + 1) & ~1;
         S1Fill P{trow0, ntr, bmw, nj, njpad, warp_words, hoff, A->tile_ptr, A->tile_columnidx, B->tile_ptr, B->tile_columnidx, B->rm2csc,
                  jlo, jhi, wptr, C->tile_ptr, light, C->tile_columnidx, C->tile_rowidx, pair_ptr, pair_end, pair_a, pair_b, pair_slot,
-                 A->mask, B->mask, C->ptr, C->mask, C->tile_nnz, A->pat, B->pat, ptab, rslot, pair_pat, bm_save, bm_stride, rep_list, nsig, rowplans ? pair_slot : nullptr};
+                 A->mask, B->mask, C->ptr, C->mask, C->tile_nnz, A->pat, B->pat, ptab, rslot, pair_pat, bm_save, bm_stride, rep_list, nsig, pair_src};
         const size_t smem = (size_t)S1_WARPS * warp_words * 4;
         if (smem > c.smem_optin) { set_error(TSG_ERR_UNSUPPORTED, "step 1: %zu B of shared memory per CTA needed (> %zu)", smem, c.smem_optin); return last_error(); }
         const int blocks = ceil_div(rowplans ? nsig : ntr, S1_WARPS);
@@ -1048,7 +1047,7 @@ static int spgemm_device_impl(const tsg_dtile *A, const tsg_dtile *B, int trow0,
         CK_LAUNCH();
         return TSG_OK;
     };
-    const RowTemplates rt{nsig, trow0, ntr, rep_list, rep_of, w, wptr, pair_ptr, pair_end, pair_a, pair_b, pair_slot};
+    const RowTemplates rt{nsig, trow0, ntr, rep_list, rep_of, w, wptr, pair_ptr, pair_end, pair_a, pair_b, pair_src};
     if (plans_on) {  // C's masks / Ptr / tile nnz from the recipe plans (or nothing useful, if the fail flag comes up)
         rc = plans_symbolic_device(A, B, C, plists, pair_pat, rslot, recipe_id, rowplans ? &rt : nullptr, &d_plan_fail);
         if (rc) return rc;
