@@ -41,12 +41,12 @@ struct PlanTable;
 // tile-row templates (rowplans.cu): what k_rows_instantiate needs besides the tiled matrices
 struct RowTemplates {
     int n, trow0, ntr;                    // distinct tile-row signatures; the slab
-    const int *rep_list, *rep_of, *w, *wptr;
+    const int *rep_list, *rep_of, *w, *wptr, *bclass;
     int *pair_ptr, *pair_end, *pair_a, *pair_b;
     const unsigned *pair_src;             // beside the representative's pairs: (A tile of the row << 16) | (tile of B's tile-row)
 };
 bool rowplans_env_on();
-int rowplans_signatures(const tsg_dtile *A, const tsg_dtile *B, int trow0, int ntr, int *w, int *sig_slot, int *rep_of, int *sc_err,
+int rowplans_signatures(const tsg_dtile *A, const tsg_dtile *B, int trow0, int ntr, int *w, int *sig_slot, int *rep_of, int *bclass, int *sc_err,
                         const int **rep_list, int *nsig);
 int rowplans_expand_counts(int ntr, const int *rep_of, int *cnt, uint8_t *light);
 int rowplans_instantiate(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const RowTemplates &rt, int *recipe_id);

@@ -854,7 +854,8 @@ static int spgemm_device_impl(const tsg_dtile *A, const tsg_dtile *B, int trow0,
     if (ntr > 0 && (size_t)ntr * bm_stride * 4 > ((size_t)128 << 20)) bm_stride = (int)((((size_t)128 << 20) / 4) / (size_t)ntr);
     const size_t bm_bytes = (size_t)ntr * bm_stride * 4;
     const bool bm_keep = ntr > 0 && bm_stride >= 8 && !(getenv("TSG_S1_KEEP_BITMAPS") && *getenv("TSG_S1_KEEP_BITMAPS") == '0');
-    if (!arena_reserve(0, 9 * arena_need(nr, 4) + arena_need(nr, 1) + (bm_keep ? arena_need(bm_bytes, 1) : 0))) return last_error();
+    if (!arena_reserve(0, 9 * arena_need(nr, 4) + arena_need(nr, 1) + arena_need((size_t)B->tilem + 1, 4) + (bm_keep ? arena_need(bm_bytes, 1) : 0)))
+        return last_error();
     int *w = arena_take<int>(0, nr), *jlo = arena_take<int>(0, nr), *jhi = arena_take<int>(0, nr);
     int *wptr = arena_take<int>(0, nr), *cnt = arena_take<int>(0, nr), *c_tile_ptr = arena_take<int>(0, nr);
     int *heavy_list = arena_take<int>(0, nr);
@@ -869,10 +870,10 @@ static int spgemm_device_impl(const tsg_dtile *A, const tsg_dtile *B, int trow0,
     // repeat, k_s1_count and k_s1_fill run on the representatives and the other rows are instantiated from them
     int nsig = 0;
     const int *rep_list = nullptr;
-    int *sig_slot = arena_take<int>(0, nr), *rep_of = arena_take<int>(0, nr);
-    if (!sig_slot || !rep_of) return last_error();
+    int *sig_slot = arena_take<int>(0, nr), *rep_of = arena_take<int>(0, nr), *bclass = arena_take<int>(0, (size_t)B->tilem + 1);
+    if (!sig_slot || !rep_of || !bclass) return last_error();
     if (try_rowplans && ntr >= 64 && plans_wanted(A, B)) {
-        int rc0 = rowplans_signatures(A, B, trow0, ntr, w, sig_slot, rep_of, scal + SC_ERR, &rep_list, &nsig);
+        int rc0 = rowplans_signatures(A, B, trow0, ntr, w, sig_slot, rep_of, bclass, scal + SC_ERR, &rep_list, &nsig);
         if (rc0) return rc0;
     }
     const bool rowplans = nsig > 0;
@@ -1047,7 +1048,7 @@ static int spgemm_device_impl(const tsg_dtile *A, const tsg_dtile *B, int trow0,
         CK_LAUNCH();
         return TSG_OK;
     };
-    const RowTemplates rt{nsig, trow0, ntr, rep_list, rep_of, w, wptr, pair_ptr, pair_end, pair_a, pair_b, pair_src};
+    const RowTemplates rt{nsig, trow0, ntr, rep_list, rep_of, w, wptr, bclass, pair_ptr, pair_end, pair_a, pair_b, pair_src};
     if (plans_on) {  // C's masks / Ptr / tile nnz from the recipe plans (or nothing useful, if the fail flag comes up)
         rc = plans_symbolic_device(A, B, C, plists, pair_pat, rslot, recipe_id, rowplans ? &rt : nullptr, &d_plan_fail);
         if (rc) return rc;
