@@ -872,7 +872,9 @@ static int spgemm_device_impl(const tsg_dtile *A, const tsg_dtile *B, int trow0,
     const int *rep_list = nullptr;
     int *sig_slot = arena_take<int>(0, nr), *rep_of = arena_take<int>(0, nr), *bclass = arena_take<int>(0, (size_t)B->tilem + 1);
     if (!sig_slot || !rep_of || !bclass) return last_error();
-    if (try_rowplans && ntr >= 64 && plans_wanted(A, B)) {
+    // below ~8 K tile-rows the dozen extra launches and the extra read-back cost more than the expansions they save
+    const int rowplans_min_rows = getenv("TSG_ROWPLANS_MIN_ROWS") ? atoi(getenv("TSG_ROWPLANS_MIN_ROWS")) : 8192;
+    if (try_rowplans && ntr >= rowplans_min_rows && ntr >= 64 && plans_wanted(A, B)) {
         int rc0 = rowplans_signatures(A, B, trow0, ntr, w, sig_slot, rep_of, bclass, scal + SC_ERR, &rep_list, &nsig);
         if (rc0) return rc0;
     }

@@ -2,6 +2,8 @@
 oracle and the committed golden vectors. Integer/index/structure arrays are compared bit-exact; FP64
 values bit-exact under the driver's value[k] = k % 10 convention (all partial sums are exact integers)
 and within 1e-12 max relative error for general positive values (BASELINE.json north_star)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -18,8 +20,11 @@ VAL_RTOL = 1e-12  # north_star: FP64 values within a max relative error of 1e-12
 
 @pytest.fixture(scope="module", autouse=True)
 def _init():
+    # tile-row templates (csrc/rowplans.cu) are worth their launches from ~8 K tile-rows on; the tests want them on small matrices too
+    os.environ["TSG_ROWPLANS_MIN_ROWS"] = "64"
     api.init(0)
     yield
+    os.environ.pop("TSG_ROWPLANS_MIN_ROWS", None)
 
 
 def oracle_c(m, n, A, B, nB, tA=None, tB=None):

@@ -15,7 +15,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available() 
 
 @pytest.mark.parametrize("world", [2])
 def test_multi_rank_path_matches_oracle(world):
-    env = dict(os.environ, NCCL_DEBUG=os.environ.get("NCCL_DEBUG", "WARN"))
+    env = dict(os.environ, NCCL_DEBUG=os.environ.get("NCCL_DEBUG", "WARN"), TSG_ROWPLANS_MIN_ROWS="64")  # tile-row templates on the small test matrices too
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900, cwd=ROOT)
