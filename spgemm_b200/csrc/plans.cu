@@ -620,6 +620,12 @@ int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, c
     PlanRows P{trow0, (int)smem, A->tile_ptr, A->tile_nnz, A->val, B->tile_nnz, B->val, C->tile_ptr, C->tile_nnz, wptr, pl.ptr, pl.a, pl.b,
                recipe_id, p.plan_off, p.plan_nslots, p.plan_cnt, p.plan_chain, p.plan_col, p.plan_slot, p.plan_jslot, p.plan_ent, C->col, C->val};
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_numeric_from_plans_rows<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {   // shared memory the 6 resident CTAs need, as a share of the SM's 228 KB: the rest stays L1 for the gathers of B's values
+        const char *cv = getenv("TSG_PLANS_CARVEOUT");
+        int pct = cv && *cv ? atoi(cv) : (int)((6 * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (pct > 100) pct = 100;
+        if (pct >= 0) CK(cudaFuncSetAttribute(k_numeric_from_plans_rows<256, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
     k_numeric_from_plans_rows<256, 6><<<ntr, 256, smem, c.stream>>>(P);
     CK_LAUNCH();
     if (stats) stats->plan_recipes = 1;  // the caller fills in the count it read back

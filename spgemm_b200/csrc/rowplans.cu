@@ -146,6 +146,7 @@ k_row_sig(int trow0, int ntr, const int *__restrict__ a_tile_ptr, const int *__r
     if (s > 0x7fffffffll) { atomicOr(sc_err, 1); s = 0x7fffffff; }
     w[i] = (int)s;
     if (s == 0) { sig_slot[i] = -1; return; }
+    if (a1 - a0 > 0xFFFF) ctl[1] = 1;  // pair_src keeps the A tile's position in the row in 16 bits: no templates for this slab
     const unsigned long long h = mix64(acc, ((unsigned long long)(unsigned)(a1 - a0) << 32) | (unsigned)s);
     const int slot = table_insert(keys, RPCAP, h, ctl, RPMAX, ctl + 1);
     sig_slot[i] = slot;
