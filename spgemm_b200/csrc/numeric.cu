@@ -167,7 +167,7 @@ k_s3_classify_rows(int ntr, int trow0, const int *__restrict__ a_tile_ptr, const
 // ---------------------------------------------------------------------------------------------
 constexpr int S3R_SPARSE_MAX = 2;   // tiles with at most this many entries are "sparse" (phase S / short path)
 constexpr int S3R_ROWS_MIN = 16;    // C tiles with at least this many entries run lane-per-row (phase R)
-constexpr unsigned PF_SPARSE = 0x80000000u, PF_INDEX = 0x7fffffffu;
+constexpr unsigned PF_SPARSE = 0x80000000u;
 constexpr int S3R_BUCKETS = 64;
 
 struct S3Rows {

@@ -7,7 +7,8 @@
 // (pair, position in A's tile, position in B's tile) in the serial SPA's order. So:
 //   * csr2tile gives every tile a pattern id (k_pattern_insert / _verify: device hash table, full-key verification);
 //   * k_s1_fill hashes each C tile's pair sequence while it writes the pair lists (spgemm.cu) and inserts it into the
-//     recipe table; k_recipe_verify compares every tile's sequence with its recipe's representative;
+//     recipe table; k_recipe_verify compares every tile's sequence with its recipe's representative (with tile-row
+//     templates, rowplans.cu, both see the representative tile-rows only and the other rows copy their recipe ids);
 //   * k_plan_build plans each distinct recipe once, from the representative tile's actual masks;
 //   * k_plan_slots packs each recipe's C nonzeros into "slots" (chains of nonzeros) of nearly equal product count;
 //   * the symbolic step becomes a 68-byte copy per C tile (k_symbolic_from_plans) and the numeric step walks an

@@ -14,9 +14,13 @@ namespace tsg {
 // One CTA per tile-row, warp r = matrix row 16*I + r, lanes = the tile-row's tiles. The number of entries in front of
 // a tile-row is already known -- tile_nnz[tile_ptr[I]], the scanned tile offsets -- so no separate counting pass or
 // global scan is needed: the 16 warps count their rows, a 16-entry prefix in shared memory gives every row pointer,
-// and the warps then append (tile_col*16 + Col, Val) tile by tile, 32 tiles at a time, each lane at the offset a warp
-// scan of the per-tile counts gives it. A tile-row with 10^5 tiles (R-MAT hubs) is walked by 512 threads, not 16.
+// and the warps then append (tile_col*16 + Col, Val) 32 tiles at a time: a warp scan of the per-tile counts, then lane k
+// of the warp moves entry k of the flattened run (coalesced stores; round 2's first version let every lane copy its own
+// tile's few entries one by one: 3x the memory instructions, strided). What the counting pass read of the first 128 tiles
+// stays in registers for the copying pass. A tile-row with 10^5 tiles (R-MAT hubs) is walked by 512 threads, not 16.
 constexpr int T2C_THREADS = TS * 32;
+
+constexpr int T2C_KEEP = 4;  // per-lane (count, source, column base) of the first 4 x 32 tiles stay in registers between the two passes
 
 __global__ void __launch_bounds__(T2C_THREADS)
 k_tile2csr_rows(int m, int tilem, const int *__restrict__ tile_ptr, const int *__restrict__ tile_col,
@@ -28,12 +32,31 @@ k_tile2csr_rows(int m, int tilem, const int *__restrict__ tile_ptr, const int *_
     const int I = blockIdx.x, r = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t0 = tile_ptr[I], t1 = tile_ptr[I + 1];
     const int row = I * TS + r;
+    // this lane's share of row r in tile t: n entries starting at src (position in the tiled payload), column base cb
+    auto slice = [&](int t, int &n, int &src, int &cb) {
+        n = 0; src = 0; cb = 0;
+        if (t < t1) {
+            const int b = tile_nnz[t], tn = tile_nnz[t + 1] - b;
+            if (tn) {  // empty C tiles are legitimate (15/16 of them on hypersparse inputs): nothing to read
+                const int p0 = ptr[(size_t)t * TS + r];
+                n = (r < TS - 1 ? (int)ptr[(size_t)t * TS + r + 1] : tn) - p0;
+                src = b + p0;
+                if (n) cb = tile_col[t] * TS;
+            }
+        }
+    };
+    int kn[T2C_KEEP], ksrc[T2C_KEEP], kcb[T2C_KEEP];
     int cnt = 0;
-    for (int t = t0 + lane; t < t1; t += 32) {
-        const int b = tile_nnz[t], tn = tile_nnz[t + 1] - b;
-        if (tn == 0) continue;  // empty C tiles are legitimate (15/16 of them on hypersparse inputs): nothing to read
-        const int p0 = ptr[(size_t)t * TS + r];
-        cnt += (r < TS - 1 ? (int)ptr[(size_t)t * TS + r + 1] : tn) - p0;
+#pragma unroll
+    for (int c = 0; c < T2C_KEEP; c++) {
+        kn[c] = 0; ksrc[c] = 0; kcb[c] = 0;
+        if (t0 + c * 32 < t1) slice(t0 + c * 32 + lane, kn[c], ksrc[c], kcb[c]);  // warp-uniform
+        cnt += kn[c];
+    }
+    for (int t = t0 + T2C_KEEP * 32 + lane; t < t1; t += 32) {
+        int n, src, cb;
+        slice(t, n, src, cb);
+        cnt += n;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(FULL_MASK, cnt, o);
@@ -44,32 +67,40 @@ k_tile2csr_rows(int m, int tilem, const int *__restrict__ tile_ptr, const int *_
     if (lane == 0 && row < m) rowptr[row] = cursor + base;
     if (I == tilem - 1 && threadIdx.x == 0) rowptr[m] = tile_nnz[t1] + base;
     if (row >= m || cnt == 0) return;
-    for (int tb = t0; tb < t1; tb += 32) {
-        const int t = tb + lane;
-        int b = 0, p0 = 0, n = 0;
-        if (t < t1) {
-            b = tile_nnz[t];
-            const int tn = tile_nnz[t + 1] - b;
-            if (tn) {
-                p0 = ptr[(size_t)t * TS + r];
-                n = (r < TS - 1 ? (int)ptr[(size_t)t * TS + r + 1] : tn) - p0;
-            }
-        }
+    // the row's entries in 32 tiles, flattened: entry k belongs to the first lane whose inclusive count exceeds k (5 shuffles),
+    // so consecutive lanes write consecutive CSR slots and read runs of one tile's row
+    auto emit = [&](int n, int src0, int cb) {
         int incl = n;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int v = __shfl_up_sync(FULL_MASK, incl, o);
             if (lane >= o) incl += v;
         }
-        if (n) {
-            const int cb = tile_col[t] * TS;
-            int dst = cursor + incl - n;
-            for (int j = b + p0; j < b + p0 + n; j++, dst++) {
-                out_col[dst] = cb + col[j];
-                out_val[dst] = val[j];
+        const int total = __shfl_sync(FULL_MASK, incl, 31);
+        for (int k0 = 0; k0 < total; k0 += 32) {
+            const int k = k0 + lane;
+            int L = 0;
+#pragma unroll
+            for (int sft = 16; sft; sft >>= 1) {
+                const int v = __shfl_sync(FULL_MASK, incl, L + sft - 1);
+                if (v <= k) L += sft;
+            }
+            const int excl_L = __shfl_sync(FULL_MASK, incl - n, L), src_L = __shfl_sync(FULL_MASK, src0, L), cb_L = __shfl_sync(FULL_MASK, cb, L);
+            if (k < total) {
+                const int j = src_L + (k - excl_L);
+                out_col[cursor + k] = cb_L + col[j];
+                out_val[cursor + k] = val[j];
             }
         }
-        cursor += __shfl_sync(FULL_MASK, incl, 31);
+        cursor += total;
+    };
+#pragma unroll
+    for (int c = 0; c < T2C_KEEP; c++)
+        if (t0 + c * 32 < t1) emit(kn[c], ksrc[c], kcb[c]);  // warp-uniform
+    for (int tb = t0 + T2C_KEEP * 32; tb < t1; tb += 32) {
+        int n, src, cb;
+        slice(tb + lane, n, src, cb);
+        emit(n, src, cb);
     }
 }
 
