@@ -10,7 +10,7 @@ constexpr int PLANS_MAX_PATTERNS = 1024; // the plan path is attempted only when
 constexpr int RCAP = 1 << 14;            // recipe table slots
 constexpr int RMAX = RCAP / 2;           // more distinct recipes than this => fail (generic kernels run)
 constexpr int PLAN_ENT_CAP = 1 << 24;    // plan entries (products of all distinct recipes) the buffer holds
-constexpr int PLANS_CHAIN_MIN = 16;      // k_plan_slots: chains of C nonzeros are built to at least this many products
+constexpr int PLANS_CHAIN_MIN = 12;      // k_plan_slots: chains of C nonzeros are built to at least this many products
 constexpr int NO_OWNER = 0x7f7f7f7f;     // what cudaMemset(0x7f) leaves; item indices stay below it
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long h, unsigned long long v)

@@ -815,6 +815,39 @@ def test_tile_row_templates_same_result(monkeypatch, case, mode):
         o.free()
 
 
+def _banded_tiles(T, offsets, pat_seed, density):
+    """T x T tiles, one 16x16 pattern repeated on the given tile diagonals: every interior tile-row is a translate of the next."""
+    import scipy.sparse as sp
+    pat = sp.random(16, 16, density=density, random_state=pat_seed, format="csr")
+    pat.data[:] = 1.0
+    S = sp.kron(sp.diags([1.0] * len(offsets), offsets, shape=(T, T)), pat, format="csr")
+    S.sort_indices()
+    return S.shape[0], S.shape[1], S.indptr.astype(np.int32), S.indices.astype(np.int32)
+
+
+@pytest.mark.parametrize("case", ["many_A_tiles", "long_B_rows"])
+def test_tile_row_templates_wide_rows(case):
+    """Templates on tile-rows that are wider than a warp: 70 A tiles per tile-row (more than the 64 whose B ranges the
+    instantiation keeps in shared memory, and more than one 32-tile chunk of the step-1 walk) and B tile-rows of 40 tiles
+    (second chunk of the per-A-tile walk). General C = A*B with different A and B."""
+    T = 400
+    if case == "many_A_tiles":
+        offA, offB = list(range(-35, 35)), list(range(-10, 10))
+    else:
+        offA, offB = [-3, -1, 0, 2, 7], list(range(-20, 20))
+    m, k, rpA, ciA = _banded_tiles(T, offA, 5, 0.03)
+    _, n, rpB, ciB = _banded_tiles(T, offB, 9, 0.04)
+    A, B = (rpA, ciA, M.set_values(len(ciA), "mod10")), (rpB, ciB, M.set_values(len(ciB), "hash"))
+    _, tC_exp = oracle_c(m, k, A, B, n)
+    dA, dB = api.DeviceCSR.upload(m, k, *A), api.DeviceCSR.upload(k, n, *B)
+    tA, tB = api.csr2tile(dA, False), api.csr2tile(dB, True)
+    tC, st = api.spgemm(tA, tB)
+    assert st["plan_recipes"] > 0 and 0 < st["row_templates"] <= T // 4, st
+    assert_tiled_equal(tC.download(), tC_exp, f"row templates, {case}", val_rtol=VAL_RTOL)
+    for o in (tC, tA, tB, dA, dB):
+        o.free()
+
+
 def test_recipe_plans_fall_back_when_recipes_do_not_repeat(monkeypatch):
     """Few tile patterns but tens of thousands of distinct pair sequences: the recipe table overflows, the fail flag
     comes up and the generic kernels produce the result (stats say -1)."""
