@@ -38,6 +38,7 @@ class _Tiled(C.Structure):
         ("val", C.POINTER(C.c_double)), ("col", C.POINTER(C.c_uint16)),
         ("ptr", C.POINTER(C.c_uint16)), ("mask", C.POINTER(C.c_uint16)),
         ("csc_tile_ptr", C.POINTER(C.c_int)), ("csc_tile_rowidx", C.POINTER(C.c_int)),
+        ("tr", C.c_int), ("tc", C.c_int),
     ]
 
 
@@ -71,10 +72,12 @@ class Tiled:
     tile_nnz: np.ndarray          # int64 exclusive offsets [numtile+1]
     val: np.ndarray
     col: np.ndarray               # uint16
-    ptr: np.ndarray               # uint16 [numtile*16]
-    mask: np.ndarray              # uint16 [numtile*16]
+    ptr: np.ndarray               # uint16 [numtile*tr]
+    mask: np.ndarray              # uint16 [numtile*tr*(tc/16)]
     csc_tile_ptr: np.ndarray | None = None
     csc_tile_rowidx: np.ndarray | None = None
+    tr: int = 16                  # rows of one tile
+    tc: int = 16                  # columns of one tile (general tiles: SURVEY.md 8(f) rank 1)
 
 
 def _arr(p, n, dtype):
@@ -85,6 +88,7 @@ def _arr(p, n, dtype):
 
 def _take_tiled(t: _Tiled) -> Tiled:
     nt = t.numtile
+    tr, tc = (t.tr or 16), (t.tc or 16)
     out = Tiled(
         m=t.m, n=t.n, tilem=t.tilem, tilen=t.tilen, numtile=nt, nnz=int(t.nnz),
         tile_ptr=_arr(t.tile_ptr, t.tilem + 1, np.int32),
@@ -93,10 +97,11 @@ def _take_tiled(t: _Tiled) -> Tiled:
         tile_nnz=_arr(t.tile_nnz, nt + 1, np.int64),
         val=_arr(t.val, int(t.nnz), np.float64),
         col=_arr(t.col, int(t.nnz), np.uint16),
-        ptr=_arr(t.ptr, nt * 16, np.uint16),
-        mask=_arr(t.mask, nt * 16, np.uint16),
+        ptr=_arr(t.ptr, nt * tr, np.uint16),
+        mask=_arr(t.mask, nt * tr * (tc // 16), np.uint16),
         csc_tile_ptr=_arr(t.csc_tile_ptr, t.tilen + 1, np.int32) if t.csc_tile_ptr else None,
         csc_tile_rowidx=_arr(t.csc_tile_rowidx, nt, np.int32) if t.csc_tile_rowidx else None,
+        tr=tr, tc=tc,
     )
     lib().orc_tiled_free(C.byref(t))
     return out
@@ -120,19 +125,24 @@ def _csr_in(rowptr, colidx, val):
     return rp, ci, v
 
 
-def csr2tile_row_major(m, n, rowptr, colidx, val) -> Tiled:
+def csr2tile_row_major(m, n, rowptr, colidx, val, tr=16, tc=16) -> Tiled:
+    """Tiles of tr rows x tc columns (the reference's csr2tile_row_major(A, tile_size_m = tr, tile_size_n = tc))."""
     rp, ci, v = _csr_in(rowptr, colidx, val)
     t = _Tiled()
-    rc = lib().orc_csr2tile_row_major(int(m), int(n), _p(rp, C.c_int64), _p(ci, C.c_int), _p(v, C.c_double), C.byref(t))
-    assert rc == 0
+    rc = lib().orc_csr2tile_row_major_g(int(m), int(n), _p(rp, C.c_int64), _p(ci, C.c_int), _p(v, C.c_double),
+                                        int(tr), int(tc), C.byref(t))
+    assert rc == 0, f"tile size {tr}x{tc} not representable"
     return _take_tiled(t)
 
 
-def csr2tile_col_major(m, n, rowptr, colidx, val) -> Tiled:
+def csr2tile_col_major(m, n, rowptr, colidx, val, tr=16, tc=16) -> Tiled:
+    """Tiles of tr rows x tc columns in CSC-tile order. NB the reference's csr2tile_col_major(B, tile_size_m,
+    tile_size_n) makes tiles of tile_size_n rows x tile_size_m columns: pass tr = tile_size_n, tc = tile_size_m."""
     rp, ci, v = _csr_in(rowptr, colidx, val)
     t = _Tiled()
-    rc = lib().orc_csr2tile_col_major(int(m), int(n), _p(rp, C.c_int64), _p(ci, C.c_int), _p(v, C.c_double), C.byref(t))
-    assert rc == 0
+    rc = lib().orc_csr2tile_col_major_g(int(m), int(n), _p(rp, C.c_int64), _p(ci, C.c_int), _p(v, C.c_double),
+                                        int(tr), int(tc), C.byref(t))
+    assert rc == 0, f"tile size {tr}x{tc} not representable"
     return _take_tiled(t)
 
 
@@ -170,17 +180,19 @@ def spgemm_spa(A, B, nB, row0=0, row1=None):
 
 
 def ctiles_from_csr(m, n, tA: Tiled, tB: Tiled, csrC, trow0=0, trow1=None) -> Tiled:
-    """Tiled C (incl. empty tiles) from CSR(C) and the tile patterns of A and B."""
+    """Tiled C (incl. empty tiles) from CSR(C) and the tile patterns of A and B. C's tiles have A's tile rows x B's
+    tile columns (tile_size_m x tile_size_m in the reference's terms)."""
+    assert tA.tc == tB.tr, "inner tile dimension: A's tile columns must equal B's tile rows"
     rp, ci, v = _csr_in(*csrC)
     if trow1 is None:
         trow1 = tA.tilem
     pa, ca = np.ascontiguousarray(tA.tile_ptr, np.int32), np.ascontiguousarray(tA.tile_columnidx, np.int32)
     pb, cb = np.ascontiguousarray(tB.tile_ptr, np.int32), np.ascontiguousarray(tB.tile_columnidx, np.int32)
     t = _Tiled()
-    rc = lib().orc_ctiles_from_csr(int(m), int(n), int(tA.tilem), _p(pa, C.c_int), _p(ca, C.c_int),
-                                   int(tB.tilen), _p(pb, C.c_int), _p(cb, C.c_int),
-                                   int(trow0), int(trow1),
-                                   _p(rp, C.c_int64), _p(ci, C.c_int), _p(v, C.c_double), C.byref(t))
+    rc = lib().orc_ctiles_from_csr_g(int(m), int(n), int(tA.tilem), _p(pa, C.c_int), _p(ca, C.c_int),
+                                     int(tB.tilen), _p(pb, C.c_int), _p(cb, C.c_int),
+                                     int(trow0), int(trow1),
+                                     _p(rp, C.c_int64), _p(ci, C.c_int), _p(v, C.c_double), int(tA.tr), int(tB.tc), C.byref(t))
     assert rc == 0, "C has an entry outside the tile-level product"
     return _take_tiled(t)
 
@@ -195,6 +207,7 @@ def tile2csr(t: Tiled):
         setattr(s, name, _p(a, ct))
 
     s.m, s.n, s.tilem, s.tilen, s.numtile, s.nnz = t.m, t.n, t.tilem, t.tilen, t.numtile, t.nnz
+    s.tr, s.tc = t.tr, t.tc
     put("tile_ptr", t.tile_ptr, C.c_int, np.int32)
     put("tile_columnidx", t.tile_columnidx, C.c_int, np.int32)
     put("tile_nnz", t.tile_nnz, C.c_int64, np.int64)

@@ -65,7 +65,7 @@ def _arr(p, n, dtype):
     return np.ctypeslib.as_array(p, shape=(n,)).astype(dtype, copy=True)
 
 
-def _csr2tile(m, n, rowptr, colidx, val, colmajor: bool) -> Tiled:
+def _csr2tile(m, n, rowptr, colidx, val, colmajor: bool, tile_size_m: int = 16, tile_size_n: int = 16) -> Tiled:
     rp = np.ascontiguousarray(rowptr, dtype=np.int32)
     ci = np.ascontiguousarray(colidx, dtype=np.int32)
     v = np.ascontiguousarray(val, dtype=np.float64)
@@ -73,10 +73,12 @@ def _csr2tile(m, n, rowptr, colidx, val, colmajor: bool) -> Tiled:
     s.m, s.n, s.nnz, s.isSymmetric = int(m), int(n), int(rp[m]), 0
     s.rowpointer, s.columnindex, s.value = _p(rp, C.c_int), _p(ci, C.c_int), _p(v, C.c_double)
     if colmajor:
-        _cpu().ref_csr2tile_col_major(C.byref(s))
+        _cpu().ref_csr2tile_col_major_g(C.byref(s), int(tile_size_m), int(tile_size_n))
     else:
-        _cpu().ref_csr2tile_row_major(C.byref(s))
+        _cpu().ref_csr2tile_row_major_g(C.byref(s), int(tile_size_m), int(tile_size_n))
     nt, nnz = s.numtile, s.nnz
+    # rows x columns of one tile: A's are tile_size_m x tile_size_n, B's tile_size_n x tile_size_m (src/main.cu:84)
+    tr, tc = (tile_size_n, tile_size_m) if colmajor else (tile_size_m, tile_size_n)
     out = Tiled(
         m=s.m, n=s.n, tilem=s.tilem, tilen=s.tilen, numtile=nt, nnz=nnz,
         tile_ptr=_arr(s.tile_ptr, s.tilem + 1, np.int32),
@@ -85,23 +87,24 @@ def _csr2tile(m, n, rowptr, colidx, val, colmajor: bool) -> Tiled:
         tile_nnz=_arr(s.tile_nnz, nt + 1, np.int64),
         val=_arr(s.tile_csr_Value, nnz, np.float64),
         col=_arr(s.tile_csr_Col, nnz, np.uint16),
-        ptr=_arr(s.tile_csr_Ptr, nt * 16, np.uint16),
-        mask=_arr(s.mask, nt * 16, np.uint16),
+        ptr=_arr(s.tile_csr_Ptr, nt * tr, np.uint16),
+        mask=_arr(s.mask, nt * tr * (tc // 16), np.uint16),
         csc_tile_ptr=_arr(s.csc_tile_ptr, s.tilen + 1, np.int32) if colmajor else None,
         csc_tile_rowidx=_arr(s.csc_tile_rowidx, nt, np.int32) if colmajor else None,
+        tr=tr, tc=tc,
     )
     _cpu().ref_matrix_destroy(C.byref(s))  # frees what src/csr2tile.h:509 frees (the rest leaks, as upstream)
     return out
 
 
-def csr2tile_row_major(m, n, rowptr, colidx, val) -> Tiled:
+def csr2tile_row_major(m, n, rowptr, colidx, val, tile_size_m=16, tile_size_n=16) -> Tiled:
     """Reference src/csr2tile.h:205, unmodified."""
-    return _csr2tile(m, n, rowptr, colidx, val, False)
+    return _csr2tile(m, n, rowptr, colidx, val, False, tile_size_m, tile_size_n)
 
 
-def csr2tile_col_major(m, n, rowptr, colidx, val) -> Tiled:
-    """Reference src/csr2tile.h:279, unmodified."""
-    return _csr2tile(m, n, rowptr, colidx, val, True)
+def csr2tile_col_major(m, n, rowptr, colidx, val, tile_size_m=16, tile_size_n=16) -> Tiled:
+    """Reference src/csr2tile.h:279, unmodified (tiles of tile_size_n rows x tile_size_m columns)."""
+    return _csr2tile(m, n, rowptr, colidx, val, True, tile_size_m, tile_size_n)
 
 
 def tile2csr(t: Tiled):
@@ -121,7 +124,7 @@ def tile2csr(t: Tiled):
     s.tile_csr_Value = _p(put(t.val, np.float64), C.c_double)
     s.tile_csr_Col = _p(put(t.col, np.uint16), C.c_uint16)
     s.tile_csr_Ptr = _p(put(t.ptr, np.uint16), C.c_uint16)
-    _cpu().ref_tile2csr(C.byref(s))
+    _cpu().ref_tile2csr_g(C.byref(s), int(t.tr), int(t.tc))
     nnz = s.nnz
     out = (_arr(s.rowpointer, s.m + 1, np.int32), _arr(s.columnindex, nnz, np.int32), _arr(s.value, nnz, np.float64))
     for p in (s.rowpointer, s.columnindex, s.value):

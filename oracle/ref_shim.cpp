@@ -32,6 +32,10 @@ void ref_csr2tile_col_major(void *mat) { csr2tile_col_major((SMatrix *)mat, 16, 
 /* src/tile2csr.h:72 (main.cu:327 passes (tile_size_m, tile_size_m)) */
 void ref_tile2csr(void *mat) { tile2csr((SMatrix *)mat, 16, 16); }
 void ref_matrix_destroy(void *mat) { matrix_destroy((SMatrix *)mat); }
+/* the fork's runtime tile sizes (src/main.cu:84-91: "the tile of A is m x n, and the tile of B is n x m") */
+void ref_csr2tile_row_major_g(void *mat, int tile_size_m, int tile_size_n) { csr2tile_row_major((SMatrix *)mat, tile_size_m, tile_size_n); }
+void ref_csr2tile_col_major_g(void *mat, int tile_size_m, int tile_size_n) { csr2tile_col_major((SMatrix *)mat, tile_size_m, tile_size_n); }
+void ref_tile2csr_g(void *mat, int tile_size_m, int tile_size_n) { tile2csr((SMatrix *)mat, tile_size_m, tile_size_n); }
 
 /* src/utils.h:161 */
 void ref_matrix_transposition(int m, int n, int nnz, const int *rp, const int *ci, const double *v,

@@ -33,7 +33,7 @@ static int omp_get_thread_num(void) { return 0; }
 static void omp_set_num_threads(int n) { (void)n; }
 #endif
 
-#define T 16 /* tile edge; src/common.h:36 BLOCK_SIZE, MaskBits = 16 (src/common.h:146) */
+#define T16 16 /* the paper's tile edge; src/common.h:36 BLOCK_SIZE. MaskBits = 16 (src/common.h:146): one mask word covers 16 columns */
 
 typedef struct {
     int m, n, tilem, tilen, numtile;
@@ -48,6 +48,8 @@ typedef struct {
     uint16_t *mask;        /* [numtile*16] bit (15-c) <-> column c          */
     int *csc_tile_ptr;     /* [tilen+1]  (B only)                           */
     int *csc_tile_rowidx;  /* [numtile]  (B only)                           */
+    int tr, tc;            /* rows x columns of one tile (16 x 16 unless a *_g entry point made it):
+                              ptr holds tr slots per tile, mask tr*(tc/16) words per tile */
 } orc_tiled;
 
 typedef struct {
@@ -88,23 +90,23 @@ static int cmp_int(const void *a, const void *b)
  * ascending tile-col emission of step2_kernel (:91-105). The per-thread flag
  * array is reset through a touched list instead of a tilen-byte memset.
  * ---------------------------------------------------------------------- */
-static void tile_structure(int m, int n, const int64_t *rowptr, const int *colidx,
+static void tile_structure(int m, int n, const int64_t *rowptr, const int *colidx, int TR, int TC,
                            int *tilem_out, int *tilen_out, int **tile_ptr_out, int **tile_col_out)
 {
-    int tilem = (m + T - 1) / T, tilen = (n + T - 1) / T; /* src/csr2tile.h:210-211 */
+    int tilem = (m + TR - 1) / TR, tilen = (n + TC - 1) / TC; /* src/csr2tile.h:210-211 */
     int *tile_ptr = (int *)calloc((size_t)tilem + 1, sizeof(int));
     int nth = omp_get_max_threads();
     char *flag_g = (char *)calloc((size_t)nth * (tilen > 0 ? tilen : 1), 1);
 #pragma omp parallel for schedule(dynamic, 64)
     for (int bi = 0; bi < tilem; bi++) {
         char *flag = flag_g + (size_t)omp_get_thread_num() * tilen;
-        int r0 = bi * T, r1 = (bi + 1) * T < m ? (bi + 1) * T : m;
+        int r0 = bi * TR, r1 = (bi + 1) * TR < m ? (bi + 1) * TR : m;
         int cnt = 0;
         for (int64_t j = rowptr[r0]; j < rowptr[r1]; j++) {
-            int jc = colidx[j] / T;
+            int jc = colidx[j] / TC;
             if (!flag[jc]) { flag[jc] = 1; cnt++; }
         }
-        for (int64_t j = rowptr[r0]; j < rowptr[r1]; j++) flag[colidx[j] / T] = 0;
+        for (int64_t j = rowptr[r0]; j < rowptr[r1]; j++) flag[colidx[j] / TC] = 0;
         tile_ptr[bi + 1] = cnt;
     }
     for (int bi = 0; bi < tilem; bi++) tile_ptr[bi + 1] += tile_ptr[bi];
@@ -113,11 +115,11 @@ static void tile_structure(int m, int n, const int64_t *rowptr, const int *colid
 #pragma omp parallel for schedule(dynamic, 64)
     for (int bi = 0; bi < tilem; bi++) {
         char *flag = flag_g + (size_t)omp_get_thread_num() * tilen;
-        int r0 = bi * T, r1 = (bi + 1) * T < m ? (bi + 1) * T : m;
+        int r0 = bi * TR, r1 = (bi + 1) * TR < m ? (bi + 1) * TR : m;
         int *out = tile_col + tile_ptr[bi];
         int cnt = 0;
         for (int64_t j = rowptr[r0]; j < rowptr[r1]; j++) {
-            int jc = colidx[j] / T;
+            int jc = colidx[j] / TC;
             if (!flag[jc]) { flag[jc] = 1; out[cnt++] = jc; }
         }
         for (int k = 0; k < cnt; k++) flag[out[k]] = 0;
@@ -144,19 +146,24 @@ static int find_tile(const int *cols, int len, int key)
  * Col = r*16 + c (:192); Ptr = exclusive scan over 16 slots (:243-246), rows
  * past the matrix edge repeat the tile total; mask bit (15-c) (:195).
  * ---------------------------------------------------------------------- */
-int orc_csr2tile_row_major(int m, int n, const int64_t *rowptr, const int *colidx, const double *val,
-                           orc_tiled *out)
+int orc_csr2tile_row_major_g(int m, int n, const int64_t *rowptr, const int *colidx, const double *val,
+                             int TR, int TC, orc_tiled *out)
 {
+    /* general tiles (the fork's runtime tile_size_m x tile_size_n, src/csr2tile.h:205-277 with tile_size_m = TR rows and
+     * tile_size_n = TC columns; TC a multiple of MaskBits, :193): Ptr has TR slots per tile, the mask of row r is
+     * W = TC/16 words, column c <-> word c/16, bit 15 - c%16 (:194-195), Col = r*TC + c (:192) */
+    if (TR <= 0 || TC <= 0 || TC % 16 || (int64_t)TR * TC > 65536) return -2;
+    const int W = TC / 16;
     memset(out, 0, sizeof(*out));
-    out->m = m; out->n = n; out->nnz = rowptr[m];
-    tile_structure(m, n, rowptr, colidx, &out->tilem, &out->tilen, &out->tile_ptr, &out->tile_columnidx);
+    out->m = m; out->n = n; out->nnz = rowptr[m]; out->tr = TR; out->tc = TC;
+    tile_structure(m, n, rowptr, colidx, TR, TC, &out->tilem, &out->tilen, &out->tile_ptr, &out->tile_columnidx);
     int tilem = out->tilem, numtile = out->tile_ptr[tilem];
     out->numtile = numtile;
     size_t nt = (size_t)(numtile > 0 ? numtile : 1);
     out->tile_rowidx = (int *)calloc(nt, sizeof(int));
     out->tile_nnz = (int64_t *)calloc(nt + 1, sizeof(int64_t));
-    out->ptr = (uint16_t *)calloc(nt * T, sizeof(uint16_t));
-    out->mask = (uint16_t *)calloc(nt * T, sizeof(uint16_t));
+    out->ptr = (uint16_t *)calloc(nt * TR, sizeof(uint16_t));
+    out->mask = (uint16_t *)calloc(nt * TR * W, sizeof(uint16_t));
     out->val = (double *)calloc((size_t)(out->nnz > 0 ? out->nnz : 1), sizeof(double));
     out->col = (uint16_t *)calloc((size_t)(out->nnz > 0 ? out->nnz : 1), sizeof(uint16_t));
 
@@ -165,43 +172,49 @@ int orc_csr2tile_row_major(int m, int n, const int64_t *rowptr, const int *colid
     for (int bi = 0; bi < tilem; bi++) {
         int t0 = out->tile_ptr[bi], nt_row = out->tile_ptr[bi + 1] - t0;
         const int *cols = out->tile_columnidx + t0;
-        int r1 = (bi + 1) * T < m ? (bi + 1) * T : m;
+        int r1 = (bi + 1) * TR < m ? (bi + 1) * TR : m;
         for (int k = 0; k < nt_row; k++) out->tile_rowidx[t0 + k] = bi; /* :97 */
-        for (int row = bi * T; row < r1; row++)
+        for (int row = bi * TR; row < r1; row++)
             for (int64_t j = rowptr[row]; j < rowptr[row + 1]; j++) {
-                int k = find_tile(cols, nt_row, colidx[j] / T);
-                out->ptr[(size_t)(t0 + k) * T + (row - bi * T)]++;
+                int k = find_tile(cols, nt_row, colidx[j] / TC);
+                out->ptr[(size_t)(t0 + k) * TR + (row - bi * TR)]++;
                 out->tile_nnz[t0 + k + 1]++;
             }
     }
     for (int t = 0; t < numtile; t++) out->tile_nnz[t + 1] += out->tile_nnz[t]; /* :241 */
 #pragma omp parallel for
     for (int t = 0; t < numtile; t++) { /* exclusive_scan_uint16 over 16 slots, :243-246 */
-        uint16_t *p = out->ptr + (size_t)t * T, run = 0;
-        for (int r = 0; r < T; r++) { uint16_t c = p[r]; p[r] = run; run += c; }
+        uint16_t *p = out->ptr + (size_t)t * TR, run = 0;
+        for (int r = 0; r < TR; r++) { uint16_t c = p[r]; p[r] = run; run += c; }
     }
     /* scatter (step3_kernel, :112-203) */
 #pragma omp parallel for schedule(dynamic, 64)
     for (int bi = 0; bi < tilem; bi++) {
         int t0 = out->tile_ptr[bi], nt_row = out->tile_ptr[bi + 1] - t0;
         const int *cols = out->tile_columnidx + t0;
-        int r1 = (bi + 1) * T < m ? (bi + 1) * T : m;
-        uint16_t *cursor = (uint16_t *)calloc((size_t)(nt_row > 0 ? nt_row : 1) * T, sizeof(uint16_t));
-        for (int row = bi * T; row < r1; row++) {
-            int r = row - bi * T;
+        int r1 = (bi + 1) * TR < m ? (bi + 1) * TR : m;
+        uint16_t *cursor = (uint16_t *)calloc((size_t)(nt_row > 0 ? nt_row : 1) * TR, sizeof(uint16_t));
+        for (int row = bi * TR; row < r1; row++) {
+            int r = row - bi * TR;
             for (int64_t j = rowptr[row]; j < rowptr[row + 1]; j++) {
-                int jc = colidx[j] / T, c = colidx[j] - jc * T;
+                int jc = colidx[j] / TC, c = colidx[j] - jc * TC;
                 int k = find_tile(cols, nt_row, jc);
                 size_t t = (size_t)(t0 + k);
-                int64_t dst = out->tile_nnz[t] + out->ptr[t * T + r] + cursor[(size_t)k * T + r]++;
+                int64_t dst = out->tile_nnz[t] + out->ptr[t * TR + r] + cursor[(size_t)k * TR + r]++;
                 out->val[dst] = val[j];
-                out->col[dst] = (uint16_t)(r * T + c);
-                out->mask[t * T + r] |= (uint16_t)(1u << (T - 1 - c));
+                out->col[dst] = (uint16_t)(r * TC + c);
+                out->mask[(t * TR + r) * W + (c >> 4)] |= (uint16_t)(1u << (15 - (c & 15)));
             }
         }
         free(cursor);
     }
     return 0;
+}
+
+int orc_csr2tile_row_major(int m, int n, const int64_t *rowptr, const int *colidx, const double *val,
+                           orc_tiled *out)
+{
+    return orc_csr2tile_row_major_g(m, n, rowptr, colidx, val, T16, T16, out);
 }
 
 /* CSR -> CSC, stable (matrix_transposition, src/utils.h:161-198). */
@@ -231,20 +244,26 @@ void orc_transpose(int m, int n, const int64_t *rowptr, const int *colidx, const
  * Col = c (:475), Ptr padded with the tile total past the edge (:477-483),
  * mask (:474). tile_rowidx is allocated and left zero (:336-337).
  * ---------------------------------------------------------------------- */
-int orc_csr2tile_col_major(int m, int n, const int64_t *rowptr, const int *colidx, const double *val,
-                           orc_tiled *out)
+int orc_csr2tile_col_major_g(int m, int n, const int64_t *rowptr, const int *colidx, const double *val,
+                             int TR, int TC, orc_tiled *out)
 {
+    /* general tiles: a tile of B has TR rows and TC columns. The reference's csr2tile_col_major(B, tile_size_m,
+     * tile_size_n) makes them tile_size_n x tile_size_m ("the tile of A is m x n, and the tile of B is n x m",
+     * src/main.cu:84; tilem = ceil(m/tile_size_n), tilen = ceil(n/tile_size_m), src/csr2tile.h:282-283), so the caller
+     * passes TR = tile_size_n, TC = tile_size_m. Ptr: TR slots per tile (:477-483), mask: TR rows of TC/16 words (:472-474). */
+    if (TR <= 0 || TC <= 0 || TC % 16 || (int64_t)TR * TC > 65536) return -2;
+    const int W = TC / 16;
     memset(out, 0, sizeof(*out));
-    out->m = m; out->n = n; out->nnz = rowptr[m];
-    tile_structure(m, n, rowptr, colidx, &out->tilem, &out->tilen, &out->tile_ptr, &out->tile_columnidx);
+    out->m = m; out->n = n; out->nnz = rowptr[m]; out->tr = TR; out->tc = TC;
+    tile_structure(m, n, rowptr, colidx, TR, TC, &out->tilem, &out->tilen, &out->tile_ptr, &out->tile_columnidx);
     int tilem = out->tilem, tilen = out->tilen, numtile = out->tile_ptr[tilem];
     out->numtile = numtile;
     size_t nt = (size_t)(numtile > 0 ? numtile : 1);
     int64_t nnz = out->nnz;
     out->tile_rowidx = (int *)calloc(nt, sizeof(int));
     out->tile_nnz = (int64_t *)calloc(nt + 1, sizeof(int64_t));
-    out->ptr = (uint16_t *)calloc(nt * T, sizeof(uint16_t));
-    out->mask = (uint16_t *)calloc(nt * T, sizeof(uint16_t));
+    out->ptr = (uint16_t *)calloc(nt * TR, sizeof(uint16_t));
+    out->mask = (uint16_t *)calloc(nt * TR * W, sizeof(uint16_t));
     out->val = (double *)calloc((size_t)(nnz > 0 ? nnz : 1), sizeof(double));
     out->col = (uint16_t *)calloc((size_t)(nnz > 0 ? nnz : 1), sizeof(uint16_t));
     out->csc_tile_ptr = (int *)calloc((size_t)tilen + 1, sizeof(int));
@@ -269,19 +288,19 @@ int orc_csr2tile_col_major(int m, int n, const int64_t *rowptr, const int *colid
     for (int bi = 0; bi < tilem; bi++) {
         int t0 = out->tile_ptr[bi], nt_row = out->tile_ptr[bi + 1] - t0;
         const int *cols = out->tile_columnidx + t0;
-        int r1 = (bi + 1) * T < m ? (bi + 1) * T : m;
-        for (int row = bi * T; row < r1; row++)
+        int r1 = (bi + 1) * TR < m ? (bi + 1) * TR : m;
+        for (int row = bi * TR; row < r1; row++)
             for (int64_t j = rowptr[row]; j < rowptr[row + 1]; j++) {
-                size_t t = (size_t)rm2csc[t0 + find_tile(cols, nt_row, colidx[j] / T)];
-                out->ptr[t * T + (row - bi * T)]++;
+                size_t t = (size_t)rm2csc[t0 + find_tile(cols, nt_row, colidx[j] / TC)];
+                out->ptr[t * TR + (row - bi * TR)]++;
                 out->tile_nnz[t + 1]++;
             }
     }
     for (int t = 0; t < numtile; t++) out->tile_nnz[t + 1] += out->tile_nnz[t];
 #pragma omp parallel for
     for (int t = 0; t < numtile; t++) {
-        uint16_t *p = out->ptr + (size_t)t * T, run = 0;
-        for (int r = 0; r < T; r++) { uint16_t c = p[r]; p[r] = run; run += c; }
+        uint16_t *p = out->ptr + (size_t)t * TR, run = 0;
+        for (int r = 0; r < TR; r++) { uint16_t c = p[r]; p[r] = run; run += c; }
     }
     /* scatter; columns inside a (tile,row) run end up ascending and stable, which is
      * what transposing the tile twice produces (:455-457). */
@@ -289,16 +308,16 @@ int orc_csr2tile_col_major(int m, int n, const int64_t *rowptr, const int *colid
     for (int bi = 0; bi < tilem; bi++) {
         int t0 = out->tile_ptr[bi], nt_row = out->tile_ptr[bi + 1] - t0;
         const int *cols = out->tile_columnidx + t0;
-        int r1 = (bi + 1) * T < m ? (bi + 1) * T : m;
-        uint16_t *cursor = (uint16_t *)calloc((size_t)(nt_row > 0 ? nt_row : 1) * T, sizeof(uint16_t));
-        for (int row = bi * T; row < r1; row++) {
-            int r = row - bi * T;
+        int r1 = (bi + 1) * TR < m ? (bi + 1) * TR : m;
+        uint16_t *cursor = (uint16_t *)calloc((size_t)(nt_row > 0 ? nt_row : 1) * TR, sizeof(uint16_t));
+        for (int row = bi * TR; row < r1; row++) {
+            int r = row - bi * TR;
             for (int64_t j = rowptr[row]; j < rowptr[row + 1]; j++) {
-                int jc = colidx[j] / T, c = colidx[j] - jc * T;
+                int jc = colidx[j] / TC, c = colidx[j] - jc * TC;
                 int k = find_tile(cols, nt_row, jc);
                 size_t t = (size_t)rm2csc[t0 + k];
-                int64_t base = out->tile_nnz[t] + out->ptr[t * T + r];
-                int pos = cursor[(size_t)k * T + r]++;
+                int64_t base = out->tile_nnz[t] + out->ptr[t * TR + r];
+                int pos = cursor[(size_t)k * TR + r]++;
                 /* stable insertion by column keeps duplicates in CSR order */
                 while (pos > 0 && out->col[base + pos - 1] > (uint16_t)c) {
                     out->col[base + pos] = out->col[base + pos - 1];
@@ -307,13 +326,19 @@ int orc_csr2tile_col_major(int m, int n, const int64_t *rowptr, const int *colid
                 }
                 out->col[base + pos] = (uint16_t)c;
                 out->val[base + pos] = val[j];
-                out->mask[t * T + r] |= (uint16_t)(1u << (T - 1 - c));
+                out->mask[(t * TR + r) * W + (c >> 4)] |= (uint16_t)(1u << (15 - (c & 15)));
             }
         }
         free(cursor);
     }
     free(rm2csc);
     return 0;
+}
+
+int orc_csr2tile_col_major(int m, int n, const int64_t *rowptr, const int *colidx, const double *val,
+                           orc_tiled *out)
+{
+    return orc_csr2tile_col_major_g(m, n, rowptr, colidx, val, T16, T16, out);
 }
 
 /* nnzCub loop of the driver (src/main.cu:155-160). */
@@ -470,17 +495,22 @@ int orc_spgemm_rowcounts(int mA, int nB, const int64_t *rpA, const int *ciA, con
  *  - tile_nnz exclusive offsets (:2602).
  * Tile rows [trow0,trow1) of A only; csrC must hold rows [trow0*16, min(trow1*16,m)).
  * ---------------------------------------------------------------------- */
-int orc_ctiles_from_csr(int m, int n, int tilemA, const int *tile_ptrA, const int *tile_colA,
-                        int tilenB, const int *tile_ptrB, const int *tile_colB,
-                        int trow0, int trow1,
-                        const int64_t *rpC, const int *ciC, const double *vC, orc_tiled *out)
+int orc_ctiles_from_csr_g(int m, int n, int tilemA, const int *tile_ptrA, const int *tile_colA,
+                          int tilenB, const int *tile_ptrB, const int *tile_colB,
+                          int trow0, int trow1,
+                          const int64_t *rpC, const int *ciC, const double *vC, int TR, int TC, orc_tiled *out)
 {
+    /* general tiles: a tile of C has TR = tile_size_m rows (A's tile rows) and TC = tile_size_m columns (B's tile
+     * columns); the driver hands tile2csr(C, tile_size_m, tile_size_m), src/main.cu:327 */
+    if (TR <= 0 || TC <= 0 || TC % 16 || (int64_t)TR * TC > 65536) return -2;
+    const int W = TC / 16;
     memset(out, 0, sizeof(*out));
+    out->tr = TR; out->tc = TC;
     if (trow0 < 0) trow0 = 0;
     if (trow1 > tilemA) trow1 = tilemA;
     int trows = trow1 - trow0;
     out->n = n; out->tilem = trows; out->tilen = tilenB;
-    out->m = (trow1 * T < m ? trow1 * T : m) - trow0 * T; /* a slab is a matrix of its own */
+    out->m = (trow1 * TR < m ? trow1 * TR : m) - trow0 * TR; /* a slab is a matrix of its own */
     if (out->m < 0) out->m = 0;
     out->tile_ptr = (int *)calloc((size_t)trows + 1, sizeof(int));
     int nth = omp_get_max_threads();
@@ -525,15 +555,15 @@ int orc_ctiles_from_csr(int m, int n, int tilemA, const int *tile_ptrA, const in
             out->tile_columnidx = (int *)calloc(nt, sizeof(int));
             out->tile_rowidx = (int *)calloc(nt, sizeof(int));
             out->tile_nnz = (int64_t *)calloc(nt + 1, sizeof(int64_t));
-            out->ptr = (uint16_t *)calloc(nt * T, sizeof(uint16_t));
-            out->mask = (uint16_t *)calloc(nt * T, sizeof(uint16_t));
+            out->ptr = (uint16_t *)calloc(nt * TR, sizeof(uint16_t));
+            out->mask = (uint16_t *)calloc(nt * TR * W, sizeof(uint16_t));
         }
     }
     for (int t = 0; t < nth; t++) free(touch_g[t]);
     free(touch_g); free(tcap); free(flag_g);
 
-    int row_base = trow0 * T;
-    int row_end = trow1 * T < m ? trow1 * T : m;
+    int row_base = trow0 * TR;
+    int row_end = trow1 * TR < m ? trow1 * TR : m;
     int64_t nnz = rpC[row_end - row_base];
     out->nnz = nnz;
     out->val = (double *)calloc((size_t)(nnz > 0 ? nnz : 1), sizeof(double));
@@ -544,12 +574,12 @@ int orc_ctiles_from_csr(int m, int n, int tilemA, const int *tile_ptrA, const in
     for (int bi = trow0; bi < trow1; bi++) {
         int t0 = out->tile_ptr[bi - trow0], ntr = out->tile_ptr[bi - trow0 + 1] - t0;
         const int *cols = out->tile_columnidx + t0;
-        int r1 = (bi + 1) * T < m ? (bi + 1) * T : m;
-        for (int row = bi * T; row < r1; row++)
+        int r1 = (bi + 1) * TR < m ? (bi + 1) * TR : m;
+        for (int row = bi * TR; row < r1; row++)
             for (int64_t j = rpC[row - row_base]; j < rpC[row - row_base + 1]; j++) {
-                int k = find_tile(cols, ntr, ciC[j] / T);
+                int k = find_tile(cols, ntr, ciC[j] / TC);
                 if (k < 0) { bad = 1; continue; } /* C entry outside the tile-level product: impossible */
-                out->ptr[(size_t)(t0 + k) * T + (row - bi * T)]++;
+                out->ptr[(size_t)(t0 + k) * TR + (row - bi * TR)]++;
                 out->tile_nnz[t0 + k + 1]++;
             }
     }
@@ -557,30 +587,39 @@ int orc_ctiles_from_csr(int m, int n, int tilemA, const int *tile_ptrA, const in
     for (int t = 0; t < out->numtile; t++) out->tile_nnz[t + 1] += out->tile_nnz[t];
 #pragma omp parallel for
     for (int t = 0; t < out->numtile; t++) {
-        uint16_t *p = out->ptr + (size_t)t * T, run = 0;
-        for (int r = 0; r < T; r++) { uint16_t c = p[r]; p[r] = run; run += c; }
+        uint16_t *p = out->ptr + (size_t)t * TR, run = 0;
+        for (int r = 0; r < TR; r++) { uint16_t c = p[r]; p[r] = run; run += c; }
     }
 #pragma omp parallel for schedule(dynamic, 64)
     for (int bi = trow0; bi < trow1; bi++) {
         int t0 = out->tile_ptr[bi - trow0], ntr = out->tile_ptr[bi - trow0 + 1] - t0;
         const int *cols = out->tile_columnidx + t0;
-        int r1 = (bi + 1) * T < m ? (bi + 1) * T : m;
-        uint16_t *cursor = (uint16_t *)calloc((size_t)(ntr > 0 ? ntr : 1) * T, sizeof(uint16_t));
-        for (int row = bi * T; row < r1; row++) {
-            int r = row - bi * T;
+        int r1 = (bi + 1) * TR < m ? (bi + 1) * TR : m;
+        uint16_t *cursor = (uint16_t *)calloc((size_t)(ntr > 0 ? ntr : 1) * TR, sizeof(uint16_t));
+        for (int row = bi * TR; row < r1; row++) {
+            int r = row - bi * TR;
             for (int64_t j = rpC[row - row_base]; j < rpC[row - row_base + 1]; j++) {
-                int jc = ciC[j] / T, c = ciC[j] - jc * T;
+                int jc = ciC[j] / TC, c = ciC[j] - jc * TC;
                 int k = find_tile(cols, ntr, jc);
                 size_t t = (size_t)(t0 + k);
-                int64_t dst = out->tile_nnz[t] + out->ptr[t * T + r] + cursor[(size_t)k * T + r]++;
+                int64_t dst = out->tile_nnz[t] + out->ptr[t * TR + r] + cursor[(size_t)k * TR + r]++;
                 out->val[dst] = vC[j];
                 out->col[dst] = (uint16_t)c;
-                out->mask[t * T + r] |= (uint16_t)(1u << (T - 1 - c));
+                out->mask[(t * TR + r) * W + (c >> 4)] |= (uint16_t)(1u << (15 - (c & 15)));
             }
         }
         free(cursor);
     }
     return 0;
+}
+
+int orc_ctiles_from_csr(int m, int n, int tilemA, const int *tile_ptrA, const int *tile_colA,
+                        int tilenB, const int *tile_ptrB, const int *tile_colB,
+                        int trow0, int trow1,
+                        const int64_t *rpC, const int *ciC, const double *vC, orc_tiled *out)
+{
+    return orc_ctiles_from_csr_g(m, n, tilemA, tile_ptrA, tile_colA, tilenB, tile_ptrB, tile_colB, trow0, trow1, rpC, ciC, vC,
+                                 T16, T16, out);
 }
 
 /* ------------------------------------------------------------------------
@@ -593,19 +632,21 @@ int orc_ctiles_from_csr(int m, int n, int tilemA, const int *tile_ptrA, const in
  * ---------------------------------------------------------------------- */
 int orc_tile2csr(const orc_tiled *t, orc_csr *out)
 {
+    /* tile size from the tiled matrix (0 = a caller that never set it: 16 x 16) */
+    const int TR = t->tr > 0 ? t->tr : T16, TC = t->tc > 0 ? t->tc : T16;
     memset(out, 0, sizeof(*out));
     int m = t->m, tilem = t->tilem;
     const int row_base = 0;
     out->m = m; out->n = t->n;
     out->rowptr = (int64_t *)calloc((size_t)m + 1, sizeof(int64_t));
     for (int bi = 0; bi < tilem; bi++) {
-        int rowlen = (bi == tilem - 1) ? m - (tilem - 1) * T : T; /* :19 */
+        int rowlen = (bi == tilem - 1) ? m - (tilem - 1) * TR : TR; /* :19 */
         for (int tt = t->tile_ptr[bi]; tt < t->tile_ptr[bi + 1]; tt++) {
             int64_t tnnz = t->tile_nnz[tt + 1] - t->tile_nnz[tt];
-            const uint16_t *p = t->ptr + (size_t)tt * T;
+            const uint16_t *p = t->ptr + (size_t)tt * TR;
             for (int r = 0; r < rowlen; r++) {
                 int64_t end = (r == rowlen - 1) ? tnnz : p[r + 1]; /* :22 */
-                out->rowptr[row_base + bi * T + r + 1] += end - p[r];
+                out->rowptr[row_base + bi * TR + r + 1] += end - p[r];
             }
         }
     }
@@ -615,17 +656,17 @@ int orc_tile2csr(const orc_tiled *t, orc_csr *out)
     out->val = (double *)calloc((size_t)(out->nnz > 0 ? out->nnz : 1), sizeof(double));
     int64_t *cursor = (int64_t *)calloc((size_t)(m > 0 ? m : 1), sizeof(int64_t));
     for (int bi = 0; bi < tilem; bi++) {
-        int rowlen = (bi == tilem - 1) ? m - (tilem - 1) * T : T;
+        int rowlen = (bi == tilem - 1) ? m - (tilem - 1) * TR : TR;
         for (int tt = t->tile_ptr[bi]; tt < t->tile_ptr[bi + 1]; tt++) {
             int64_t tnnz = t->tile_nnz[tt + 1] - t->tile_nnz[tt], base = t->tile_nnz[tt];
-            const uint16_t *p = t->ptr + (size_t)tt * T;
+            const uint16_t *p = t->ptr + (size_t)tt * TR;
             int tc = t->tile_columnidx[tt];
             for (int r = 0; r < rowlen; r++) {
                 int64_t end = (r == rowlen - 1) ? tnnz : p[r + 1];
                 for (int64_t j = p[r]; j < end; j++) {
-                    int row = bi * T + r;
+                    int row = bi * TR + r;
                     int64_t d = out->rowptr[row] + cursor[row]++;
-                    out->colidx[d] = tc * T + t->col[base + j];
+                    out->colidx[d] = tc * TC + t->col[base + j];
                     out->val[d] = t->val[base + j];
                 }
             }

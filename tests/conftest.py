@@ -32,6 +32,11 @@ def golden_cases():
                   if "bitmask_h" not in p)
 
 
+def general_tile_golden_cases():
+    """gtile_<case>_<tile_size_m>x<tile_size_n>.npz: the reference's csr2tile / tile2csr at runtime tile sizes."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "gtile_*.npz")))
+
+
 def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
 

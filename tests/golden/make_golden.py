@@ -12,6 +12,11 @@ Per case the file holds the input CSR and, computed by UNMODIFIED reference func
   C_val                     spgemm_serialref    (src/external/cusparse/spgemm_serialref_spa.h:33)
   C2_*                      tile2csr            (src/tile2csr.h:72) applied to the oracle's tiled C
 plus, for random_0.1_36x36, the 36 golden row bitmasks of UnitTest/CSR2TILE/bitmask.h.
+
+gtile_<case>_<tile_size_m>x<tile_size_n>.npz: the same for the fork's runtime tile sizes (src/main.cu:84-91: tiles of A are
+tile_size_m x tile_size_n, tiles of B tile_size_n x tile_size_m, tiles of C tile_size_m x tile_size_m): A_* / B_* from the
+unmodified csr2tile_row_major / csr2tile_col_major(matrix, tile_size_m, tile_size_n), C2_* from the unmodified
+tile2csr(C, tile_size_m, tile_size_m) (src/main.cu:327) applied to the oracle's tiled C.
 """
 import os
 import re
@@ -62,6 +67,24 @@ def make_case(name, m, n, rp, ci, v):
     print(f"{name}: m={m} n={n} nnz={len(ci)} numtileA={tA.numtile}" + (f" nnzC={len(d['C_colidx'])}" if m == n else ""))
 
 
+def make_general_case(name, tm, tn, m, n, rp, ci, v):
+    d = dict(m=np.int64(m), n=np.int64(n), rowptr=rp, colidx=ci, val=v, tile_size=np.array([tm, tn], np.int64))
+    tA = ref.csr2tile_row_major(m, n, rp, ci, v, tm, tn)
+    tB = ref.csr2tile_col_major(m, n, rp, ci, v, tm, tn)
+    d.update(tiled_dict("A", tA))
+    d.update(tiled_dict("B", tB))
+    if m == n:
+        A = (rp, ci, v)
+        rpC, ciC, vC = ref.spgemm_serialref(A, A, n)
+        d.update(C_rowptr=rpC, C_colidx=ciC, C_val=vC)
+        oA, oB = orc.csr2tile_row_major(m, n, rp, ci, v, tm, tn), orc.csr2tile_col_major(m, n, rp, ci, v, tn, tm)
+        tC = orc.ctiles_from_csr(m, n, oA, oB, (rpC, ciC, vC))
+        r2, c2, v2 = ref.tile2csr(tC)
+        d.update(C2_rowptr=r2, C2_colidx=c2, C2_val=v2)
+    np.savez_compressed(os.path.join(OUT, f"gtile_{name}_{tm}x{tn}.npz"), **d)
+    print(f"gtile_{name}_{tm}x{tn}: numtileA={tA.numtile} numtileB={tB.numtile}")
+
+
 def main():
     assert ref.available(), "build oracle/_ref first (make -C oracle)"
     for nm in ["diagonal", "tridiagonal", "banded", "sparse", "random_0.05", "random_0.1", "random_0.15"]:
@@ -80,6 +103,13 @@ def main():
     make_case("ref_blockfem_50", *M.blockfem(50))
     make_case("ref_rmat_s8", *M.rmat(8, 8))
     make_case("ref_stencil27_6", *M.stencil27(6))
+    # the fork's runtime tile sizes
+    for tm, tn in [(32, 32), (16, 32), (32, 16), (48, 64), (64, 64), (128, 128)]:
+        make_general_case("lap2d_24", tm, tn, *M.lap2d(24))
+        make_general_case("rand_150", tm, tn, *M.random_sparse(150, 150, 0.04, seed=5))
+    make_general_case("rect_90x210", 32, 32, *M.random_sparse(90, 210, 0.05, seed=6))
+    make_general_case("rect_90x210", 48, 16, *M.random_sparse(90, 210, 0.05, seed=6))
+    make_general_case("blockfem_30", 32, 32, *M.blockfem(30))
 
 
 if __name__ == "__main__":

@@ -49,6 +49,26 @@ def test_spa_and_tile2csr(name):
         assert np.array_equal(got[0], rpC) and np.array_equal(got[1], ciC) and np.array_equal(got[2], vC)
 
 
+@pytest.mark.parametrize("tile", [(32, 32), (16, 48), (64, 32), (128, 128)])
+@pytest.mark.parametrize("name", ["lap2d_33x17", "stencil27_7", "blockfem_40", "rmat_s9", "rand_rect_wide", "rand_rect_tall", "single_entry", "empty"])
+def test_general_tile_sizes(name, tile):
+    """Runtime tile sizes: the restatement against the reference's csr2tile_row_major /
+    csr2tile_col_major(matrix, tile_size_m, tile_size_n) and tile2csr(C, tile_size_m, tile_size_m)."""
+    tm, tn = tile
+    m, n, rp, ci, v = CASES[name]()
+    tA, tB = orc.csr2tile_row_major(m, n, rp, ci, v, tm, tn), orc.csr2tile_col_major(m, n, rp, ci, v, tn, tm)
+    assert_tiled_equal(tA, ref.csr2tile_row_major(m, n, rp, ci, v, tm, tn), name + " A")
+    # tile_rowidx of B: allocated and left zero by the reference (src/csr2tile.h:336-337); not compared
+    assert_tiled_equal(tB, ref.csr2tile_col_major(m, n, rp, ci, v, tm, tn), name + " B",
+                       fields=("tile_ptr", "tile_columnidx", "tile_nnz", "val", "col", "ptr", "mask", "csc_tile_ptr", "csc_tile_rowidx"))
+    if m == n:
+        A = (rp, ci, v)
+        C = orc.spgemm_spa(A, A, n)
+        tC = orc.ctiles_from_csr(m, n, tA, tB, C)
+        for got in (orc.tile2csr(tC), ref.tile2csr(tC)):
+            assert np.array_equal(got[0], C[0]) and np.array_equal(got[1], C[1]) and np.array_equal(got[2], C[2])
+
+
 def test_rectangular_product():
     m, k, rpA, ciA, vA = M.random_sparse(70, 100, 0.05, seed=21)
     k2, n, rpB, ciB, vB = M.random_sparse(100, 45, 0.06, seed=22)
