@@ -69,8 +69,10 @@ typedef struct
 
 /* ------------------------------------------------------------------------------------------
  * Part 1 -- drop-in entry points (host buffers in, host buffers out; malloc()-owned results so
- * the driver's free()/matrix_destroy() keep working). Only 16x16 tiles are implemented;
- * any other tile_size_m/tile_size_n sets TSG_ERR_UNSUPPORTED.
+ * the driver's free()/matrix_destroy() keep working). tile_size_m / tile_size_n: 16 x 16 runs the tuned kernels;
+ * any other pair of multiples of 16 up to 128 runs the general-tile path (Part 3: tiles of A are tile_size_m x
+ * tile_size_n, of B tile_size_n x tile_size_m, of C tile_size_m x tile_size_m, as in src/main.cu:84-91); anything
+ * else sets TSG_ERR_UNSUPPORTED.
  * Input contract: CSR rows sorted by column and duplicate-free. csr2tile_row_major / csr2tile_col_major accept rows
  * that are not (they sort and merge on the device first, see tsg_csr_canonicalize); the tsg_* API reports TSG_ERR_INPUT.
  * ---------------------------------------------------------------------------------------- */
@@ -117,7 +119,7 @@ void matrix_transposition(const int m, const int n, const MAT_PTR_TYPE nnz,
 enum {
     TSG_OK = 0,
     TSG_ERR_CUDA = 1,          /* a CUDA runtime call or kernel failed / no device            */
-    TSG_ERR_UNSUPPORTED = 2,   /* tile size other than 16x16, or a shape the path cannot take  */
+    TSG_ERR_UNSUPPORTED = 2,   /* tile size not a multiple of 16 in [16,128], or a shape the path cannot take */
     TSG_ERR_OVERFLOW = 3,      /* a 32-bit size of SMatrix would overflow (use the slab API)   */
     TSG_ERR_INPUT = 4,         /* CSR rows not sorted / duplicate columns / index out of range */
     TSG_ERR_NOMEM = 5
@@ -295,6 +297,53 @@ int tsg_plan_slabs(const long long *weights, int trow0, int trow1, int nslabs, i
 int tsg_spgemm_csr_host_into(int m, int k, int n, const int *a_rowptr, const int *a_colidx, const double *a_val,
                              const int *b_rowptr, const int *b_colidx, const double *b_val, int aat, int *c_rowptr,
                              int *c_colidx, double *c_val, long long c_cap, long long *c_nnz, tsg_stats *stats);
+
+/* ------------------------------------------------------------------------------------------
+ * Part 3 -- general tile sizes (the feature this fork adds: runtime tile_size_m x tile_size_n,
+ * reference src/main.cu:84-91, src/common.h:138-146, src/csr2tile.h:192-195,255,472-474, src/tilespgemm-cuda.h:495-705).
+ * With the driver's (tile_size_m, tile_size_n): a tile of A is tile_size_m x tile_size_n, a tile of B tile_size_n x
+ * tile_size_m, a tile of C tile_size_m x tile_size_m. Both must be multiples of 16 (MaskBits) between 16 and 128.
+ * Format per tile of R rows x Q columns: Ptr R slots, mask R rows of Q/16 words (column c <-> word c/16, bit 15 - c%16),
+ * Col = r*Q + c for A and c for B and C. Everything else is as for 16 x 16. The drop-in entry points of Part 1 take any
+ * such size and route 16 x 16 to the tuned kernels and every other size here (csrc/gentile.cu); at 16 x 16 this path
+ * produces bit-identical arrays. Sizes of one call: < 2^31 tile pairs, < 2^31 nonzeros of C.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int m, n;
+    int tile_rows, tile_cols;   /* rows x columns of ONE tile of this matrix                              */
+    int tilem, tilen, numtile;
+    int col_major;              /* 1: B layout (CSC-tile order, Col = col); 0: A / C layout               */
+    long long nnz;
+    int *tile_ptr;              /* [tilem+1]                                                              */
+    int *tile_columnidx;        /* [numtile]                                                              */
+    int *tile_rowidx;           /* [numtile] tile row of each tile, row-major order                       */
+    int *tile_nnz;              /* [numtile+1] storage order                                              */
+    double *val;                /* [nnz]                                                                  */
+    uint16_t *col;              /* [nnz]                                                                  */
+    uint16_t *ptr;              /* [numtile*tile_rows]                                                    */
+    uint16_t *mask;             /* [numtile*tile_rows*(tile_cols/16)]                                     */
+    int *csc_tile_ptr;          /* [tilen+1]  col_major only                                              */
+    int *csc_tile_rowidx;       /* [numtile]  col_major only                                              */
+    int *rm2csc;                /* [numtile]  col_major only: row-major tile index -> storage id          */
+    void *slab[2];              /* device allocations owned by this object (tsg_gtile_free)               */
+    size_t slab_bytes[2];
+} tsg_gtile;
+
+/* 1 if tiles of tile_rows x tile_cols are representable (multiples of 16 in [16, 128]). */
+int tsg_gtile_size_ok(int tile_rows, int tile_cols);
+/* CSR -> tiles of tile_rows x tile_cols on the device (col_major = 0: csr2tile_row_major, Col = r*tile_cols + c;
+ * 1: csr2tile_col_major, CSC-tile order, Col = c). For the reference's csr2tile_col_major(B, tile_size_m, tile_size_n)
+ * pass tile_rows = tile_size_n, tile_cols = tile_size_m. */
+int tsg_gtile_csr2tile(const tsg_dcsr *a, int col_major, int tile_rows, int tile_cols, tsg_gtile *out);
+/* Host SMatrix tile arrays of that tile size -> device, and back (download malloc()s the host arrays). */
+int tsg_gtile_upload(const SMatrix *host, int col_major, int tile_rows, int tile_cols, tsg_gtile *out);
+int tsg_gtile_download(const tsg_gtile *t, SMatrix *host);
+void tsg_gtile_free(tsg_gtile *t);
+/* Steps 1-3: C = A*B with A row-major (R x Q tiles), B column-major (Q x P tiles); C comes out row-major with R x P
+ * tiles, empty tiles kept. stats (may be NULL): numblkC, nnzC, pairs, step times, launches, algorithmic_bytes. */
+int tsg_gtile_spgemm(const tsg_gtile *a, const tsg_gtile *b, tsg_gtile *c, tsg_stats *stats);
+/* tiles -> CSR on the device (row-major storage, Col = c: what tsg_gtile_spgemm returns). */
+int tsg_gtile_tile2csr(const tsg_gtile *t, tsg_dcsr *out);
 
 #ifdef __cplusplus
 }

@@ -68,8 +68,9 @@ class HostMatrix:
         self._keep = other._keep
         return self
 
-    # numpy copies of the library-produced arrays
-    def tiles(self) -> dict:
+    # numpy copies of the library-produced arrays. tile_rows x tile_cols = the size of ONE tile of this matrix
+    # (general tile sizes: A tile_size_m x tile_size_n, B tile_size_n x tile_size_m, C tile_size_m x tile_size_m)
+    def tiles(self, tile_rows: int = 16, tile_cols: int = 16) -> dict:
         s = self.s
         nt, nnz = s.numtile, s.nnz
         d = dict(m=s.m, n=s.n, tilem=s.tilem, tilen=s.tilen, numtile=nt, nnz=nnz,
@@ -79,8 +80,8 @@ class HostMatrix:
                  tile_nnz=_take(s.tile_nnz, nt + 1, np.int32),
                  val=_take(s.tile_csr_Value, nnz, np.float64),
                  col=_take(s.tile_csr_Col, nnz, np.uint16),
-                 ptr=_take(s.tile_csr_Ptr, nt * 16, np.uint16),
-                 mask=_take(s.mask, nt * 16, np.uint16))
+                 ptr=_take(s.tile_csr_Ptr, nt * tile_rows, np.uint16),
+                 mask=_take(s.mask, nt * tile_rows * (tile_cols // 16), np.uint16))
         if s.csc_tile_ptr:
             d["csc_tile_ptr"] = _take(s.csc_tile_ptr, s.tilen + 1, np.int32)
             d["csc_tile_rowidx"] = _take(s.csc_tile_rowidx, nt, np.int32)
@@ -297,6 +298,64 @@ def tile_upload(h: HostMatrix, col_major: bool) -> DeviceTiled:
     t = DeviceTiled()
     L.check(L.load().tsg_tile_upload(C.byref(h.s), int(bool(col_major)), C.byref(t.d)))
     return t
+
+
+# ----------------------------------------------------------------------------------------------
+# General tile sizes (include/tilespgemm.h Part 3, csrc/gentile.cu)
+# ----------------------------------------------------------------------------------------------
+class DeviceGTiled:
+    """A tiled matrix on the device whose tiles are tile_rows x tile_cols (multiples of 16 up to 128)."""
+
+    def __init__(self):
+        self.d = L.GTile()
+
+    def __getattr__(self, k):
+        if k in ("m", "n", "tilem", "tilen", "numtile", "nnz", "col_major", "tile_rows", "tile_cols"):
+            return getattr(self.d, k)
+        raise AttributeError(k)
+
+    def download(self) -> dict:
+        h = HostMatrix()
+        L.check(L.load().tsg_gtile_download(C.byref(self.d), C.byref(h.s)))
+        h._tile_owned = True
+        out = h.tiles(self.d.tile_rows, self.d.tile_cols)
+        matrix_destroy(h)
+        return out
+
+    def free(self):
+        L.load().tsg_gtile_free(C.byref(self.d))
+
+
+def gtile_size_ok(tile_rows: int, tile_cols: int) -> bool:
+    return bool(L.load().tsg_gtile_size_ok(int(tile_rows), int(tile_cols)))
+
+
+def gtile_csr2tile(a: DeviceCSR, col_major: bool, tile_rows: int, tile_cols: int) -> DeviceGTiled:
+    """CSR -> tiles of tile_rows x tile_cols. For the reference's csr2tile_col_major(B, tile_size_m, tile_size_n) pass
+    tile_rows = tile_size_n, tile_cols = tile_size_m."""
+    t = DeviceGTiled()
+    L.check(L.load().tsg_gtile_csr2tile(C.byref(a.d), int(bool(col_major)), int(tile_rows), int(tile_cols), C.byref(t.d)))
+    return t
+
+
+def gtile_upload(h: HostMatrix, col_major: bool, tile_rows: int, tile_cols: int) -> DeviceGTiled:
+    t = DeviceGTiled()
+    L.check(L.load().tsg_gtile_upload(C.byref(h.s), int(bool(col_major)), int(tile_rows), int(tile_cols), C.byref(t.d)))
+    return t
+
+
+def gtile_spgemm(a: DeviceGTiled, b: DeviceGTiled):
+    """Steps 1-3 for general tiles. Returns (C, stats dict)."""
+    c = DeviceGTiled()
+    st = L.Stats()
+    L.check(L.load().tsg_gtile_spgemm(C.byref(a.d), C.byref(b.d), C.byref(c.d), C.byref(st)))
+    return c, st.as_dict()
+
+
+def gtile_tile2csr(t: DeviceGTiled) -> DeviceCSR:
+    out = DeviceCSR()
+    L.check(L.load().tsg_gtile_tile2csr(C.byref(t.d), C.byref(out.d)))
+    return out
 
 
 def transpose(a: DeviceCSR) -> DeviceCSR:

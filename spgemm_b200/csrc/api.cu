@@ -213,10 +213,12 @@ static int ensure_init()
     return tsg_init(dev);
 }
 
-static bool tiles_16(int tm, int tn)
+// 16 x 16 runs the tuned kernels; every other representable size the general-tile path (gentile.cu)
+static bool tiles_16(int tm, int tn) { return tm == TS && tn == TS; }
+static bool tiles_general(int tm, int tn)
 {
-    if (tm == TS && tn == TS) return true;
-    set_error(TSG_ERR_UNSUPPORTED, "tile size %dx%d: only 16x16 tiles are implemented", tm, tn);
+    if (gtile_size_ok(tm, tn)) return true;
+    set_error(TSG_ERR_UNSUPPORTED, "tile size %d x %d: tile_size_m and tile_size_n must be multiples of 16 between 16 and 128", tm, tn);
     return false;
 }
 
@@ -852,9 +854,35 @@ int tsg_spgemm_csr_host_into(int m, int k, int n, const int *a_rowptr, const int
 
 /* ------------------------------- drop-in entry points ------------------------------- */
 
+// general tile sizes: tiles of A are tm x tn, tiles of B tn x tm (reference src/main.cu:84, src/csr2tile.h:282-283)
+static void csr2tile_host_general(SMatrix *mat, int tm, int tn, int col_major)
+{
+    const int TR = col_major ? tn : tm, TC = col_major ? tm : tn;
+    tsg_dcsr A, An;
+    tsg_gtile t;
+    memset(&t, 0, sizeof(t)); memset(&An, 0, sizeof(An));
+    if (tsg_csr_upload(mat->m, mat->n, mat->rowpointer, mat->columnindex, mat->value, &A)) return;
+    int rc = gtile_csr2tile_device(&A, col_major, TR, TC, &t);
+    if (rc == TSG_ERR_INPUT && gtile_last_input_flags() == 2) {  // unsorted rows / duplicates: canonicalise and retry, as for 16 x 16
+        tilespgemm_clear_error();
+        gtile_free(&t);
+        const char *pol = getenv("TSG_DUP_POLICY");
+        rc = tsg_csr_canonicalize(&A, pol && !strcmp(pol, "first") ? 1 : 0, &An);
+        if (!rc) rc = gtile_csr2tile_device(&An, col_major, TR, TC, &t);
+    }
+    if (rc == TSG_OK) gtile_download(&t, mat);
+    gtile_free(&t);
+    tsg_csr_free(&A);
+    tsg_csr_free(&An);
+}
+
 static void csr2tile_host(SMatrix *mat, int tm, int tn, int col_major)
 {
-    if (ensure_init() || !tiles_16(tm, tn)) return;
+    if (ensure_init()) return;
+    if (!tiles_16(tm, tn)) {
+        if (tiles_general(tm, tn)) csr2tile_host_general(mat, tm, tn, col_major);
+        return;
+    }
     tsg_dcsr A, An;
     tsg_dtile t;
     memset(&t, 0, sizeof(t)); memset(&An, 0, sizeof(An));
@@ -894,7 +922,34 @@ void tilespgemm(SMatrix *matrixA, SMatrix *matrixB, SMatrix *matrixC, unsigned i
 {
     (void)blk_intersec_bitmask_A; (void)blk_intersec_bitmask_B; (void)blk_intersec_bitmask_len;  // dense tile bitmaps: never needed
     (void)densityA; (void)densityB; (void)filename;
-    if (ensure_init() || !tiles_16(tile_size_m, tile_size_n)) return;
+    if (ensure_init()) return;
+    if (!tiles_16(tile_size_m, tile_size_n)) {
+        if (!tiles_general(tile_size_m, tile_size_n)) return;
+        tsg_gtile gA, gB, gC;
+        tsg_stats st;
+        memset(&gA, 0, sizeof(gA)); memset(&gB, 0, sizeof(gB)); memset(&gC, 0, sizeof(gC)); memset(&st, 0, sizeof(st));
+        if (gtile_upload(matrixA, 0, tile_size_m, tile_size_n, &gA) == TSG_OK && gtile_upload(matrixB, 1, tile_size_n, tile_size_m, &gB) == TSG_OK &&
+            gtile_spgemm_device(&gA, &gB, &gC, &st) == TSG_OK) {
+            int keep_sym = matrixC->isSymmetric;
+            if (gtile_download(&gC, matrixC) == TSG_OK) {
+                matrixC->isSymmetric = keep_sym;
+                if (nnzC_computed) *nnzC_computed = (unsigned long long)st.nnzC;
+                if (compression_rate) *compression_rate = st.nnzC ? (double)nnzCub / (double)st.nnzC : 0.0;
+                if (time_tile) *time_tile = st.ms_total;
+                if (gflops_tile) *gflops_tile = st.ms_total > 0 ? 2.0 * (double)nnzCub / (st.ms_total * 1e6) : 0.0;
+                if (time_step1) *time_step1 = st.ms_step1;
+                if (time_step2) *time_step2 = st.ms_step2;
+                if (time_step3) *time_step3 = st.ms_step3;
+                if (time_malloc) *time_malloc = st.ms_alloc;
+                printf("Non-empty tiles of C = %i\n", (int)st.numblkC);
+                printf("nnzC = %i\n", (int)st.nnzC);
+                printf("CUDA  TileSpGEMM runtime is %4.2f ms, gflops = %4.2f\n", st.ms_total,
+                       st.ms_total > 0 ? 2.0 * (double)nnzCub / (st.ms_total * 1e6) : 0.0);
+            }
+        }
+        gtile_free(&gA); gtile_free(&gB); gtile_free(&gC);
+        return;
+    }
     tsg_dtile tA, tB, tC;
     tsg_stats st;
     memset(&tA, 0, sizeof(tA)); memset(&tB, 0, sizeof(tB)); memset(&tC, 0, sizeof(tC)); memset(&st, 0, sizeof(st));
@@ -925,11 +980,16 @@ void tilespgemm(SMatrix *matrixA, SMatrix *matrixB, SMatrix *matrixC, unsigned i
 
 void tile2csr(SMatrix *matrix, int tile_size_m, int tile_size_n)
 {
-    if (ensure_init() || !tiles_16(tile_size_m, tile_size_n)) return;
+    if (ensure_init()) return;
+    const bool general = !tiles_16(tile_size_m, tile_size_n);
+    if (general && !tiles_general(tile_size_m, tile_size_n)) return;
     tsg_dtile t;
+    tsg_gtile g;
     tsg_dcsr c;
-    memset(&t, 0, sizeof(t)); memset(&c, 0, sizeof(c));
-    if (tsg_tile_upload(matrix, 0, &t) == TSG_OK && tsg_tile2csr(&t, &c) == TSG_OK) {
+    memset(&t, 0, sizeof(t)); memset(&c, 0, sizeof(c)); memset(&g, 0, sizeof(g));
+    // general: tiles of tile_size_m rows x tile_size_n columns (the driver passes (tile_size_m, tile_size_m) for C, src/main.cu:327)
+    if (general ? (gtile_upload(matrix, 0, tile_size_m, tile_size_n, &g) == TSG_OK && gtile_tile2csr_device(&g, &c) == TSG_OK)
+                : (tsg_tile_upload(matrix, 0, &t) == TSG_OK && tsg_tile2csr(&t, &c) == TSG_OK)) {
         matrix->rowpointer = (int *)malloc(((size_t)c.m + 1) * 4);
         matrix->columnindex = (int *)malloc((size_t)(c.nnz > 0 ? c.nnz : 1) * 4);
         matrix->value = (double *)malloc((size_t)(c.nnz > 0 ? c.nnz : 1) * 8);
@@ -938,7 +998,47 @@ void tile2csr(SMatrix *matrix, int tile_size_m, int tile_size_n)
             matrix->nnz = (int)c.nnz;  // reference src/tile2csr.h:103-104
     }
     tsg_tile_free(&t);
+    gtile_free(&g);
     tsg_csr_free(&c);
+}
+
+/* ------------------------------- general tile sizes (Part 3) ------------------------------- */
+int tsg_gtile_size_ok(int tile_rows, int tile_cols) { return gtile_size_ok(tile_rows, tile_cols) ? 1 : 0; }
+
+int tsg_gtile_csr2tile(const tsg_dcsr *a, int col_major, int tile_rows, int tile_cols, tsg_gtile *out)
+{
+    if (ensure_init()) return g_err;
+    return gtile_csr2tile_device(a, col_major, tile_rows, tile_cols, out);
+}
+
+int tsg_gtile_upload(const SMatrix *host, int col_major, int tile_rows, int tile_cols, tsg_gtile *out)
+{
+    if (ensure_init()) return g_err;
+    return gtile_upload(host, col_major, tile_rows, tile_cols, out);
+}
+
+int tsg_gtile_download(const tsg_gtile *t, SMatrix *host)
+{
+    if (ensure_init()) return g_err;
+    return gtile_download(t, host);
+}
+
+void tsg_gtile_free(tsg_gtile *t)
+{
+    if (!g_ready) { memset(t, 0, sizeof(*t)); return; }
+    gtile_free(t);
+}
+
+int tsg_gtile_spgemm(const tsg_gtile *a, const tsg_gtile *b, tsg_gtile *c, tsg_stats *stats)
+{
+    if (ensure_init()) return g_err;
+    return gtile_spgemm_device(a, b, c, stats);
+}
+
+int tsg_gtile_tile2csr(const tsg_gtile *t, tsg_dcsr *out)
+{
+    if (ensure_init()) return g_err;
+    return gtile_tile2csr_device(t, out);
 }
 
 void matrix_destroy(SMatrix *matrix)

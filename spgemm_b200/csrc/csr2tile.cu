@@ -198,6 +198,13 @@ static int bits_for(int domain)
     return b;
 }
 
+int sort_pairs_device(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, long long n, int key_bits,
+                      uint32_t **keys_res, uint32_t **vals_res)
+{
+    if (n >= (1ll << 31)) { set_error(TSG_ERR_OVERFLOW, "sort: %lld items do not fit int32 positions", n); return last_error(); }
+    return radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, n, key_bits, keys_res, vals_res, vals_a);
+}
+
 // Layout of a tiled matrix inside ONE device slab; a pure function of the sizes so that a peer
 // GPU can allocate the same layout and receive the slab with a single broadcast.
 int tile_alloc_layout(int m, int n, int numtile, long long nnz, int col_major, tsg_dtile *out)

@@ -14,6 +14,10 @@ int csr_check_device(const tsg_dcsr *A);
 int csr_row_slice_device(const tsg_dcsr *A, int r0, int r1, tsg_dcsr *out);
 int csr_canonicalize_device(const tsg_dcsr *A, int dup_policy, tsg_dcsr *out);
 int last_input_flags();
+// stable LSD radix sort of (key, value) pairs by the low key_bits bits of the key (radix_sort.cuh); the result is in
+// the a or the b pair of buffers, *keys_res / *vals_res say which. n < 2^31.
+int sort_pairs_device(uint32_t *keys_a, uint32_t *vals_a, uint32_t *keys_b, uint32_t *vals_b, long long n, int key_bits,
+                      uint32_t **keys_res, uint32_t **vals_res);
 
 // spgemm.cu
 int tilerow_weights_device(const tsg_dtile *A, const tsg_dtile *B, int **d_w, int **d_jlo, int **d_jhi);
@@ -62,6 +66,16 @@ int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, c
 size_t plans_rows_need_bound(int max_nnzA_row, int maxJ, int wmax);
 const int *plans_recipe_count_ptr();
 void plans_shutdown();
+
+// gentile.cu (general tile sizes: csr2tile, steps 1-3, tile2csr)
+bool gtile_size_ok(int tile_rows, int tile_cols);
+int gtile_csr2tile_device(const tsg_dcsr *A, int col_major, int tile_rows, int tile_cols, tsg_gtile *out);
+int gtile_spgemm_device(const tsg_gtile *A, const tsg_gtile *B, tsg_gtile *C, tsg_stats *stats);
+int gtile_tile2csr_device(const tsg_gtile *T, tsg_dcsr *out);
+int gtile_upload(const SMatrix *h, int col_major, int tile_rows, int tile_cols, tsg_gtile *out);
+int gtile_download(const tsg_gtile *t, SMatrix *h);
+void gtile_free(tsg_gtile *t);
+int gtile_last_input_flags();
 
 // tile2csr.cu
 int tile2csr_device(const tsg_dtile *T, tsg_dcsr *out);

@@ -21,6 +21,9 @@ EXPORTS = [
     "tsg_transpose", "tsg_nnzcub", "tsg_csr2tile", "tsg_tile_upload", "tsg_tile_download", "tsg_tile_alloc",
     "tsg_tile_free", "tsg_tilerow_weights", "tsg_spgemm", "tsg_tile2csr", "tsg_tile_rowsums", "tsg_spgemm_csr_host",
     "tsg_spgemm_to_host", "tsg_spgemm_csr_host_into", "tsg_plan_slabs", "tsg_spgemm_slabs",
+    # Part 3: general tile sizes
+    "tsg_gtile_size_ok", "tsg_gtile_csr2tile", "tsg_gtile_upload", "tsg_gtile_download", "tsg_gtile_free", "tsg_gtile_spgemm",
+    "tsg_gtile_tile2csr",
 ]
 
 
@@ -53,6 +56,18 @@ class DTile(C.Structure):
         ("csc_tile_ptr", C.c_void_p), ("csc_tile_rowidx", C.c_void_p), ("rm2csc", C.c_void_p),
         ("pat", C.c_void_p), ("npat", C.c_int),
         ("slab", C.c_void_p * 4), ("slab_bytes", C.c_size_t * 4),
+    ]
+
+
+class GTile(C.Structure):
+    """tsg_gtile: a tiled matrix on the device with tiles of tile_rows x tile_cols (include/tilespgemm.h, Part 3)."""
+    _fields_ = [
+        ("m", C.c_int), ("n", C.c_int), ("tile_rows", C.c_int), ("tile_cols", C.c_int),
+        ("tilem", C.c_int), ("tilen", C.c_int), ("numtile", C.c_int), ("col_major", C.c_int), ("nnz", C.c_longlong),
+        ("tile_ptr", C.c_void_p), ("tile_columnidx", C.c_void_p), ("tile_rowidx", C.c_void_p), ("tile_nnz", C.c_void_p),
+        ("val", C.c_void_p), ("col", C.c_void_p), ("ptr", C.c_void_p), ("mask", C.c_void_p),
+        ("csc_tile_ptr", C.c_void_p), ("csc_tile_rowidx", C.c_void_p), ("rm2csc", C.c_void_p),
+        ("slab", C.c_void_p * 2), ("slab_bytes", C.c_size_t * 2),
     ]
 
 
@@ -90,7 +105,7 @@ def load() -> C.CDLL:
     lib.tsg_stream.restype = C.c_void_p
     lib.tsg_launch_count.restype = C.c_longlong
     for name in ("csr2tile_row_major", "csr2tile_col_major", "tile2csr", "matrix_destroy", "tilespgemm",
-                 "matrix_transposition", "tilespgemm_clear_error", "tsg_shutdown", "tsg_csr_free", "tsg_tile_free"):
+                 "matrix_transposition", "tilespgemm_clear_error", "tsg_shutdown", "tsg_csr_free", "tsg_tile_free", "tsg_gtile_free"):
         getattr(lib, name).restype = None
     _lib = lib
     return lib

@@ -32,14 +32,15 @@ def test_struct_layouts(tmp_path):
     src = tmp_path / "sz.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "tilespgemm.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(SMatrix), sizeof(tsg_dcsr), sizeof(tsg_dtile),'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(SMatrix), sizeof(tsg_dcsr), sizeof(tsg_dtile),'
         ' sizeof(tsg_stats), offsetof(SMatrix, tile_csr_Ptr), offsetof(tsg_dtile, rm2csc), offsetof(tsg_dtile, slab_bytes),'
-        ' offsetof(tsg_stats, launches));return 0;}\n')
+        ' offsetof(tsg_stats, launches), sizeof(tsg_gtile), offsetof(tsg_gtile, nnz), offsetof(tsg_gtile, slab_bytes));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     exp = [C.sizeof(L.SMatrix), C.sizeof(L.DCsr), C.sizeof(L.DTile), C.sizeof(L.Stats), L.SMatrix.tile_csr_Ptr.offset,
-           L.DTile.rm2csc.offset, L.DTile.slab_bytes.offset, L.Stats.launches.offset]
+           L.DTile.rm2csc.offset, L.DTile.slab_bytes.offset, L.Stats.launches.offset, C.sizeof(L.GTile), L.GTile.nnz.offset,
+           L.GTile.slab_bytes.offset]
     assert got == exp
 
 

@@ -204,7 +204,7 @@ def test_error_paths_fail_loudly():
     m, n, rp, ci, v = M.lap2d(8)
     A = api.HostMatrix.from_csr(m, n, rp, ci, v)
     with pytest.raises(api.TsgError) as e:
-        api.csr2tile_row_major(A, 32, 32)           # only 16x16 tiles
+        api.csr2tile_row_major(A, 24, 16)           # tile sizes are multiples of 16 (one mask word = 16 columns)
     assert e.value.code == 2
     bad = ci.copy()
     bad[0], bad[1] = bad[1], bad[0]                  # unsorted row
