@@ -490,6 +490,126 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_general_tiles(args):
+    """--tile M N with (M, N) != (16, 16): the general-tile path (csrc/gentile.cu) on ONE GPU, same
+    metric. Tiles of A are M x N, of B N x M, of C M x M (reference src/main.cu:84-91). `value`: steps 1-3 with the tiled A
+    and B resident; `e2e`: pinned host CSR -> csr2tile x2 -> steps 1-3 -> tile2csr -> host CSR(C). Parity: the CSR(C) the
+    end-to-end leg brought back, against the CPU (C*ones exact, nnz of every row against the oracle's count pass)."""
+    import torch
+    from spgemm_b200 import api
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    assert int(os.environ.get("WORLD_SIZE", "1")) == 1, "--tile other than 16 16 runs on one GPU"
+    tm, tn = args.tile
+    torch.cuda.set_device(0)
+    api.init(0)
+    gen, aat, desc = WORKLOADS[args.workload]
+    K, W = args.steps, args.warmup
+    m, n, rp, ci, v = gen()
+    dA = api.DeviceCSR.upload(m, n, rp, ci, v)
+    dB = api.transpose(dA) if aat else dA
+    nB = m if aat else n
+    nnzCub = api.nnzcub(dA, dB)
+    tA, tB = api.gtile_csr2tile(dA, False, tm, tn), api.gtile_csr2tile(dB, True, tn, tm)
+
+    def step():
+        c, st = api.gtile_spgemm(tA, tB)
+        c.free()
+        return st
+
+    for _ in range(W):
+        step()
+    api.sync()
+    stats = []
+    launches0 = api.launch_count()
+    with ClockSampler(0) as clk:
+        api.timer_start()
+        for _ in range(K):
+            stats.append(step())
+        dev_ms = api.timer_stop()
+    gpu_launches = api.launch_count() - launches0
+    clocks = clk.summary()
+    last = stats[-1]
+
+    # end to end from pinned host buffers
+    pin = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in (rp, ci, v)]
+    nnzC = int(last["nnzC"])
+    out_pin = [torch.empty(m + 1, dtype=torch.int32).pin_memory(), torch.empty(max(nnzC, 1), dtype=torch.int32).pin_memory(),
+               torch.empty(max(nnzC, 1), dtype=torch.float64).pin_memory()]
+
+    def e2e_step():
+        a = api.DeviceCSR.upload_ptrs(m, n, pin[0].data_ptr(), pin[1].data_ptr(), pin[2].data_ptr())
+        b = api.transpose(a) if aat else a
+        ta, tb = api.gtile_csr2tile(a, False, tm, tn), api.gtile_csr2tile(b, True, tn, tm)
+        tc, _ = api.gtile_spgemm(ta, tb)
+        cc = api.gtile_tile2csr(tc)
+        cc.download_into(out_pin[0].data_ptr(), out_pin[1].data_ptr(), out_pin[2].data_ptr())
+        for o in (cc, tc, ta, tb) + ((b,) if aat else ()) + (a,):
+            o.free()
+
+    e2e_K = max(1, min(K, args.e2e_steps))
+    e2e_step()
+    api.sync()
+    t0 = time.perf_counter()
+    for _ in range(e2e_K):
+        e2e_step()
+    api.sync()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_K
+
+    ms_step = dev_ms / K
+    s3_ms = float(np.mean([s["ms_step3"] for s in stats]))
+    W16 = tm // 16
+    # algorithmic bytes of the numeric kernel (k_g_numeric): A's payload and row offsets, B's values, row offsets and row masks,
+    # the pair lists, C's row offsets / masks / tile offsets read and C's payload written
+    s3_bytes = (tA.nnz * 10 + tA.numtile * (2 * tm + 4) + tB.nnz * 8 + tB.numtile * (2 * tn + 2 * tn * W16 + 4) + last["pairs"] * 8
+                + last["numblkC"] * (2 * tm + 2 * tm * W16 + 8) + nnzC * 10)
+    peak, peak_src = measured_peak_gbs()
+    achieved = s3_bytes / (s3_ms * 1e-3) / 1e9 if s3_ms > 0 else 0.0
+    line = {
+        "metric": "spgemm_gflops", "value": 2.0 * nnzCub / (ms_step * 1e6), "unit": "GFLOP/s", "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "tile": f"{tm}x{tn}", "tiles_of": {"A": [tm, tn], "B": [tn, tm], "C": [tm, tm]},
+                   "path": "general tiles (csrc/gentile.cu)", "aat": int(aat), "m": m, "n": n, "nnzA": int(len(ci)), "nnzCub": int(nnzCub),
+                   "nnzC": nnzC, "A_tiles": int(tA.numtile), "B_tiles": int(tB.numtile), "C_tiles": int(last["numblkC"]),
+                   "tile_pairs": int(last["pairs"]),
+                   "l2": "inputs larger than L2" if last["algorithmic_bytes"] > 4 * 126e6 else "working set fits L2",
+                   "steps_ms": {"step1": float(np.mean([s["ms_step1"] for s in stats])), "step2": float(np.mean([s["ms_step2"] for s in stats])),
+                                "step3": s3_ms},
+                   "pipeline_roofline": {"algorithmic_bytes": int(last["algorithmic_bytes"]),
+                                         "achieved_gbs": last["algorithmic_bytes"] / (ms_step * 1e-3) / 1e9,
+                                         "frac_of_peak": last["algorithmic_bytes"] / (ms_step * 1e-3) / 1e9 / peak}},
+        "clocks": clocks,
+        "e2e": {"value": 2.0 * nnzCub / (e2e_ms * 1e6), "unit": "GFLOP/s", "ms_per_step": e2e_ms, "steps": e2e_K,
+                "h2d_bytes_per_step": sum(int(t.numel() * t.element_size()) for t in pin), "d2h_bytes_per_step": (m + 1) * 4 + nnzC * 12},
+        "gpu_launches": int(gpu_launches),
+        "roofline": {"bound": "hbm", "kernel": "numeric step: k_g_numeric (thread per C nonzero)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": s3_ms,
+                     "algorithmic_bytes_per_launch": int(s3_bytes)},
+    }
+    if not args.no_parity or not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        A = (rp, ci, v)
+        B = A
+        if aat:
+            cp, ri, cv = orc.transpose(m, n, rp, ci, v)
+            B = (cp.astype(np.int64), ri, cv)
+        if not args.no_parity:
+            crp = out_pin[0].numpy().astype(np.int64)
+            cvv = out_pin[2].numpy()[:nnzC]
+            cnts = np.diff(crp)
+            csum = np.concatenate([[0.0], np.cumsum(cvv)])
+            # row sums in one pass (exact: every partial sum of the driver's integer-valued inputs is an integer below 2^53)
+            sums = csum[crp[1:]] - csum[crp[:-1]]
+            line["parity"] = parity_check(A, B, nB, sums, cnts, args.parity_counts or nnzCub <= 4e9)
+            cols = out_pin[1].numpy()[:nnzC]
+            drops = np.flatnonzero(np.diff(cols) <= 0) + 1   # a column index may only fall where a new row starts
+            line["parity"]["columns_sorted_in_rows"] = bool(np.all(np.isin(drops, crp)))
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(A, B, nB, nnzCub)
+    print(json.dumps(line), flush=True)
+    for o in (tA, tB) + ((dB,) if aat else ()) + (dA,):
+        o.free()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -505,6 +625,9 @@ def main():
     ap.add_argument("--parity-counts", action="store_true",
                     help="also compare nnz per row of C with the oracle's count pass on workloads above 4e9 products (minutes of CPU)")
     ap.add_argument("--bcast", default="csr", choices=["csr", "tiled"], help="N > 1: broadcast B as its CSR (default) or as the tiled matrix")
+    ap.add_argument("--tile", type=int, nargs=2, default=[16, 16], metavar=("M", "N"),
+                    help="tile_size_m tile_size_n (multiples of 16 up to 128). 16 16: the tuned kernels (default, the BASELINE metric); "
+                         "anything else: the general-tile path on one GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -512,7 +635,10 @@ def main():
     else:
         if args.warmup < 3:
             args.warmup = 3  # timing rule: at least 3 warm-up steps
-        run_ours(args)
+        if tuple(args.tile) != (16, 16):
+            run_general_tiles(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == "__main__":

@@ -380,7 +380,7 @@ int main(int argc, char **argv)
     if (argc > 9 && strcmp(argv[8], "-slabs") == 0) {
         /* slab-wise product through the device-resident API: C never exists whole, totals are 64-bit */
         const long long max_pairs = atoll(argv[9]);
-        if (tile_size_m != 16 || tile_size_n != 16) { fprintf(stderr, "only 16x16 tiles are implemented\n"); return 2; }
+        if (tile_size_m != 16 || tile_size_n != 16) { fprintf(stderr, "-slabs runs the 16 x 16 kernels (tsg_spgemm_slabs); other tile sizes take the whole-matrix path\n"); return 2; }
         tsg_dcsr dA, dB;
         tsg_dtile tA, tB;
         tsg_stats tot;

@@ -375,7 +375,13 @@ def test_c_driver_cli(tmp_path):
     assert len(rows) >= 3 and rows[0].split(",")[1:4] == ["120", "120", str(len(ci))]
     for name in ("step_runtime.csv", "mem-cost.csv", "preprocessing.csv"):
         assert len(open(tmp_path / name).read().strip().splitlines()) == 3
-    bad = subprocess.run([exe, "-d", "0", "-aat", "0", str(mtx), "32", "32"], capture_output=True, text=True, env=env, timeout=60)
+    for name in ("results_tile.csv", "step_runtime.csv", "mem-cost.csv", "preprocessing.csv"):
+        os.remove(tmp_path / name)
+    # the fork's runtime tile sizes (tiles of A 32 x 48, of B 48 x 32, of C 32 x 32): the general-tile path, same check
+    for tm, tn in (("32", "32"), ("32", "48")):
+        out = subprocess.run([exe, "-d", "0", "-aat", "1", str(mtx), tm, tn], capture_output=True, text=True, env=env, timeout=120)
+        assert out.returncode == 0 and "[PASSED]" in out.stdout and f"the tile_size_n = {tn}" in out.stdout, out.stdout + out.stderr
+    bad = subprocess.run([exe, "-d", "0", "-aat", "0", str(mtx), "24", "16"], capture_output=True, text=True, env=env, timeout=60)
     assert bad.returncode != 0  # unsupported tile size: the driver exits non-zero instead of printing garbage
     # the reference's loader keeps file order and duplicates (TSG_MTX_RAW=1 does the same): the drop-in csr2tile_* canonicalise
     scr = tmp_path / "scrambled.mtx"
