@@ -453,6 +453,104 @@ GT_KERNEL k_g_numeric(long long nnzC, int numblkC, int TRc, int TCa, int Wc, con
     valC[g] = sum;
 }
 
+#ifndef GT_EMULATE
+// ------------------------------------------------------------------------------------------------------------------
+// step 3 for 32-row C tiles that are well filled: dense accumulator in REGISTERS (the only warp-level kernel of this
+// file; CUDA only -- the emulated build always takes k_g_numeric, and the GPU tests run both on the same inputs).
+// A warp owns a C tile of 32 x 32, lane = row, 32 accumulators per lane. Per pair the B tile (TRb rows x 32 columns) is
+// expanded to a dense tile in shared memory (row stride 33 doubles: lanes reading different rows hit different banks),
+// then every lane walks the A entries (r, k) of its row and adds a * Bd[k][0..31] -- 32 LDS + 32 DFMA per A entry,
+// no search, no mask test. Absent B entries contribute a * 0 = 0 to an accumulator, which leaves it unchanged, so every
+// C entry is still the fma() chain of its products in pair order, then in the order of A's row: bit-identical to
+// k_g_numeric and the oracle. Compaction through C's row mask at the end.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int GD_WARPS = 4;
+constexpr int GD_STRIDE = 33;
+constexpr int GD_MAXTRB = 64;  // rows of a B tile this kernel takes (columns of an A tile)
+
+__global__ void __launch_bounds__(GD_WARPS * 32, 4)
+k_g_numeric_dense32(int numblkC, int TCa, const int *__restrict__ pair_ptr, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
+                    const int *__restrict__ tile_nnzA, const uint16_t *__restrict__ ptrA, const uint16_t *__restrict__ colA,
+                    const double *__restrict__ valA, const int *__restrict__ tile_nnzB, const uint16_t *__restrict__ ptrB,
+                    const uint16_t *__restrict__ colB, const double *__restrict__ valB, const int *__restrict__ tile_nnzC,
+                    const uint16_t *__restrict__ ptrC, const uint16_t *__restrict__ maskC, uint16_t *__restrict__ colC,
+                    double *__restrict__ valC)
+{
+    extern __shared__ double gd_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int TRb = TCa;
+    double *Bd = gd_smem + (size_t)warp * (TRb * GD_STRIDE + GD_MAXTRB / 2);
+    int *sp = (int *)(Bd + TRb * GD_STRIDE);  // row offsets of the B tile being expanded
+    const int r = lane;
+    // a warp walks C tiles with a stride of the grid's warps: 40 % of a block-FEM product's listed tiles are empty,
+    // one warp per tile would leave the CTAs half idle
+    for (int t = blockIdx.x * GD_WARPS + warp; t < numblkC; t += gridDim.x * GD_WARPS) {
+        const int outbase = tile_nnzC[t];
+        if (tile_nnzC[t + 1] == outbase) continue;  // empty tile
+        double acc[32];
+#pragma unroll
+        for (int c = 0; c < 32; c++) acc[c] = 0.0;
+        const int q0 = pair_ptr[t], q1 = pair_ptr[t + 1];
+        for (int q = q0; q < q1; q++) {
+            const size_t a = (size_t)pair_a[q], b = (size_t)pair_b[q];
+            // everything the pair needs from global memory is requested before anything waits:
+            // A's row range and first entry of this lane's row, B's row offsets
+            const int baseA = tile_nnzA[a], nA = tile_nnzA[a + 1] - baseA;
+            const int baseB = tile_nnzB[b], nB = tile_nnzB[b + 1] - baseB;
+            const int s = ptrA[a * 32 + r], e = r + 1 < 32 ? ptrA[a * 32 + r + 1] : nA;
+            const int pk0 = lane < TRb ? (int)ptrB[b * TRb + lane] : 0x7fffffff;
+            const int pk1 = lane + 32 < TRb ? (int)ptrB[b * TRb + lane + 32] : 0x7fffffff;
+            int kc = 0;
+            double av = 0.0;
+            if (s < e) { kc = colA[baseA + s]; av = valA[baseA + s]; }
+            for (int i = lane; i < TRb * GD_STRIDE; i += 32) Bd[i] = 0.0;
+            sp[lane] = pk0; sp[lane + 32] = pk1;
+            __syncwarp();
+            // B's entries, lane per entry (coalesced), two per lane in flight; the row of entry x = last k with sp[k] <= x
+            for (int x0 = 0; x0 < nB; x0 += 64) {
+                const int xa = x0 + lane, xb = x0 + 32 + lane;
+                int ca = 0, cb = 0;
+                double va = 0.0, vb = 0.0;
+                if (xa < nB) { ca = colB[baseB + xa]; va = valB[baseB + xa]; }
+                if (xb < nB) { cb = colB[baseB + xb]; vb = valB[baseB + xb]; }
+                if (xa < nB) {
+                    int lo = 0, hi = TRb;
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sp[mid] <= xa) lo = mid; else hi = mid; }
+                    Bd[lo * GD_STRIDE + ca] = va;
+                }
+                if (xb < nB) {
+                    int lo = 0, hi = TRb;
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sp[mid] <= xb) lo = mid; else hi = mid; }
+                    Bd[lo * GD_STRIDE + cb] = vb;
+                }
+            }
+            __syncwarp();
+            for (int x = s; x < e; x++) {
+                int kn = 0;
+                double avn = 0.0;
+                if (x + 1 < e) { kn = colA[baseA + x + 1]; avn = valA[baseA + x + 1]; }  // next entry's loads fly under this entry's FMAs
+                const double *brow = Bd + (kc - r * TCa) * GD_STRIDE;
+#pragma unroll
+                for (int c = 0; c < 32; c++) acc[c] = fma(av, brow[c], acc[c]);
+                kc = kn; av = avn;
+            }
+            __syncwarp();
+        }
+        const unsigned m0 = maskC[((size_t)t * 32 + r) * 2], m1 = maskC[((size_t)t * 32 + r) * 2 + 1];
+        int pos = outbase + (int)ptrC[(size_t)t * 32 + r];
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+            const unsigned mw = c < 16 ? m0 : m1;
+            if ((mw >> (15 - (c & 15))) & 1u) {
+                valC[pos] = acc[c];
+                colC[pos] = (uint16_t)c;
+                pos++;
+            }
+        }
+    }
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------------------------
 // tile2csr, general (reference src/tile2csr.h:72-140): thread per matrix row, count then fill
 // ------------------------------------------------------------------------------------------------------------------
@@ -781,8 +879,27 @@ int gtile_spgemm_device(const tsg_gtile *A, const tsg_gtile *B, tsg_gtile *C, ts
     meta.val = (double *)payload; meta.col = (uint16_t *)(payload + o_col);
     meta.slab[1] = payload; meta.slab_bytes[1] = o_col + nzc * 2;
     meta.nnz = nnzC;
-    GT_LAUNCH(k_g_numeric, nnzC, nnzC, numblkC, TRc, TCa, Wc, pair_ptr, pair_a, pair_b, A->tile_nnz, A->ptr, A->col, A->val, B->tile_nnz,
-              B->ptr, B->mask, B->val, meta.tile_nnz, meta.ptr, meta.mask, meta.col, meta.val);
+    bool dense32 = false;
+#ifndef GT_EMULATE
+    {   // 32 x 32 C tiles holding >= 64 entries on average: dense accumulator in registers (TSG_GT_NUMERIC=gather|dense overrides the rule)
+        const char *e = getenv("TSG_GT_NUMERIC");
+        const bool can = TRc == 32 && TCc == 32 && TCa <= 64 && numblkC > 0 && nnzC > 0;
+        dense32 = can && (e && *e ? !strcmp(e, "dense") : nnzC >= 64ll * numblkC);
+        if (dense32) {
+            const size_t smem = (size_t)GD_WARPS * (TCa * GD_STRIDE + GD_MAXTRB / 2) * sizeof(double);
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_g_numeric_dense32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int grid = (numblkC + GD_WARPS - 1) / GD_WARPS;
+            if (grid > ctx().num_sms * 16) grid = ctx().num_sms * 16;  // 4 resident CTAs per SM, four rounds: the warps stride over the tiles
+            k_g_numeric_dense32<<<grid, GD_WARPS * 32, smem, ctx().stream>>>(
+                numblkC, TCa, pair_ptr, pair_a, pair_b, A->tile_nnz, A->ptr, A->col, A->val, B->tile_nnz, B->ptr, B->col, B->val, meta.tile_nnz,
+                meta.ptr, meta.mask, meta.col, meta.val);
+            CK_LAUNCH();
+        }
+    }
+#endif
+    if (!dense32)
+        GT_LAUNCH(k_g_numeric, nnzC, nnzC, numblkC, TRc, TCa, Wc, pair_ptr, pair_a, pair_b, A->tile_nnz, A->ptr, A->col, A->val, B->tile_nnz,
+                  B->ptr, B->mask, B->val, meta.tile_nnz, meta.ptr, meta.mask, meta.col, meta.val);
     tm.mark(4);
     CK(cudaStreamSynchronize(ctx().stream));
     guard.g = nullptr;
@@ -791,6 +908,7 @@ int gtile_spgemm_device(const tsg_gtile *A, const tsg_gtile *B, tsg_gtile *C, ts
         stats->numblkC = numblkC; stats->nnzC = nnzC; stats->pairs = npairs;
         stats->ms_step1 = tm.ms(0, 2); stats->ms_step2 = tm.ms(2, 3); stats->ms_step3 = tm.ms(3, 4); stats->ms_total = tm.ms(0, 4);
         stats->launches = (int)(ctx().launches - launches0);
+        stats->tiles_dense = dense32 ? numblkC : 0;   // C tiles computed by k_g_numeric_dense32
         // algorithmic bytes, SURVEY.md 8(d), with this tile size's metadata: Ptr 2*TR, mask 2*TR*W, column index 4, tile nnz 4
         const long long mA = 2ll * A->tile_rows * (1 + A->tile_cols / 16) + 8, mB = 2ll * B->tile_rows * (1 + B->tile_cols / 16) + 8,
                         mC = 2ll * TRc * (1 + Wc) + 12;

@@ -88,6 +88,29 @@ def test_general_tiles_rectangular_product(tile):
     run_device_case(tile[0], tile[1], A, B, what="rect")
 
 
+@pytest.mark.parametrize("mode", ["gather", "dense"])
+@pytest.mark.parametrize("tn", [16, 32, 48, 64])
+@pytest.mark.parametrize("name", ["blockfem_120", "stencil27_20x7x5", "full_48", "rmat_s10", "rand_ragged_203", "single_entry"])
+def test_general_tiles_numeric_kernels_32_row_tiles(monkeypatch, name, tn, mode):
+    """C tiles of 32 x 32 have two numeric kernels: the gather (thread per C nonzero) and the dense accumulator in
+    registers (warp per C tile, lane = row; B's tile expanded in shared memory). Same C, bit for bit, from either."""
+    monkeypatch.setenv("TSG_GT_NUMERIC", mode)
+    m, n, rp, ci, _ = CASES[name]()
+    for values, exact in (("mod10", True), ("hash", False)):
+        st = run_device_case(32, tn, (m, n, rp, ci, M.set_values(len(ci), values)), exact=exact, what=f"{name}/{mode}")
+        assert (st["tiles_dense"] > 0) == (mode == "dense" and st["nnzC"] > 0), st
+
+
+def test_general_tiles_dense32_selected_for_well_filled_tiles(monkeypatch):
+    monkeypatch.delenv("TSG_GT_NUMERIC", raising=False)
+    m, n, rp, ci, _ = M.blockfem(400)
+    v = M.set_values(len(ci), "mod10")
+    assert run_device_case(32, 32, (m, n, rp, ci, v), what="blockfem auto")["tiles_dense"] > 0
+    m, n, rp, ci, _ = M.rmat(11, 4, seed=7)
+    v = M.set_values(len(ci), "mod10")
+    assert run_device_case(32, 32, (m, n, rp, ci, v), what="rmat auto")["tiles_dense"] == 0
+
+
 @pytest.mark.parametrize("name", general_tile_golden_cases())
 def test_general_tiles_vs_reference_golden(name):
     """The arrays the REFERENCE's csr2tile_row_major / csr2tile_col_major(matrix, tile_size_m, tile_size_n) produce
