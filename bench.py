@@ -581,7 +581,8 @@ def run_general_tiles(args):
         "e2e": {"value": 2.0 * nnzCub / (e2e_ms * 1e6), "unit": "GFLOP/s", "ms_per_step": e2e_ms, "steps": e2e_K,
                 "h2d_bytes_per_step": sum(int(t.numel() * t.element_size()) for t in pin), "d2h_bytes_per_step": (m + 1) * 4 + nnzC * 12},
         "gpu_launches": int(gpu_launches),
-        "roofline": {"bound": "hbm", "kernel": "numeric step: k_g_numeric (thread per C nonzero)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "numeric step: " + ("k_g_numeric_dense32 (warp per 32x32 C tile, register accumulators)" if last.get("tiles_dense", 0) > 0
+                                                 else "k_g_numeric (thread per C nonzero)"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": s3_ms,
                      "algorithmic_bytes_per_launch": int(s3_bytes)},
     }
