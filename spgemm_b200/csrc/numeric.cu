@@ -658,33 +658,67 @@ k_step3_dense(const __grid_constant__ S3Dense P)
     double acc[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[j] = 0.0;
-    const int p1 = P.pair_end[t];
-    for (int p = P.pair_ptr[t]; p < p1; p++) {
-        const int a = P.pair_a[p], b = P.pair_b[p];
-        const int abase = P.a_tile_nnz[a], bbase = P.b_tile_nnz[b];
-        // dense B tile: zero, then lanes 0..15 scatter their row
-        double2 *z = reinterpret_cast<double2 *>(Bd + r * S3D_LD + 8 * h);
-        z[0] = z[1] = z[2] = z[3] = make_double2(0.0, 0.0);
-        __syncwarp();
-        if (lane < TS) {
-            int ib = P.b_ptr[(size_t)b * TS + lane];
-            const int ib1 = lane < TS - 1 ? (int)P.b_ptr[(size_t)b * TS + lane + 1] : P.b_tile_nnz[b + 1] - bbase;
-            for (; ib < ib1; ib++) Bd[lane * S3D_LD + P.b_col[bbase + ib]] = P.b_val[bbase + ib];
-        }
-        __syncwarp();
+    // Software pipeline over the pairs (round 2, after ncu showed the 32 x 32 sibling of this kernel, gentile.cu, waiting on
+    // dependent global loads 51 % of the time): the tile ids of pair p+1 are requested at the top of pair p, what depends
+    // on them (offsets, row ranges) after B's expansion, the next A entry under the current entry's FMAs; B's entries are
+    // expanded lane per ENTRY (coalesced, two per lane in flight; the row of entry x = last k with Ptr[k] <= x, found by
+    // four shuffles over the offsets held by lanes 0..15) instead of lane per row with one dependent load chain per entry.
+    const int p0 = P.pair_ptr[t], p1 = P.pair_end[t];
+    if (p0 < p1) {
+        int a = P.pair_a[p0], b = P.pair_b[p0];
+        int abase = P.a_tile_nnz[a], bbase = P.b_tile_nnz[b], nB = P.b_tile_nnz[b + 1] - bbase;
         int ia = P.a_ptr[(size_t)a * TS + r];
-        const int ia1 = r < TS - 1 ? (int)P.a_ptr[(size_t)a * TS + r + 1] : P.a_tile_nnz[a + 1] - abase;
-        for (; ia < ia1; ia++) {
-            const int k = P.a_col[abase + ia] & 15;  // A stores row*16+col
-            const double av = P.a_val[abase + ia];
-            const double2 *br = reinterpret_cast<const double2 *>(Bd + k * S3D_LD + 8 * h);
-            const double2 b0 = br[0], b1 = br[1], b2 = br[2], b3 = br[3];
-            acc[0] = fma(av, b0.x, acc[0]); acc[1] = fma(av, b0.y, acc[1]);
-            acc[2] = fma(av, b1.x, acc[2]); acc[3] = fma(av, b1.y, acc[3]);
-            acc[4] = fma(av, b2.x, acc[4]); acc[5] = fma(av, b2.y, acc[5]);
-            acc[6] = fma(av, b3.x, acc[6]); acc[7] = fma(av, b3.y, acc[7]);
+        int ia1 = r < TS - 1 ? (int)P.a_ptr[(size_t)a * TS + r + 1] : P.a_tile_nnz[a + 1] - abase;
+        int pb = lane < TS ? (int)P.b_ptr[(size_t)b * TS + lane] : 0x7fffffff;
+        for (int p = p0; p < p1; p++) {
+            const bool more = p + 1 < p1;
+            int an = 0, bn = 0;
+            if (more) { an = P.pair_a[p + 1]; bn = P.pair_b[p + 1]; }
+            int kc = 0;
+            double av = 0.0;
+            if (ia < ia1) { kc = P.a_col[abase + ia] & 15; av = P.a_val[abase + ia]; }  // A stores row*16+col
+            double2 *z = reinterpret_cast<double2 *>(Bd + r * S3D_LD + 8 * h);
+            z[0] = z[1] = z[2] = z[3] = make_double2(0.0, 0.0);
+            __syncwarp();
+            for (int x0 = 0; x0 < nB; x0 += 64) {  // warp-uniform trip count
+                const int xa = x0 + lane, xb = x0 + 32 + lane;
+                int ca = 0, cb = 0;
+                double va = 0.0, vb = 0.0;
+                if (xa < nB) { ca = P.b_col[bbase + xa]; va = P.b_val[bbase + xa]; }
+                if (xb < nB) { cb = P.b_col[bbase + xb]; vb = P.b_val[bbase + xb]; }
+                int ka = 0, kb = 0;
+#pragma unroll
+                for (int st = 8; st; st >>= 1) {
+                    const int va_ = __shfl_sync(FULL_MASK, pb, ka + st), vb_ = __shfl_sync(FULL_MASK, pb, kb + st);
+                    if (va_ <= xa) ka += st;
+                    if (vb_ <= xb) kb += st;
+                }
+                if (xa < nB) Bd[ka * S3D_LD + ca] = va;
+                if (xb < nB) Bd[kb * S3D_LD + cb] = vb;
+            }
+            __syncwarp();
+            int abase_n = 0, bbase_n = 0, nB_n = 0, ia_n = 0, ia1_n = 0, pb_n = 0x7fffffff;
+            if (more) {
+                abase_n = P.a_tile_nnz[an]; bbase_n = P.b_tile_nnz[bn]; nB_n = P.b_tile_nnz[bn + 1] - bbase_n;
+                ia_n = P.a_ptr[(size_t)an * TS + r];
+                ia1_n = r < TS - 1 ? (int)P.a_ptr[(size_t)an * TS + r + 1] : P.a_tile_nnz[an + 1] - abase_n;
+                if (lane < TS) pb_n = (int)P.b_ptr[(size_t)bn * TS + lane];
+            }
+            for (; ia < ia1; ia++) {
+                int kn = 0;
+                double avn = 0.0;
+                if (ia + 1 < ia1) { kn = P.a_col[abase + ia + 1] & 15; avn = P.a_val[abase + ia + 1]; }
+                const double2 *br = reinterpret_cast<const double2 *>(Bd + kc * S3D_LD + 8 * h);
+                const double2 b0 = br[0], b1 = br[1], b2 = br[2], b3 = br[3];
+                acc[0] = fma(av, b0.x, acc[0]); acc[1] = fma(av, b0.y, acc[1]);
+                acc[2] = fma(av, b1.x, acc[2]); acc[3] = fma(av, b1.y, acc[3]);
+                acc[4] = fma(av, b2.x, acc[4]); acc[5] = fma(av, b2.y, acc[5]);
+                acc[6] = fma(av, b3.x, acc[6]); acc[7] = fma(av, b3.y, acc[7]);
+                kc = kn; av = avn;
+            }
+            __syncwarp();  // Bd is rewritten for the next pair
+            abase = abase_n; bbase = bbase_n; nB = nB_n; ia = ia_n; ia1 = ia1_n; pb = pb_n;
         }
-        __syncwarp();  // Bd is rewritten for the next pair
     }
     const unsigned cm = P.c_mask[(size_t)t * TS + r];
     const int rowbase = cbase + P.c_ptr[(size_t)t * TS + r];
