@@ -225,6 +225,7 @@ k_recipe_verify(int numblkC, const int *__restrict__ pair_ptr, const int *__rest
 // nonzero's in the serial SPA's order, ITERATION-MAJOR over slots: product i of the nonzero that starts at iteration
 // `start` of slot v lives at plan_off[R] + (start + i) * nslots + v, so the lanes of the numeric kernel -- consecutive
 // slots of a tile, all at the same iteration -- read consecutive words.
+constexpr int PB_SPLIT = 4;
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, const int *__restrict__ pair_ptr,
@@ -234,7 +235,11 @@ k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, c
              const int *__restrict__ plan_off, uint16_t *plan_cnt, uint8_t *plan_col, const unsigned *__restrict__ plan_jslot,
              const int *__restrict__ plan_nslots, unsigned *plan_ent, int *fail)
 {
-    const int R = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, r = threadIdx.x & 15;
+    // PB_SPLIT half-warps per recipe: each computes the row masks and offsets (cheap), then walks every PB_SPLIT-th C nonzero of
+    // its rows -- the chain of dependent loads per thread is what this kernel's time is made of (42 recipes on config 2: 21
+    // warps in all, 43 + 60 us for the two passes before the split, a quarter of the non-numeric time of a 64^3-sized slab)
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int R = gt / (16 * PB_SPLIT), r = threadIdx.x & 15, sub = (gt >> 4) % PB_SPLIT;
     const unsigned hm = 0xFFFFu << (threadIdx.x & 16);
     const int nrec = *nrec_p;
     if (*(volatile int *)fail) return;
@@ -262,7 +267,7 @@ k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, c
         if (r >= o) incl += v;
     }
     const int rowbase = incl - n, nnz = __shfl_sync(hm, incl, 15, 16);
-    if (!FILL) {
+    if (!FILL && sub == 0) {
         plan_ptr[R * TS + r] = (uint16_t)rowbase;
         plan_mask[R * TS + r] = (uint16_t)cm;
         if (r == 0) plan_nnz[R] = nnz;
@@ -274,6 +279,7 @@ k_plan_build(const int *__restrict__ nrec_p, const int *__restrict__ rep_tile, c
         const int c = __clz(rowm) - 16;
         rowm ^= 0x8000u >> c;
         const unsigned cbit = 0x8000u >> c;
+        if ((j - rowbase) % PB_SPLIT != sub) { j++; continue; }  // another half-warp's nonzero
         const unsigned js = FILL ? plan_jslot[(size_t)R * 256 + j] : 0u;  // slot | first iteration << 8
         unsigned i = js >> 8;
         const unsigned i0 = i, ilast = FILL ? i0 + plan_cnt[(size_t)R * 256 + j] - 1u : 0u;
@@ -587,7 +593,7 @@ int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, 
         if (rc) return rc;
     }
     const int *nrec = p.rdense + RCAP;
-    k_plan_build<false><<<ceil_div(RMAX * 16, 128), 128, 0, c.stream>>>(nrec, p.rep_tile, pl.ptr, pl.end, pl.a, pl.b, A->mask, A->ptr, B->mask,
+    k_plan_build<false><<<ceil_div(RMAX * 16 * PB_SPLIT, 128), 128, 0, c.stream>>>(nrec, p.rep_tile, pl.ptr, pl.end, pl.a, pl.b, A->mask, A->ptr, B->mask,
                                                                         B->ptr, p.plan_mask, p.plan_ptr, p.plan_nnz, nullptr, p.plan_cnt,
                                                                         p.plan_col, nullptr, nullptr, nullptr, fail);
     CK_LAUNCH();
@@ -598,7 +604,7 @@ int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, 
     CK_LAUNCH();
     rc = exclusive_scan<int>(p.plan_tot, p.plan_off, RMAX);
     if (rc) return rc;
-    k_plan_build<true><<<ceil_div(RMAX * 16, 128), 128, 0, c.stream>>>(nrec, p.rep_tile, pl.ptr, pl.end, pl.a, pl.b, A->mask, A->ptr, B->mask,
+    k_plan_build<true><<<ceil_div(RMAX * 16 * PB_SPLIT, 128), 128, 0, c.stream>>>(nrec, p.rep_tile, pl.ptr, pl.end, pl.a, pl.b, A->mask, A->ptr, B->mask,
                                                                        B->ptr, p.plan_mask, p.plan_ptr, p.plan_nnz, p.plan_off, p.plan_cnt,
                                                                        p.plan_col, p.plan_jslot, p.plan_nslots, p.plan_ent, fail);
     CK_LAUNCH();
