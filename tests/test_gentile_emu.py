@@ -189,3 +189,18 @@ def test_general_tiles_emulated_errors(emu):
     h = Host(m, n, rp, bad, v)
     assert emu.emu_csr2tile(C.byref(h.s), 32, 32, 0) == 4      # unsorted row: TSG_ERR_INPUT (the drop-in canonicalises and retries)
     emu.emu_clear_error()
+
+
+def test_general_tiles_emulated_under_address_sanitizer(tmp_path):
+    """The same cases with the emulated build compiled -fsanitize=address: out-of-bounds loads as well as stores, in the
+    kernels and in the host orchestration, abort the run (compute-sanitizer is not available on the GPU pool)."""
+    import sys
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not asan or not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan.so not installed")
+    so = str(tmp_path / "libgentile_emu_asan.so")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-w", "-mfma", "-fsanitize=address", "-fno-omit-frame-pointer",
+                           "-I", EMU_DIR, "-x", "c++", os.path.join(EMU_DIR, "gentile_emu.cpp"), "-o", so])
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+    out = subprocess.run([sys.executable, os.path.join(EMU_DIR, "run_asan.py"), so], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0 and "asan cases ok: 83" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
