@@ -62,7 +62,9 @@ int plans_begin(PlanTable *out);
 int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const unsigned *pair_pat, const int *rslot, int *recipe_id,
                           const RowTemplates *rt, const int **d_fail);
 int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const int *recipe_id,
-                         int trow0, int ntr, const int *wptr, int max_need, tsg_stats *stats);
+                         int trow0, int ntr, const int *wptr, int max_need, tsg_stats *stats, const RowTemplates *rt, const int *tau,
+                         int max_nnzA_row, int wmax);
+int plans_rowplan_build(const tsg_dtile *C, const RowTemplates &rt, const int *recipe_id, const int *pair_ptr, int **d_tau, const int **d_fail);
 size_t plans_rows_need_bound(int max_nnzA_row, int maxJ, int wmax);
 const int *plans_recipe_count_ptr();
 void plans_shutdown();

@@ -61,6 +61,11 @@ k_pattern_verify(int numtile, const uint16_t *__restrict__ mask, const int *__re
     if (!(a.x == x.x && a.y == x.y && a.z == x.z && a.w == x.w && b.x == y.x && b.y == y.y && b.z == y.z && b.w == y.w)) *fail = 2;
 }
 
+constexpr int RP_TMAX = 256;             // tile-row templates that get a row plan (more: the per-recipe plans are walked)
+constexpr int RP_SCAP = 2048;            // slots of one tile-row
+constexpr int RP_GCAP = RP_SCAP / 32;    // groups of 32 slots = one warp's share
+constexpr int RP_WCAP = 1 << 15;         // plan words of one tile-row template
+
 struct PlanCtx {
     // pattern table scratch (reused by every csr2tile)
     unsigned long long *pkeys = nullptr;
@@ -77,7 +82,14 @@ struct PlanCtx {
     unsigned *plan_jslot = nullptr;  // per recipe, 256 nonzeros: slot | first iteration << 8
     uint16_t *plan_chain = nullptr;  // per recipe, 256 chain entries: position in the tile | column << 8
     int *plan_nslots = nullptr;
-    int *ctl = nullptr;  // [0] pattern count, [1] pattern fail, [2] recipe count, [3] recipe / plan fail
+    int *ctl = nullptr;  // [0] pattern count, [1] pattern fail, [2] recipe count, [3] recipe / plan fail, [4] row plan fail
+    // row plans (k_numeric_from_rowplans): per tile-row template, the slots of the whole tile-row and their plan words laid out
+    // warp by warp
+    int4 *rp_rec = nullptr;      // [RP_TMAX][RP_SCAP] per slot: products, first chain entry, C nnz offset of its tile in the row, pair offset
+    int2 *rp_src = nullptr;      // [RP_TMAX][RP_SCAP] per slot: first plan word, stride (the recipe's slot count)
+    unsigned *rp_words = nullptr;  // [RP_TMAX][RP_WCAP] plan words, group (32 slots) after group, iteration-major inside a group
+    int *rp_goff = nullptr;      // [RP_TMAX][RP_GCAP + 1] first word of every group
+    int *rp_nslots = nullptr;    // [RP_TMAX]
     int device = -1;
 };
 static PlanCtx g_plan;
@@ -614,12 +626,245 @@ int plans_symbolic_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, 
     return TSG_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row plans. With tile-row templates (rowplans.cu) the sequence of recipes along a tile-row is the template's, so the
+// slots of the whole tile-row -- and the plan words they walk -- can be laid out once per template in the order the
+// numeric kernel's warps take them: group g = slots 32g .. 32g+31, its words iteration-major (word of slot 32g+l at
+// iteration it: goff[g] + 32 it + l). A warp then reads ONE 128-byte line per iteration instead of one piece per tile it
+// spans (measured on config 2: 3.4 lines), and a slot's constants come from one 16-byte record instead of a binary
+// search over the tile-row's tiles and four table lookups.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_rowplan_slots(int ntpl, const int *__restrict__ rep_list, const int *__restrict__ c_tile_ptr, const int *__restrict__ c_tile_nnz,
+                const int *__restrict__ wptr, const int *__restrict__ pair_ptr, const int *__restrict__ recipe_id,
+                const int *__restrict__ plan_nslots, const int *__restrict__ plan_off, const unsigned *__restrict__ plan_slot,
+                int4 *__restrict__ rec, int2 *__restrict__ src, int *__restrict__ nslots, int *__restrict__ tau, int *fail)
+{
+    const int tpl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (tpl >= ntpl) return;  // whole warps
+    const int i = rep_list[tpl];
+    if (lane == 0) tau[i] = tpl;
+    const int c0 = c_tile_ptr[i], numJ = c_tile_ptr[i + 1] - c0;
+    const int n0 = c_tile_nnz[c0], w0 = wptr[i];
+    int carry = 0;
+    for (int k0 = 0; k0 < numJ; k0 += 32) {
+        const int k = k0 + lane;
+        const int R = k < numJ ? recipe_id[c0 + k] : -1;
+        const int nsl = R >= 0 ? plan_nslots[R] : 0;
+        int incl = nsl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += u;
+        }
+        const int s0 = carry + incl - nsl;
+        carry += __shfl_sync(FULL_MASK, incl, 31);
+        if (R >= 0 && s0 + nsl <= RP_SCAP) {
+            const int outoff = c_tile_nnz[c0 + k] - n0, pp = pair_ptr[c0 + k] - w0, po = plan_off[R];
+            for (int v = 0; v < nsl; v++) {
+                const unsigned si = plan_slot[R * 128 + v];
+                rec[(size_t)tpl * RP_SCAP + s0 + v] = make_int4((int)(si & 0xFFFFu), R * 256 + (int)(si >> 16), outoff, pp);
+                src[(size_t)tpl * RP_SCAP + s0 + v] = make_int2(po + v, nsl);
+            }
+        }
+    }
+    if (lane == 0) {
+        nslots[tpl] = carry;
+        if (carry > RP_SCAP) *fail = 1;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_rowplan_groups(int ntpl, const int4 *__restrict__ rec, const int *__restrict__ nslots, int *__restrict__ goff, int *fail)
+{
+    const int tpl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (tpl >= ntpl) return;
+    const int S = nslots[tpl];
+    if (S > RP_SCAP) return;
+    const int G = (S + 31) >> 5;
+    int carry = 0;
+    for (int g0 = 0; g0 < G; g0 += 32) {
+        const int g = g0 + lane;
+        int len = 0;
+        if (g < G)
+            for (int j = 0; j < 32; j++) {
+                const int q = g * 32 + j;
+                if (q < S) len = max(len, rec[(size_t)tpl * RP_SCAP + q].x);
+            }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (g < G) goff[tpl * (RP_GCAP + 1) + g] = 32 * (carry + incl - len);
+        carry += __shfl_sync(FULL_MASK, incl, 31);
+    }
+    if (lane == 0) {
+        goff[tpl * (RP_GCAP + 1) + G] = 32 * carry;
+        if (32 * carry > RP_WCAP) *fail = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_rowplan_words(const int4 *__restrict__ rec, const int2 *__restrict__ src, const int *__restrict__ nslots, const int *__restrict__ goff,
+                const unsigned *__restrict__ plan_ent, unsigned *__restrict__ words, const int *__restrict__ fail)
+{
+    if (*fail) return;
+    const int tpl = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int S = nslots[tpl], G = (S + 31) >> 5, g = q >> 5;
+    if (g >= G) return;
+    const int o0 = goff[tpl * (RP_GCAP + 1) + g], glen = (goff[tpl * (RP_GCAP + 1) + g + 1] - o0) >> 5;
+    int n = 0, base = 0, stride = 0;
+    if (q < S) {
+        n = rec[(size_t)tpl * RP_SCAP + q].x;
+        const int2 sr = src[(size_t)tpl * RP_SCAP + q];
+        base = sr.x; stride = sr.y;
+    }
+    unsigned *dst = words + (size_t)tpl * RP_WCAP + o0 + (q & 31);
+    for (int it = 0; it < glen; it++) dst[it * 32] = it < n ? plan_ent[base + it * stride] : 0u;
+}
+
+struct RowPlanRows {
+    int trow0;
+    const int *a_tile_ptr, *a_tile_nnz;
+    const double *a_val;
+    const int *b_tile_nnz;
+    const double *b_val;
+    const int *c_tile_ptr, *c_tile_nnz, *wptr, *pair_a, *pair_b, *rep_of, *tau;
+    const int4 *rec;
+    const unsigned *words;
+    const int *goff, *nslots;
+    const uint16_t *plan_chain;
+    uint16_t *c_col;
+    double *c_val;
+};
+
+__host__ __device__ __forceinline__ size_t rowplan_rows_need(int nnzA, int W)
+{
+    return (((size_t)nnzA * 8 + 15) & ~(size_t)15) + (((size_t)W * 8 + 15) & ~(size_t)15);
+}
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_numeric_from_rowplans(const __grid_constant__ RowPlanRows P)
+{
+    extern __shared__ __align__(16) unsigned char rr_smem[];
+    const int i = blockIdx.x, tid = threadIdx.x, I = P.trow0 + i;
+    const int rep = P.rep_of[i];
+    if (rep < 0) return;  // a tile-row without pairs
+    const int tpl = P.tau[rep];
+    const int c0 = P.c_tile_ptr[i], numJ = P.c_tile_ptr[i + 1] - c0;
+    if (numJ == 0) return;
+    const int n0 = P.c_tile_nnz[c0];
+    if (P.c_tile_nnz[c0 + numJ] == n0) return;
+    const int a0 = P.a_tile_ptr[I], a1 = P.a_tile_ptr[I + 1];
+    const int av0 = P.a_tile_nnz[a0], nnzA = P.a_tile_nnz[a1] - av0;
+    const int w0 = P.wptr[i], W = P.wptr[i + 1] - w0;
+    double *s_aval = (double *)rr_smem;
+    int2 *s_base = (int2 *)(rr_smem + (((size_t)nnzA * 8 + 15) & ~(size_t)15));
+    for (int k = tid; k < nnzA; k += THREADS) s_aval[k] = P.a_val[av0 + k];
+    for (int k = tid; k < W; k += THREADS) s_base[k] = make_int2(P.a_tile_nnz[P.pair_a[w0 + k]] - av0, P.b_tile_nnz[P.pair_b[w0 + k]]);
+    __syncthreads();
+    const int S = P.nslots[tpl];
+    const int4 *rec = P.rec + (size_t)tpl * RP_SCAP;
+    const unsigned *words = P.words + (size_t)tpl * RP_WCAP;
+    const int *goff = P.goff + tpl * (RP_GCAP + 1);
+    for (int q = tid; q < S; q += THREADS) {
+        const int4 rc = __ldg(rec + q);
+        const int n = rc.x, out = n0 + rc.z, pp = rc.w;
+        int ch = rc.y;
+        const unsigned *wp = words + __ldg(goff + (q >> 5)) + (q & 31);
+        unsigned oc = __ldg(P.plan_chain + ch);  // position of the chain's current nonzero in the tile | its column << 8
+        double acc = 0.0;
+        for (int it = 0; it < n; it += 4, wp += 128) {  // four products at a time: all their loads first, then the sums in order
+            unsigned e[4];
+            double av[4], bv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) e[u] = it + u < n ? __ldg(wp + u * 32) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int2 base = s_base[pp + (int)((e[u] >> 16) & 0x7FFFu)];
+                av[u] = s_aval[base.x + (int)(e[u] & 255u)];
+                bv[u] = it + u < n ? __ldg(P.b_val + (base.y + (int)((e[u] >> 8) & 255u))) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (it + u < n) acc = fma(av[u], bv[u], acc);
+                if (e[u] >> 31) {  // the nonzero's last product
+                    const int o = out + (int)(oc & 255u);
+                    P.c_val[o] = acc;
+                    P.c_col[o] = (uint16_t)(oc >> 8);
+                    acc = 0.0;
+                    if (it + u + 1 < n) oc = __ldg(P.plan_chain + ++ch);
+                }
+            }
+        }
+    }
+}
+
+static bool rowplan_numeric_env_on()
+{
+    const char *e = getenv("TSG_ROWPLAN_NUMERIC");
+    return !(e && *e == '0');
+}
+
+// Builds the row plans of the slab's templates (after the scan of C's tile nnz); *d_fail = the device flag that says
+// "caps exceeded: walk the per-recipe plans". Returns with *d_fail = nullptr when row plans are not attempted.
+int plans_rowplan_build(const tsg_dtile *C, const RowTemplates &rt, const int *recipe_id, const int *pair_ptr, int **d_tau, const int **d_fail)
+{
+    Ctx &c = ctx();
+    PlanCtx &p = g_plan;
+    *d_fail = nullptr;
+    *d_tau = nullptr;
+    if (!rowplan_numeric_env_on() || rt.n <= 0 || rt.n > RP_TMAX) return TSG_OK;
+    if (!p.rp_rec) {
+        p.rp_rec = dalloc_n<int4>((size_t)RP_TMAX * RP_SCAP);
+        p.rp_src = dalloc_n<int2>((size_t)RP_TMAX * RP_SCAP);
+        p.rp_words = dalloc_n<unsigned>((size_t)RP_TMAX * RP_WCAP);
+        p.rp_goff = dalloc_n<int>((size_t)RP_TMAX * (RP_GCAP + 1));
+        p.rp_nslots = dalloc_n<int>(RP_TMAX);
+        if (!p.rp_rec || !p.rp_src || !p.rp_words || !p.rp_goff || !p.rp_nslots) { p.rp_rec = nullptr; return last_error(); }
+    }
+    int *tau = dalloc_n<int>((size_t)rt.ntr + 1);
+    if (!tau) return last_error();
+    int *fail = p.ctl + 4;
+    CK(cudaMemsetAsync(fail, 0, sizeof(int), c.stream));
+    k_rowplan_slots<<<ceil_div(rt.n * 32, 128), 128, 0, c.stream>>>(rt.n, rt.rep_list, C->tile_ptr, C->tile_nnz, rt.wptr, pair_ptr, recipe_id,
+                                                                    p.plan_nslots, p.plan_off, p.plan_slot, p.rp_rec, p.rp_src, p.rp_nslots, tau, fail);
+    CK_LAUNCH();
+    k_rowplan_groups<<<ceil_div(rt.n * 32, 128), 128, 0, c.stream>>>(rt.n, p.rp_rec, p.rp_nslots, p.rp_goff, fail);
+    CK_LAUNCH();
+    k_rowplan_words<<<dim3(RP_SCAP / 256, rt.n), 256, 0, c.stream>>>(p.rp_rec, p.rp_src, p.rp_nslots, p.rp_goff, p.plan_ent, p.rp_words, fail);
+    CK_LAUNCH();
+    *d_fail = fail;
+    *d_tau = tau;
+    return TSG_OK;
+}
+
 int plans_numeric_device(const tsg_dtile *A, const tsg_dtile *B, tsg_dtile *C, const PairLists &pl, const int *recipe_id, int trow0, int ntr,
-                         const int *wptr, int max_need, tsg_stats *stats)
+                         const int *wptr, int max_need, tsg_stats *stats, const RowTemplates *rt, const int *tau, int max_nnzA_row, int wmax)
 {
     Ctx &c = ctx();
     PlanCtx &p = g_plan;
     if (C->nnz <= 0 || C->numtile <= 0) return TSG_OK;
+    if (rt && tau) {  // row plans: every tile-row walks its template's slots, laid out warp by warp (see k_rowplan_slots)
+        size_t smem = rowplan_rows_need(max_nnzA_row, wmax);
+        smem = (smem + 1023) & ~(size_t)1023;
+        if (smem <= (size_t)64 * 1024) {
+            RowPlanRows P{trow0, A->tile_ptr, A->tile_nnz, A->val, B->tile_nnz, B->val, C->tile_ptr, C->tile_nnz, wptr, pl.a, pl.b, rt->rep_of, tau,
+                          p.rp_rec, p.rp_words, p.rp_goff, p.rp_nslots, p.plan_chain, C->col, C->val};
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_numeric_from_rowplans<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const char *cv = getenv("TSG_PLANS_CARVEOUT");
+            int pct = cv && *cv ? atoi(cv) : (int)((6 * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+            if (pct > 100) pct = 100;
+            if (pct >= 0) CK(cudaFuncSetAttribute(k_numeric_from_rowplans<256, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            k_numeric_from_rowplans<256, 6><<<ntr, 256, smem, c.stream>>>(P);
+            CK_LAUNCH();
+            if (stats) stats->plan_recipes = 1;
+            return TSG_OK;
+        }
+    }
     const char *kb = getenv("TSG_PLANS_SMEM_KB");  // tests: a small budget sends tile-rows down the unstaged branch
     const size_t cap = kb && *kb ? (size_t)atoi(kb) * 1024 : (size_t)64 * 1024;
     size_t smem = (size_t)max_need < cap ? (size_t)max_need : cap;

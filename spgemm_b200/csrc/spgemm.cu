@@ -1064,7 +1064,16 @@ static int spgemm_device_impl(const tsg_dtile *A, const tsg_dtile *B, int trow0,
     int *d_ns = (int *)(c.d_scalars + 16);
     long long nnzC = 0;
     int plan_recipes = 0;
+    int *d_tau = nullptr;              // row plans (plans.cu): template index of every representative tile-row
+    const int *d_rowplan_fail = nullptr;
+    struct TauGuard { int *&p; ~TauGuard() { if (p) dfree(p); } } tau_guard{d_tau};
     if (plans_on) {
+        if (rowplans) {  // the slots of every template's tile-row laid out warp by warp for the numeric kernel
+            rc = plans_rowplan_build(C, rt, recipe_id, pair_ptr, &d_tau, &d_rowplan_fail);
+            if (rc) return rc;
+            if (d_rowplan_fail) rc = publish_words(&c.h_scalars[28], d_rowplan_fail, 1);
+            if (rc) return rc;
+        }
         rc = publish_words(&c.h_scalars[20], d_plan_fail, 1);
         if (!rc) rc = publish_words(&c.h_scalars[21], plans_recipe_count_ptr(), 1);
         if (!rc && rowplans) rc = publish_words(&c.h_scalars[25], rowplans_fail_ptr(), 1);
@@ -1118,7 +1127,9 @@ static int spgemm_device_impl(const tsg_dtile *A, const tsg_dtile *B, int trow0,
     if (plans_on) {
         // the largest tile-row: A values, C tiles and pairs as k_s1_count saw them (every tile-row is light on this path)
         const size_t need = plans_rows_need_bound(hs[SC_MAXNNZA], hs[SC_MAXJ], hs[SC_WMAX]);
-        rc = plans_numeric_device(A, B, C, plists, recipe_id, trow0, ntr, wptr, need > (1u << 30) ? (1 << 30) : (int)need, &nst);
+        const bool rowplan_ok = d_tau && d_rowplan_fail && *(const volatile int *)&c.h_scalars[28] == 0;
+        rc = plans_numeric_device(A, B, C, plists, recipe_id, trow0, ntr, wptr, need > (1u << 30) ? (1 << 30) : (int)need, &nst,
+                                  rowplan_ok ? &rt : nullptr, rowplan_ok ? d_tau : nullptr, hs[SC_MAXNNZA], hs[SC_WMAX]);
     }
     else rc = numeric_device(A, B, C, trow0, ntr, wptr, plists, nbufs, h_ns, heavy_rows, &nst);
     if (rc) return rc;
