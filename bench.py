@@ -133,6 +133,8 @@ def numeric_kernels(st):
     """Names of the numeric (step 3) kernels this workload actually launched (tsg_stats)."""
     names = []
     if st.get("plan_recipes", 0) > 0:
+        if st.get("row_templates", 0) > 0 and os.environ.get("TSG_ROWPLAN_NUMERIC", "1") != "0" and st["row_templates"] <= 256:
+            return f"k_numeric_from_rowplans ({st['plan_recipes']} recipes, {st['row_templates']} tile-row templates)"
         return f"k_numeric_from_plans_rows ({st['plan_recipes']} recipes)"
     if st.get("rows_staged", 0) > 0:
         names.append(f"k_step3_rows ({st['rows_staged']} tile-rows, {st['rows_smem']} B smem)")
