@@ -7,6 +7,8 @@ exchange step and no collective on the compute path. The reference has nothing h
     totals, per_slab = multigpu.spgemm(shard, sink=...)               # local: this rank's C tile-rows
     offsets = multigpu.concat(shard, totals)                          # 64-bit offsets of this rank's C inside the whole C
     csr = multigpu.gather_csr(shard, local_csr)                       # optional: whole CSR(C) on rank 0
+or, in one call (SURVEY.md 8b's additive `tilespgemm_multi`):
+    res = multigpu.run(A_host_on_rank0, aat, dist, device, gather=True)
 
 distribute():
   * B is broadcast ONCE over NCCL -- as the CSR it is built from (mode "csr", default: for C = A^2 that CSR is A itself
@@ -336,3 +338,54 @@ def gather_csr(shard: Shard, local_csr, dist=None, device=None):
         cols.append(ci.cpu().numpy()[:nnz])
         vals.append(v.cpu().numpy()[:nnz])
     return rowptr, np.concatenate(cols), np.concatenate(vals)
+
+
+def stitch_slab_csr(pieces):
+    """One CSR out of the CSRs of consecutive row slabs (each (rowptr, colidx, val) with rowptr[0] == 0), row pointers
+    rebased in 64 bits. Pure numpy (covered on CPU)."""
+    if not pieces:
+        return np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.float64)
+    offs = np.cumsum([0] + [int(len(p[1])) for p in pieces[:-1]], dtype=np.int64)
+    rp = np.concatenate([np.zeros(1, np.int64)] + [np.asarray(p[0][1:], np.int64) + o for p, o in zip(pieces, offs)])
+    return rp, np.concatenate([p[1] for p in pieces]), np.concatenate([p[2] for p in pieces])
+
+
+def run(A_host, aat: bool, dist=None, device=None, mode: str = "csr", slab_pairs: int | None = None, gather: bool = False) -> dict:
+    """Collective: the whole multi-GPU product in one call -- SURVEY.md 8(b)'s additive `tilespgemm_multi` (the
+    reference picks one device, src/main.cu:41-49). A_host = (m, n, rowptr, colidx, val) on rank 0; C = A^2 or, with
+    aat, A A^T. Every rank computes its tile-rows of C (distribute -> steps 1-3 -> tile2csr, slab by slab when
+    `slab_pairs` bounds the tile pairs of a slab) and keeps them as host CSR: the returned dict holds
+      "local_csr": (rowptr int64, colidx, val) of this rank's rows, "row0"/"row1": which rows of C they are,
+      "offsets": concat()'s 64-bit offsets of this rank inside the whole C and the global totals,
+      "csr": the whole CSR(C) on rank 0 when `gather` (None elsewhere and otherwise), "nnzCub", "cuts", "imbalance".
+    C larger than 2^31-1 nonzeros per rank cannot be gathered into one int32-indexed device CSR: leave `gather` off."""
+    from . import api
+    sh = distribute(A_host, aat, dist, device, mode=mode)
+    try:
+        pieces = []
+
+        def sink(tC, st):
+            csr = api.tile2csr_device(tC)
+            pieces.append(csr.download())
+            csr.free()
+
+        totals, _ = spgemm(sh, slab_pairs, sink)
+        rp, ci, v = stitch_slab_csr(pieces)
+        row0, row1 = min(sh.trow0 * 16, sh.m), min(sh.trow1 * 16, sh.m)
+        if len(rp) != row1 - row0 + 1 or int(rp[-1]) != int(totals["nnzC"]):
+            raise RuntimeError(f"multigpu.run: rank {sh.rank} assembled {len(rp) - 1} rows / {int(rp[-1])} nonzeros, "
+                               f"expected {row1 - row0} / {int(totals['nnzC'])}")
+        offsets = concat(sh, totals, dist, device if device is not None else "cuda")
+        whole = None
+        if gather:
+            if int(rp[-1]) >= 2 ** 31:
+                raise OverflowError("multigpu.run(gather=True): this rank's part of C passes 2^31-1 nonzeros")
+            local = api.DeviceCSR.upload(row1 - row0, sh.nB, rp.astype(np.int32), ci, v)
+            try:
+                whole = gather_csr(sh, local, dist, device)
+            finally:
+                local.free()
+        return {"local_csr": (rp, ci, v), "row0": row0, "row1": row1, "offsets": offsets, "csr": whole, "nnzCub": sh.nnzCub,
+                "cuts": sh.cuts.copy(), "imbalance": sh.imbalance, "bcast_ms": sh.bcast_ms, "bcast_bytes": sh.bcast_bytes}
+    finally:
+        sh.free()

@@ -66,6 +66,20 @@ def main():
                   f"B broadcast {sh.bcast_bytes} B in {sh.bcast_ms:.3f} ms ({mode})", flush=True)
         sh.free()
         dist.barrier()
+    # the one-call form (multigpu.run = SURVEY 8b's tilespgemm_multi): A A^T in slabs, whole CSR(C) gathered on rank 0
+    A_host = M.stencil27(14, 9, 11) if rank == 0 else None
+    res = mg.run(A_host, True, dist, dev, slab_pairs=60000, gather=True)
+    assert res["offsets"]["row_offset"] == res["row0"] and len(res["local_csr"][0]) == res["row1"] - res["row0"] + 1
+    if rank == 0:
+        m, n, arp, aci, av = A_host
+        B = orc.transpose(m, n, arp, aci, av)
+        er, ec, ev = orc.spgemm_spa((arp, aci, av), B, m)
+        assert np.array_equal(res["csr"][0], er) and np.array_equal(res["csr"][1], ec) and np.array_equal(res["csr"][2], ev), "run()"
+        assert res["offsets"]["nnzC"] == er[-1] and res["nnzCub"] == orc.nnzcub(aci, B[0])
+        print(f"ok: multigpu.run AA^T: {world} ranks, nnzC {er[-1]}", flush=True)
+    else:
+        assert res["csr"] is None
+    dist.barrier()
     if rank == 0:
         print("MGPU_OK", flush=True)
     dist.destroy_process_group()

@@ -129,3 +129,67 @@ def test_c_slab_planner_of_the_overlapped_copy_out():
     assert len(cuts) - 1 >= 3
     assert api.plan_to_host_slabs(np.zeros(5, np.int64), 0) == [0, 5]
     assert api.plan_to_host_slabs(np.zeros(0, np.int64), 0) == []
+
+
+def test_stitch_slab_csr():
+    m, n, rp, ci, v = M.stencil27(6)
+    cuts = [0, 16, 16, 100, m]
+    pieces = [mg.csr_row_slice(rp, ci, v, a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+    srp, sci, sv = mg.stitch_slab_csr(pieces)
+    assert srp.dtype == np.int64 and np.array_equal(srp, rp) and np.array_equal(sci, ci) and np.array_equal(sv, v)
+    e = mg.stitch_slab_csr([])
+    assert e[0].tolist() == [0] and len(e[1]) == 0 and len(e[2]) == 0
+
+
+def test_run_composes_the_path(monkeypatch):
+    """multigpu.run() on one rank without a GPU: distribute / steps 1-3 / tile2csr are stood in for by the oracle, so
+    what is checked is run()'s own logic (slab stitching, row range, totals check, offsets, clean-up)."""
+    from spgemm_b200 import api
+    m, n, rp, ci, v = M.stencil27(7, 5, 6)
+    A = (rp, ci, v)
+    whole = orc.spgemm_spa(A, A, n)
+    tilem = (m + 15) // 16
+    freed = []
+
+    class FakeShard:
+        rank, world, nB, nnzCub = 0, 1, n, int(orc.nnzcub(ci, rp))
+        cuts, imbalance, bcast_ms, bcast_bytes = np.array([0, tilem]), 1.0, 0.0, 0
+        trow0, trow1 = 0, tilem
+
+        def free(self):
+            freed.append(True)
+
+    FakeShard.m = m
+
+    class FakeCsr:
+        def __init__(self, piece):
+            self.piece = piece
+
+        def download(self):
+            return self.piece
+
+        def free(self):
+            pass
+
+    slabs = [(0, 5), (5, 6), (6, tilem)]
+
+    def fake_spgemm(sh, slab_pairs, sink, weights=None):
+        for t0, t1 in slabs:
+            r0, r1 = t0 * 16, min(t1 * 16, m)
+            sink(mg.csr_row_slice(*whole, r0, r1), {})
+        return {"numblkC": 123, "nnzC": int(whole[0][-1])}, []
+
+    monkeypatch.setattr(mg, "distribute", lambda *a, **k: FakeShard())
+    monkeypatch.setattr(mg, "spgemm", fake_spgemm)
+    monkeypatch.setattr(api, "tile2csr_device", lambda piece: FakeCsr(piece))
+    res = mg.run((m, n, rp, ci, v), False, None, "cpu", slab_pairs=1000)
+    assert freed == [True]
+    assert res["row0"] == 0 and res["row1"] == m and res["csr"] is None
+    assert np.array_equal(res["local_csr"][0], whole[0]) and np.array_equal(res["local_csr"][1], whole[1])
+    assert np.array_equal(res["local_csr"][2], whole[2])
+    assert res["offsets"]["nnzC"] == whole[0][-1] and res["offsets"]["nnz_offset"] == 0 and res["offsets"]["row_offset"] == 0
+    # a rank whose slabs do not add up to its totals must fail loudly, and still free its shard
+    monkeypatch.setattr(mg, "spgemm", lambda sh, sp, sink, weights=None: ({"numblkC": 1, "nnzC": 5}, []))
+    with pytest.raises(RuntimeError):
+        mg.run((m, n, rp, ci, v), False, None, "cpu")
+    assert freed == [True, True]
