@@ -244,8 +244,8 @@ void tsg_tile_free(tsg_dtile *t);
 int tsg_tilerow_weights(const tsg_dtile *a, const tsg_dtile *b, long long *w_host);
 
 /* Limits of one call / slab (TSG_ERR_OVERFLOW, "use smaller slabs"): < 2^31 matched tile pairs, < 2^30 C tiles, < 2^31 C
- * nonzeros. Tile-rows with more than 2048 tile pairs (R-MAT hubs) keep pair lists longer than 64 entries in arrival order:
- * for non-integer values the low bits of those C entries may differ from run to run (<= 1e-12 relative).
+ * nonzeros. Every C entry is summed in a fixed order (pair lists ascending by A tile, also those of hub tile-rows, which are
+ * collected with atomics and sorted afterwards): values are reproducible run to run.
  * SpGEMM steps 1-3 for C tile-rows [trow0, trow1) (trow1 < 0: to the end). C is a slab: a tiled
  * matrix of its own with tilem = trow1-trow0 and m = its row count. stats may be NULL. */
 int tsg_spgemm(const tsg_dtile *a, const tsg_dtile *b, int trow0, int trow1, tsg_dtile *c, tsg_stats *stats);

@@ -32,12 +32,13 @@
 #include "scan.cuh"
 #include "kernels.h"
 #include "plans.cuh"
+#include "pair_sort.h"
 
 namespace tsg {
 
 constexpr int S1_LIGHT_MAX = 2048;   // tile-rows with <= this many pairs run on one warp (deterministic pair order)
 constexpr int S1_HEAVY_THREADS = 1024;  // one CTA per heavy tile-row: its window bitmap can take most of the SM's shared memory
-constexpr int S1_SORT_MAX = 64;      // heavy path: pair lists up to this length are re-sorted by A tile
+constexpr int S1_SORT_MAX = 64;      // heavy path: pair lists up to this length are re-sorted by A tile with an insertion sort, longer ones with pair_sort.h
 
 // ---------------------------------------------------------------------------------------------
 // Step 1a: per tile-row weight w = #matched tile pairs, and the window [jlo, jhi] of tile columns
@@ -636,8 +637,9 @@ k_s1_heavy(int trow0, int nw_max, int n_heavy, unsigned *__restrict__ gscratch, 
         pair_b[pos] = rec.w;
     }
     __syncthreads();
-    // several warps appended concurrently: restore ascending-A-tile order for short lists so the FP64 summation
-    // order is reproducible (lists longer than S1_SORT_MAX keep arrival order; include/tilespgemm.h says so)
+    // several warps appended concurrently: restore ascending-A-tile order so that the FP64 summation order of every C
+    // entry is the serial SPA's and values are reproducible run to run (insertion sort for short lists, an in-place
+    // heap sort -- pair_sort.h -- for the long ones of hub tile-rows; a thread owns a list)
     for (int sidx = tid; sidx < numJ; sidx += THREADS) {
         int b = pair_ptr[cbase + sidx], e = pair_end[cbase + sidx], len = e - b;
         if (len > 1 && len <= S1_SORT_MAX) {
@@ -646,6 +648,8 @@ k_s1_heavy(int trow0, int nw_max, int n_heavy, unsigned *__restrict__ gscratch, 
                 while (y >= b && pair_a[y] > ka) { pair_a[y + 1] = pair_a[y]; pair_b[y + 1] = pair_b[y]; y--; }
                 pair_a[y + 1] = ka; pair_b[y + 1] = kb;
             }
+        } else if (len > S1_SORT_MAX) {
+            pair_heap_sort(pair_a + b, pair_b + b, len);
         }
     }
     }  // heavy_list loop
