@@ -27,7 +27,7 @@
 //   * Empty C tiles are kept with Ptr = mask = 0 and nnz 0 (the reference leaves them uninitialised).
 //   * One scan per array (64-bit total next to 32-bit offsets), scratch in grow-only arenas, two host read-backs per
 //     call on the light path (sizes of the two allocations), one more when heavy tile-rows exist.
-// Superseded kernels measured on the way are described in profiles/README.md; some are kept as text under scratch/.
+// Superseded kernels measured on the way are described in profiles/README.md.
 #include "common.cuh"
 #include "scan.cuh"
 #include "kernels.h"
